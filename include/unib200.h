@@ -1,0 +1,144 @@
+/* unib200 -- C ABI of the B200-native (sm_100a) kernels behind the Uni-Renderer dual-stream denoising hot path.
+ *
+ * The reference has NO native/FFI boundary on this path: the boundary a drop-in must honour is the Python
+ * nn.Module surface of models/controlnet.py (UNet2DConditionModel.forward :781, AttributeEncoderModel.forward :1657,
+ * AttributeDecoderModel.forward :2342) whose arithmetic is executed by torch (cuDNN conv, cuBLAS GEMM, SDPA,
+ * native GroupNorm/LayerNorm).  This header is therefore the boundary of OUR replacement for those torch leaf
+ * calls: uni_renderer_b200/ (Python, mirrors the reference classes) binds these symbols with ctypes.
+ * Each entry point names the reference call site(s) whose device work it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless stated;
+ * activations are NHWC fp16 ([B*H*W, C] row-major); all calls are asynchronous on `stream` (a cudaStream_t);
+ * return 0 on success, negative on error with unib200_last_error() giving the reason; never throws.
+ * If `prog` is non-NULL the op is RECORDED into the program (tensor maps pre-encoded) instead of launched;
+ * unib200_program_run / unib200_program_graph_launch replay the recorded list.
+ */
+#ifndef UNIB200_H_
+#define UNIB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIB200_VERSION 100
+
+typedef struct unib200_program unib200_program;
+
+/* ---- library / device ------------------------------------------------------------------------------------- */
+int unib200_version(void);
+const char* unib200_last_error(void);                 /* thread-local, valid until the next failing call */
+int unib200_device_info(int* num_sms, int* cc_major, int* cc_minor);
+
+/* ---- programs (recorded op lists; optionally instantiated as a CUDA graph) --------------------------------- */
+unib200_program* unib200_program_create(void);
+void unib200_program_destroy(unib200_program* prog);
+int unib200_program_num_launches(const unib200_program* prog);   /* kernels launched by one run */
+int unib200_program_run(unib200_program* prog, void* stream);
+int unib200_program_graph_instantiate(unib200_program* prog, void* stream);   /* capture run() into a CUDA graph */
+int unib200_program_graph_launch(unib200_program* prog, void* stream);
+
+/* ---- implicit-GEMM convolution / linear (tcgen05) ----------------------------------------------------------
+ * Replaces: nn.Conv2d 3x3/1x1 inside ResnetBlock2D, Transformer2DModel.proj_in/out, Down/Upsample2D, conv_in,
+ * conv_out, the 26 exchange zero-convs (models/controlnet.py:1019,1157,1754-1775,2456,2476,2521) and every
+ * nn.Linear of Attention / FeedForward (diffusers leaves called from models/unet_2d_blocks.py:803,1207,2576).
+ *   out[m, n] = epilogue( sum over segments/taps/channels  A_seg[pixel(m)+tap, c] * weight[n, k] )
+ */
+enum { UNIB200_SEG_1x1 = 0, UNIB200_SEG_3x3 = 1, UNIB200_SEG_3x3_S2 = 2 };
+enum {
+  UNIB200_EPI_GEGLU = 1,     /* weight rows interleaved per N-tile: out = (a+ba) * gelu(g+bg); N_out = N/2        */
+  UNIB200_EPI_OUT_NCHW = 2,  /* store NCHW (fp16, or fp32 with OUT_F32) instead of NHWC fp16                      */
+  UNIB200_EPI_OUT_F32 = 4,
+  UNIB200_EPI_SILU = 8,
+  UNIB200_EPI_AXPBY = 16     /* scheduler update fused behind conv_out: see unib200_gemm_desc.axpby              */
+};
+
+typedef struct {
+  const void* ptr;   /* NHWC fp16 base of this source                                                            */
+  int C;             /* channels taken from this source                                                           */
+  int ld;            /* elements between consecutive pixels (>= C; lets a source be a column slice)               */
+  int kind;          /* UNIB200_SEG_*                                                                             */
+} unib200_seg;
+
+typedef struct {
+  int M, N;                 /* output rows (B*H*W or tokens) and output channels (pre-GEGLU)                     */
+  int B, H, W;              /* OUTPUT image dims for conv segments; H = W = 0 => plain [M, K] row-major A        */
+  int nseg;
+  unib200_seg seg[4];       /* accumulated in order; weight K layout = [seg][tap][ceil(C/64)*64]                  */
+  const void* weight;       /* packed fp16 [N, Ktot]                                                              */
+  const float* bias;        /* fp32 [N] or [B][N] (bias_bstride = N), may be NULL                                 */
+  int bias_bstride;
+  const void* res;          /* optional fp16 residual [M, ldr] added before the activation                        */
+  int ldr;
+  void* out;                /* fp16 [M, ldc] (or NCHW, see flags)                                                 */
+  int ldc;
+  int flags;                /* UNIB200_EPI_*                                                                       */
+  int splits;               /* split-K factor; 0 = choose automatically                                           */
+  float* partial;           /* split-K fp32 workspace (may be NULL => no split-K)                                 */
+  size_t partial_bytes;
+  const float* axpby;       /* EPI_AXPBY: device [steps][2] (c_out, c_x) table, row = *axpby_step (or row 0)       */
+  const int* axpby_step;
+  const float* aux;         /* EPI_AXPBY: current latent x_t, NCHW fp32                                           */
+  float* aux_out;           /* EPI_AXPBY: x_{t-1} NCHW fp32 (may alias aux)                                       */
+  int axpby_first_channel;  /* channels below this keep aux unchanged (the clean mask group, pipeline.py:2691)    */
+} unib200_gemm_desc;
+
+int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);
+size_t unib200_packed_k(int nseg, const unib200_seg* seg);      /* Ktot of the packed weight matrix               */
+
+/* ---- fused attention (tcgen05 flash attention, no mask) ----------------------------------------------------
+ * Replaces F.scaled_dot_product_attention inside diffusers Attention (AttnProcessor2_0) for attn1/attn2 of every
+ * BasicTransformerBlock.  q/k/v are fp16 row-major token matrices; head h uses columns [h*d, (h+1)*d).
+ */
+typedef struct {
+  const void* q; int ldq;
+  const void* k; int ldk;
+  const void* v; int ldv;
+  void* out; int ldo;
+  int B, heads, Nq, Nk, d;
+  float scale;
+} unib200_attn_desc;
+int unib200_attention(unib200_program* prog, const unib200_attn_desc* desc, void* stream);
+
+/* ---- GroupNorm(+SiLU) over NHWC with optional second source (virtual torch.cat, unet_2d_blocks.py:2546,2677) - */
+typedef struct {
+  const void* x1; int ld1; int C1;
+  const void* x2; int ld2; int C2;
+  int B, HW, groups;
+  float eps;
+  const float* gamma; const float* beta;
+  void* out;                 /* fp16 [B*HW, C1+C2]                                                                */
+  int silu;
+  float* scratch;            /* fp32 scratch, scratch_floats >= B * chunks * groups * 2 for some chunks >= 1       */
+  size_t scratch_floats;
+} unib200_gn_desc;
+int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* desc, void* stream);
+
+/* ---- LayerNorm over channels of [rows, C] fp16 (BasicTransformerBlock.norm1/2/3) ---------------------------- */
+int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float* gamma, const float* beta, int rows,
+                      int C, float eps, void* stream);
+
+/* ---- layout / resampling ------------------------------------------------------------------------------------ */
+int unib200_to_nhwc(unib200_program* prog, const void* src, int src_is_f32, void* dst, int B, int C, int H, int W,
+                    int64_t sb, int64_t sc, int64_t sh, int64_t sw, int Cpad, void* stream);
+int unib200_from_nhwc(unib200_program* prog, const void* src, void* dst, int dst_is_f32, int B, int C, int HW, int ld,
+                      void* stream);
+int unib200_upsample2x(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream);
+
+/* ---- timestep embedding (Timesteps + TimestepEmbedding + all time_emb_proj, controlnet.py:909-916) ---------- */
+int unib200_timestep_sinusoid(unib200_program* prog, const float* t, const int* step_idx, int t_stride, float* out,
+                              int B, int dim, void* stream);
+int unib200_gemv(unib200_program* prog, const float* x, const void* w_fp16, const float* bias, float* y, int B, int K,
+                 int N, int act_silu, void* stream);
+
+/* ---- scheduler update x_prev = c_out*model_out + c_x*x (DDIMScheduler.step, eta=0; pipeline.py:1649,2725) ---- */
+int unib200_axpby(unib200_program* prog, const float* model_out, const float* x, float* out, const float* coef,
+                  const int* step_idx, int64_t n, void* stream);
+int unib200_add_int(unib200_program* prog, int* p, int v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIB200_H_ */

@@ -1,0 +1,108 @@
+"""ctypes binding of libunib200.so (include/unib200.h).  The product path FAILS LOUDLY when the library is missing;
+there is no CPU / PyTorch fallback for any op."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libunib200.so")
+
+SEG_1x1, SEG_3x3, SEG_3x3_S2 = 0, 1, 2
+EPI_GEGLU, EPI_OUT_NCHW, EPI_OUT_F32, EPI_SILU, EPI_AXPBY = 1, 2, 4, 8, 16
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int), ("ld", C.c_int), ("kind", C.c_int)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("nseg", C.c_int),
+        ("seg", Seg * 4),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("bias_bstride", C.c_int),
+        ("res", C.c_void_p), ("ldr", C.c_int),
+        ("out", C.c_void_p), ("ldc", C.c_int),
+        ("flags", C.c_int), ("splits", C.c_int),
+        ("partial", C.c_void_p), ("partial_bytes", C.c_size_t),
+        ("axpby", C.c_void_p), ("axpby_step", C.c_void_p), ("aux", C.c_void_p), ("aux_out", C.c_void_p),
+        ("axpby_first_channel", C.c_int),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_int),
+        ("B", C.c_int), ("heads", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("d", C.c_int), ("scale", C.c_float),
+    ]
+
+
+class GnDesc(C.Structure):
+    _fields_ = [
+        ("x1", C.c_void_p), ("ld1", C.c_int), ("C1", C.c_int),
+        ("x2", C.c_void_p), ("ld2", C.c_int), ("C2", C.c_int),
+        ("B", C.c_int), ("HW", C.c_int), ("groups", C.c_int), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p), ("silu", C.c_int),
+        ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t),
+    ]
+
+
+# every symbol include/unib200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "unib200_version", "unib200_last_error", "unib200_device_info",
+    "unib200_program_create", "unib200_program_destroy", "unib200_program_num_launches", "unib200_program_run",
+    "unib200_program_graph_instantiate", "unib200_program_graph_launch",
+    "unib200_conv_gemm", "unib200_packed_k", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
+    "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
+    "unib200_axpby", "unib200_add_int",
+]
+
+_lib = None
+
+
+class Unib200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libunib200.so or raise -- never falls back to another implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Unib200Error(f"{LIB_PATH} is missing: build it with `python -m uni_renderer_b200.build` "
+                           "(or __graft_entry__.build()); there is no fallback path")
+    lib = C.CDLL(LIB_PATH)
+    vp, ci, cf, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+    lib.unib200_version.restype = ci
+    lib.unib200_last_error.restype = C.c_char_p
+    lib.unib200_device_info.argtypes = [C.POINTER(ci)] * 3
+    lib.unib200_program_create.restype = vp
+    lib.unib200_program_destroy.argtypes = [vp]
+    lib.unib200_program_destroy.restype = None
+    lib.unib200_program_num_launches.argtypes = [vp]
+    lib.unib200_program_run.argtypes = [vp, vp]
+    lib.unib200_program_graph_instantiate.argtypes = [vp, vp]
+    lib.unib200_program_graph_launch.argtypes = [vp, vp]
+    lib.unib200_conv_gemm.argtypes = [vp, C.POINTER(GemmDesc), vp]
+    lib.unib200_packed_k.argtypes = [ci, C.POINTER(Seg)]
+    lib.unib200_packed_k.restype = C.c_size_t
+    lib.unib200_attention.argtypes = [vp, C.POINTER(AttnDesc), vp]
+    lib.unib200_groupnorm.argtypes = [vp, C.POINTER(GnDesc), vp]
+    lib.unib200_layernorm.argtypes = [vp, vp, vp, vp, vp, ci, ci, cf, vp]
+    lib.unib200_to_nhwc.argtypes = [vp, vp, ci, vp, ci, ci, ci, ci, i64, i64, i64, i64, ci, vp]
+    lib.unib200_from_nhwc.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.unib200_upsample2x.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_timestep_sinusoid.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp]
+    lib.unib200_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_axpby.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.unib200_add_int.argtypes = [vp, vp, ci, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().unib200_last_error()
+        raise Unib200Error(f"{what}: {msg.decode() if msg else rc}")

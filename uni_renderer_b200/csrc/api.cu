@@ -1,0 +1,413 @@
+// C ABI (include/unib200.h): argument validation, TMA tensor-map encoding, split-K planning, program recording and
+// CUDA-graph replay.  No torch types, no exceptions across the boundary.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/unib200.h"
+#include "attention_sm100.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+
+using namespace unib;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return -2;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// fp16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides[i] is the byte stride of dim i+1.
+bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, std::string* why) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { *why = "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"; return false; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { *why = "tensor base not 16-byte aligned"; return false; }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gs[i] % 16 != 0) { *why = "tensor stride not a multiple of 16 bytes"; return false; }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *why = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+typedef std::function<cudaError_t(cudaStream_t)> Op;
+
+}  // namespace
+
+struct unib200_program {
+  std::vector<Op> ops;
+  int launches = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+namespace {
+int submit(unib200_program* prog, Op op, int launches, void* stream, const char* what) {
+  if (prog) {
+    prog->ops.push_back(std::move(op));
+    prog->launches += launches;
+    return 0;
+  }
+  cudaError_t e = op(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(what, e);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int unib200_version(void) { return UNIB200_VERSION; }
+const char* unib200_last_error(void) { return g_err.c_str(); }
+
+int unib200_device_info(int* sms, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda("cudaGetDevice", e);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
+  if (sms) *sms = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+unib200_program* unib200_program_create(void) { return new (std::nothrow) unib200_program(); }
+
+void unib200_program_destroy(unib200_program* prog) {
+  if (!prog) return;
+  if (prog->exec) cudaGraphExecDestroy(prog->exec);
+  if (prog->graph) cudaGraphDestroy(prog->graph);
+  delete prog;
+}
+
+int unib200_program_num_launches(const unib200_program* prog) { return prog ? prog->launches : 0; }
+
+int unib200_program_run(unib200_program* prog, void* stream) {
+  if (!prog) return fail("null program");
+  for (size_t i = 0; i < prog->ops.size(); ++i) {
+    cudaError_t e = prog->ops[i](static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(("program op " + std::to_string(i)).c_str(), e);
+  }
+  return 0;
+}
+
+int unib200_program_graph_instantiate(unib200_program* prog, void* stream) {
+  if (!prog) return fail("null program");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (prog->exec) { cudaGraphExecDestroy(prog->exec); prog->exec = nullptr; }
+  if (prog->graph) { cudaGraphDestroy(prog->graph); prog->graph = nullptr; }
+  cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return fail_cuda("cudaStreamBeginCapture", e);
+  int rc = unib200_program_run(prog, stream);
+  cudaGraph_t g = nullptr;
+  e = cudaStreamEndCapture(s, &g);
+  if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail_cuda("cudaStreamEndCapture", e);
+  prog->graph = g;
+  e = cudaGraphInstantiate(&prog->exec, g, 0);
+  if (e != cudaSuccess) return fail_cuda("cudaGraphInstantiate", e);
+  return 0;
+}
+
+int unib200_program_graph_launch(unib200_program* prog, void* stream) {
+  if (!prog || !prog->exec) return fail("program has no instantiated graph");
+  cudaError_t e = cudaGraphLaunch(prog->exec, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda("cudaGraphLaunch", e);
+  return 0;
+}
+
+size_t unib200_packed_k(int nseg, const unib200_seg* seg) {
+  size_t k = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const int taps = seg[i].kind == UNIB200_SEG_1x1 ? 1 : 9;
+    k += static_cast<size_t>(taps) * ((seg[i].C + 63) / 64) * 64;
+  }
+  return k;
+}
+
+int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* stream) {
+  if (!d) return fail("null desc");
+  if (d->M <= 0 || d->N <= 0 || d->nseg < 1 || d->nseg > kMaxSeg) return fail("conv_gemm: bad M/N/nseg");
+  const bool linear = (d->H == 0 || d->W == 0);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M;
+  p.N = d->N;
+  std::string why;
+  int bw = 128, bh = 1, bb = 1;
+  if (linear) {
+    p.W = 1 << 30;
+    p.H = 1;
+    p.rows_per_batch = d->B > 0 ? d->M / d->B : d->M;
+    if (p.rows_per_batch <= 0) p.rows_per_batch = d->M;
+  } else {
+    if (d->B * d->H * d->W != d->M) return fail("conv_gemm: M != B*H*W");
+    auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+    if (!pow2(d->W) || !pow2(d->H) || d->W > 128) return fail("conv_gemm: H and W must be powers of two, W <= 128");
+    p.W = d->W;
+    p.H = d->H;
+    p.rows_per_batch = d->H * d->W;
+    bw = d->W < 128 ? d->W : 128;
+    bh = 128 / bw;
+    if (bh > d->H) bh = d->H;
+    bb = 128 / (bw * bh);
+  }
+  int nmaps = 0, total_kb = 0;
+  p.nseg = d->nseg;
+  for (int i = 0; i < d->nseg; ++i) {
+    const unib200_seg& s = d->seg[i];
+    if (s.C <= 0 || s.ld < s.C || s.ld % 8 != 0) return fail("conv_gemm: bad segment C/ld (ld must be a multiple of 8)");
+    if (linear && s.kind != UNIB200_SEG_1x1) return fail("conv_gemm: linear A only supports 1x1 segments");
+    p.seg[i].tmap = nmaps;
+    p.seg[i].kind = s.kind;
+    p.seg[i].nkb = (s.C + 63) / 64;
+    p.seg[i].ntaps = s.kind == UNIB200_SEG_1x1 ? 1 : 9;
+    total_kb += p.seg[i].ntaps * p.seg[i].nkb;
+    const uint64_t pix = static_cast<uint64_t>(s.ld) * 2;
+    if (linear) {
+      if (nmaps + 1 > kMaxAMaps) return fail("conv_gemm: too many tensor maps");
+      const uint64_t dims[4] = {static_cast<uint64_t>(s.C), static_cast<uint64_t>(d->M), 1, 1};
+      const uint64_t st[3] = {pix, pix * d->M, pix * d->M};
+      const uint32_t box[4] = {64, 128, 1, 1};
+      if (!encode_map(&maps.a[nmaps++], s.ptr, 4, dims, st, box, &why)) return fail("conv_gemm A map: " + why);
+    } else if (s.kind == UNIB200_SEG_3x3_S2) {
+      if (nmaps + 4 > kMaxAMaps) return fail("conv_gemm: too many tensor maps");
+      const int Hi = 2 * d->H, Wi = 2 * d->W;   // source image is twice the output size
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const char* base = static_cast<const char*>(s.ptr) + (static_cast<uint64_t>(ph) * Wi + pw) * pix;
+          const uint64_t dims[4] = {static_cast<uint64_t>(s.C), static_cast<uint64_t>(d->W),
+                                    static_cast<uint64_t>(d->H), static_cast<uint64_t>(d->B)};
+          const uint64_t st[3] = {2 * pix, 2 * pix * Wi, pix * Wi * Hi};
+          const uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+          if (!encode_map(&maps.a[nmaps++], base, 4, dims, st, box, &why)) return fail("conv_gemm A map: " + why);
+        }
+    } else {
+      if (nmaps + 1 > kMaxAMaps) return fail("conv_gemm: too many tensor maps");
+      const uint64_t dims[4] = {static_cast<uint64_t>(s.C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                                static_cast<uint64_t>(d->B)};
+      const uint64_t st[3] = {pix, pix * d->W, pix * d->W * d->H};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+      if (!encode_map(&maps.a[nmaps++], s.ptr, 4, dims, st, box, &why)) return fail("conv_gemm A map: " + why);
+    }
+  }
+  for (int i = nmaps; i < kMaxAMaps; ++i) maps.a[i] = maps.a[0];
+  p.total_kb = total_kb;
+  const int bn = gemm_pick_bn(d->N, d->flags);
+  if ((d->flags & UNIB200_EPI_GEGLU) && (d->N % bn != 0 || (bn / 2) % 16 != 0))
+    return fail("conv_gemm: GEGLU needs N divisible by the tile width");
+  {
+    const uint64_t ktot = static_cast<uint64_t>(total_kb) * 64;
+    const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->N)};
+    const uint64_t st[1] = {ktot * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (!encode_map(&maps.b, d->weight, 2, dims, st, box, &why)) return fail("conv_gemm B map: " + why);
+  }
+  p.m_tiles = (d->M + kBM - 1) / kBM;
+  p.n_tiles = (d->N + bn - 1) / bn;
+  p.bias = d->bias;
+  p.bias_bstride = d->bias_bstride;
+  p.res = static_cast<const __half*>(d->res);
+  p.ldr = d->ldr;
+  p.out = d->out;
+  p.ldc = d->ldc;
+  p.flags = d->flags;
+  p.axpby = d->axpby;
+  p.axpby_step = d->axpby_step;
+  p.aux = d->aux;
+  p.aux_out = d->aux_out;
+  p.axpby_n0 = d->axpby_first_channel;
+  if (!(d->flags & UNIB200_EPI_OUT_NCHW)) {
+    if (d->ldc % 8 != 0) return fail("conv_gemm: ldc must be a multiple of 8");
+    if (d->res && d->ldr % 8 != 0) return fail("conv_gemm: ldr must be a multiple of 8");
+  }
+  if ((d->flags & UNIB200_EPI_AXPBY) && (!(d->flags & UNIB200_EPI_OUT_NCHW) || !d->axpby || !d->aux || !d->aux_out))
+    return fail("conv_gemm: EPI_AXPBY needs EPI_OUT_NCHW, axpby, aux and aux_out");
+  // split-K: fill the machine when the output has too few tiles (tiny-M layers are weight-bandwidth bound)
+  int splits = d->splits;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int sms = num_sms();
+  const bool can_split = d->partial != nullptr && !(d->flags & (UNIB200_EPI_GEGLU));
+  if (splits <= 0) {
+    splits = 1;
+    if (can_split && tiles * 2 <= sms) {
+      splits = sms / tiles;
+      const int max_by_k = total_kb / 4 > 0 ? total_kb / 4 : 1;   // keep >= 4 K blocks per split
+      if (splits > max_by_k) splits = max_by_k;
+      if (splits > 16) splits = 16;
+    }
+  }
+  if (splits > 1) {
+    if (!can_split) return fail("conv_gemm: split-K requested without workspace / with GEGLU");
+    const size_t need = static_cast<size_t>(splits) * d->M * d->N * sizeof(float);
+    if (need > d->partial_bytes) {
+      splits = static_cast<int>(d->partial_bytes / (static_cast<size_t>(d->M) * d->N * sizeof(float)));
+      if (splits < 1) splits = 1;
+    }
+    if (splits > total_kb) splits = total_kb;
+  }
+  p.splits = splits;
+  p.partial = d->partial;
+  Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
+  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm");
+}
+
+int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* stream) {
+  if (!d) return fail("null desc");
+  if (d->d % 8 != 0 || d->d < 8 || d->d > 192) return fail("attention: head dim must be a multiple of 8 in [8,192]");
+  if (d->ldq % 8 || d->ldk % 8 || d->ldv % 8 || d->ldo % 8) return fail("attention: leading dims must be multiples of 8");
+  AttnMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string why;
+  const int bkv = attention_bkv(d->d);
+  auto mk = [&](CUtensorMap* m, const void* base, int ld, int tokens, int box_rows) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->d), static_cast<uint64_t>(tokens),
+                              static_cast<uint64_t>(d->heads), static_cast<uint64_t>(d->B)};
+    const uint64_t st[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(d->d) * 2,
+                            static_cast<uint64_t>(ld) * 2 * tokens};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), 1, 1};
+    return encode_map(m, base, 4, dims, st, box, &why);
+  };
+  if (!mk(&maps.q, d->q, d->ldq, d->Nq, 128)) return fail("attention Q map: " + why);
+  if (!mk(&maps.k, d->k, d->ldk, d->Nk, bkv)) return fail("attention K map: " + why);
+  if (!mk(&maps.v, d->v, d->ldv, d->Nk, bkv)) return fail("attention V map: " + why);
+  AttnParams p;
+  p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.d = d->d;
+  p.scale = d->scale;
+  p.out = static_cast<__half*>(d->out);
+  p.ldo = d->ldo;
+  Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
+  return submit(prog, std::move(op), 1, stream, "attention");
+}
+
+int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* stream) {
+  if (!d) return fail("null desc");
+  GnParams p;
+  memset(&p, 0, sizeof(p));
+  p.x1 = static_cast<const __half*>(d->x1); p.ld1 = d->ld1; p.C1 = d->C1;
+  p.x2 = static_cast<const __half*>(d->x2); p.ld2 = d->ld2; p.C2 = d->x2 ? d->C2 : 0;
+  p.HW = d->HW; p.G = d->groups; p.eps = d->eps; p.gamma = d->gamma; p.beta = d->beta;
+  p.out = static_cast<__half*>(d->out); p.silu = d->silu; p.partial = d->scratch;
+  const int C = p.C1 + p.C2;
+  if (C % 8 || p.C1 % 8 || d->groups <= 0 || C % d->groups || C / d->groups < 4 || C / 8 > 1024 || d->ld1 % 8 ||
+      (d->x2 && d->ld2 % 8))
+    return fail("groupnorm: unsupported channel configuration");
+  const size_t per_chunk = static_cast<size_t>(d->B) * d->groups * 2;
+  const size_t mc = per_chunk ? d->scratch_floats / per_chunk : 0;
+  if (mc < 1 || !d->scratch) return fail("groupnorm: scratch too small");
+  p.max_chunks = mc > 4096 ? 4096 : static_cast<int>(mc);
+  const int B = d->B, sms = num_sms();
+  Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm(p, B, sms, s); };
+  return submit(prog, std::move(op), 2, stream, "groupnorm");
+}
+
+int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float* gamma, const float* beta, int rows,
+                      int C, float eps, void* stream) {
+  if (C % 8 || C > 2048) return fail("layernorm: C must be a multiple of 8 and <= 2048");
+  Op op = [=](cudaStream_t s) {
+    return launch_layernorm(static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, rows, C, eps, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "layernorm");
+}
+
+int unib200_to_nhwc(unib200_program* prog, const void* src, int src_is_f32, void* dst, int B, int C, int H, int W,
+                    int64_t sb, int64_t sc, int64_t sh, int64_t sw, int Cpad, void* stream) {
+  if (Cpad < C) return fail("to_nhwc: Cpad < C");
+  Op op = [=](cudaStream_t s) {
+    return launch_to_nhwc(src, src_is_f32, static_cast<__half*>(dst), B, C, H, W, sb, sc, sh, sw, Cpad, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "to_nhwc");
+}
+
+int unib200_from_nhwc(unib200_program* prog, const void* src, void* dst, int dst_is_f32, int B, int C, int HW, int ld,
+                      void* stream) {
+  Op op = [=](cudaStream_t s) {
+    return launch_from_nhwc(static_cast<const __half*>(src), dst, dst_is_f32, B, C, HW, ld, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "from_nhwc");
+}
+
+int unib200_upsample2x(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream) {
+  if (C % 8) return fail("upsample2x: C must be a multiple of 8");
+  Op op = [=](cudaStream_t s) {
+    return launch_upsample2x(static_cast<const __half*>(src), static_cast<__half*>(dst), B, H, W, C, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "upsample2x");
+}
+
+int unib200_timestep_sinusoid(unib200_program* prog, const float* t, const int* step_idx, int t_stride, float* out,
+                              int B, int dim, void* stream) {
+  if (dim % 2) return fail("timestep_sinusoid: dim must be even");
+  Op op = [=](cudaStream_t s) { return launch_timestep_sinusoid(t, step_idx, t_stride, out, B, dim, s); };
+  return submit(prog, std::move(op), 1, stream, "timestep_sinusoid");
+}
+
+int unib200_gemv(unib200_program* prog, const float* x, const void* w_fp16, const float* bias, float* y, int B, int K,
+                 int N, int act_silu, void* stream) {
+  if (K % 8 || static_cast<size_t>(K) * 8 * 4 > 48 * 1024) return fail("gemv: K must be a multiple of 8 and <= 1536");
+  Op op = [=](cudaStream_t s) {
+    return launch_gemv(x, static_cast<const __half*>(w_fp16), bias, y, B, K, N, act_silu, s);
+  };
+  return submit(prog, std::move(op), (B + 7) / 8, stream, "gemv");
+}
+
+int unib200_axpby(unib200_program* prog, const float* model_out, const float* x, float* out, const float* coef,
+                  const int* step_idx, int64_t n, void* stream) {
+  Op op = [=](cudaStream_t s) { return launch_axpby(model_out, x, out, coef, step_idx, n, s); };
+  return submit(prog, std::move(op), 1, stream, "axpby");
+}
+
+int unib200_add_int(unib200_program* prog, int* p, int v, void* stream) {
+  Op op = [=](cudaStream_t s) { return launch_add_int(p, v, s); };
+  return submit(prog, std::move(op), 1, stream, "add_int");
+}
+
+}  // extern "C"

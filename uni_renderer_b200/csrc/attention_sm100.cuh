@@ -1,0 +1,21 @@
+// Fused attention for sm_100a -- host-visible parameter blocks (see attention_sm100.cu).
+#pragma once
+#include "common.cuh"
+
+namespace unib {
+
+struct AttnParams {
+  int B, heads, Nq, Nk, d;
+  float scale;       // softmax scale (d^-1/2)
+  __half* out;       // [B*Nq, ldo] fp16; head h writes columns [h*d, (h+1)*d)
+  int ldo;
+};
+
+struct alignas(64) AttnMaps {
+  CUtensorMap q, k, v;   // 4-D {d, tokens, heads, batch}, box {64, 128 | BKV, 1, 1}, SWIZZLE_128B
+};
+
+int attention_bkv(int d);
+cudaError_t launch_attention(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream);
+
+}  // namespace unib

@@ -1,0 +1,288 @@
+"""Torch-tensor front end of the C ABI: builds the descriptor structs from tensors (device pointers, leading dims)
+and calls libunib200.so.  PyTorch is used for device memory and streams only; no torch compute op is on this path.
+Every function takes `prog` (a recorded program handle or None for an immediate launch)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2)
+
+__all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
+           "timestep_sinusoid", "gemv", "axpby", "add_int", "Program", "pack_weight", "pack_geglu", "device_info",
+           "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_2d(t: torch.Tensor, what: str) -> int:
+    """fp16 CUDA matrix with unit column stride; returns its leading dimension (row stride in elements)."""
+    if not (t.is_cuda and t.dtype == torch.float16 and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError(f"{what}: expected a CUDA fp16 [rows, cols] tensor with unit column stride, got "
+                         f"{tuple(t.shape)} {t.dtype} strides {t.stride()} on {t.device}")
+    return t.stride(0)
+
+
+def device_info() -> Tuple[int, int, int]:
+    lib = L.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    L.check(lib.unib200_device_info(C.byref(a), C.byref(b), C.byref(c)), "device_info")
+    return a.value, b.value, c.value
+
+
+class Program:
+    """A recorded op list (include/unib200.h unib200_program): replayed op by op or as one CUDA graph."""
+
+    def __init__(self):
+        self.lib = L.load()
+        self.handle = self.lib.unib200_program_create()
+        if not self.handle:
+            raise L.Unib200Error("program_create failed")
+        self._keep: list = []          # tensors referenced by recorded ops
+        self.has_graph = False
+
+    def keep(self, *tensors):
+        self._keep.extend(t for t in tensors if t is not None)
+
+    @property
+    def num_launches(self) -> int:
+        return self.lib.unib200_program_num_launches(self.handle)
+
+    def run(self):
+        L.check(self.lib.unib200_program_run(self.handle, _stream()), "program_run")
+
+    def instantiate_graph(self):
+        L.check(self.lib.unib200_program_graph_instantiate(self.handle, _stream()), "graph_instantiate")
+        self.has_graph = True
+
+    def launch_graph(self):
+        L.check(self.lib.unib200_program_graph_launch(self.handle, _stream()), "graph_launch")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.unib200_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _h(prog: Optional[Program]):
+    return prog.handle if prog is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weight packing (one-time, at load): reference layout (diffusers state dict) -> [N, Ktot] fp16 K-major
+# ---------------------------------------------------------------------------------------------------------------
+def pack_weight(parts: Sequence[Tuple[torch.Tensor, int]], device=None) -> torch.Tensor:
+    """parts: list of (weight, kind) accumulated into the same output, in K order.
+    weight is [O, I] (linear), [O, I, 1, 1] or [O, I, 3, 3]; kind is SEG_*.  Channels are padded to a multiple of
+    64 per tap, taps are row-major (dy, dx) -- the order the kernel's K loop walks (csrc/gemm_sm100.cu)."""
+    cols = []
+    for w, kind in parts:
+        w = w.detach().float()
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        O, I, kh, kw = w.shape
+        if kind == SEG_1x1:
+            assert kh == 1 and kw == 1
+        else:
+            assert kh == 3 and kw == 3
+        Ipad = (I + 63) // 64 * 64
+        wp = torch.zeros(O, kh * kw, Ipad, dtype=torch.float32, device=w.device)
+        wp[:, :, :I] = w.permute(0, 2, 3, 1).reshape(O, kh * kw, I)
+        cols.append(wp.reshape(O, kh * kw * Ipad))
+    out = torch.cat(cols, dim=1).to(torch.float16).contiguous()
+    return out.to(device) if device is not None else out
+
+
+def pick_bn(N: int) -> int:
+    for bn in (160, 128, 64, 32):
+        if N % bn == 0:
+            return bn
+    return 128 if N >= 128 else (64 if N > 32 else 32)
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU projection [2*inner, C] (+bias): interleave value/gate rows per N-tile so one accumulator tile holds
+    both halves of the same output columns (EPI_GEGLU)."""
+    two_inner = w.shape[0]
+    inner = two_inner // 2
+    bn = pick_bn(two_inner)
+    half = bn // 2
+    assert two_inner % bn == 0 and half % 16 == 0 and inner % half == 0
+    idx = []
+    for t in range(two_inner // bn):
+        idx.append(torch.arange(t * half, (t + 1) * half))
+        idx.append(inner + torch.arange(t * half, (t + 1) * half))
+    idx = torch.cat(idx).to(w.device)
+    return w[idx].contiguous(), b[idx].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------------------------
+def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, int]], weight: torch.Tensor,
+              out: torch.Tensor, *, M: int, N: int, B: int = 0, H: int = 0, W: int = 0,
+              bias: Optional[torch.Tensor] = None, bias_bstride: int = 0, res: Optional[torch.Tensor] = None,
+              flags: int = 0, splits: int = 0, partial: Optional[torch.Tensor] = None,
+              axpby: Optional[torch.Tensor] = None, axpby_step: Optional[torch.Tensor] = None,
+              aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
+              axpby_first_channel: int = 0, ldc: Optional[int] = None):
+    """segs: (matrix [pixels, >=C] fp16, C, kind).  H = W = 0 selects the plain row-major [M, K] path."""
+    lib = L.load()
+    d = L.GemmDesc()
+    d.M, d.N, d.B, d.H, d.W, d.nseg = M, N, B, H, W, len(segs)
+    ktot = 0
+    for i, (t, c, kind) in enumerate(segs):
+        ld = _check_2d(t, f"conv_gemm seg {i}")
+        d.seg[i].ptr, d.seg[i].C, d.seg[i].ld, d.seg[i].kind = t.data_ptr(), c, ld, kind
+        ktot += (1 if kind == SEG_1x1 else 9) * ((c + 63) // 64 * 64)
+    if weight.dtype != torch.float16 or tuple(weight.shape) != (N, ktot) or not weight.is_contiguous():
+        raise ValueError(f"conv_gemm: packed weight must be contiguous fp16 [{N}, {ktot}], got {tuple(weight.shape)}")
+    d.weight = weight.data_ptr()
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1
+    d.bias, d.bias_bstride = _ptr(bias), bias_bstride
+    if res is not None:
+        d.ldr = _check_2d(res, "conv_gemm res")
+    d.res = _ptr(res)
+    d.out = _ptr(out)
+    if ldc is not None:
+        d.ldc = ldc
+    elif out is not None and not (flags & EPI_OUT_NCHW):
+        d.ldc = _check_2d(out, "conv_gemm out")
+    d.flags, d.splits = flags, splits
+    if partial is not None:
+        d.partial, d.partial_bytes = partial.data_ptr(), partial.numel() * partial.element_size()
+    d.axpby, d.axpby_step, d.aux, d.aux_out = _ptr(axpby), _ptr(axpby_step), _ptr(aux), _ptr(aux_out)
+    d.axpby_first_channel = axpby_first_channel
+    L.check(lib.unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
+    if prog is not None:
+        prog.keep(*(s[0] for s in segs), weight, out, bias, res, partial, axpby, axpby_step, aux, aux_out)
+
+
+def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *,
+              B: int, heads: int, Nq: int, Nk: int, d: int, scale: Optional[float] = None):
+    lib = L.load()
+    a = L.AttnDesc()
+    a.q, a.ldq = q.data_ptr(), _check_2d(q, "attention q")
+    a.k, a.ldk = k.data_ptr(), _check_2d(k, "attention k")
+    a.v, a.ldv = v.data_ptr(), _check_2d(v, "attention v")
+    a.out, a.ldo = out.data_ptr(), _check_2d(out, "attention out")
+    a.B, a.heads, a.Nq, a.Nk, a.d = B, heads, Nq, Nk, d
+    a.scale = float(scale if scale is not None else d ** -0.5)
+    L.check(lib.unib200_attention(_h(prog), C.byref(a), _stream()), "attention")
+    if prog is not None:
+        prog.keep(q, k, v, out)
+
+
+def groupnorm(prog: Optional[Program], x1: torch.Tensor, C1: int, x2: Optional[torch.Tensor], C2: int,
+              gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, scratch: torch.Tensor, *, B: int, HW: int,
+              groups: int, eps: float, silu: bool):
+    lib = L.load()
+    g = L.GnDesc()
+    g.x1, g.ld1, g.C1 = x1.data_ptr(), _check_2d(x1, "groupnorm x1"), C1
+    if x2 is not None:
+        g.x2, g.ld2, g.C2 = x2.data_ptr(), _check_2d(x2, "groupnorm x2"), C2
+    g.B, g.HW, g.groups, g.eps = B, HW, groups, eps
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and scratch.dtype == torch.float32
+    g.gamma, g.beta, g.out, g.silu = gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), int(silu)
+    assert out.is_contiguous() and out.shape[-1] == C1 + (C2 if x2 is not None else 0)
+    g.scratch, g.scratch_floats = scratch.data_ptr(), scratch.numel()
+    L.check(lib.unib200_groupnorm(_h(prog), C.byref(g), _stream()), "groupnorm")
+    if prog is not None:
+        prog.keep(x1, x2, gamma, beta, out, scratch)
+
+
+def layernorm(prog: Optional[Program], x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+              eps: float = 1e-5):
+    lib = L.load()
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float16 and y.dtype == torch.float16
+    rows, Cn = x.shape
+    L.check(lib.unib200_layernorm(_h(prog), x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, Cn,
+                                  eps, _stream()), "layernorm")
+    if prog is not None:
+        prog.keep(x, y, gamma, beta)
+
+
+def to_nhwc(prog: Optional[Program], src: torch.Tensor, dst: torch.Tensor, Cpad: int):
+    """src: logical [B, C, H, W] fp32/fp16 with arbitrary strides -> dst [B*H*W, Cpad] fp16 (zero padded)."""
+    lib = L.load()
+    assert src.dtype in (torch.float32, torch.float16) and dst.dtype == torch.float16 and dst.is_contiguous()
+    B, Cn, H, W = src.shape
+    sb, sc, sh, sw = src.stride()
+    L.check(lib.unib200_to_nhwc(_h(prog), src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cn, H, W,
+                                sb, sc, sh, sw, Cpad, _stream()), "to_nhwc")
+    if prog is not None:
+        prog.keep(src, dst)
+
+
+def from_nhwc(prog: Optional[Program], src: torch.Tensor, dst: torch.Tensor, *, B: int, Cn: int, HW: int):
+    """src [B*HW, ld] fp16 (first Cn channels) -> contiguous NCHW dst (fp32 or fp16)."""
+    lib = L.load()
+    ld = _check_2d(src, "from_nhwc src")
+    assert dst.is_contiguous() and dst.dtype in (torch.float32, torch.float16)
+    L.check(lib.unib200_from_nhwc(_h(prog), src.data_ptr(), dst.data_ptr(), int(dst.dtype == torch.float32), B, Cn, HW,
+                                  ld, _stream()), "from_nhwc")
+    if prog is not None:
+        prog.keep(src, dst)
+
+
+def upsample2x(prog: Optional[Program], src: torch.Tensor, dst: torch.Tensor, *, B: int, H: int, W: int, Cn: int):
+    lib = L.load()
+    assert src.is_contiguous() and dst.is_contiguous()
+    L.check(lib.unib200_upsample2x(_h(prog), src.data_ptr(), dst.data_ptr(), B, H, W, Cn, _stream()), "upsample2x")
+    if prog is not None:
+        prog.keep(src, dst)
+
+
+def timestep_sinusoid(prog: Optional[Program], t: torch.Tensor, out: torch.Tensor, *, B: int, dim: int,
+                      step_idx: Optional[torch.Tensor] = None, t_stride: int = 0):
+    lib = L.load()
+    assert t.dtype == torch.float32 and out.dtype == torch.float32
+    L.check(lib.unib200_timestep_sinusoid(_h(prog), t.data_ptr(), _ptr(step_idx), t_stride, out.data_ptr(), B, dim,
+                                          _stream()), "timestep_sinusoid")
+    if prog is not None:
+        prog.keep(t, out, step_idx)
+
+
+def gemv(prog: Optional[Program], x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *,
+         silu: bool):
+    lib = L.load()
+    B, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.float32 and w.dtype == torch.float16 and y.dtype == torch.float32
+    assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous() and w.shape[1] == K and y.shape == (B, N)
+    L.check(lib.unib200_gemv(_h(prog), x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), B, K, N, int(silu),
+                             _stream()), "gemv")
+    if prog is not None:
+        prog.keep(x, w, bias, y)
+
+
+def axpby(prog: Optional[Program], model_out: torch.Tensor, x: torch.Tensor, out: torch.Tensor, coef: torch.Tensor,
+          step_idx: Optional[torch.Tensor] = None):
+    lib = L.load()
+    assert model_out.dtype == x.dtype == out.dtype == coef.dtype == torch.float32
+    assert model_out.is_contiguous() and x.is_contiguous() and out.is_contiguous()
+    L.check(lib.unib200_axpby(_h(prog), model_out.data_ptr(), x.data_ptr(), out.data_ptr(), coef.data_ptr(),
+                              _ptr(step_idx), x.numel(), _stream()), "axpby")
+    if prog is not None:
+        prog.keep(model_out, x, out, coef, step_idx)
+
+
+def add_int(prog: Optional[Program], p: torch.Tensor, v: int):
+    lib = L.load()
+    assert p.dtype == torch.int32
+    L.check(lib.unib200_add_int(_h(prog), p.data_ptr(), v, _stream()), "add_int")
+    if prog is not None:
+        prog.keep(p)
