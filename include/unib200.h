@@ -138,6 +138,10 @@ int unib200_axpby(unib200_program* prog, const float* model_out, const float* x,
                   const int* step_idx, int64_t n, void* stream);
 int unib200_add_int(unib200_program* prog, int* p, int v, void* stream);
 
+/* ---- out = a + b over contiguous fp16 (skip + external residual when the three modules are called separately,
+ *      models/controlnet.py:1084,1115; the fused step folds these adds into the zero-conv GEMM epilogue) -------- */
+int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

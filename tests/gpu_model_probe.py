@@ -1,0 +1,88 @@
+"""Model-level GPU probe: the three drop-in modules called in the reference's 3-call sequence vs the golden tensors
+recorded from the reference (tests/golden/*.pt).  Prints one JSON dict of per-tensor errors."""
+import json
+import os
+import sys
+from dataclasses import replace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from oracle import uni_oracle as uo  # noqa: E402  (test-side checker only)
+from uni_renderer_b200.models import (AttributeDecoderModel, AttributeEncoderModel,  # noqa: E402
+                                      UNet2DConditionModel)
+
+UP = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D")
+
+
+def err(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    d = (got - ref).abs()
+    return {"max_abs": round(d.max().item(), 6), "rel_l2": round((d.norm() / (ref.norm() + 1e-12)).item(), 6),
+            "ref_absmax": round(ref.abs().max().item(), 4)}
+
+
+def build_modules(gc, device="cuda"):
+    kw = dict(block_out_channels=tuple(gc["block_out_channels"]), attention_head_dim=gc["num_heads"],
+              cross_attention_dim=gc["cross_attention_dim"], norm_num_groups=gc["norm_num_groups"])
+    base = uo.NetConfig(block_out_channels=tuple(gc["block_out_channels"]), num_heads=gc["num_heads"],
+                        cross_attention_dim=gc["cross_attention_dim"], norm_num_groups=gc["norm_num_groups"])
+    cfgs = (replace(base), replace(base, in_channels=28), replace(base, out_channels=28))
+    unet = UNet2DConditionModel(in_channels=4, out_channels=4, _init_weights=False, **kw)
+    enc = AttributeEncoderModel(in_channels=28, _init_weights=False, **kw)
+    dec = AttributeDecoderModel(out_channels=28, up_block_types=UP, _init_weights=False, **kw)
+    sds = []
+    for m, k, c, s in zip((unet, enc, dec), ("unet", "attr_enc", "attr_dec"), cfgs, gc["seeds"]):
+        sd = uo.random_state_dict(k, c, s)
+        m.load_state_dict(sd)
+        m.to(device)
+        sds.append(sd)
+    return (unet, enc, dec), sds, cfgs
+
+
+def run_golden(name):
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", name), weights_only=False)
+    gc = gold["config"]
+    (unet, enc, dec), _, _ = build_modules(gc)
+    B = gc["B"]
+    if gc["scalar_t"]:
+        ti, ta = gc["t_img"], gc["t_attr"]
+    else:
+        ti = torch.full((B,), gc["t_img"], dtype=torch.long, device="cuda")
+        ta = torch.full((B,), gc["t_attr"], dtype=torch.long, device="cuda")
+    x_img, x_attr, ehs = gold["x_img"].cuda(), gold["x_attr"].cuda(), gold["ehs"].cuda()
+    # the reference's 3-call sequence (train/train.py:1324-1354, models/pipeline.py:2660-2690)
+    d, m, raw_a, raw_a_mid = enc(x_img, ta, encoder_hidden_states=ehs, controlnet_cond=x_attr, return_dict=False)
+    img_pred, raw_u, raw_u_mid, taps = unet(x_img, ti, encoder_hidden_states=ehs, down_block_additional_residuals=d,
+                                            mid_block_additional_residual=m, return_dict=False)
+    attr_pred = dec(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=ta, encoder_hidden_states=ehs,
+                    down_block_additional_residuals=raw_u, mid_block_additional_residual=raw_u_mid, return_dict=False)
+    torch.cuda.synchronize()
+    res = {"unet_sample": err(img_pred, gold["unet_sample"]), "dec_sample": err(attr_pred, gold["dec_sample"]),
+           "enc_mid": err(m, gold["enc_mid"]), "enc_raw_mid": err(raw_a_mid, gold["enc_raw_mid"]),
+           "unet_raw_mid": err(raw_u_mid, gold["unet_raw_mid"])}
+    for i in range(12):
+        res[f"enc_down{i}"] = err(d[i], gold["enc_down"][i])
+        res[f"enc_raw{i}"] = err(raw_a[i], gold["enc_raw_down"][i])
+        res[f"unet_raw{i}"] = err(raw_u[i], gold["unet_raw_down"][i])
+    for i in range(13):
+        res[f"unet_tap{i}"] = err(taps[i], gold["unet_up_taps"][i])
+    img_plain = unet(x_img, ti, encoder_hidden_states=ehs, return_dict=False)[0]
+    torch.cuda.synchronize()
+    res["unet_sample_plain"] = err(img_plain, gold["unet_sample_plain"])
+    # second call must reproduce the first bit-for-bit (static buffers, deterministic kernels)
+    d2 = enc(x_img, ta, encoder_hidden_states=ehs, controlnet_cond=x_attr, return_dict=False)[0]
+    img2 = unet(x_img, ti, encoder_hidden_states=ehs, down_block_additional_residuals=d2,
+                mid_block_additional_residual=m, return_dict=False)[0]
+    torch.cuda.synchronize()
+    res["rerun_bit_exact"] = bool(torch.equal(img2, img_pred))
+    return res
+
+
+if __name__ == "__main__":
+    name = sys.argv[1] if len(sys.argv) > 1 else "tiny_step_vec_t.pt"
+    out = run_golden(name)
+    worst = max((v["rel_l2"] for v in out.values() if isinstance(v, dict)), default=0)
+    print(json.dumps(out))
+    print("WORST rel_l2", worst, file=sys.stderr)

@@ -55,7 +55,7 @@ EXPORTS = [
     "unib200_program_graph_instantiate", "unib200_program_graph_launch",
     "unib200_conv_gemm", "unib200_packed_k", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
-    "unib200_axpby", "unib200_add_int",
+    "unib200_axpby", "unib200_add_int", "unib200_add_f16",
 ]
 
 _lib = None
@@ -98,6 +98,7 @@ def load() -> C.CDLL:
     lib.unib200_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.unib200_axpby.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
     lib.unib200_add_int.argtypes = [vp, vp, ci, vp]
+    lib.unib200_add_f16.argtypes = [vp, vp, vp, vp, i64, vp]
     _lib = lib
     return lib
 

@@ -405,6 +405,14 @@ int unib200_axpby(unib200_program* prog, const float* model_out, const float* x,
   return submit(prog, std::move(op), 1, stream, "axpby");
 }
 
+int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* out, int64_t n, void* stream) {
+  if (n % 8) return fail("add_f16: n must be a multiple of 8");
+  Op op = [=](cudaStream_t s) {
+    return launch_add_f16(static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(out), n, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "add_f16");
+}
+
 int unib200_add_int(unib200_program* prog, int* p, int v, void* stream) {
   Op op = [=](cudaStream_t s) { return launch_add_int(p, v, s); };
   return submit(prog, std::move(op), 1, stream, "add_int");

@@ -401,6 +401,33 @@ cudaError_t launch_axpby(const float* model_out, const float* x, float* out, con
   return cudaGetLastError();
 }
 
+// out = a + b over fp16 vectors (module-level API: UNet skip + externally supplied residual, controlnet.py:1084,1115)
+__global__ void add_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                               long long nvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 x = a[i], y = b[i];
+    const __half2* hx = reinterpret_cast<const __half2*>(&x);
+    const __half2* hy = reinterpret_cast<const __half2*>(&y);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fx = __half22float2(hx[j]), fy = __half22float2(hy[j]);
+      o[j] = pack_half2(fx.x + fy.x, fx.y + fy.y);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+cudaError_t launch_add_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream) {
+  if (n % 8) return cudaErrorInvalidValue;
+  const long long nvec = n / 8;
+  int blocks = static_cast<int>((nvec + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                             reinterpret_cast<uint4*>(out), nvec);
+  return cudaGetLastError();
+}
+
 __global__ void add_int_kernel(int* p, int v) { *p += v; }
 cudaError_t launch_add_int(int* p, int v, cudaStream_t stream) {
   add_int_kernel<<<1, 1, 0, stream>>>(p, v);

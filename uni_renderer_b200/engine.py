@@ -1,0 +1,427 @@
+"""Network assembly on top of the C-ABI ops: packs a diffusers-layout state dict once, then RECORDS the layer
+sequence of the SD-1.x-shaped streams into unib200 programs (static NHWC fp16 buffers, pre-encoded tensor maps) that
+are replayed per call / per denoising step, optionally as one CUDA graph.
+
+Mirrors (does not copy) the wiring of the reference:
+  * models/controlnet.py  UNet2DConditionModel.forward :781-1166, AttributeEncoderModel.forward :1657-1778,
+    AttributeDecoderModel.forward :2342-2527 (skip order, exchange, taps)
+  * models/unet_2d_blocks.py  CrossAttnDownBlock2D :1155, DownBlock2D :1276, UNetMidBlock2DCrossAttn :764,
+    CrossAttnUpBlock2D :2508, UpBlock2D :2643
+Fusions relative to the reference's op-per-kernel execution: conv bias + time-embedding add in the conv1 epilogue;
+the ResNet 1x1 shortcut accumulated into conv2's TMEM accumulator (or the identity residual added in its epilogue);
+torch.cat never materialised (GroupNorm reads two sources, the shortcut GEMM walks two K segments); q/k/v as one
+GEMM; GEGLU gate in the GEMM epilogue; every transformer residual add in a GEMM epilogue; the dual-stream exchange
+(zero-conv + add) as one GEMM epilogue per skip; the scheduler update behind conv_out.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2, Program)
+
+
+@dataclass
+class NetConfig:
+    """The part of the diffusers config the SD-1.x wiring uses (models/controlnet.py:146-205)."""
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    layers_per_block: int = 2
+    num_heads: int = 8            # the reference calls this `attention_head_dim` (controlnet.py:216-222)
+    cross_attention_dim: int = 768
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    down_has_attn: Tuple[bool, ...] = (True, True, True, False)
+    up_has_attn: Tuple[bool, ...] = (False, True, True, True)
+
+    @property
+    def time_embed_dim(self) -> int:
+        return self.block_out_channels[0] * 4
+
+
+@dataclass
+class Act:
+    """An NHWC fp16 activation: t is [B*H*W, C] (unit column stride)."""
+    t: torch.Tensor
+    B: int
+    H: int
+    W: int
+    C: int
+
+    @property
+    def M(self) -> int:
+        return self.B * self.H * self.W
+
+    def nchw(self) -> torch.Tensor:
+        """Zero-copy NCHW-shaped (channels_last strided) view -- the shape the reference's callers expect."""
+        return self.t.view(self.B, self.H, self.W, self.t.shape[1])[..., :self.C].permute(0, 3, 1, 2)
+
+
+class Workspace:
+    """Per-lane scratch shared by sequentially executed ops + a recycling pool for temporaries."""
+
+    def __init__(self, device):
+        self.device = device
+        self.gn_scratch = torch.empty(1 << 18, device=device, dtype=torch.float32)
+        self.partial = torch.empty(16 << 20, device=device, dtype=torch.float32)      # 64 MiB split-K partials
+        self._free: Dict[Tuple[int, int], List[torch.Tensor]] = {}
+        self.bytes_allocated = 0
+
+    def get(self, rows: int, cols: int) -> torch.Tensor:
+        lst = self._free.get((rows, cols))
+        if lst:
+            return lst.pop()
+        self.bytes_allocated += rows * cols * 2
+        return torch.empty(rows, cols, device=self.device, dtype=torch.float16)
+
+    def put(self, *ts: torch.Tensor):
+        for t in ts:
+            self._free.setdefault((t.shape[0], t.shape[1]), []).append(t)
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class StreamNet:
+    """Packed weights of one network ("unet" | "attr_enc" | "attr_dec") + the recorders for its sub-graphs."""
+
+    def __init__(self, kind: str, cfg: NetConfig, sd: Dict[str, torch.Tensor], device):
+        assert kind in ("unet", "attr_enc", "attr_dec")
+        self.kind, self.cfg, self.device = kind, cfg, torch.device(device)
+        self.has_encoder = kind in ("unet", "attr_enc")
+        self.has_decoder = kind in ("unet", "attr_dec")
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(sd)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # weight ingest: diffusers state-dict layout -> packed K-major fp16 + fp32 vectors
+    # ------------------------------------------------------------------------------------------------------------
+    def _pack(self, sd):
+        dev, cfg, w = self.device, self.cfg, self.w
+        need = lambda k: sd[k].detach().to(dev)    # noqa: E731
+
+        def conv3(name, kind=SEG_3x3):
+            w[name + ".w"] = ops.pack_weight([(need(name + ".weight"), kind)])
+            w[name + ".b"] = _f32(sd[name + ".bias"], dev)
+
+        def norm(name):
+            w[name + ".g"] = _f32(sd[name + ".weight"], dev)
+            w[name + ".bt"] = _f32(sd[name + ".bias"], dev)
+
+        w["te1.w"] = need("time_embedding.linear_1.weight").half().contiguous()
+        w["te1.b"] = _f32(sd["time_embedding.linear_1.bias"], dev)
+        w["te2.w"] = need("time_embedding.linear_2.weight").half().contiguous()
+        w["te2.b"] = _f32(sd["time_embedding.linear_2.bias"], dev)
+
+        self.resnets: List[str] = [k[:-len(".time_emb_proj.weight")] for k in sd if k.endswith(".time_emb_proj.weight")]
+        self.temb_off: Dict[str, int] = {}
+        tw, tb, off = [], [], 0
+        for r in self.resnets:
+            cout = sd[r + ".conv1.weight"].shape[0]
+            self.temb_off[r] = off
+            off += cout
+            tw.append(need(r + ".time_emb_proj.weight"))
+            tb.append(sd[r + ".time_emb_proj.bias"].detach().to(dev).float() + sd[r + ".conv1.bias"].detach().to(dev).float())
+            norm(r + ".norm1")
+            norm(r + ".norm2")
+            w[r + ".conv1.w"] = ops.pack_weight([(need(r + ".conv1.weight"), SEG_3x3)])
+        self.temb_total = off
+        w["tproj.w"] = torch.cat(tw, 0).half().contiguous()
+        w["tproj.b"] = torch.cat(tb, 0).contiguous()
+
+        self.transformers = [k[:-len(".proj_in.weight")] for k in sd if k.endswith(".proj_in.weight")]
+        for a in self.transformers:
+            t = a + ".transformer_blocks.0"
+            norm(a + ".norm")
+            w[a + ".proj_in.w"] = ops.pack_weight([(need(a + ".proj_in.weight"), SEG_1x1)])
+            w[a + ".proj_in.b"] = _f32(sd[a + ".proj_in.bias"], dev)
+            for n in ("norm1", "norm2", "norm3"):
+                norm(f"{t}.{n}")
+            qkv = torch.cat([need(f"{t}.attn1.to_q.weight"), need(f"{t}.attn1.to_k.weight"),
+                             need(f"{t}.attn1.to_v.weight")], 0)
+            w[t + ".qkv.w"] = ops.pack_weight([(qkv, SEG_1x1)])
+            w[t + ".out1.w"] = ops.pack_weight([(need(f"{t}.attn1.to_out.0.weight"), SEG_1x1)])
+            w[t + ".out1.b"] = _f32(sd[f"{t}.attn1.to_out.0.bias"], dev)
+            w[t + ".q2.w"] = ops.pack_weight([(need(f"{t}.attn2.to_q.weight"), SEG_1x1)])
+            kv = torch.cat([need(f"{t}.attn2.to_k.weight"), need(f"{t}.attn2.to_v.weight")], 0)
+            w[t + ".kv2.w"] = ops.pack_weight([(kv, SEG_1x1)])
+            w[t + ".out2.w"] = ops.pack_weight([(need(f"{t}.attn2.to_out.0.weight"), SEG_1x1)])
+            w[t + ".out2.b"] = _f32(sd[f"{t}.attn2.to_out.0.bias"], dev)
+            gw, gb = ops.pack_geglu(need(f"{t}.ff.net.0.proj.weight").float(), need(f"{t}.ff.net.0.proj.bias").float())
+            w[t + ".geglu.w"] = ops.pack_weight([(gw, SEG_1x1)])
+            w[t + ".geglu.b"] = gb.float().contiguous()
+            w[t + ".ff2.w"] = ops.pack_weight([(need(f"{t}.ff.net.2.weight"), SEG_1x1)])
+            w[t + ".ff2.b"] = _f32(sd[f"{t}.ff.net.2.bias"], dev)
+            w[a + ".proj_out.w"] = ops.pack_weight([(need(a + ".proj_out.weight"), SEG_1x1)])
+            w[a + ".proj_out.b"] = _f32(sd[a + ".proj_out.bias"], dev)
+
+        if self.has_encoder:
+            conv3("conv_in")
+            for i in range(len(cfg.block_out_channels) - 1):
+                conv3(f"down_blocks.{i}.downsamplers.0.conv", SEG_3x3_S2)
+        if self.has_decoder:
+            for i in range(len(cfg.block_out_channels) - 1):
+                conv3(f"up_blocks.{i}.upsamplers.0.conv")
+            norm("conv_norm_out")
+            conv3("conv_out")
+        zc = {"attr_enc": "controlnet", "attr_dec": "control"}.get(self.kind)
+        if zc:
+            names = [k[:-len(".weight")] for k in sd if k.startswith(zc + "_") and k.endswith(".weight")]
+            for n in names:
+                w[n + ".w"] = ops.pack_weight([(need(n + ".weight"), SEG_1x1)])
+                w[n + ".b"] = _f32(sd[n + ".bias"], dev)
+            self.zc_prefix = zc
+        self._sd_conv2 = {}
+        for r in self.resnets:      # conv2 (+ fused shortcut) is packed lazily: the split of the shortcut's input
+            self._sd_conv2[r] = (need(r + ".conv2.weight"), sd[r + ".conv2.bias"].detach().to(dev).float(),
+                                 need(r + ".conv_shortcut.weight") if r + ".conv_shortcut.weight" in sd else None,
+                                 sd[r + ".conv_shortcut.bias"].detach().to(dev).float()
+                                 if r + ".conv_shortcut.bias" in sd else None)
+
+    def _conv2_packed(self, r: str, src_channels: Sequence[int]):
+        """conv2 3x3 followed by the 1x1 shortcut segments over the (possibly two-source) block input."""
+        key = r + ".conv2.w"
+        if key not in self.w:
+            w2, b2, wsc, bsc = self._sd_conv2.pop(r)
+            parts = [(w2, SEG_3x3)]
+            bias = b2
+            if wsc is not None:
+                c0 = 0
+                for c in src_channels:
+                    parts.append((wsc[:, c0:c0 + c], SEG_1x1))
+                    c0 += c
+                assert c0 == wsc.shape[1]
+                bias = b2 + bsc
+            self.w[key] = ops.pack_weight(parts)
+            self.w[r + ".conv2.b"] = bias.contiguous()
+            self.w[r + ".has_sc"] = torch.tensor(int(wsc is not None))
+        return self.w[key], self.w[r + ".conv2.b"], bool(self.w[r + ".has_sc"].item())
+
+    def weight_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+    # ------------------------------------------------------------------------------------------------------------
+    # recorders
+    # ------------------------------------------------------------------------------------------------------------
+    def rec_temb(self, prog, ws: Workspace, t_buf: torch.Tensor, B: int, step_idx=None, t_stride: int = 0):
+        """Timesteps -> TimestepEmbedding -> SiLU -> every resnet's time_emb_proj (+conv1 bias), as one fp32
+        [B, sum Cout] table the conv1 epilogues index (controlnet.py:909-916; ResnetBlock2D temb path)."""
+        cfg, dev = self.cfg, self.device
+        D = cfg.time_embed_dim
+        sin = torch.empty(B, cfg.block_out_channels[0], device=dev, dtype=torch.float32)
+        e1 = torch.empty(B, D, device=dev, dtype=torch.float32)
+        e2 = torch.empty(B, D, device=dev, dtype=torch.float32)
+        tproj = torch.empty(B, self.temb_total, device=dev, dtype=torch.float32)
+        ops.timestep_sinusoid(prog, t_buf, sin, B=B, dim=cfg.block_out_channels[0], step_idx=step_idx, t_stride=t_stride)
+        ops.gemv(prog, sin, self.w["te1.w"], self.w["te1.b"], e1, silu=True)
+        ops.gemv(prog, e1, self.w["te2.w"], self.w["te2.b"], e2, silu=True)     # silu(temb): every consumer applies it
+        ops.gemv(prog, e2, self.w["tproj.w"], self.w["tproj.b"], tproj, silu=False)
+        return tproj
+
+    def rec_kv(self, prog, ws: Workspace, ehs: torch.Tensor, B: int, L: int):
+        """attn2 to_k/to_v of every transformer block on the text context (step-invariant: ehs is constant over the
+        whole sampling loop)."""
+        kv = {}
+        for a in self.transformers:
+            t = a + ".transformer_blocks.0"
+            N = self.w[t + ".kv2.w"].shape[0]
+            out = torch.empty(B * L, N, device=self.device, dtype=torch.float16)
+            ops.conv_gemm(prog, [(ehs, ehs.shape[1], SEG_1x1)], self.w[t + ".kv2.w"], out, M=B * L, N=N, B=B)
+            kv[a] = out
+        return kv
+
+    def _gn(self, prog, ws, name, srcs: Sequence[Act], eps, silu) -> torch.Tensor:
+        a = srcs[0]
+        b = srcs[1] if len(srcs) > 1 else None
+        Ct = a.C + (b.C if b else 0)
+        out = ws.get(a.M, Ct)
+        ops.groupnorm(prog, a.t, a.C, b.t if b else None, b.C if b else 0, self.w[name + ".g"], self.w[name + ".bt"], out,
+                      ws.gn_scratch, B=a.B, HW=a.H * a.W, groups=self.cfg.norm_num_groups, eps=eps, silu=silu)
+        return out
+
+    def rec_resnet(self, prog, ws, r: str, srcs: Sequence[Act], tproj: torch.Tensor) -> Act:
+        a = srcs[0]
+        B, H, W, M = a.B, a.H, a.W, a.M
+        Cin = sum(s.C for s in srcs)
+        Cout = self.w[r + ".conv1.w"].shape[0]
+        n1 = self._gn(prog, ws, r + ".norm1", srcs, self.cfg.norm_eps, True)
+        h1 = ws.get(M, Cout)
+        off = self.temb_off[r]
+        ops.conv_gemm(prog, [(n1, Cin, SEG_3x3)], self.w[r + ".conv1.w"], h1, M=M, N=Cout, B=B, H=H, W=W,
+                      bias=tproj[:, off:off + Cout], bias_bstride=self.temb_total, partial=ws.partial)
+        ws.put(n1)
+        n2 = self._gn(prog, ws, r + ".norm2", [Act(h1, B, H, W, Cout)], self.cfg.norm_eps, True)
+        ws.put(h1)
+        w2, b2, has_sc = self._conv2_packed(r, [s.C for s in srcs])
+        out = ws.get(M, Cout)
+        segs = [(n2, Cout, SEG_3x3)]
+        res = None
+        if has_sc:
+            segs += [(s.t, s.C, SEG_1x1) for s in srcs]
+        else:
+            assert len(srcs) == 1 and Cin == Cout
+            res = a.t
+        ops.conv_gemm(prog, segs, w2, out, M=M, N=Cout, B=B, H=H, W=W, bias=b2, res=res, partial=ws.partial)
+        ws.put(n2)
+        return Act(out, B, H, W, Cout)
+
+    def rec_transformer(self, prog, ws, a: str, x: Act, kv: torch.Tensor, L: int) -> Act:
+        cfg = self.cfg
+        B, H, W, M, Cc = x.B, x.H, x.W, x.M, x.C
+        heads, d = cfg.num_heads, x.C // cfg.num_heads
+        N = H * W
+        t = a + ".transformer_blocks.0"
+        w = self.w
+        g = self._gn(prog, ws, a + ".norm", [x], 1e-6, False)
+        h = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(g, Cc, SEG_1x1)], w[a + ".proj_in.w"], h, M=M, N=Cc, B=B, bias=w[a + ".proj_in.b"],
+                      partial=ws.partial)
+        ws.put(g)
+        # self-attention
+        y = ws.get(M, Cc)
+        ops.layernorm(prog, h, y, w[t + ".norm1.g"], w[t + ".norm1.bt"])
+        qkv = ws.get(M, 3 * Cc)
+        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".qkv.w"], qkv, M=M, N=3 * Cc, B=B, partial=ws.partial)
+        ao = y   # reuse
+        ops.attention(prog, qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], ao, B=B, heads=heads, Nq=N, Nk=N, d=d)
+        h2 = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(ao, Cc, SEG_1x1)], w[t + ".out1.w"], h2, M=M, N=Cc, B=B, bias=w[t + ".out1.b"], res=h,
+                      partial=ws.partial)
+        ws.put(qkv, h)
+        # cross-attention on the (precomputed) text keys/values
+        ops.layernorm(prog, h2, y, w[t + ".norm2.g"], w[t + ".norm2.bt"])
+        q = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".q2.w"], q, M=M, N=Cc, B=B, partial=ws.partial)
+        ops.attention(prog, q, kv[:, :Cc], kv[:, Cc:], y, B=B, heads=heads, Nq=N, Nk=L, d=d)
+        h3 = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".out2.w"], h3, M=M, N=Cc, B=B, bias=w[t + ".out2.b"], res=h2,
+                      partial=ws.partial)
+        ws.put(q, h2)
+        # GEGLU feed-forward
+        ops.layernorm(prog, h3, y, w[t + ".norm3.g"], w[t + ".norm3.bt"])
+        ff = ws.get(M, 4 * Cc)
+        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".geglu.w"], ff, M=M, N=8 * Cc, B=B, bias=w[t + ".geglu.b"],
+                      flags=EPI_GEGLU)
+        h4 = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(ff, 4 * Cc, SEG_1x1)], w[t + ".ff2.w"], h4, M=M, N=Cc, B=B, bias=w[t + ".ff2.b"], res=h3,
+                      partial=ws.partial)
+        ws.put(ff, h3, y)
+        out = ws.get(M, Cc)
+        ops.conv_gemm(prog, [(h4, Cc, SEG_1x1)], w[a + ".proj_out.w"], out, M=M, N=Cc, B=B, bias=w[a + ".proj_out.b"],
+                      res=x.t, partial=ws.partial)
+        ws.put(h4)
+        return Act(out, B, H, W, Cc)
+
+    def rec_encoder(self, prog, ws, x_in: Act, tproj, kv, L: int):
+        """conv_in + down blocks + mid block.  Returns (skips[12], mid).  Skip buffers are never recycled."""
+        cfg = self.cfg
+        B, H, W = x_in.B, x_in.H, x_in.W
+        c0 = cfg.block_out_channels[0]
+        h = Act(torch.empty(x_in.M, c0, device=self.device, dtype=torch.float16), B, H, W, c0)
+        ops.conv_gemm(prog, [(x_in.t, x_in.C, SEG_3x3)], self.w["conv_in.w"], h.t, M=h.M, N=c0, B=B, H=H, W=W,
+                      bias=self.w["conv_in.b"])
+        skips = [h]
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            for j in range(cfg.layers_per_block):
+                r = self.rec_resnet(prog, ws, f"down_blocks.{i}.resnets.{j}", [h], tproj)
+                if cfg.down_has_attn[i]:
+                    a = f"down_blocks.{i}.attentions.{j}"
+                    h = self.rec_transformer(prog, ws, a, r, kv[a], L)
+                    ws.put(r.t)
+                else:
+                    h = r
+                skips.append(h)
+            if i != nb - 1:
+                n = f"down_blocks.{i}.downsamplers.0.conv"
+                o = Act(torch.empty(h.M // 4, h.C, device=self.device, dtype=torch.float16), B, h.H // 2, h.W // 2, h.C)
+                ops.conv_gemm(prog, [(h.t, h.C, SEG_3x3_S2)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=B, H=o.H, W=o.W,
+                              bias=self.w[n + ".b"], partial=ws.partial)
+                h = o
+                skips.append(h)
+        r0 = self.rec_resnet(prog, ws, "mid_block.resnets.0", [h], tproj)
+        a = "mid_block.attentions.0"
+        tr = self.rec_transformer(prog, ws, a, r0, kv[a], L)
+        ws.put(r0.t)
+        mid = self.rec_resnet(prog, ws, "mid_block.resnets.1", [tr], tproj)
+        ws.put(tr.t)
+        return skips, mid
+
+    def rec_decoder(self, prog, ws, mid: Act, skips: Sequence[Act], tproj, kv, L: int, *, out_nchw: torch.Tensor,
+                    taps: Optional[list] = None, axpby: Optional[dict] = None):
+        """up blocks + conv_norm_out/SiLU/conv_out.  `skips` are the 12 (already exchanged) skip tensors; they are
+        consumed from the end (controlnet.py:1124-1125).  The prediction is written NCHW fp32 into `out_nchw`, or,
+        with `axpby`, the scheduler update is applied in the conv_out epilogue (latent updated in place)."""
+        cfg = self.cfg
+        skips = list(skips)
+        h = mid
+        if taps is not None:
+            taps.append(h)
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            for j in range(cfg.layers_per_block + 1):
+                s = skips.pop()
+                r = self.rec_resnet(prog, ws, f"up_blocks.{i}.resnets.{j}", [h, s], tproj)
+                if h is not mid and taps is None:
+                    ws.put(h.t)
+                if cfg.up_has_attn[i]:
+                    a = f"up_blocks.{i}.attentions.{j}"
+                    h = self.rec_transformer(prog, ws, a, r, kv[a], L)
+                    ws.put(r.t)
+                else:
+                    h = r
+                if taps is not None:
+                    taps.append(h)
+            if i != nb - 1:
+                n = f"up_blocks.{i}.upsamplers.0.conv"
+                up = ws.get(h.M * 4, h.C)
+                ops.upsample2x(prog, h.t, up, B=h.B, H=h.H, W=h.W, Cn=h.C)
+                o = Act(ws.get(h.M * 4, h.C), h.B, h.H * 2, h.W * 2, h.C)
+                ops.conv_gemm(prog, [(up, h.C, SEG_3x3)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=o.B, H=o.H, W=o.W,
+                              bias=self.w[n + ".b"], partial=ws.partial)
+                ws.put(up)
+                if taps is None:
+                    ws.put(h.t)
+                h = o
+        g = self._gn(prog, ws, "conv_norm_out", [h], cfg.norm_eps, True)
+        N = cfg.out_channels
+        if axpby is None:
+            ops.conv_gemm(prog, [(g, h.C, SEG_3x3)], self.w["conv_out.w"], out_nchw, M=h.M, N=N, B=h.B, H=h.H, W=h.W,
+                          bias=self.w["conv_out.b"], flags=EPI_OUT_NCHW | EPI_OUT_F32)
+        else:
+            ops.conv_gemm(prog, [(g, h.C, SEG_3x3)], self.w["conv_out.w"], axpby.get("nhwc"), M=h.M, N=N, B=h.B, H=h.H,
+                          W=h.W, bias=self.w["conv_out.b"], flags=EPI_OUT_NCHW | EPI_AXPBY, axpby=axpby["coef"],
+                          axpby_step=axpby.get("step"), aux=axpby["latent"], aux_out=axpby["latent"],
+                          axpby_first_channel=axpby.get("first_channel", 0),
+                          ldc=axpby["nhwc"].shape[1] if axpby.get("nhwc") is not None else 0)
+        ws.put(g)
+        if taps is None and h is not mid:
+            ws.put(h.t)
+
+    def rec_exchange(self, prog, ws, src: Sequence[Act], src_mid: Act, dst: Sequence[Act], dst_mid: Act):
+        """out_i = dst_i + zero_conv_i(src_i): the dual-stream residual exchange (controlnet.py:1754-1775 + :1078-1087
+        for attr->RGB, :2446-2461,2476-2477 for RGB->attr) as ONE 1x1-GEMM per skip with the add in its epilogue."""
+        zc = self.zc_prefix
+        outs = []
+        for i, (s, dd) in enumerate(zip(src, dst)):
+            o = Act(torch.empty(s.M, s.C, device=self.device, dtype=torch.float16), s.B, s.H, s.W, s.C)
+            ops.conv_gemm(prog, [(s.t, s.C, SEG_1x1)], self.w[f"{zc}_down_blocks.{i}.w"], o.t, M=s.M, N=s.C, B=s.B,
+                          bias=self.w[f"{zc}_down_blocks.{i}.b"], res=dd.t if dd is not None else None,
+                          partial=ws.partial)
+            outs.append(o)
+        m = Act(torch.empty(src_mid.M, src_mid.C, device=self.device, dtype=torch.float16), src_mid.B, src_mid.H,
+                src_mid.W, src_mid.C)
+        ops.conv_gemm(prog, [(src_mid.t, src_mid.C, SEG_1x1)], self.w[f"{zc}_mid_block.w"], m.t, M=m.M, N=m.C, B=m.B,
+                      bias=self.w[f"{zc}_mid_block.b"], res=dst_mid.t if dst_mid is not None else None,
+                      partial=ws.partial)
+        return outs, m
+
+
+def pad_channels(c: int) -> int:
+    """Channel padding of the tiny network inputs so a pixel row is a multiple of 16 bytes (TMA stride rule)."""
+    return (c + 7) // 8 * 8

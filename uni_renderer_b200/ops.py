@@ -12,7 +12,7 @@ from . import _lib as L
 from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
-           "timestep_sinusoid", "gemv", "axpby", "add_int", "Program", "pack_weight", "pack_geglu", "device_info",
+           "timestep_sinusoid", "gemv", "axpby", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "device_info",
            "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
@@ -286,3 +286,12 @@ def add_int(prog: Optional[Program], p: torch.Tensor, v: int):
     L.check(lib.unib200_add_int(_h(prog), p.data_ptr(), v, _stream()), "add_int")
     if prog is not None:
         prog.keep(p)
+
+
+def add_f16(prog: Optional[Program], a: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+    lib = L.load()
+    assert a.dtype == b.dtype == out.dtype == torch.float16
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous() and a.numel() == b.numel() == out.numel()
+    L.check(lib.unib200_add_f16(_h(prog), a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "add_f16")
+    if prog is not None:
+        prog.keep(a, b, out)
