@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the dual-stream denoising hot path (BASELINE.json: 512x512 dual-stream 50-step DDIM images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's arithmetic on the host cores (CPU)
+
+A bench "step" = one full 50-step DDIM sampling pass of one batch (default: BASELINE configs[1], B=4 at 64x64 latent,
+joint dual-stream, fp16 storage / fp32 accumulate, random-init SD-1.5-shaped networks, synthetic latents).
+  value   images/sec with the inputs already resident in HBM (device-to-device reset of the latents per step)
+  e2e     images/sec through DualStreamSampler.joint_sample()-style calls with PINNED HOST inputs: H2D of latents and
+          text embeddings and D2H of the final latents inside the timed region (+ the NCCL all-gather for N > 1)
+  roofline  the dominant kernel family (tcgen05 implicit-GEMM conv/linear): algorithmic FLOPs of its launches in one
+          denoising step / their summed device time (CUDA events around every launch, measured here), against the
+          measured sustained tensor peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (oracle/uni_oracle.py, the restatement of the reference's PyTorch path) timed on this
+          box's host cores on a bounded sample (B=1, a few denoising steps, extrapolated to 50)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec, 512x512 dual-stream 50-step DDIM"
+UNIT = "images/s"
+MODE_CONFIG = {"joint": "configs[1]: batch=4 512x512 dual-stream 50-step DDIM, fp16, 1xB200",
+               "forward": "configs[2] per-GPU shard: forward rendering (attribute->RGB) 50-step, batch 4/GPU",
+               "inverse": "configs[3] per-GPU shard: inverse rendering (RGB->attributes) 50-step, batch 4/GPU",
+               "cycle": "configs[4] per-GPU shard: 1024x1024 dual-stream + cycle-consistency double pass, batch 2/GPU"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="joint", choices=["joint", "forward", "inverse", "cycle"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 4; 2 for --mode cycle)")
+    ap.add_argument("--latent", type=int, default=None, help="latent side (default 64; 128 for --mode cycle)")
+    ap.add_argument("--denoise-steps", type=int, default=50)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-denoise-steps", type=int, default=2, help="timed CPU denoising steps of the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.batch is None:
+        a.batch = 2 if a.mode == "cycle" else 4
+    if a.latent is None:
+        a.latent = 128 if a.mode == "cycle" else 64
+    return a
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops_sustained": d.get("bf16_tflops_sustained", 1402.9), "tflops_burst": d.get("bf16_tflops", 1664.2),
+                "hbm_gbs": d.get("hbm_gbs", 6551.7), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle (restatement of the reference's PyTorch path) on the host cores
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(mode: str, latent: int, denoise_steps: int, timed: int, warm: int):
+    """Times `timed` denoising steps (after `warm`) of the reference arithmetic at B=1 on all host cores; returns
+    (seconds per denoising step, cores, description).  Uses oracle/ -- the one place bench.py may do so."""
+    import torch
+    from dataclasses import replace
+    from oracle import uni_oracle as uo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    base = uo.SD15
+    cfgs = (replace(base), replace(base, in_channels=28), replace(base, out_channels=28))
+    sds = [uo.random_state_dict(k, c, s) for k, c, s in zip(("unet", "attr_enc", "attr_dec"), cfgs, (11, 12, 13))]
+    g = torch.Generator().manual_seed(1234)
+    x_img = torch.randn(1, 4, latent, latent, generator=g)
+    x_attr = torch.randn(1, 28, latent, latent, generator=g)
+    ehs = torch.randn(1, 77, 768, generator=g)
+    sched = uo.DDIM()
+    ts = sched.set_timesteps(denoise_steps)
+
+    def one(i, x_img, x_attr):
+        t = ts[i]
+        if mode == "forward":       # pipeline.py:1586-1653 as shipped (the attribute encoder is re-run every step)
+            d, m, _, _ = uo.attr_encoder_forward(sds[1], cfgs[1], 0, ehs, x_attr)
+            pred = uo.unet_forward(sds[0], cfgs[0], x_img, t, ehs, d, m)[0]
+            return sched.step(pred, t, x_img), x_attr
+        if mode == "inverse":       # pipeline.py:2627-2733 as shipped (full 3-call step, RGB output discarded)
+            _, attr = uo.dual_stream_step(*sds, *cfgs, x_img, 0, x_attr, t, ehs)
+            x_attr = torch.cat([x_attr[:, :4], sched.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
+            return x_img, x_attr
+        img, attr = uo.dual_stream_step(*sds, *cfgs, x_img, t, x_attr, t, ehs)
+        if mode == "cycle":         # train.py:1388-1413
+            x2 = torch.cat([x_attr[:, :4], attr[:, 4:]], 1)
+            d, m, _, _ = uo.attr_encoder_forward(sds[1], cfgs[1], 0, ehs, x2)
+            img = uo.unet_forward(sds[0], cfgs[0], x_img, t, ehs, d, m)[0]
+        x_attr = torch.cat([x_attr[:, :4], sched.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
+        return sched.step(img, t, x_img), x_attr
+
+    times = []
+    with torch.no_grad():
+        for i in range(warm + timed):
+            t0 = time.perf_counter()
+            x_img, x_attr = one(i % denoise_steps, x_img, x_attr)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    sample = (f"oracle fp32 PyTorch-CPU, B=1, {latent}x{latent} latent, mode={mode}: {warm} warm + {timed} timed "
+              f"denoising steps, extrapolated x{denoise_steps} steps per image")
+    return sec, times, cores, sample
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, times, cores, sample = cpu_reference_run(a.mode, a.latent, a.denoise_steps, a.steps, a.warmup)
+    value = 1.0 / (sec * a.denoise_steps)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": MODE_CONFIG[a.mode], "mode": a.mode, "batch": 1, "latent": a.latent,
+                       "denoise_steps": a.denoise_steps,
+                       "note": "one bench step of this arm = ONE denoising step at B=1 (bounded sample); value = "
+                               "1 / (50 x mean step seconds)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from uni_renderer_b200 import _lib
+    from uni_renderer_b200.engine import NetConfig
+    from uni_renderer_b200.models import random_init_state_dict
+    from uni_renderer_b200.pipeline import DualStreamSampler, all_gather_latents
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU leg)")
+    _lib.load()                                  # fail loudly when the extension is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, T, L = a.batch, a.latent, a.denoise_steps, 77
+
+    cfg = NetConfig(cross_attention_dim=768)
+    from dataclasses import replace
+    cfgs = (replace(cfg), replace(cfg, in_channels=28), replace(cfg, out_channels=28))
+    sds = [random_init_state_dict(k, c, s, dev) for k, c, s in zip(("unet", "attr_enc", "attr_dec"), cfgs, (11, 12, 13))]
+    sampler = DualStreamSampler.from_state_dicts(*sds, *cfgs, device=dev, use_graph=not a.no_graph)
+    del sds
+    plan = sampler.plan(a.mode, B, S, L, T)
+    torch.cuda.synchronize()
+
+    # synthetic inputs: per-rank seeds so every rank denoises different images (weak scaling: B per GPU is fixed)
+    g = torch.Generator().manual_seed(1234 + rank)
+    h_img = torch.randn(B, 4, S, S, generator=g).pin_memory()
+    h_attr = torch.randn(B, 28, S, S, generator=g).pin_memory()
+    h_ehs = torch.randn(B, L, 768, generator=g).half().pin_memory()
+    d_img, d_attr, d_ehs = h_img.to(dev), h_attr.to(dev), h_ehs.to(dev)
+    out_c = {"joint": 28 + 4, "cycle": 28 + 4, "forward": 4, "inverse": 24}[a.mode]
+    h_out = torch.empty(world * B, out_c, S, S).pin_memory() if rank == 0 else None
+
+    def final_latents():
+        b = plan.bufs
+        if a.mode == "forward":
+            return b["lat_img"]
+        if a.mode == "inverse":
+            return b["lat_attr"][:, 4:].contiguous()
+        return torch.cat([b["lat_img"], b["lat_attr"]], 1)
+
+    def step_resident():
+        sampler.load_inputs(plan, d_img, d_attr, d_ehs)
+        sampler.run(plan)
+
+    def step_e2e():
+        sampler.load_inputs(plan, h_img, h_attr, h_ehs)            # H2D from pinned memory
+        sampler.run(plan)
+        out = all_gather_latents(final_latents())                  # the one collective (no-op at N=1)
+        if rank == 0:
+            h_out.copy_(out, non_blocking=True)                    # D2H of the final latents
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(a.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_res = timed(step_resident, a.steps)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    clk = clocks.stop()
+
+    images = world * B * a.steps
+    value = images / (ms_res * 1e-3)
+    e2e_value = images / (ms_e2e * 1e-3)
+    h2d = h_img.numel() * 4 + h_attr.numel() * 4 + h_ehs.numel() * 2
+    d2h = world * B * out_c * S * S * 4
+
+    peaks = load_peaks()
+    flops_call = plan.flops_setup + T * plan.flops_step
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": MODE_CONFIG[a.mode], "mode": a.mode, "per_gpu_batch": B, "global_batch": world * B,
+                       "latent": S, "denoise_steps": T, "text_tokens": L, "weights": "random-init SD-1.5 shape "
+                       "(859.5M + 360.3M + 524.4M params)", "cuda_graph": not a.no_graph,
+                       "l2": "every denoising step streams 3.5 GB of weights + activations >> 126 MB L2; no flush needed"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": a.steps * sampler.launches_per_call(plan),
+            "denoise_step_ms": ms_res / a.steps / T,
+            "step_tflops_per_gpu": flops_call * a.steps / (ms_res * 1e-3) / 1e12,
+            "step_frac_of_tensor_peak": flops_call * a.steps / (ms_res * 1e-3) / 1e12 / peaks["tflops_sustained"]}
+
+    if rank == 0 and not a.no_roofline:
+        # per-op device times of ONE denoising step (events around every launch on the launching stream)
+        sampler.load_inputs(plan, d_img, d_attr, d_ehs)
+        plan.bufs["step"].zero_()
+        plan.setup.run()
+        ms_ops = plan.step.profile(3)
+        info = plan.step.op_info()
+        by = {}
+        for (kind, fl, by_, nl), ms in zip(info, ms_ops):
+            d = by.setdefault(_lib.OP_NAMES[kind], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += ms; d["flops"] += fl; d["bytes"] += by_; d["launches"] += nl
+        tot = sum(d["ms"] for d in by.values())
+        gm = by["conv_gemm"]
+        ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv / linear family)",
+                            "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                            "launches_per_denoise_step": gm["launches"], "share_of_step": gm["ms"] / tot,
+                            "flops_per_denoise_step": gm["flops"]}
+        line["kernel_breakdown_ms_per_denoise_step"] = {
+            k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4), "launches": v["launches"],
+                "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
+                "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
+            for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+    barrier()
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sec, _, cores, sample = cpu_reference_run(a.mode, S, T, a.cpu_denoise_steps, 1)
+        line["cpu_baseline"] = {"value": 1.0 / (sec * T), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "sec_per_denoise_step_b1": sec}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,15 @@ int unib200_program_num_launches(const unib200_program* prog);   /* kernels laun
 int unib200_program_run(unib200_program* prog, void* stream);
 int unib200_program_graph_instantiate(unib200_program* prog, void* stream);   /* capture run() into a CUDA graph */
 int unib200_program_graph_launch(unib200_program* prog, void* stream);
+/* accounting + measurement of a recorded program: per-op kind, algorithmic FLOPs (2*MAC, unpadded) and HBM bytes
+ * (operands read once, result written once); _profile replays the program `iters` times with a CUDA-event pair
+ * around every op on `stream` and returns each op's mean device time in ms (ms_out[num_ops]); host-synchronous. */
+enum { UNIB200_OP_OTHER = 0, UNIB200_OP_GEMM = 1, UNIB200_OP_ATTENTION = 2, UNIB200_OP_GROUPNORM = 3,
+       UNIB200_OP_LAYERNORM = 4 };
+int unib200_program_num_ops(const unib200_program* prog);
+int unib200_program_op_info(const unib200_program* prog, int i, int* kind, double* flops, double* bytes,
+                            int* launches);
+int unib200_program_profile(unib200_program* prog, void* stream, int iters, float* ms_out);
 
 /* ---- implicit-GEMM convolution / linear (tcgen05) ----------------------------------------------------------
  * Replaces: nn.Conv2d 3x3/1x1 inside ResnetBlock2D, Transformer2DModel.proj_in/out, Down/Upsample2D, conv_in,
@@ -83,6 +92,9 @@ typedef struct {
   const float* aux;         /* EPI_AXPBY: current latent x_t, NCHW fp32                                           */
   float* aux_out;           /* EPI_AXPBY: x_{t-1} NCHW fp32 (may alias aux)                                       */
   int axpby_first_channel;  /* channels below this keep aux unchanged (the clean mask group, pipeline.py:2691)    */
+                            /* EPI_AXPBY with out != NULL: out receives, NHWC fp16 [M, ldc], the raw prediction   */
+                            /* with the clean channels passed through (= cat(latents_mask, mask_pred), the        */
+                            /* attribute input of the cycle pass, train/train.py:1393)                            */
 } unib200_gemm_desc;
 
 int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);

@@ -1,0 +1,103 @@
+"""CPU tests of the host-side logic: DDIM schedule vs the oracle, batch sharding + the final all-gather over gloo
+(world_size 2), the bench's reference leg on a tiny configuration, and loud failure without CUDA."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("ptype", ["epsilon", "sample", "v_prediction"])
+@pytest.mark.parametrize("n", [50, 20, 250])
+def test_schedule_matches_oracle_ddim(ptype, n):
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.scheduler import DDIMSchedule
+    s, o = DDIMSchedule(prediction_type=ptype), uo.DDIM(prediction_type=ptype)
+    ts, coefs = s.table(n)
+    assert ts == o.set_timesteps(n)
+    if n == 50:
+        assert ts[0] == 981 and ts[-1] == 1
+    g = torch.Generator().manual_seed(0)
+    x, out = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for t, (c_out, c_x) in list(zip(ts, coefs))[:: max(1, n // 10)]:
+        torch.testing.assert_close(c_out * out + c_x * x, o.step(out, t, x), rtol=2e-5, atol=2e-5)
+
+
+def test_schedule_rejects_bad_arguments():
+    from uni_renderer_b200.scheduler import DDIMSchedule
+    with pytest.raises(ValueError):
+        DDIMSchedule(prediction_type="nope")
+    with pytest.raises(ValueError):
+        DDIMSchedule().timesteps(0)
+
+
+def test_shard_batch():
+    from uni_renderer_b200.pipeline import shard_batch
+    assert [shard_batch(32, r, 8) for r in range(8)] == [(4 * r, 4 * r + 4) for r in range(8)]
+    with pytest.raises(ValueError):
+        shard_batch(10, 0, 4)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from uni_renderer_b200.pipeline import all_gather_latents, shard_batch
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+full = torch.arange(4 * 3 * 2 * 2, dtype=torch.float32).reshape(4, 3, 2, 2)
+lo, hi = shard_batch(4, rank, world)
+out = all_gather_latents(full[lo:hi] * 1.0)
+assert torch.equal(out, full), (rank, out)
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_all_gather_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("OK") == 2
+
+
+def test_sampler_requires_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from dataclasses import replace
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.engine import NetConfig
+    from uni_renderer_b200.pipeline import DualStreamSampler
+    from uni_renderer_b200.models import UNet2DConditionModel
+    m = UNet2DConditionModel(in_channels=4, out_channels=4, block_out_channels=(32, 64, 128, 128), attention_head_dim=4,
+                             cross_attention_dim=48, norm_num_groups=8)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 16, 16), 1, torch.zeros(1, 77, 48))
+
+
+def test_bench_reference_leg_tiny(monkeypatch):
+    """The CPU leg of bench.py (oracle port) on the tiny configuration: runs, returns a positive step time."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import uni_oracle as uo
+    monkeypatch.setattr(uo, "SD15", uo.NetConfig(block_out_channels=(32, 64, 128, 128), num_heads=4,
+                                                  cross_attention_dim=768, norm_num_groups=8))
+    for mode in ("joint", "forward", "inverse", "cycle"):
+        sec, times, cores, sample = bench.cpu_reference_run(mode, 16, 50, timed=1, warm=0)
+        assert sec > 0 and len(times) == 1 and cores >= 1 and "oracle" in sample
+
+
+def test_bench_b200_arm_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=240)
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)

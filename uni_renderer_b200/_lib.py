@@ -9,6 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libunib200.so")
 
 SEG_1x1, SEG_3x3, SEG_3x3_S2 = 0, 1, 2
+OP_OTHER, OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM = 0, 1, 2, 3, 4
+OP_NAMES = {OP_OTHER: "other", OP_GEMM: "conv_gemm", OP_ATTENTION: "attention", OP_GROUPNORM: "groupnorm",
+            OP_LAYERNORM: "layernorm"}
 EPI_GEGLU, EPI_OUT_NCHW, EPI_OUT_F32, EPI_SILU, EPI_AXPBY = 1, 2, 4, 8, 16
 
 
@@ -53,6 +56,7 @@ EXPORTS = [
     "unib200_version", "unib200_last_error", "unib200_device_info",
     "unib200_program_create", "unib200_program_destroy", "unib200_program_num_launches", "unib200_program_run",
     "unib200_program_graph_instantiate", "unib200_program_graph_launch",
+    "unib200_program_num_ops", "unib200_program_op_info", "unib200_program_profile",
     "unib200_conv_gemm", "unib200_packed_k", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16",
@@ -85,6 +89,10 @@ def load() -> C.CDLL:
     lib.unib200_program_run.argtypes = [vp, vp]
     lib.unib200_program_graph_instantiate.argtypes = [vp, vp]
     lib.unib200_program_graph_launch.argtypes = [vp, vp]
+    lib.unib200_program_num_ops.argtypes = [vp]
+    lib.unib200_program_op_info.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(ci)]
+    lib.unib200_program_profile.argtypes = [vp, vp, ci, C.POINTER(cf)]
     lib.unib200_conv_gemm.argtypes = [vp, C.POINTER(GemmDesc), vp]
     lib.unib200_packed_k.argtypes = [ci, C.POINTER(Seg)]
     lib.unib200_packed_k.restype = C.c_size_t

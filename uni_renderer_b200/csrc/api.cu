@@ -77,19 +77,32 @@ int num_sms() {
 
 typedef std::function<cudaError_t(cudaStream_t)> Op;
 
+// what an op is, for per-kind accounting of a recorded program (unib200_program_op_info / _profile)
+struct OpInfo {
+  int kind = UNIB200_OP_OTHER;
+  double flops = 0.0;     // algorithmic (2 * MAC, unpadded shapes)
+  double bytes = 0.0;     // algorithmic HBM bytes (each operand read once, result written once)
+  int launches = 1;
+};
+
 }  // namespace
 
 struct unib200_program {
   std::vector<Op> ops;
+  std::vector<OpInfo> info;
   int launches = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };
 
 namespace {
-int submit(unib200_program* prog, Op op, int launches, void* stream, const char* what) {
+int submit(unib200_program* prog, Op op, int launches, void* stream, const char* what, int kind = UNIB200_OP_OTHER,
+           double flops = 0.0, double bytes = 0.0) {
   if (prog) {
     prog->ops.push_back(std::move(op));
+    OpInfo oi;
+    oi.kind = kind; oi.flops = flops; oi.bytes = bytes; oi.launches = launches;
+    prog->info.push_back(oi);
     prog->launches += launches;
     return 0;
   }
@@ -134,6 +147,54 @@ int unib200_program_run(unib200_program* prog, void* stream) {
     cudaError_t e = prog->ops[i](static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda(("program op " + std::to_string(i)).c_str(), e);
   }
+  return 0;
+}
+
+int unib200_program_num_ops(const unib200_program* prog) { return prog ? static_cast<int>(prog->ops.size()) : 0; }
+
+int unib200_program_op_info(const unib200_program* prog, int i, int* kind, double* flops, double* bytes,
+                            int* launches) {
+  if (!prog || i < 0 || i >= static_cast<int>(prog->info.size())) return fail("op_info: bad program / index");
+  const OpInfo& oi = prog->info[i];
+  if (kind) *kind = oi.kind;
+  if (flops) *flops = oi.flops;
+  if (bytes) *bytes = oi.bytes;
+  if (launches) *launches = oi.launches;
+  return 0;
+}
+
+// Replays the program `iters` times with a CUDA event pair around every op (on `stream`, the launching stream) and
+// returns the mean device time of each op in milliseconds.  Host-synchronous; for measurement only.
+int unib200_program_profile(unib200_program* prog, void* stream, int iters, float* ms_out) {
+  if (!prog || !ms_out || iters < 1) return fail("program_profile: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = prog->ops.size();
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (size_t i = 0; i < 2 * n; ++i) {
+    cudaError_t e = cudaEventCreate(&ev[i]);
+    if (e != cudaSuccess) return fail_cuda("cudaEventCreate", e);
+  }
+  std::vector<double> acc(n, 0.0);
+  int rc = 0;
+  for (int it = 0; it < iters && rc == 0; ++it) {
+    for (size_t i = 0; i < n; ++i) {
+      cudaEventRecord(ev[2 * i], s);
+      cudaError_t e = prog->ops[i](s);
+      cudaEventRecord(ev[2 * i + 1], s);
+      if (e != cudaSuccess) { rc = fail_cuda(("program op " + std::to_string(i)).c_str(), e); break; }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == 0 && e != cudaSuccess) rc = fail_cuda("cudaStreamSynchronize", e);
+    if (rc != 0) break;
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+      acc[i] += ms;
+    }
+  }
+  for (size_t i = 0; i < 2 * n; ++i) cudaEventDestroy(ev[i]);
+  if (rc != 0) return rc;
+  for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
   return 0;
 }
 
@@ -297,7 +358,18 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   p.splits = splits;
   p.partial = d->partial;
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
-  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm");
+  double kreal = 0.0, a_bytes = 0.0;
+  for (int i = 0; i < d->nseg; ++i) {
+    const int taps = d->seg[i].kind == UNIB200_SEG_1x1 ? 1 : 9;
+    kreal += static_cast<double>(taps) * d->seg[i].C;
+    // each source pixel is read once algorithmically (a stride-2 conv reads 4x the output pixels)
+    a_bytes += 2.0 * d->seg[i].C * d->M * (d->seg[i].kind == UNIB200_SEG_3x3_S2 ? 4.0 : 1.0);
+  }
+  const double n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2.0 : d->N;
+  const double flops = 2.0 * d->M * d->N * kreal;
+  const double bytes = a_bytes + 2.0 * d->N * kreal + ((d->flags & UNIB200_EPI_OUT_F32) ? 4.0 : 2.0) * d->M * n_out +
+                       (d->res ? 2.0 * d->M * d->N : 0.0);
+  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes);
 }
 
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* stream) {
@@ -325,7 +397,9 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
-  return submit(prog, std::move(op), 1, stream, "attention");
+  const double bh = static_cast<double>(d->B) * d->heads;
+  return submit(prog, std::move(op), 1, stream, "attention", UNIB200_OP_ATTENTION, 4.0 * bh * d->Nq * d->Nk * d->d,
+                2.0 * bh * d->d * (2.0 * d->Nq + 2.0 * d->Nk));
 }
 
 int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* stream) {
@@ -346,7 +420,8 @@ int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* str
   p.max_chunks = mc > 4096 ? 4096 : static_cast<int>(mc);
   const int B = d->B, sms = num_sms();
   Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm(p, B, sms, s); };
-  return submit(prog, std::move(op), 2, stream, "groupnorm");
+  return submit(prog, std::move(op), 2, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
+                4.0 * static_cast<double>(d->B) * d->HW * C);
 }
 
 int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float* gamma, const float* beta, int rows,
@@ -355,7 +430,7 @@ int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float
   Op op = [=](cudaStream_t s) {
     return launch_layernorm(static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, rows, C, eps, s);
   };
-  return submit(prog, std::move(op), 1, stream, "layernorm");
+  return submit(prog, std::move(op), 1, stream, "layernorm", UNIB200_OP_LAYERNORM, 0.0, 4.0 * rows * C);
 }
 
 int unib200_to_nhwc(unib200_program* prog, const void* src, int src_is_f32, void* dst, int B, int C, int H, int W,

@@ -59,9 +59,12 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
       if (p.flags & EPI_AXPBY) {
         const float* cf = p.axpby + (p.axpby_step ? 2 * static_cast<size_t>(*p.axpby_step) : 0);
         const float x = p.aux[idx];
-        val = (n + j < p.axpby_n0) ? x : cf[0] * val + cf[1] * x;
-        p.aux_out[idx] = val;
-        if (p.out != nullptr) reinterpret_cast<__half*>(p.out)[static_cast<size_t>(m) * p.ldc + n + j] = __float2half_rn(val);
+        const bool keep = n + j < p.axpby_n0;
+        // optional NHWC fp16 copy of the raw prediction with the clean channels passed through: the attribute
+        // input of a follow-up pass (cat(latents_mask, mask_pred), train/train.py:1393)
+        if (p.out != nullptr)
+          reinterpret_cast<__half*>(p.out)[static_cast<size_t>(m) * p.ldc + n + j] = __float2half_rn(keep ? x : val);
+        p.aux_out[idx] = keep ? x : cf[0] * val + cf[1] * x;
       } else if (p.flags & EPI_OUT_F32) {
         reinterpret_cast<float*>(p.out)[idx] = val;
       } else {

@@ -598,3 +598,33 @@ class AttributeDecoderModel(_NetModule):
         if not return_dict:
             return out
         return UNet2DConditionOutput(sample=out)
+
+
+def random_init_state_dict(kind: str, cfg: NetConfig, seed: int, device="cuda", zero_conv_std: float = 0.02,
+                           dtype=torch.float16) -> Dict[str, torch.Tensor]:
+    """Random-init weights in the reference's state-dict layout, generated directly on `device` (synthetic
+    benchmarks: there is no network for checkpoints).  Linear/conv weights U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like
+    torch's default init, norm scales 1 +- 0.1, and the exchange zero-convs N(0, zero_conv_std) instead of the
+    reference's zeros (controlnet.py:1360-1415) so that the dual-stream exchange is numerically live."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shp in _param_shapes(kind, cfg).items():
+        if name.startswith(("controlnet_", "control_")):
+            t = torch.randn(shp, generator=g, device=device, dtype=torch.float32) * zero_conv_std
+        elif "norm" in name and len(shp) == 1:
+            t = 0.1 * torch.randn(shp, generator=g, device=device, dtype=torch.float32)
+            if name.endswith("weight"):
+                t += 1.0
+        else:
+            fan_in = 1
+            for s in shp[1:]:
+                fan_in *= s
+            if len(shp) == 1:                       # bias: fan_in of the matching weight
+                wshape = _param_shapes(kind, cfg)[name[:-len("bias")] + "weight"]
+                fan_in = 1
+                for s in wshape[1:]:
+                    fan_in *= s
+            k = fan_in ** -0.5
+            t = (torch.rand(shp, generator=g, device=device, dtype=torch.float32) * 2 - 1) * k
+        sd[name] = t.to(dtype)
+    return sd

@@ -67,6 +67,27 @@ class Program:
     def launch_graph(self):
         L.check(self.lib.unib200_program_graph_launch(self.handle, _stream()), "graph_launch")
 
+    @property
+    def num_ops(self) -> int:
+        return self.lib.unib200_program_num_ops(self.handle)
+
+    def op_info(self):
+        """[(kind, flops, bytes, launches)] per recorded op (algorithmic counts, see include/unib200.h)."""
+        out = []
+        k, f, b, n = C.c_int(), C.c_double(), C.c_double(), C.c_int()
+        for i in range(self.num_ops):
+            L.check(self.lib.unib200_program_op_info(self.handle, i, C.byref(k), C.byref(f), C.byref(b), C.byref(n)),
+                    "op_info")
+            out.append((k.value, f.value, b.value, n.value))
+        return out
+
+    def profile(self, iters: int = 3):
+        """Mean device ms of every op (CUDA events around each op on the current stream); host-synchronous."""
+        n = self.num_ops
+        buf = (C.c_float * n)()
+        L.check(self.lib.unib200_program_profile(self.handle, _stream(), iters, buf), "program_profile")
+        return list(buf)
+
     def __del__(self):
         try:
             if self.handle:

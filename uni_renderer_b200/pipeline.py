@@ -1,0 +1,312 @@
+"""Fused dual-stream sampling loops (the `for t in timesteps:` bodies of the reference's pipelines) on the B200 path.
+
+What the reference does per denoising step (models/pipeline_new_d4p.py:1391-1453 joint; models/pipeline.py:1586-1653
+forward rendering; :2627-2733 inverse rendering; train/train.py:1324-1416 for the cycle double pass):
+
+    d, m, rawA, rawA_mid = controlnet(x_img, t_attr, ehs, controlnet_cond=x_attr28)
+    img_pred, rawU, rawU_mid, _ = unet(x_img, t_img, ehs, down_block_additional_residuals=d, mid_block_additional_residual=m)
+    attr_pred = controldec(rawA_mid, rawA, t_attr, ehs, down_block_additional_residuals=rawU, mid_block_additional_residual=rawU_mid)
+    x_img  = scheduler_img.step(img_pred, t, x_img);   x_attr[:, 4:] = scheduler_attr.step(attr_pred[:, 4:], t, x_attr[:, 4:])
+
+Here ONE recorded program (replayed as one CUDA graph per step) executes the whole step on static NHWC fp16 buffers:
+both encoders, the two-way residual exchange as 1x1-GEMM epilogues (no torch.cat, no separate adds), both decoders and
+the DDIM updates fused behind each stream's conv_out (device-side step counter indexes the timestep and coefficient
+tables, so the graph is replayed without host involvement).  Work that does not change across steps is hoisted into a
+per-call "setup" program: attn2 K/V of the text context for all 32 transformer blocks, the whole attribute encoder +
+zero-convs for forward rendering (attr28 and t_attr = 0 are constant, pipeline.py:1455,1577-1583), the RGB encoder +
+mid + decoder-side zero-convs for inverse rendering (x_img and t_img = 0 are constant, :2475; the RGB decoder output is
+discarded there, :2670).  Results are identical to executing the reference's step.
+
+No CPU / eager fallback: constructing a sampler without CUDA or without libunib200.so raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .engine import Act, NetConfig, StreamNet, Workspace, pad_channels
+from .scheduler import DDIMSchedule
+
+MODES = ("joint", "forward", "inverse", "cycle")
+MASK_CHANNELS = 4          # the clean mask group in front of the 24 noisy attribute channels (train/train.py:1310)
+
+
+@dataclass
+class _Plan:
+    mode: str
+    B: int
+    S: int
+    L: int
+    steps: int
+    setup: ops.Program
+    step: ops.Program
+    bufs: Dict[str, torch.Tensor]
+    flops_setup: float = 0.0
+    flops_step: float = 0.0
+
+
+class DualStreamSampler:
+    """Owns the packed weights of the three networks and the recorded programs of the sampling loops.
+
+    Build it from the drop-in modules (`DualStreamSampler(unet, controlnet, controldec)`), or straight from
+    diffusers-layout state dicts (`from_state_dicts`).  Public entry points mirror the reference pipeline's loops:
+
+      joint_sample(latents_img, latents_attr, prompt_embeds, num_inference_steps)   # pipeline_new_d4p.py:1287
+      forward_render(latents_img, attr_latents, prompt_embeds, num_inference_steps) # pipeline.py:1368 (loop :1586)
+      inverse_render(image_latents, latents_attr, prompt_embeds, num_inference_steps)  # pipeline.py:1990 (loop :2627)
+      cycle_sample(...)                                                             # joint + train.py:1388-1413 pass
+
+    Latents are [B, C, S, S] tensors on any device (host tensors are copied to the GPU; results come back on the
+    device of the inputs).  `latents_attr` / `attr_latents` carry 28 channels: 4 clean mask channels + 24 attribute
+    channels (pipeline.py:2647-2650).
+    """
+
+    def __init__(self, unet=None, controlnet=None, controldec=None, *, nets: Optional[Sequence[StreamNet]] = None,
+                 prediction_type: str = "epsilon", device=None, use_graph: bool = True):
+        if nets is None:
+            if unet is None or controlnet is None or controldec is None:
+                raise ValueError("need the three modules or three StreamNets")
+            nets = (unet.finalize(device), controlnet.finalize(device), controldec.finalize(device))
+        self.unet, self.enc, self.dec = nets
+        self.device = self.unet.device
+        if self.device.type != "cuda":
+            raise RuntimeError("DualStreamSampler runs on CUDA (sm_100a) only")
+        self.schedule = DDIMSchedule(prediction_type=prediction_type)
+        self.use_graph = use_graph
+        self.ws = Workspace(self.device)
+        self._plans: Dict[Tuple, _Plan] = {}
+
+    @classmethod
+    def from_state_dicts(cls, sd_unet, sd_enc, sd_dec, cfg_unet: NetConfig, cfg_enc: NetConfig, cfg_dec: NetConfig,
+                         device="cuda", **kw):
+        nets = (StreamNet("unet", cfg_unet, sd_unet, device), StreamNet("attr_enc", cfg_enc, sd_enc, device),
+                StreamNet("attr_dec", cfg_dec, sd_dec, device))
+        return cls(nets=nets, **kw)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # recording
+    # ------------------------------------------------------------------------------------------------------------
+    def plan(self, mode: str, B: int, S: int, L: int = 77, steps: int = 50) -> _Plan:
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {MODES}")
+        key = (mode, B, S, L, steps)
+        if key in self._plans:
+            return self._plans[key]
+        dev, ws = self.device, self.ws
+        unet, enc, dec = self.unet, self.enc, self.dec
+        f32 = dict(device=dev, dtype=torch.float32)
+        f16 = dict(device=dev, dtype=torch.float16)
+        ci, ca = unet.cfg.in_channels, enc.cfg.in_channels
+        b: Dict[str, torch.Tensor] = {}
+        b["lat_img"] = torch.zeros(B, ci, S, S, **f32)                 # x_t of the RGB stream (NCHW fp32 state)
+        b["lat_attr"] = torch.zeros(B, ca, S, S, **f32)                # [mask | 6 attribute groups]
+        b["ehs"] = torch.zeros(B * L, unet.cfg.cross_attention_dim, **f16)
+        b["step"] = torch.zeros(1, device=dev, dtype=torch.int32)       # device-side step counter
+        b["t_img"] = torch.zeros(steps, B, **f32)                       # per-step timestep tables
+        b["t_attr"] = torch.zeros(steps, B, **f32)
+        b["coef_img"] = torch.zeros(steps, 2, **f32)                    # (c_out, c_x) per step
+        b["coef_attr"] = torch.zeros(steps, 2, **f32)
+        x_img = Act(torch.zeros(B * S * S, pad_channels(ci), **f16), B, S, S, pad_channels(ci))
+        x_attr = Act(torch.zeros(B * S * S, pad_channels(ca), **f16), B, S, S, pad_channels(ca))
+        b["x_img"], b["x_attr"] = x_img.t, x_attr.t
+
+        setup, step = ops.Program(), ops.Program()
+        kvU = unet.rec_kv(setup, ws, b["ehs"], B, L)
+        kvE = enc.rec_kv(setup, ws, b["ehs"], B, L)
+        kvD = dec.rec_kv(setup, ws, b["ehs"], B, L)
+        ax_img = {"coef": b["coef_img"], "step": b["step"], "latent": b["lat_img"], "first_channel": 0}
+        ax_attr = {"coef": b["coef_attr"], "step": b["step"], "latent": b["lat_attr"], "first_channel": MASK_CHANNELS}
+
+        def temb(net, prog, table, stepped=True):
+            return net.rec_temb(prog, ws, table, B, step_idx=b["step"] if stepped else None, t_stride=B)
+
+        if mode in ("joint", "cycle"):
+            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
+            tpU, tpE, tpD = temb(unet, step, b["t_img"]), temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
+            skA, midA = enc.rec_encoder(step, ws, x_attr, tpE, kvE, L)
+            skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
+            dskU, dmidU = enc.rec_exchange(step, ws, skA, midA, skU, midU)      # skipU + zc_enc(skipA)
+            dskA, dmidA = dec.rec_exchange(step, ws, skU, midU, skA, midA)      # skipA + zc_dec(skipU_raw)
+            if mode == "joint":
+                unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=None, axpby=ax_img)
+                dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+            else:
+                # pass 1 (train.py:1324-1355): full dual-stream step; the RGB prediction of this pass is kept as an
+                # auxiliary output, the attribute prediction drives the attribute update AND feeds pass 2.
+                b["img_pred_pass1"] = torch.zeros(B, unet.cfg.out_channels, S, S, **f32)
+                unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=b["img_pred_pass1"])
+                x_attr2 = Act(torch.zeros_like(x_attr.t), B, S, S, x_attr.C)
+                b["x_attr_pass2"] = x_attr2.t
+                dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=dict(ax_attr, nhwc=x_attr2.t))
+                # pass 2 (train.py:1388-1413): attribute encoder on cat(mask, attr_pred) at t_attr = 0, then the RGB
+                # stream conditioned on it.  x_img, t_img and ehs are those of pass 1, so the RGB encoder + mid of
+                # pass 1 are reused (bit-identical); only the exchange and the RGB decoder are re-run.
+                b["t_zero"] = torch.zeros(1, B, **f32)
+                tpE0 = temb(enc, step, b["t_zero"], stepped=False)
+                skA2, midA2 = enc.rec_encoder(step, ws, x_attr2, tpE0, kvE, L)
+                dskU2, dmidU2 = enc.rec_exchange(step, ws, skA2, midA2, skU, midU)
+                unet.rec_decoder(step, ws, dmidU2, dskU2, tpU, kvU, L, out_nchw=None, axpby=ax_img)
+        elif mode == "forward":
+            # step-invariant: attribute encoder + its 13 zero-convs (attr28, t_attr = 0, ehs constant)
+            b["t_zero"] = torch.zeros(1, B, **f32)
+            ops.to_nhwc(setup, b["lat_attr"], x_attr.t, x_attr.C)
+            tpE = temb(enc, setup, b["t_zero"], stepped=False)
+            skA, midA = enc.rec_encoder(setup, ws, x_attr, tpE, kvE, L)
+            d, m = enc.rec_exchange(setup, ws, skA, midA, [None] * len(skA), None)
+            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            tpU = temb(unet, step, b["t_img"])
+            skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
+            dskU = [self._add(step, s, r) for s, r in zip(skU, d)]             # controlnet.py:1078-1087
+            dmidU = self._add(step, midU, m)                                    # controlnet.py:1114-1115
+            unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=None, axpby=ax_img)
+        else:  # inverse
+            # step-invariant: RGB encoder + mid + the decoder-side zero-convs of its raw features
+            b["t_zero"] = torch.zeros(1, B, **f32)
+            ops.to_nhwc(setup, b["lat_img"], x_img.t, x_img.C)
+            tpU = temb(unet, setup, b["t_zero"], stepped=False)
+            skU, midU = unet.rec_encoder(setup, ws, x_img, tpU, kvU, L)
+            zU, zmidU = dec.rec_exchange(setup, ws, skU, midU, [None] * len(skU), None)
+            ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
+            tpE, tpD = temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
+            skA, midA = enc.rec_encoder(step, ws, x_attr, tpE, kvE, L)
+            dskA = [self._add(step, s, r) for s, r in zip(skA, zU)]            # controlnet.py:2446-2461
+            dmidA = self._add(step, midA, zmidU)                                # controlnet.py:2476-2477
+            dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+        ops.add_int(step, b["step"], 1)
+
+        plan = _Plan(mode, B, S, L, steps, setup, step, b)
+        plan.flops_setup = sum(i[1] for i in setup.op_info())
+        plan.flops_step = sum(i[1] for i in step.op_info())
+        self._upload_schedule(plan)
+        if self.use_graph:
+            # one eager pass first (sets every kernel's function attributes outside capture), then capture on a side
+            # stream: the legacy default stream cannot be captured
+            setup.run()
+            step.run()
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                step.instantiate_graph()
+            side.synchronize()
+        self._plans[key] = plan
+        return plan
+
+    def _add(self, prog, a: Act, r: Act) -> Act:
+        o = Act(torch.empty_like(a.t), a.B, a.H, a.W, a.C)
+        ops.add_f16(prog, a.t, r.t, o.t)
+        return o
+
+    def _upload_schedule(self, plan: _Plan):
+        ts, coefs = self.schedule.table(plan.steps)
+        t = torch.tensor(ts, dtype=torch.float32).reshape(-1, 1).expand(plan.steps, plan.B).contiguous()
+        c = torch.tensor(coefs, dtype=torch.float64).to(torch.float32)
+        b = plan.bufs
+        # joint/cycle: both streams walk the same timesteps; forward: t_attr = 0; inverse: t_img = 0 (hoisted)
+        b["t_img"].copy_(t)
+        b["t_attr"].copy_(t)
+        b["coef_img"].copy_(c)
+        b["coef_attr"].copy_(c)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------------------------
+    def load_inputs(self, plan: _Plan, latents_img, latents_attr, prompt_embeds):
+        """Copy one batch of inputs (any device / float dtype; pinned host memory makes this an async H2D) into
+        the plan's static buffers."""
+        b = plan.bufs
+        if tuple(latents_img.shape) != tuple(b["lat_img"].shape) or tuple(latents_attr.shape) != tuple(b["lat_attr"].shape):
+            raise ValueError(f"latent shapes {tuple(latents_img.shape)} / {tuple(latents_attr.shape)} do not match "
+                             f"the plan {tuple(b['lat_img'].shape)} / {tuple(b['lat_attr'].shape)}")
+        b["lat_img"].copy_(latents_img, non_blocking=True)
+        b["lat_attr"].copy_(latents_attr, non_blocking=True)
+        b["ehs"].copy_(prompt_embeds.reshape(plan.B * plan.L, -1), non_blocking=True)
+
+    def run(self, plan: _Plan, steps: Optional[int] = None):
+        """setup + `steps` replays of the step program on the current stream (asynchronous)."""
+        plan.bufs["step"].zero_()
+        plan.setup.run()
+        n = plan.steps if steps is None else steps
+        if n > plan.steps:
+            raise ValueError("more steps than the plan's schedule")
+        if self.use_graph:
+            for _ in range(n):
+                plan.step.launch_graph()
+        else:
+            for _ in range(n):
+                plan.step.run()
+
+    def launches_per_call(self, plan: _Plan) -> int:
+        return plan.setup.num_launches + plan.steps * plan.step.num_launches
+
+    def _sample(self, mode, latents_img, latents_attr, prompt_embeds, num_inference_steps, guidance_scale):
+        if guidance_scale not in (0, 0.0, None):
+            raise NotImplementedError("classifier-free guidance is not supported (every shipped Uni-Renderer caller "
+                                      "passes guidance_scale=0, eval/test_real.py:548)")
+        B, _, S, S2 = latents_img.shape
+        if S != S2:
+            raise ValueError("square latents only")
+        L = prompt_embeds.shape[1]
+        plan = self.plan(mode, B, S, L, num_inference_steps)
+        self.load_inputs(plan, latents_img, latents_attr, prompt_embeds)
+        self.run(plan)
+        dev, dt = latents_img.device, latents_img.dtype
+        img = plan.bufs["lat_img"].to(device=dev, dtype=dt, non_blocking=False)
+        attr = plan.bufs["lat_attr"].to(device=dev, dtype=dt, non_blocking=False)
+        return plan, img, attr
+
+    @torch.no_grad()
+    def joint_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
+                     guidance_scale: float = 0.0):
+        """Both streams noisy, same timestep (pipeline_new_d4p.py:1391-1453).  Returns (latents_img, latents_attr)."""
+        _, img, attr = self._sample("joint", latents_img, latents_attr, prompt_embeds, num_inference_steps,
+                                    guidance_scale)
+        return img, attr
+
+    @torch.no_grad()
+    def forward_render(self, latents_img, attr_latents, prompt_embeds, num_inference_steps: int = 50,
+                       guidance_scale: float = 0.0):
+        """attributes -> RGB: t_attr = 0, t_img: T -> 0 (pipeline.py:1455,1586-1653).  Returns latents_img."""
+        return self._sample("forward", latents_img, attr_latents, prompt_embeds, num_inference_steps,
+                            guidance_scale)[1]
+
+    @torch.no_grad()
+    def inverse_render(self, image_latents, latents_attr, prompt_embeds, num_inference_steps: int = 50,
+                       guidance_scale: float = 0.0):
+        """RGB -> attributes: t_img = 0, t_attr: T -> 0 (pipeline.py:2475,2627-2733).  Returns the 24 attribute
+        channels (the clean mask group is sliced off like pipeline.py:2691)."""
+        return self._sample("inverse", image_latents, latents_attr, prompt_embeds, num_inference_steps,
+                            guidance_scale)[2][:, MASK_CHANNELS:]
+
+    @torch.no_grad()
+    def cycle_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
+                     guidance_scale: float = 0.0):
+        """Joint step followed by the cycle-consistency pass of train/train.py:1388-1413 (attribute encoder on
+        cat(mask, attr_pred) at t_attr = 0 -> RGB stream); the RGB update uses the second pass' prediction."""
+        _, img, attr = self._sample("cycle", latents_img, latents_attr, prompt_embeds, num_inference_steps,
+                                    guidance_scale)
+        return img, attr
+
+
+def all_gather_latents(x: torch.Tensor, group=None) -> torch.Tensor:
+    """The one collective of the sharded sampling loop: gather every rank's final latents [B_local, C, S, S] into
+    [world * B_local, C, S, S] (NCCL all-gather over NVLink on GPUs; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    world = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out
+
+
+def shard_batch(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch split: [start, stop) of the samples rank `rank` denoises."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
