@@ -47,6 +47,7 @@ enum { UNIB200_OP_OTHER = 0, UNIB200_OP_GEMM = 1, UNIB200_OP_ATTENTION = 2, UNIB
 int unib200_program_num_ops(const unib200_program* prog);
 int unib200_program_op_info(const unib200_program* prog, int i, int* kind, double* flops, double* bytes,
                             int* launches);
+const char* unib200_program_op_desc(const unib200_program* prog, int i);    /* shape summary, owned by the program */
 int unib200_program_profile(unib200_program* prog, void* stream, int iters, float* ms_out);
 
 /* ---- implicit-GEMM convolution / linear (tcgen05) ----------------------------------------------------------
@@ -99,6 +100,7 @@ typedef struct {
 
 int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);
 size_t unib200_packed_k(int nseg, const unib200_seg* seg);      /* Ktot of the packed weight matrix               */
+int unib200_pick_bn(int N, int flags);   /* N-tile width the kernel will use (EPI_GEGLU weights are interleaved per tile) */
 
 /* ---- fused attention (tcgen05 flash attention, no mask) ----------------------------------------------------
  * Replaces F.scaled_dot_product_attention inside diffusers Attention (AttnProcessor2_0) for attn1/attn2 of every

@@ -44,7 +44,7 @@ EncodeTiledFn get_encode() {
 
 // fp16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides[i] is the byte stride of dim i+1.
 bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, std::string* why) {
+                const uint32_t* box, std::string* why, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { *why = "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)"; return false; }
   cuuint64_t gd[5], gs[4];
@@ -55,7 +55,7 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
   for (int i = 0; i + 1 < rank; ++i)
     if (gs[i] % 16 != 0) { *why = "tensor stride not a multiple of 16 bytes"; return false; }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *why = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
@@ -83,6 +83,7 @@ struct OpInfo {
   double flops = 0.0;     // algorithmic (2 * MAC, unpadded shapes)
   double bytes = 0.0;     // algorithmic HBM bytes (each operand read once, result written once)
   int launches = 1;
+  std::string desc;       // human-readable shape summary (tools/profile_ops.py)
 };
 
 }  // namespace
@@ -97,11 +98,12 @@ struct unib200_program {
 
 namespace {
 int submit(unib200_program* prog, Op op, int launches, void* stream, const char* what, int kind = UNIB200_OP_OTHER,
-           double flops = 0.0, double bytes = 0.0) {
+           double flops = 0.0, double bytes = 0.0, const std::string& desc = std::string()) {
   if (prog) {
     prog->ops.push_back(std::move(op));
     OpInfo oi;
     oi.kind = kind; oi.flops = flops; oi.bytes = bytes; oi.launches = launches;
+    oi.desc = desc.empty() ? std::string(what) : desc;
     prog->info.push_back(oi);
     prog->launches += launches;
     return 0;
@@ -163,6 +165,11 @@ int unib200_program_op_info(const unib200_program* prog, int i, int* kind, doubl
   return 0;
 }
 
+const char* unib200_program_op_desc(const unib200_program* prog, int i) {
+  if (!prog || i < 0 || i >= static_cast<int>(prog->info.size())) return "";
+  return prog->info[i].desc.c_str();
+}
+
 // Replays the program `iters` times with a CUDA event pair around every op (on `stream`, the launching stream) and
 // returns the mean device time of each op in milliseconds.  Host-synchronous; for measurement only.
 int unib200_program_profile(unib200_program* prog, void* stream, int iters, float* ms_out) {
@@ -222,6 +229,8 @@ int unib200_program_graph_launch(unib200_program* prog, void* stream) {
   if (e != cudaSuccess) return fail_cuda("cudaGraphLaunch", e);
   return 0;
 }
+
+int unib200_pick_bn(int N, int flags) { return gemm_pick_bn(N, flags); }
 
 size_t unib200_packed_k(int nseg, const unib200_seg* seg) {
   size_t k = 0;
@@ -303,8 +312,8 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   for (int i = nmaps; i < kMaxAMaps; ++i) maps.a[i] = maps.a[0];
   p.total_kb = total_kb;
   const int bn = gemm_pick_bn(d->N, d->flags);
-  if ((d->flags & UNIB200_EPI_GEGLU) && (d->N % bn != 0 || (bn / 2) % 16 != 0))
-    return fail("conv_gemm: GEGLU needs N divisible by the tile width");
+  if ((d->flags & UNIB200_EPI_GEGLU) && (bn == 0 || d->N % bn != 0))
+    return fail("conv_gemm: GEGLU needs N divisible by 64 (whole value/gate sub-tiles)");
   {
     const uint64_t ktot = static_cast<uint64_t>(total_kb) * 64;
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->N)};
@@ -357,6 +366,27 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   }
   p.splits = splits;
   p.partial = d->partial;
+  // NHWC fp16 outputs leave through the smem-slot + TMA-store epilogue (residual TMA-loaded into the same slots)
+  p.epi_tma = (!(d->flags & UNIB200_EPI_OUT_NCHW) && splits == 1 && d->out != nullptr) ? 1 : 0;
+  if ((d->flags & UNIB200_EPI_GEGLU) && !p.epi_tma) return fail("conv_gemm: GEGLU cannot be combined with split-K / NCHW");
+  if (p.epi_tma) {
+    const uint64_t n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2 : d->N;
+    const uint64_t dims[2] = {n_out, static_cast<uint64_t>(d->M)};
+    const uint32_t box[2] = {32, 128};
+    const uint64_t stc[1] = {static_cast<uint64_t>(d->ldc) * 2};
+    if (!encode_map(&maps.c, d->out, 2, dims, stc, box, &why, CU_TENSOR_MAP_SWIZZLE_64B))
+      return fail("conv_gemm C map: " + why);
+    if (d->res) {
+      const uint64_t str[1] = {static_cast<uint64_t>(d->ldr) * 2};
+      if (!encode_map(&maps.r, d->res, 2, dims, str, box, &why, CU_TENSOR_MAP_SWIZZLE_64B))
+        return fail("conv_gemm R map: " + why);
+    } else {
+      maps.r = maps.c;
+    }
+  } else {
+    maps.c = maps.b;
+    maps.r = maps.b;
+  }
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   double kreal = 0.0, a_bytes = 0.0;
   for (int i = 0; i < d->nseg; ++i) {
@@ -369,7 +399,14 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   const double flops = 2.0 * d->M * d->N * kreal;
   const double bytes = a_bytes + 2.0 * d->N * kreal + ((d->flags & UNIB200_EPI_OUT_F32) ? 4.0 : 2.0) * d->M * n_out +
                        (d->res ? 2.0 * d->M * d->N : 0.0);
-  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes);
+  std::string desc = "gemm M=" + std::to_string(d->M) + " N=" + std::to_string(d->N) + " K=" +
+                     std::to_string(static_cast<long long>(kreal)) + " bn=" + std::to_string(bn) + " splits=" +
+                     std::to_string(splits) + " tiles=" + std::to_string(tiles) + " segs=";
+  for (int i = 0; i < d->nseg; ++i)
+    desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : "3x3s2:") +
+            std::to_string(d->seg[i].C);
+  if (d->flags) desc += " flags=" + std::to_string(d->flags);
+  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes, desc);
 }
 
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* stream) {
@@ -399,7 +436,9 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
   const double bh = static_cast<double>(d->B) * d->heads;
   return submit(prog, std::move(op), 1, stream, "attention", UNIB200_OP_ATTENTION, 4.0 * bh * d->Nq * d->Nk * d->d,
-                2.0 * bh * d->d * (2.0 * d->Nq + 2.0 * d->Nk));
+                2.0 * bh * d->d * (2.0 * d->Nq + 2.0 * d->Nk),
+                "attention B=" + std::to_string(d->B) + " h=" + std::to_string(d->heads) + " Nq=" +
+                    std::to_string(d->Nq) + " Nk=" + std::to_string(d->Nk) + " d=" + std::to_string(d->d));
 }
 
 int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* stream) {
@@ -411,7 +450,7 @@ int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* str
   p.HW = d->HW; p.G = d->groups; p.eps = d->eps; p.gamma = d->gamma; p.beta = d->beta;
   p.out = static_cast<__half*>(d->out); p.silu = d->silu; p.partial = d->scratch;
   const int C = p.C1 + p.C2;
-  if (C % 8 || p.C1 % 8 || d->groups <= 0 || C % d->groups || C / d->groups < 4 || C / 8 > 1024 || d->ld1 % 8 ||
+  if (C % 8 || p.C1 % 8 || d->groups <= 0 || C % d->groups || C / 8 > 512 || d->ld1 % 8 ||
       (d->x2 && d->ld2 % 8))
     return fail("groupnorm: unsupported channel configuration");
   const size_t per_chunk = static_cast<size_t>(d->B) * d->groups * 2;
@@ -421,7 +460,9 @@ int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* str
   const int B = d->B, sms = num_sms();
   Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm(p, B, sms, s); };
   return submit(prog, std::move(op), 2, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
-                4.0 * static_cast<double>(d->B) * d->HW * C);
+                4.0 * static_cast<double>(d->B) * d->HW * C,
+                "groupnorm B=" + std::to_string(d->B) + " HW=" + std::to_string(d->HW) + " C=" + std::to_string(p.C1) +
+                    "+" + std::to_string(p.C2));
 }
 
 int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float* gamma, const float* beta, int rows,
@@ -430,7 +471,8 @@ int unib200_layernorm(unib200_program* prog, const void* x, void* y, const float
   Op op = [=](cudaStream_t s) {
     return launch_layernorm(static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, rows, C, eps, s);
   };
-  return submit(prog, std::move(op), 1, stream, "layernorm", UNIB200_OP_LAYERNORM, 0.0, 4.0 * rows * C);
+  return submit(prog, std::move(op), 1, stream, "layernorm", UNIB200_OP_LAYERNORM, 0.0, 4.0 * rows * C,
+                "layernorm rows=" + std::to_string(rows) + " C=" + std::to_string(C));
 }
 
 int unib200_to_nhwc(unib200_program* prog, const void* src, int src_is_f32, void* dst, int B, int C, int H, int W,

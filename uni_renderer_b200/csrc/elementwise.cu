@@ -7,10 +7,12 @@ namespace unib {
 
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: partial (sum, sumsq) per (batch, row-chunk, group).  Each thread owns one 8-channel vector
-// column for all rows it visits, so group membership of its 8 lanes is loop-invariant (<= 3 groups for cpg >= 4).
+// column for the rows it visits (4 independent 128-bit loads in flight), per-channel sums are combined across the
+// block's row lanes and then across a group's channels in a FIXED order through shared memory: no atomics, so the
+// result is bit-reproducible run to run.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) gn_stats_kernel(GnParams p) {
-  extern __shared__ float sm[];            // [G][2]
+__global__ void __launch_bounds__(512) gn_stats_kernel(GnParams p) {
+  extern __shared__ float sm[];            // [2][rpb][C]
   const int C = p.C1 + p.C2;
   const int CV = C >> 3;
   const int cpg = C / p.G;
@@ -21,88 +23,113 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(GnParams p) {
   const int chunk = blockIdx.x;
   const int r0 = static_cast<int>((static_cast<long long>(chunk) * p.HW) / gridDim.x);
   const int r1 = static_cast<int>((static_cast<long long>(chunk + 1) * p.HW) / gridDim.x);
-  for (int i = threadIdx.x; i < 2 * p.G; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  if (rsub < rpb) {
+  float* ssum = sm;
+  float* ssq = sm + rpb * C;
+  {
     const int c0 = v * 8;
-    const int g0 = c0 / cpg;
-    int gi[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gi[j] = (c0 + j) / cpg - g0;
     const __half* src;
     int ld, cc;
     if (c0 < p.C1) { src = p.x1; ld = p.ld1; cc = c0; } else { src = p.x2; ld = p.ld2; cc = c0 - p.C1; }
-    float s[3] = {0.f, 0.f, 0.f}, ss[3] = {0.f, 0.f, 0.f};
-    for (int r = r0 + rsub; r < r1; r += rpb) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(src + (static_cast<size_t>(b) * p.HW + r) * ld + cc);
+    src += static_cast<size_t>(b) * p.HW * ld + cc;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    auto acc = [&](const uint4& raw) {
       const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
-        const int ga = gi[2 * j], gb = gi[2 * j + 1];
-        s[0] += (ga == 0 ? f.x : 0.f) + (gb == 0 ? f.y : 0.f);
-        s[1] += (ga == 1 ? f.x : 0.f) + (gb == 1 ? f.y : 0.f);
-        s[2] += (ga == 2 ? f.x : 0.f) + (gb == 2 ? f.y : 0.f);
-        ss[0] += (ga == 0 ? f.x * f.x : 0.f) + (gb == 0 ? f.y * f.y : 0.f);
-        ss[1] += (ga == 1 ? f.x * f.x : 0.f) + (gb == 1 ? f.y * f.y : 0.f);
-        ss[2] += (ga == 2 ? f.x * f.x : 0.f) + (gb == 2 ? f.y * f.y : 0.f);
+        s[2 * j] += f.x; s[2 * j + 1] += f.y;
+        q[2 * j] += f.x * f.x; q[2 * j + 1] += f.y * f.y;
       }
+    };
+    int r = r0 + rsub;
+    for (; r + 3 * rpb < r1; r += 4 * rpb) {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + rpb) * ld);
+      const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * rpb) * ld);
+      const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * rpb) * ld);
+      acc(a0); acc(a1); acc(a2); acc(a3);
     }
+    for (; r < r1; r += rpb) acc(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (g0 + k < p.G && k <= gi[7]) {
-        atomicAdd(&sm[2 * (g0 + k)], s[k]);
-        atomicAdd(&sm[2 * (g0 + k) + 1], ss[k]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      ssum[rsub * C + c0 + j] = s[j];
+      ssq[rsub * C + c0 + j] = q[j];
     }
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    for (int r = 0; r < rpb; ++r) { a += ssum[r * C + c]; q2 += ssq[r * C + c]; }
+    ssum[c] = a;
+    ssq[c] = q2;
+  }
+  __syncthreads();
   float* dst = p.partial + (static_cast<size_t>(b) * gridDim.x + chunk) * 2 * p.G;
-  for (int i = threadIdx.x; i < 2 * p.G; i += blockDim.x) dst[i] = sm[i];
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += ssum[c]; q2 += ssq[c]; }
+    dst[2 * g] = a;
+    dst[2 * g + 1] = q2;
+  }
 }
 
 // GroupNorm apply (+ optional SiLU): reduces the chunk partials in a fixed order, builds per-channel scale/shift in
-// shared memory and streams rows.  Writes the concatenated [rows, C1+C2] tensor.
+// shared memory and streams rows (4 independent 128-bit loads in flight per thread).  Writes the concatenated
+// [rows, C1+C2] tensor.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
-  extern __shared__ float sm[];            // scale[C], shift[C], mean[G], rstd[G]
+  extern __shared__ float sm[];            // scale[C], shift[C], red[8][G][2]
   const int C = p.C1 + p.C2;
   const int cpg = C / p.G;
   float* scale = sm;
   float* shift = sm + C;
-  float* mean = sm + 2 * C;
-  float* rstd = mean + p.G;
+  float* red = sm + 2 * C;
   const int b = blockIdx.y;
-  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int k = 0; k < p.stat_chunks; ++k) {
-      const float* src = p.partial + (static_cast<size_t>(b) * p.stat_chunks + k) * 2 * p.G;
-      s += src[2 * g];
-      ss += src[2 * g + 1];
+  {
+    // 8 lanes per group each sum chunks k = lane, lane+8, ... ; the 8 lane partials are then added in order
+    const int slices = 8;
+    for (int t = threadIdx.x; t < slices * p.G; t += blockDim.x) {
+      const int g = t % p.G, sl = t / p.G;
+      float s = 0.f, ss = 0.f;
+      for (int k = sl; k < p.stat_chunks; k += slices) {
+        const float* src = p.partial + (static_cast<size_t>(b) * p.stat_chunks + k) * 2 * p.G;
+        s += src[2 * g];
+        ss += src[2 * g + 1];
+      }
+      red[(sl * p.G + g) * 2] = s;
+      red[(sl * p.G + g) * 2 + 1] = ss;
     }
-    const float inv_n = 1.0f / (static_cast<float>(cpg) * p.HW);
-    const float mu = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mu * mu, 0.f);
-    mean[g] = mu;
-    rstd[g] = rsqrtf(var + p.eps);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < slices; ++sl) { s += red[(sl * p.G + g) * 2]; ss += red[(sl * p.G + g) * 2 + 1]; }
+      const float inv_n = 1.0f / (static_cast<float>(cpg) * p.HW);
+      const float mu = s * inv_n;
+      const float var = fmaxf(ss * inv_n - mu * mu, 0.f);
+      const float sc = rsqrtf(var + p.eps) * p.gamma[c];
+      scale[c] = sc;
+      shift[c] = p.beta[c] - mu * sc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = rstd[g] * p.gamma[c];
-    scale[c] = sc;
-    shift[c] = p.beta[c] - mean[g] * sc;
-  }
-  __syncthreads();
   const int CV = C >> 3;
   const int r0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.HW) / gridDim.x);
   const int r1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.HW) / gridDim.x);
   const long long total = static_cast<long long>(r1 - r0) * CV;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+  auto load = [&](long long i) -> uint4 {
     const int r = r0 + static_cast<int>(i / CV);
     const int c0 = static_cast<int>(i % CV) * 8;
     const size_t row = static_cast<size_t>(b) * p.HW + r;
     const __half* src = (c0 < p.C1) ? p.x1 + row * p.ld1 + c0 : p.x2 + row * p.ld2 + (c0 - p.C1);
-    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    return *reinterpret_cast<const uint4*>(src);
+  };
+  auto emit = [&](long long i, const uint4& raw) {
+    const int r = r0 + static_cast<int>(i / CV);
+    const int c0 = static_cast<int>(i % CV) * 8;
+    const size_t row = static_cast<size_t>(b) * p.HW + r;
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     uint32_t o[4];
 #pragma unroll
@@ -114,30 +141,37 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
       o[j] = pack_half2(y0, y1);
     }
     *reinterpret_cast<uint4*>(p.out + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  long long i = threadIdx.x;
+  const long long st = blockDim.x;
+  for (; i + 3 * st < total; i += 4 * st) {
+    const uint4 a0 = load(i), a1 = load(i + st), a2 = load(i + 2 * st), a3 = load(i + 3 * st);
+    emit(i, a0); emit(i + st, a1); emit(i + 2 * st, a2); emit(i + 3 * st, a3);
   }
+  for (; i < total; i += st) emit(i, load(i));
 }
 
 cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStream_t stream) {
   GnParams p = p_in;
   const int C = p.C1 + p.C2;
-  if (C % 8 || p.C1 % 8 || C % p.G || (C >> 3) > 1024) return cudaErrorInvalidValue;
-  const int cpg = C / p.G;
-  if (cpg < 4) return cudaErrorInvalidValue;
+  if (C % 8 || p.C1 % 8 || C % p.G || (C >> 3) > 512) return cudaErrorInvalidValue;
   int chunks = (2 * num_sms + B - 1) / B;
   if (chunks > p.HW / 4) chunks = p.HW / 4 > 0 ? p.HW / 4 : 1;
   if (chunks > p.max_chunks) chunks = p.max_chunks;
   if (chunks < 1) chunks = 1;
   p.stat_chunks = chunks;
   const int CV = C >> 3;
-  int rpb = 256 / CV;
+  int rpb = 512 / CV;
   if (rpb < 1) rpb = 1;
+  const int rows_per_chunk = (p.HW + chunks - 1) / chunks;
+  if (rpb > rows_per_chunk) rpb = rows_per_chunk;
   const int threads = rpb * CV;
-  gn_stats_kernel<<<dim3(chunks, B), threads, 2 * p.G * sizeof(float), stream>>>(p);
+  gn_stats_kernel<<<dim3(chunks, B), threads, 2 * rpb * C * sizeof(float), stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   int achunks = (4 * num_sms + B - 1) / B;
   if (achunks > p.HW) achunks = p.HW;
-  gn_apply_kernel<<<dim3(achunks, B), 256, (2 * C + 2 * p.G) * sizeof(float), stream>>>(p);
+  gn_apply_kernel<<<dim3(achunks, B), 256, (2 * C + 16 * p.G) * sizeof(float), stream>>>(p);
   return cudaGetLastError();
 }
 

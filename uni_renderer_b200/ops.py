@@ -81,6 +81,9 @@ class Program:
             out.append((k.value, f.value, b.value, n.value))
         return out
 
+    def op_desc(self, i: int) -> str:
+        return self.lib.unib200_program_op_desc(self.handle, i).decode()
+
     def profile(self, iters: int = 3):
         """Mean device ms of every op (CUDA events around each op on the current stream); host-synchronous."""
         n = self.num_ops
@@ -126,11 +129,9 @@ def pack_weight(parts: Sequence[Tuple[torch.Tensor, int]], device=None) -> torch
     return out.to(device) if device is not None else out
 
 
-def pick_bn(N: int) -> int:
-    for bn in (160, 128, 64, 32):
-        if N % bn == 0:
-            return bn
-    return 128 if N >= 128 else (64 if N > 32 else 32)
+def pick_bn(N: int, flags: int = 0) -> int:
+    """N-tile width the kernel uses for this (N, flags) -- asked from the library so packing always agrees."""
+    return L.load().unib200_pick_bn(N, flags)
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
@@ -138,9 +139,9 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     both halves of the same output columns (EPI_GEGLU)."""
     two_inner = w.shape[0]
     inner = two_inner // 2
-    bn = pick_bn(two_inner)
+    bn = pick_bn(two_inner, EPI_GEGLU)
     half = bn // 2
-    assert two_inner % bn == 0 and half % 16 == 0 and inner % half == 0
+    assert bn > 0 and two_inner % bn == 0 and half % 32 == 0 and inner % half == 0
     idx = []
     for t in range(two_inner // bn):
         idx.append(torch.arange(t * half, (t + 1) * half))
