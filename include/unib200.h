@@ -115,6 +115,9 @@ typedef struct {
   float scale;
 } unib200_attn_desc;
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* desc, void* stream);
+/* debug only: attention kernels launched after this call write clock64 stamps of CTA (0,0,0) into dev_buf
+ * (>= 4*16*8 int64); NULL switches tracing off. */
+void unib200_debug_set_trace(void* dev_buf);
 
 /* ---- GroupNorm(+SiLU) over NHWC with optional second source (virtual torch.cat, unet_2d_blocks.py:2546,2677) - */
 typedef struct {

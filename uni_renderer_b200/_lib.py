@@ -57,7 +57,7 @@ EXPORTS = [
     "unib200_program_create", "unib200_program_destroy", "unib200_program_num_launches", "unib200_program_run",
     "unib200_program_graph_instantiate", "unib200_program_graph_launch",
     "unib200_program_num_ops", "unib200_program_op_info", "unib200_program_op_desc", "unib200_program_profile",
-    "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
+    "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16",
 ]
@@ -99,6 +99,8 @@ def load() -> C.CDLL:
     lib.unib200_packed_k.argtypes = [ci, C.POINTER(Seg)]
     lib.unib200_packed_k.restype = C.c_size_t
     lib.unib200_pick_bn.argtypes = [ci, ci]
+    lib.unib200_debug_set_trace.argtypes = [vp]
+    lib.unib200_debug_set_trace.restype = None
     lib.unib200_attention.argtypes = [vp, C.POINTER(AttnDesc), vp]
     lib.unib200_groupnorm.argtypes = [vp, C.POINTER(GnDesc), vp]
     lib.unib200_layernorm.argtypes = [vp, vp, vp, vp, vp, ci, ci, cf, vp]

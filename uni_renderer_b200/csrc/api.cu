@@ -64,6 +64,7 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
   return true;
 }
 
+long long* g_attn_trace = nullptr;
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -229,6 +230,8 @@ int unib200_program_graph_launch(unib200_program* prog, void* stream) {
   if (e != cudaSuccess) return fail_cuda("cudaGraphLaunch", e);
   return 0;
 }
+
+void unib200_debug_set_trace(void* dev_buf) { g_attn_trace = static_cast<long long*>(dev_buf); }
 
 int unib200_pick_bn(int N, int flags) { return gemm_pick_bn(N, flags); }
 
@@ -433,6 +436,7 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   p.scale = d->scale;
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
+  p.trace = g_attn_trace;
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
   const double bh = static_cast<double>(d->B) * d->heads;
   return submit(prog, std::move(op), 1, stream, "attention", UNIB200_OP_ATTENTION, 4.0 * bh * d->Nq * d->Nk * d->d,

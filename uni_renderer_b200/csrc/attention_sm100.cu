@@ -1,71 +1,136 @@
 // FlashAttention-style fused softmax(Q K^T * scale) V for sm_100a (tcgen05 + TMEM + TMA), no mask.
 //
-// One CTA = 128 query rows of one (batch, head).  S = Q K^T and O += P V both run on tcgen05 with the accumulators
-// in TMEM (S: BKV fp32 columns, O: round16(d) fp32 columns); the online softmax runs one thread per query row
-// (tcgen05.ld 32x32b gives each thread its own row, so no cross-lane reductions), P is written back to shared
-// memory as fp16 in the 128B-swizzled K-major layout and fed to the second MMA; O is rescaled in place in TMEM.
-// Warp roles (192 threads): warps 0-3 softmax/epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner.
+// One CTA = TWO 128-row query tiles of one (batch, head) that ping-pong on the tensor core: while softmax warpgroup 0
+// exponentiates S0(j), the MMA warp runs S1(j) = Q1 K(j)^T and O0 += P0(j-1) V(j-1), and vice versa.  S = Q K^T and
+// O += P V both run on tcgen05 with the accumulators in TMEM (per tile: S BKV fp32 columns, O round16(d) columns).
+// The online softmax runs one thread per query row (tcgen05.ld 32x32b gives each thread its own row, so no cross-lane
+// reductions) in a SINGLE pass over S held in registers, with fp32 statistics; O is rescaled in TMEM only when a
+// row's running maximum moved by more than 2^8 (lazy rescale; the final normalisation is exact either way).  P goes
+// back to shared memory as fp16 in the 128B-swizzled K-major layout and feeds the second MMA.
+// At head dim 40 the kernel is bound by the MUFU unit (ex2: 16/clk/SM on B200), not by the tensor core: the two
+// warpgroups exist to keep MUFU busy while the other tile waits on its MMAs.
+// Warp roles (320 threads): warps 0-3 softmax/epilogue of tile 0, warps 4-7 of tile 1, warp 8 TMA producer,
+// warp 9 MMA issuer + TMEM owner.
 // Q/K/V are read straight out of the (fused) projection outputs through 4-D tensor maps {d, tokens, heads, batch};
 // head dims that are not multiples of 64 rely on TMA out-of-bounds zero fill, so nothing is padded in HBM.
 #include "attention_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace unib {
 
-template <int NCH, int BKV>
+template <int NCH>
 struct AttnCfg {
-  static constexpr int kQBytes = NCH * 128 * 128;          // NCH chunks of [128 rows x 64 fp16]
-  static constexpr int kKBytes = NCH * BKV * 128;          // NCH chunks of [BKV rows x 64 fp16]
+  static constexpr int kBKV = (NCH == 1) ? 128 : 64;       // kv rows per block
+  static constexpr int kQBytes = NCH * 128 * 128;          // per tile: NCH chunks of [128 rows x 64 fp16]
+  static constexpr int kKBytes = NCH * kBKV * 128;         // NCH chunks of [BKV rows x 64 fp16]
   static constexpr int kStageBytes = 2 * kKBytes;          // K + V
-  static constexpr int kPBytes = (BKV / 64) * 128 * 128;   // [128 rows x BKV fp16] as 64-wide chunks
-  static constexpr int kStages = 2;
-  static constexpr int kBarOff = kQBytes + kStages * kStageBytes + kPBytes;
-  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
-  static constexpr int kTmemCols = 256;                    // S (BKV <= 128) + O (<= 128 when BKV = 128, <= 192 when 64)
+  static constexpr int kPBytes = (kBKV / 64) * 128 * 128;  // per tile: [128 rows x BKV fp16] as 64-wide chunks
+  static constexpr int kStages = (NCH == 3) ? 2 : 3;
+  static constexpr int kKvOff = 2 * kQBytes;
+  static constexpr int kPOff = kKvOff + kStages * kStageBytes;
+  static constexpr int kBarOff = kPOff + 2 * kPBytes;
+  static constexpr int kSmemBytes = kBarOff + 128;         // base is declared 1024-aligned (checked at run time)
+  static constexpr int kTmemCols = 512;                    // 2 x S (BKV) + 2 x O (<= 64 | 128 | 192)
+  static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget");
 };
 
-template <int NCH, int BKV>
-__global__ void __launch_bounds__(192, 1)
+// Fully unrolled MMA issue sequences: descriptors differ from a precomputed base only by compile-time constants, so
+// the issuing thread spends one add per operand between tcgen05.mma instructions (the issue loop, not the tensor
+// pipe, was the limiter when descriptors were rebuilt per instruction).
+template <int KS, int BKV>
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint64_t q_desc, uint64_t k_desc, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int ch = ks >> 2, within = ks & 3;
+    umma_f16_ss(d_tmem, q_desc + static_cast<uint64_t>((ch * 16384 + within * 32) >> 4),
+                k_desc + static_cast<uint64_t>((ch * (BKV * 128) + within * 32) >> 4), idesc, ks > 0 ? 1u : 0u);
+  }
+}
+template <int BKV>
+__device__ __forceinline__ void issue_qk_dyn(int ks_count, uint32_t d_tmem, uint64_t q_desc, uint64_t k_desc,
+                                             uint32_t idesc) {
+  switch (ks_count) {
+    case 1: issue_qk<1, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 2: issue_qk<2, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 3: issue_qk<3, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 4: issue_qk<4, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 5: issue_qk<5, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 6: issue_qk<6, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 7: issue_qk<7, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 8: issue_qk<8, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 9: issue_qk<9, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 10: issue_qk<10, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    case 11: issue_qk<11, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+    default: issue_qk<12, BKV>(d_tmem, q_desc, k_desc, idesc); break;
+  }
+}
+template <int BKV>
+__device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint64_t p_desc, uint64_t v_desc, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int ks = 0; ks < BKV / 16; ++ks) {
+    const int ch = ks >> 2, within = ks & 3;
+    umma_f16_ss(d_tmem, p_desc + static_cast<uint64_t>((ch * 16384 + within * 32) >> 4),
+                v_desc + static_cast<uint64_t>((ks * 2048) >> 4), idesc, (!first || ks > 0) ? 1u : 0u);
+  }
+}
+
+// debug stamps: slot layout trace[(who * 16 + j) * 8 + k]
+#define ATTN_TRACE(who, j, k)                                                                                   \
+  do {                                                                                                          \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 16)                \
+      p.trace[((who) * 16 + (j)) * 8 + (k)] = clock64();                                                        \
+  } while (0)
+
+template <int NCH>
+__global__ void __launch_bounds__(320, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
-  using Cfg = AttnCfg<NCH, BKV>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t q_smem = base;
-  const uint32_t kv_smem = base + Cfg::kQBytes;
-  const uint32_t p_smem = kv_smem + Cfg::kStages * Cfg::kStageBytes;
+  using Cfg = AttnCfg<NCH>;
+  constexpr int BKV = Cfg::kBKV;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0) {                // SWIZZLE_128B tiles need a 1024 B aligned base (no static smem here)
+    if (threadIdx.x == 0) printf("unib200: attention smem base 0x%x is not 1024-byte aligned\n", base);
+    __trap();
+  }
+  const uint32_t kv_smem = base + Cfg::kKvOff;
   const uint32_t bar_base = base + Cfg::kBarOff;
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (3 + s); };
-  const uint32_t s_full = bar_base + 8u * 5;
-  const uint32_t p_full = bar_base + 8u * 6;
-  const uint32_t o_ready = bar_base + 8u * 7;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOff + 64);
+  auto kv_empty = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto s_full = [&](int t) { return bar_base + 8u * (7 + t); };
+  auto p_full = [&](int t) { return bar_base + 8u * (9 + t); };
+  auto o_ready = [&](int t) { return bar_base + 8u * (11 + t); };
+  auto pv_done = [&](int t) { return bar_base + 8u * (13 + t); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOff + 120);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
+  const int q_base = blockIdx.x * 256;
+  const int ntile = (q_base + 128 < p.Nq) ? 2 : 1;     // second tile may not exist
   const int nblk = (p.Nk + BKV - 1) / BKV;
   const int dpad = (p.d + 15) & ~15;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&maps.q);
     tma_prefetch_desc(&maps.k);
     tma_prefetch_desc(&maps.v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_ready, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 128);
+      mbar_init(o_ready(s), 1);
+      mbar_init(pv_done(s), 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -73,15 +138,20 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: [S0 | S1 | O0 | O1]
+  auto t_s_col = [&](int t) { return static_cast<uint32_t>(t * BKV); };
+  auto t_o_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + t * (NCH * 64)); };
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
-      for (int ch = 0; ch < NCH; ++ch) tma_load_4d(q_smem + ch * 16384, &maps.q, q_full, ch * 64, q0, head, b);
+      mbar_arrive_expect_tx(q_full, ntile * Cfg::kQBytes);
+      for (int t = 0; t < ntile; ++t)
+        for (int ch = 0; ch < NCH; ++ch)
+          tma_load_4d(base + t * Cfg::kQBytes + ch * 16384, &maps.q, q_full, ch * 64, q_base + t * 128, head, b);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % Cfg::kStages;
+        const uint32_t ph = (j / Cfg::kStages) & 1;
         mbar_wait(kv_empty(st), ph ^ 1);
         mbar_arrive_expect_tx(kv_full(st), Cfg::kStageBytes);
         const uint32_t kdst = kv_smem + st * Cfg::kStageBytes;
@@ -91,139 +161,174 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, BKV);
       const uint32_t idesc_o = make_idesc_f16(128, dpad, 0, 1);   // B (= V) is MN-major
-      const uint32_t t_s = tmem_base;
-      const uint32_t t_o = tmem_base + BKV;
+      const int ks_s = dpad / 16;
+      // operand descriptors of tile t / stage st differ from tile 0 / stage 0 by constants (16-byte units)
+      const uint64_t q_desc0 = make_desc_kmajor_sw128(base);
+      const uint64_t p_desc0 = make_desc_kmajor_sw128(base + Cfg::kPOff);
+      const uint64_t k_desc0 = make_desc_kmajor_sw128(kv_smem);
+      const uint64_t v_desc0 = make_desc_mnmajor_sw128(kv_smem + Cfg::kKBytes, BKV * 128, 1024);
+      constexpr uint64_t kStage16 = Cfg::kStageBytes >> 4;
       mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      for (int t = 0; t < ntile; ++t) {
+        issue_qk_dyn<BKV>(ks_s, tmem_base + t_s_col(t), q_desc0 + t * (Cfg::kQBytes >> 4), k_desc0, idesc_s);
+        umma_commit(s_full(t));
+      }
+      int st = 0;
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(kv_full(st), ph);
-        tc_fence_after();
-        const uint32_t k_addr = kv_smem + st * Cfg::kStageBytes;
-        const uint32_t v_addr = k_addr + Cfg::kKBytes;
-        // S = Q K^T : K loop over the head dim in steps of 16
-        for (int ks = 0; ks < dpad / 16; ++ks) {
-          const int ch = ks >> 2, within = ks & 3;
-          const uint64_t a_desc = make_desc_kmajor_sw128(q_smem + ch * 16384 + within * 32);
-          const uint64_t b_desc = make_desc_kmajor_sw128(k_addr + ch * (BKV * 128) + within * 32);
-          umma_f16_ss(t_s, a_desc, b_desc, idesc_s, ks > 0 ? 1u : 0u);
+        const int stn = (st + 1 == Cfg::kStages) ? 0 : st + 1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < ntile) {
+            mbar_wait(p_full(t), j & 1);       // softmax_t(j) has read S_t(j) and written P_t(j)
+            tc_fence_after();
+            ATTN_TRACE(2 + t, j, 0);
+            // S_t(j+1) first: the next softmax can start while P_t(j) V(j) is still running
+            if (j + 1 < nblk) {
+              if (t == 0) {
+                mbar_wait(kv_full(stn), ((j + 1) / Cfg::kStages) & 1);
+                tc_fence_after();
+              }
+              ATTN_TRACE(2 + t, j, 2);
+              issue_qk_dyn<BKV>(ks_s, tmem_base + t_s_col(t), q_desc0 + t * (Cfg::kQBytes >> 4),
+                                k_desc0 + stn * kStage16, idesc_s);
+              ATTN_TRACE(2 + t, j, 3);
+              umma_commit(s_full(t));
+            }
+            ATTN_TRACE(2 + t, j, 4);
+            // O_t += P_t V : K loop over the kv rows of this block in steps of 16
+            issue_pv<BKV>(tmem_base + t_o_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), v_desc0 + st * kStage16, idesc_o,
+                          j == 0);
+            ATTN_TRACE(2 + t, j, 5);
+            umma_commit(pv_done(t));                          // P_t buffer + O_t free again
+            if (t == ntile - 1) umma_commit(kv_empty(st));   // K(j)/V(j) fully consumed by both tiles
+            if (j == nblk - 1) umma_commit(o_ready(t));
+            ATTN_TRACE(2 + t, j, 1);
+          }
         }
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        // O += P V : K loop over the kv rows of this block in steps of 16
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          const int ch = ks >> 2, within = ks & 3;
-          const uint64_t a_desc = make_desc_kmajor_sw128(p_smem + ch * 16384 + within * 32);
-          const uint64_t b_desc = make_desc_mnmajor_sw128(v_addr + ks * 2048, BKV * 128, 1024);
-          umma_f16_ss(t_o, a_desc, b_desc, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(kv_empty(st));
-        umma_commit(o_ready);
+        st = stn;
       }
     }
   } else {
-    // =============================== softmax + epilogue (warps 0..3) ===============================
-    const int qd = warp;                    // TMEM lane quadrant
-    const int row = qd * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    const uint32_t t_o = t_s + BKV;
-    const float sl2 = p.scale * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t p_row = p_smem + row * 128;
-    const int sw = row & 7;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int kv_valid = p.Nk - j * BKV;     // columns >= kv_valid are padding
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_s + c * 32, v);
+    // =============================== softmax + epilogue (warpgroup t = warp / 4) ===============================
+    const int t = warp >> 2;
+    if (t < ntile) {
+      const int qd = warp & 3;                // TMEM lane quadrant
+      const int row = qd * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_off + t_s_col(t);
+      const uint32_t t_o = tmem_base + lane_off + t_o_col(t);
+      const float sl2 = p.scale * 1.4426950408889634f;
+      float m_ref = -INFINITY, l_run = 0.f;
+      const uint32_t p_row = base + Cfg::kPOff + t * Cfg::kPBytes + row * 128;
+      const int sw = row & 7;
+      for (int j = 0; j < nblk; ++j) {
+        const bool tr = (lane == 0 && qd == 0);
+        if (tr) ATTN_TRACE(t, j, 0);
+        mbar_wait(s_full(t), j & 1);
+        tc_fence_after();
+        if (tr) ATTN_TRACE(t, j, 1);
+        float v[BKV];
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) tmem_ld32(t_s + c * 32, v + c * 32);
         tmem_ld_wait();
+        if (tr) ATTN_TRACE(t, j, 2);
+        const int kv_valid = p.Nk - j * BKV;     // columns >= kv_valid are padding (last block only)
+        if (kv_valid < BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < kv_valid) ? v[i] : -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < BKV; ++i)
+            if (i >= kv_valid) v[i] = -INFINITY;
         }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2((m_run - m_new) * sl2);
-      const float mb = m_new * sl2;
-      float rowsum = 0.f;
+        float mx4[4] = {v[0], v[1], v[2], v[3]};              // 4 independent chains (FMNMX latency, not issue, bounds)
+#pragma unroll
+        for (int i = 4; i < BKV; i += 4) {
+          mx4[0] = fmaxf(mx4[0], v[i]);
+          mx4[1] = fmaxf(mx4[1], v[i + 1]);
+          mx4[2] = fmaxf(mx4[2], v[i + 2]);
+          mx4[3] = fmaxf(mx4[3], v[i + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // P_t V(j-1) was issued AFTER S_t(j): wait for it before O_t is rescaled or the P_t buffer is overwritten
+        if (j > 0) {
+          mbar_wait(pv_done(t), (j - 1) & 1);
+          tc_fence_after();
+        }
+        // lazy rescale: move the reference maximum only when some row of this warp grew by more than 2^8
+        const bool need = (mx - m_ref) * sl2 > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx);
+          const float alpha = fast_exp2((m_ref - m_new) * sl2);     // 0 on the first block (m_ref = -inf)
+          m_ref = m_new;
+          l_run *= alpha;
+          if (j > 0) {
+            // P_t V(j-1) is complete (pv_done) and P_t V(j) is not issued before this warpgroup arrives on p_full,
+            // so O_t is stable here
 #pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        float v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+            for (int c = 0; c < dpad / 16; ++c) {
+              float o[16];
+              tmem_ld16(t_o + c * 16, o);
+              tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(v[i] * sl2 - mb);
-          float p1 = fast_exp2(v[i + 1] * sl2 - mb);
-          if (c * 32 + i >= kv_valid) p0 = 0.f;
-          if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
-          rowsum += p0 + p1;
-          pk[i >> 1] = pack_half2(p0, p1);
+              for (int i = 0; i < 16; ++i) o[i] *= alpha;
+              tmem_st16(t_o + c * 16, o);
+            }
+            tmem_st_wait();
+          }
         }
-        // 32 columns = 4 x 16 B units; unit u of the 64-wide chunk lands at (u ^ (row & 7))
-        const int chunk = (c * 32) >> 6;
-        const int u0 = ((c * 32) & 63) >> 3;
+        if (tr) ATTN_TRACE(t, j, 3);
+        const float mb = m_ref * sl2;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t dst = p_row + chunk * 16384 + (((u0 + u) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
-                       "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+        for (int u = 0; u < BKV / 8; ++u) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = u * 8 + 2 * e;
+            const float p0 = fast_exp2(v[i] * sl2 - mb);
+            const float p1 = fast_exp2(v[i + 1] * sl2 - mb);
+            rs4[e] += p0 + p1;
+            pk[e] = pack_half2(p0, p1);
+          }
+          // 16 B unit (u & 7) of this row lands at ((u & 7) ^ (row & 7)) in the 128B-swizzled 64-column chunk u >> 3
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (u >> 3) * 16384 + (((u & 7) ^ sw) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                        : "memory");
         }
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        if (tr) ATTN_TRACE(t, j, 4);
+        fence_proxy_async_shared();           // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(p_full(t));
+        if (tr) ATTN_TRACE(t, j, 5);
       }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-      if (j > 0) {
-        mbar_wait(o_ready, (j - 1) & 1);      // previous P V must have landed before O is rescaled
-        tc_fence_after();
+      mbar_wait(o_ready(t), 0);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int q = q_base + t * 128 + row;
+      __half* op = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * p.d;
 #pragma unroll 1
-        for (int c = 0; c < dpad / 16; ++c) {
-          float o[16];
-          tmem_ld16(t_o + c * 16, o);
-          tmem_ld_wait();
+      for (int c = 0; c < dpad / 16; ++c) {
+        float o[16];
+        tmem_ld16(t_o + c * 16, o);
+        tmem_ld_wait();
+        if (q < p.Nq) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] *= alpha;
-          tmem_st16(t_o + c * 16, o);
-        }
-        tmem_st_wait();
-      }
-      fence_proxy_async_shared();             // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    mbar_wait(o_ready, (nblk - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int q = q0 + row;
-    __half* op = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * p.d;
-#pragma unroll 1
-    for (int c = 0; c < dpad / 16; ++c) {
-      float o[16];
-      tmem_ld16(t_o + c * 16, o);
-      tmem_ld_wait();
-      if (q < p.Nq) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int col = c * 16 + u * 8;
-          if (col + 8 <= p.d) {
-            uint4 w;
-            w.x = pack_half2(o[u * 8 + 0] * inv_l, o[u * 8 + 1] * inv_l);
-            w.y = pack_half2(o[u * 8 + 2] * inv_l, o[u * 8 + 3] * inv_l);
-            w.z = pack_half2(o[u * 8 + 4] * inv_l, o[u * 8 + 5] * inv_l);
-            w.w = pack_half2(o[u * 8 + 6] * inv_l, o[u * 8 + 7] * inv_l);
-            *reinterpret_cast<uint4*>(op + col) = w;
+          for (int u = 0; u < 2; ++u) {
+            const int col = c * 16 + u * 8;
+            if (col + 8 <= p.d) {
+              uint4 w;
+              w.x = pack_half2(o[u * 8 + 0] * inv_l, o[u * 8 + 1] * inv_l);
+              w.y = pack_half2(o[u * 8 + 2] * inv_l, o[u * 8 + 3] * inv_l);
+              w.z = pack_half2(o[u * 8 + 4] * inv_l, o[u * 8 + 5] * inv_l);
+              w.w = pack_half2(o[u * 8 + 6] * inv_l, o[u * 8 + 7] * inv_l);
+              *reinterpret_cast<uint4*>(op + col) = w;
+            }
           }
         }
       }
@@ -232,34 +337,34 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int NCH, int BKV>
+template <int NCH>
 static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
-  using Cfg = AttnCfg<NCH, BKV>;
+  using Cfg = AttnCfg<NCH>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH, BKV>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((p.Nq + 127) / 128, p.heads, p.B);
-  attention_tcgen05_kernel<NCH, BKV><<<grid, 192, Cfg::kSmemBytes, stream>>>(maps, p);
+  dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
+  attention_tcgen05_kernel<NCH><<<grid, 320, Cfg::kSmemBytes, stream>>>(maps, p);
   return cudaGetLastError();
 }
 
-int attention_bkv(int d) { return d <= 128 ? 128 : 64; }
+int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
 
 cudaError_t launch_attention(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
   if (p.d % 8 != 0 || p.d > 192 || p.d < 8) return cudaErrorInvalidValue;
-  if (p.d <= 64) return launch_cfg<1, 128>(maps, p, stream);
-  if (p.d <= 128) return launch_cfg<2, 128>(maps, p, stream);
-  return launch_cfg<3, 64>(maps, p, stream);
+  if (p.d <= 64) return launch_cfg<1>(maps, p, stream);
+  if (p.d <= 128) return launch_cfg<2>(maps, p, stream);
+  return launch_cfg<3>(maps, p, stream);
 }
 
 }  // namespace unib
