@@ -37,6 +37,13 @@ unib200_program* unib200_program_create(void);
 void unib200_program_destroy(unib200_program* prog);
 int unib200_program_num_launches(const unib200_program* prog);   /* kernels launched by one run */
 int unib200_program_run(unib200_program* prog, void* stream);
+/* Lanes: ops recorded after set_lane(l) run on lane l (0 = the caller's stream, 1..3 = side streams owned by the
+ * program).  Lanes run concurrently between barriers; a barrier joins every lane into lane 0 and forks again, and the
+ * end of the program is an implicit join.  The RGB stream and the attribute stream of the dual-stream step are
+ * data-independent between exchanges (models/controlnet.py:1078-1087 vs :2446-2461), so they are recorded on two
+ * lanes and become two parallel branches of the step's CUDA graph. */
+int unib200_program_set_lane(unib200_program* prog, int lane);
+int unib200_program_barrier(unib200_program* prog);
 int unib200_program_graph_instantiate(unib200_program* prog, void* stream);   /* capture run() into a CUDA graph */
 int unib200_program_graph_launch(unib200_program* prog, void* stream);
 /* accounting + measurement of a recorded program: per-op kind, algorithmic FLOPs (2*MAC, unpadded) and HBM bytes

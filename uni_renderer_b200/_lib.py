@@ -55,7 +55,8 @@ class GnDesc(C.Structure):
 EXPORTS = [
     "unib200_version", "unib200_last_error", "unib200_device_info",
     "unib200_program_create", "unib200_program_destroy", "unib200_program_num_launches", "unib200_program_run",
-    "unib200_program_graph_instantiate", "unib200_program_graph_launch",
+    "unib200_program_graph_instantiate", "unib200_program_graph_launch", "unib200_program_set_lane",
+    "unib200_program_barrier",
     "unib200_program_num_ops", "unib200_program_op_info", "unib200_program_op_desc", "unib200_program_profile",
     "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
@@ -89,6 +90,8 @@ def load() -> C.CDLL:
     lib.unib200_program_run.argtypes = [vp, vp]
     lib.unib200_program_graph_instantiate.argtypes = [vp, vp]
     lib.unib200_program_graph_launch.argtypes = [vp, vp]
+    lib.unib200_program_set_lane.argtypes = [vp, ci]
+    lib.unib200_program_barrier.argtypes = [vp]
     lib.unib200_program_num_ops.argtypes = [vp]
     lib.unib200_program_op_info.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.POINTER(ci)]

@@ -89,12 +89,20 @@ struct OpInfo {
 
 }  // namespace
 
+constexpr int kMaxLanes = 4;
+constexpr int kBarrierLane = -1;
+
 struct unib200_program {
   std::vector<Op> ops;
   std::vector<OpInfo> info;
+  std::vector<int> lane;          // execution lane of each op; kBarrierLane marks a fork/join point
+  int cur_lane = 0;
   int launches = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  // lanes 1.. run on side streams owned by the program; events are handed out in order and reused run to run
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> events;
 };
 
 namespace {
@@ -102,6 +110,7 @@ int submit(unib200_program* prog, Op op, int launches, void* stream, const char*
            double flops = 0.0, double bytes = 0.0, const std::string& desc = std::string()) {
   if (prog) {
     prog->ops.push_back(std::move(op));
+    prog->lane.push_back(prog->cur_lane);
     OpInfo oi;
     oi.kind = kind; oi.flops = flops; oi.bytes = bytes; oi.launches = launches;
     oi.desc = desc.empty() ? std::string(what) : desc;
@@ -139,17 +148,96 @@ void unib200_program_destroy(unib200_program* prog) {
   if (!prog) return;
   if (prog->exec) cudaGraphExecDestroy(prog->exec);
   if (prog->graph) cudaGraphDestroy(prog->graph);
+  for (int l = 1; l < kMaxLanes; ++l)
+    if (prog->lane_stream[l]) cudaStreamDestroy(prog->lane_stream[l]);
+  for (cudaEvent_t e : prog->events) cudaEventDestroy(e);
   delete prog;
+}
+
+int unib200_program_set_lane(unib200_program* prog, int lane) {
+  if (!prog) return fail("null program");
+  if (lane < 0 || lane >= kMaxLanes) return fail("program_set_lane: lane must be in [0, 4)");
+  prog->cur_lane = lane;
+  return 0;
+}
+
+int unib200_program_barrier(unib200_program* prog) {
+  if (!prog) return fail("null program");
+  prog->ops.push_back(Op());
+  prog->lane.push_back(kBarrierLane);
+  OpInfo oi;
+  oi.launches = 0;
+  oi.desc = "barrier";
+  prog->info.push_back(oi);
+  return 0;
 }
 
 int unib200_program_num_launches(const unib200_program* prog) { return prog ? prog->launches : 0; }
 
+// Lane 0 ops are launched on `stream`; ops of lanes 1.. on the program's side streams, forked from `stream` at the last
+// barrier (or the start of the program) and joined back at the next barrier (or the end).  Works identically in
+// eager mode and under stream capture, where the forks/joins become parallel branches of the CUDA graph.
 int unib200_program_run(unib200_program* prog, void* stream) {
   if (!prog) return fail("null program");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  size_t next_ev = 0;
+  cudaError_t e = cudaSuccess;
+  auto event = [&]() -> cudaEvent_t {
+    if (next_ev == prog->events.size()) {
+      cudaEvent_t ev = nullptr;
+      e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) return nullptr;
+      prog->events.push_back(ev);
+    }
+    return prog->events[next_ev++];
+  };
+  bool active[kMaxLanes] = {false, false, false, false};
+  cudaEvent_t fork = nullptr;        // recorded on `s` lazily, when the first side-lane op after a barrier shows up
+  auto join = [&]() -> cudaError_t {
+    for (int l = 1; l < kMaxLanes; ++l) {
+      if (!active[l]) continue;
+      cudaEvent_t ev = event();
+      if (!ev) return e;
+      if ((e = cudaEventRecord(ev, prog->lane_stream[l])) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(s, ev, 0)) != cudaSuccess) return e;
+      active[l] = false;
+    }
+    fork = nullptr;
+    return cudaSuccess;
+  };
+  // fork events must be recorded at the barrier itself (not later, after more lane-0 work was queued)
+  bool has_side = false;
+  for (int l : prog->lane) has_side = has_side || l > 0;
+  auto record_fork = [&]() -> cudaError_t {
+    if (!has_side) return cudaSuccess;
+    fork = event();
+    if (!fork) return e;
+    return cudaEventRecord(fork, s);
+  };
+  if ((e = record_fork()) != cudaSuccess) return fail_cuda("program fork", e);
   for (size_t i = 0; i < prog->ops.size(); ++i) {
-    cudaError_t e = prog->ops[i](static_cast<cudaStream_t>(stream));
+    const int l = prog->lane[i];
+    if (l == kBarrierLane) {
+      if ((e = join()) != cudaSuccess) return fail_cuda("program barrier (join)", e);
+      if ((e = record_fork()) != cudaSuccess) return fail_cuda("program barrier (fork)", e);
+      continue;
+    }
+    cudaStream_t target = s;
+    if (l > 0) {
+      if (!prog->lane_stream[l]) {
+        e = cudaStreamCreateWithFlags(&prog->lane_stream[l], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return fail_cuda("cudaStreamCreate (lane)", e);
+      }
+      if (!active[l]) {
+        if ((e = cudaStreamWaitEvent(prog->lane_stream[l], fork, 0)) != cudaSuccess) return fail_cuda("lane fork", e);
+        active[l] = true;
+      }
+      target = prog->lane_stream[l];
+    }
+    e = prog->ops[i](target);
     if (e != cudaSuccess) return fail_cuda(("program op " + std::to_string(i)).c_str(), e);
   }
+  if ((e = join()) != cudaSuccess) return fail_cuda("program join", e);
   return 0;
 }
 
@@ -187,7 +275,7 @@ int unib200_program_profile(unib200_program* prog, void* stream, int iters, floa
   for (int it = 0; it < iters && rc == 0; ++it) {
     for (size_t i = 0; i < n; ++i) {
       cudaEventRecord(ev[2 * i], s);
-      cudaError_t e = prog->ops[i](s);
+      cudaError_t e = prog->lane[i] == kBarrierLane ? cudaSuccess : prog->ops[i](s);   // lanes are serialised here
       cudaEventRecord(ev[2 * i + 1], s);
       if (e != cudaSuccess) { rc = fail_cuda(("program op " + std::to_string(i)).c_str(), e); break; }
     }

@@ -60,6 +60,14 @@ class Program:
     def run(self):
         L.check(self.lib.unib200_program_run(self.handle, _stream()), "program_run")
 
+    def lane(self, n: int):
+        """Ops recorded from now on run on lane n (0 = caller's stream; lanes run concurrently between barriers)."""
+        L.check(self.lib.unib200_program_set_lane(self.handle, n), "program_set_lane")
+
+    def barrier(self):
+        """Join every lane into lane 0, then fork again."""
+        L.check(self.lib.unib200_program_barrier(self.handle), "program_barrier")
+
     def instantiate_graph(self):
         L.check(self.lib.unib200_program_graph_instantiate(self.handle, _stream()), "graph_instantiate")
         self.has_graph = True

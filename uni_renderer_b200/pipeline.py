@@ -76,7 +76,8 @@ class DualStreamSampler:
             raise RuntimeError("DualStreamSampler runs on CUDA (sm_100a) only")
         self.schedule = DDIMSchedule(prediction_type=prediction_type)
         self.use_graph = use_graph
-        self.ws = Workspace(self.device)
+        self.ws = Workspace(self.device)          # lane 0 (RGB stream)
+        self.ws1 = Workspace(self.device)         # lane 1 (attribute stream): lanes run concurrently, no shared scratch
         self._plans: Dict[Tuple, _Plan] = {}
 
     @classmethod
@@ -95,7 +96,7 @@ class DualStreamSampler:
         key = (mode, B, S, L, steps)
         if key in self._plans:
             return self._plans[key]
-        dev, ws = self.device, self.ws
+        dev, ws, ws1 = self.device, self.ws, self.ws1
         unet, enc, dec = self.unet, self.enc, self.dec
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
@@ -124,30 +125,43 @@ class DualStreamSampler:
             return net.rec_temb(prog, ws, table, B, step_idx=b["step"] if stepped else None, t_stride=B)
 
         if mode in ("joint", "cycle"):
-            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            # The RGB stream (lane 0) and the attribute stream (lane 1) only meet at the exchange: two parallel
+            # branches of the step graph, so the small-M layers of one stream fill the SMs the other leaves idle.
+            step.lane(1)
             ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
-            tpU, tpE, tpD = temb(unet, step, b["t_img"]), temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
-            skA, midA = enc.rec_encoder(step, ws, x_attr, tpE, kvE, L)
+            tpE, tpD = temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
+            skA, midA = enc.rec_encoder(step, ws1, x_attr, tpE, kvE, L)
+            step.lane(0)
+            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            tpU = temb(unet, step, b["t_img"])
             skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
+            step.barrier()
             dskU, dmidU = enc.rec_exchange(step, ws, skA, midA, skU, midU)      # skipU + zc_enc(skipA)
-            dskA, dmidA = dec.rec_exchange(step, ws, skU, midU, skA, midA)      # skipA + zc_dec(skipU_raw)
+            step.lane(1)
+            dskA, dmidA = dec.rec_exchange(step, ws1, skU, midU, skA, midA)     # skipA + zc_dec(skipU_raw)
             if mode == "joint":
+                dec.rec_decoder(step, ws1, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+                step.lane(0)
                 unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=None, axpby=ax_img)
-                dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+                step.barrier()
             else:
+                step.lane(0)
                 # pass 1 (train.py:1324-1355): full dual-stream step; the RGB prediction of this pass is kept as an
                 # auxiliary output, the attribute prediction drives the attribute update AND feeds pass 2.
                 b["img_pred_pass1"] = torch.zeros(B, unet.cfg.out_channels, S, S, **f32)
                 unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=b["img_pred_pass1"])
+                step.lane(1)
                 x_attr2 = Act(torch.zeros_like(x_attr.t), B, S, S, x_attr.C)
                 b["x_attr_pass2"] = x_attr2.t
-                dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=dict(ax_attr, nhwc=x_attr2.t))
+                dec.rec_decoder(step, ws1, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=dict(ax_attr, nhwc=x_attr2.t))
                 # pass 2 (train.py:1388-1413): attribute encoder on cat(mask, attr_pred) at t_attr = 0, then the RGB
                 # stream conditioned on it.  x_img, t_img and ehs are those of pass 1, so the RGB encoder + mid of
                 # pass 1 are reused (bit-identical); only the exchange and the RGB decoder are re-run.
                 b["t_zero"] = torch.zeros(1, B, **f32)
                 tpE0 = temb(enc, step, b["t_zero"], stepped=False)
-                skA2, midA2 = enc.rec_encoder(step, ws, x_attr2, tpE0, kvE, L)
+                skA2, midA2 = enc.rec_encoder(step, ws1, x_attr2, tpE0, kvE, L)
+                step.barrier()
+                step.lane(0)
                 dskU2, dmidU2 = enc.rec_exchange(step, ws, skA2, midA2, skU, midU)
                 unet.rec_decoder(step, ws, dmidU2, dskU2, tpU, kvU, L, out_nchw=None, axpby=ax_img)
         elif mode == "forward":
