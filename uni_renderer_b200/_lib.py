@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libunib200.so")
+# UNIB200_LIB selects another build of the SAME library (A/B measurements of kernel variants); never a fallback
+LIB_PATH = os.environ.get("UNIB200_LIB") or os.path.join(HERE, "libunib200.so")
 
 SEG_1x1, SEG_3x3, SEG_3x3_S2 = 0, 1, 2
 OP_OTHER, OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM = 0, 1, 2, 3, 4

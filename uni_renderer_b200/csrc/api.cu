@@ -426,6 +426,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   p.aux = d->aux;
   p.aux_out = d->aux_out;
   p.axpby_n0 = d->axpby_first_channel;
+  p.trace = g_attn_trace;
   if (!(d->flags & UNIB200_EPI_OUT_NCHW)) {
     if (d->ldc % 8 != 0) return fail("conv_gemm: ldc must be a multiple of 8");
     if (d->res && d->ldr % 8 != 0) return fail("conv_gemm: ldr must be a multiple of 8");
@@ -457,27 +458,15 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   }
   p.splits = splits;
   p.partial = d->partial;
-  // NHWC fp16 outputs leave through the smem-slot + TMA-store epilogue (residual TMA-loaded into the same slots)
-  p.epi_tma = (!(d->flags & UNIB200_EPI_OUT_NCHW) && splits == 1 && d->out != nullptr) ? 1 : 0;
-  if ((d->flags & UNIB200_EPI_GEGLU) && !p.epi_tma) return fail("conv_gemm: GEGLU cannot be combined with split-K / NCHW");
-  if (p.epi_tma) {
-    const uint64_t n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2 : d->N;
-    const uint64_t dims[2] = {n_out, static_cast<uint64_t>(d->M)};
-    const uint32_t box[2] = {32, 128};
-    const uint64_t stc[1] = {static_cast<uint64_t>(d->ldc) * 2};
-    if (!encode_map(&maps.c, d->out, 2, dims, stc, box, &why, CU_TENSOR_MAP_SWIZZLE_64B))
-      return fail("conv_gemm C map: " + why);
-    if (d->res) {
-      const uint64_t str[1] = {static_cast<uint64_t>(d->ldr) * 2};
-      if (!encode_map(&maps.r, d->res, 2, dims, str, box, &why, CU_TENSOR_MAP_SWIZZLE_64B))
-        return fail("conv_gemm R map: " + why);
-    } else {
-      maps.r = maps.c;
-    }
-  } else {
-    maps.c = maps.b;
-    maps.r = maps.b;
+  // NHWC fp16 outputs leave through the register -> vector-store epilogue; 256-bit accesses when rows are 32 B aligned
+  p.epi_vec = 0;
+  if (!(d->flags & UNIB200_EPI_OUT_NCHW) && splits == 1 && d->out != nullptr) {
+    auto al32 = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0; };
+    p.epi_vec = (al32(d->out, d->ldc) && (!d->res || al32(d->res, d->ldr))) ? 2 : 1;
+    if ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->res && (reinterpret_cast<uintptr_t>(d->res) & 15)))
+      return fail("conv_gemm: out / res must be 16-byte aligned");
   }
+  if ((d->flags & UNIB200_EPI_GEGLU) && !p.epi_vec) return fail("conv_gemm: GEGLU cannot be combined with split-K / NCHW");
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   double kreal = 0.0, a_bytes = 0.0;
   for (int i = 0; i < d->nseg; ++i) {

@@ -3,11 +3,12 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
 // Persistent: each CTA walks work items (split, m_tile, n_tile) with stride gridDim.x.
 //
-// Epilogue (NHWC fp16 outputs): the 128 x BN tile is drained in 32-column sub-tiles through a ring of 64B-swizzled
-// shared-memory slots.  The residual sub-tile (ResNet identity / transformer skip / exchange add) is TMA-LOADED into
-// the slot a few sub-tiles ahead, each thread adds its own row in place (bias from a per-tile smem copy, SiLU / GEGLU
-// gate in registers) and the slot is TMA-STORED to HBM -- coalesced 64 B rows, no per-thread global latency on the
-// critical path.  fp32 split-K partials and the tiny NCHW outputs (conv_out + fused scheduler update) use direct
+// Epilogue (NHWC fp16 outputs): each of the four epilogue warps drains its 32 rows of the 128 x BN tile in 32-column
+// sub-tiles straight from TMEM through registers: bias from a per-warp smem copy, the residual (ResNet identity /
+// transformer skip / exchange add) read with 256-bit global loads one sub-tile ahead, SiLU / GEGLU gate in registers,
+// 256-bit global stores (64 contiguous bytes per row and sub-tile = full sectors).  No smem staging, proxy fence or
+// block-wide barrier on the critical path (a TMA-store slot ring measured ~1000 cycles of serial latency per
+// sub-tile and made every small-K GEMM epilogue-bound).  fp32 split-K partials and the tiny NCHW outputs (conv_out + fused scheduler update) use direct
 // per-thread stores.
 #include "gemm_sm100.cuh"
 
@@ -18,14 +19,15 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlots = (BN >= 256) ? 3 : 4;           // epilogue slot ring (8 KB each)
-  static constexpr int kLookahead = kSlots - 2;                  // residual sub-tiles requested ahead
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160) ? 5 : 6;
-  static constexpr int kSlotBytes = kBM * 64;                    // [128 rows x 32 fp16], SWIZZLE_64B
-  static constexpr int kEpiOff = kStages * kStageBytes;
-  static constexpr int kBiasOff = kEpiOff + kSlots * kSlotBytes; // [2][BN] fp32
-  static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
-  static constexpr int kNumBars = 2 * kStages + 4 + kSlots;
+  static constexpr int kBiasBytes = 4 * 2 * BN * 4;              // per epilogue warp: [2 batch rows][BN] fp32
+  static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes) / kStageBytes;
+#ifndef UNIB_MAX_STAGES
+#define UNIB_MAX_STAGES 8
+#endif
+  static constexpr int kStages = kStagesFit > UNIB_MAX_STAGES ? UNIB_MAX_STAGES : kStagesFit;
+  static constexpr int kBiasOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kBiasOff + kBiasBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128 / 32-column epilogue sub-tiles");
@@ -63,12 +65,16 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
       }
     } else {
-      for (int j = 0; j < 16 && n + j < N; ++j) v[j] += bp[j];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n + j < N) v[j] += bp[j];
     }
   }
   if (p.flags & EPI_OUT_NCHW) {
     const int hw = m - b * p.rows_per_batch;
-    for (int j = 0; j < 16 && n + j < N; ++j) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (n + j >= N) break;
       const size_t idx = (static_cast<size_t>(b) * N + (n + j)) * p.rows_per_batch + hw;
       float val = v[j];
       if (p.flags & EPI_AXPBY) {
@@ -114,7 +120,9 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
     reinterpret_cast<uint4*>(op)[0] = o0;
     reinterpret_cast<uint4*>(op)[1] = o1;
   } else {
-    for (int j = 0; j < 16 && n + j < N; ++j) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (n + j >= N) break;
       float val = v[j];
       if (p.res != nullptr) val += __half2float(p.res[static_cast<size_t>(m) * p.ldr + n + j]);
       if (p.flags & EPI_SILU) val = silu_f(val);
@@ -122,6 +130,19 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
     }
   }
 }
+
+// debug stamps of CTA 0: trace[16 + slot * 16 + k] = globaltimer (ns); slot = launch ordinal.  Compiled in only with
+// -DUNIB_GEMM_TRACE (tools/gemm_trace.py builds that variant): the producer and MMA-issue loops are single-thread
+// latency chains, and even a predicated-off stamp inside them costs measurable mainloop throughput.
+#ifdef UNIB_GEMM_TRACE
+#define GEMM_TRACE(k)                                                                      \
+  do {                                                                                     \
+    if (p.trace != nullptr && blockIdx.x == 0 && *trace_slot < 4000)                       \
+      p.trace[16 + *trace_slot * 16 + (k)] = static_cast<long long>(global_timer_ns());    \
+  } while (0)
+#else
+#define GEMM_TRACE(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -138,19 +159,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
-  auto res_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 4 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOff + Cfg::kNumBars * 8);
+  volatile int* trace_slot = reinterpret_cast<volatile int*>(smem + Cfg::kBarOff + Cfg::kNumBars * 8 + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+#ifdef UNIB_GEMM_TRACE
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    *trace_slot = static_cast<int>(atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull));
+    GEMM_TRACE(0);
+  }
+#else
+  (void)trace_slot;
+#endif
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
-    if (p.epi_tma) {
-      tma_prefetch_desc(&maps.c);
-      if (p.res != nullptr) tma_prefetch_desc(&maps.r);
-    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -159,7 +184,6 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);
     }
-    for (int s = 0; s < Cfg::kSlots; ++s) mbar_init(res_bar(s), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -170,72 +194,86 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(p, w);
-        const int p0 = wi.mt * kBM;
-        const int w0 = p0 % p.W;
-        const int h0 = (p0 / p.W) % p.H;
-        const int b0 = p0 / (p.W * p.H);
-        int seg = 0, tap = 0, cb = 0;
-        {
-          int k = wi.kb0;
-          while (seg < p.nseg) {
-            const int per = p.seg[seg].ntaps * p.seg[seg].nkb;
-            if (k < per) { tap = k / p.seg[seg].nkb; cb = k - tap * p.seg[seg].nkb; break; }
-            k -= per;
-            ++seg;
-          }
+    // The WHOLE warp walks the loop (warp-uniform control flow keeps stage / coordinates in uniform registers, so
+    // UTMALDG takes them directly); one elected lane issues.  The loop body is a single-thread latency chain that
+    // paces the whole mainloop, so everything that only changes per tap / per tile is hoisted out of it.
+    uint32_t stage = 0, ph = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const WorkItem wi = decode_work(p, w);
+      const int p0 = wi.mt * kBM;
+      const int w0 = p0 % p.W;
+      const int h0 = (p0 / p.W) % p.H;
+      const int b0 = p0 / (p.W * p.H);
+      int seg = 0, tap = 0, cb = 0;
+      {
+        int k = wi.kb0;
+        while (seg < p.nseg) {
+          const int per = p.seg[seg].ntaps * p.seg[seg].nkb;
+          if (k < per) { tap = k / p.seg[seg].nkb; cb = k - tap * p.seg[seg].nkb; break; }
+          k -= per;
+          ++seg;
         }
-        for (int kb = wi.kb0; kb < wi.kb1; ++kb, ++it) {
-          const int stage = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          mbar_wait(empty_bar(stage), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          const ConvSeg sg = p.seg[seg];
-          int dw = 0, dh = 0, tm = sg.tmap;
-          if (sg.kind == SEG_3x3) {
-            dh = tap / 3 - 1;
-            dw = tap % 3 - 1;
-          } else if (sg.kind == SEG_3x3_S2) {
-            const int dy = tap / 3, dx = tap % 3;   // input row = 2*oh + dy - 1 -> parity (dy != 1), half-res shift
-            tm += ((dy != 1) ? 2 : 0) + ((dx != 1) ? 1 : 0);
-            dh = (dy == 0) ? -1 : 0;
-            dw = (dx == 0) ? -1 : 0;
-          }
+      }
+      int nkb = 1, ntaps = 1, cw = w0, ch = h0;
+      const CUtensorMap* amap = &maps.a[0];
+      auto set_tap = [&]() {                   // geometry of (seg, tap): tensor map + shifted tile origin
+        const ConvSeg sg = p.seg[seg < p.nseg ? seg : 0];
+        nkb = sg.nkb;
+        ntaps = sg.ntaps;
+        int dw = 0, dh = 0, tm = sg.tmap;
+        if (sg.kind == SEG_3x3) {
+          dh = tap / 3 - 1;
+          dw = tap % 3 - 1;
+        } else if (sg.kind == SEG_3x3_S2) {
+          const int dy = tap / 3, dx = tap % 3;   // input row = 2*oh + dy - 1 -> parity (dy != 1), half-res shift
+          tm += ((dy != 1) ? 2 : 0) + ((dx != 1) ? 1 : 0);
+          dh = (dy == 0) ? -1 : 0;
+          dw = (dx == 0) ? -1 : 0;
+        }
+        amap = &maps.a[tm];
+        cw = w0 + dw;
+        ch = h0 + dh;
+      };
+      set_tap();
+      const int brow = wi.nt * BN;
+      for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+        mbar_wait(empty_bar(stage), ph ^ 1);
+        if (elect_one()) {
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-          tma_load_4d(a_dst, &maps.a[tm], full_bar(stage), cb * kBK, w0 + dw, h0 + dh, b0);
-          tma_load_2d(a_dst + Cfg::kABytes, &maps.b, full_bar(stage), kb * kBK, wi.nt * BN);
-          if (++cb == sg.nkb) {
-            cb = 0;
-            if (++tap == sg.ntaps) { tap = 0; ++seg; }
-          }
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_4d(a_dst, amap, full_bar(stage), cb * kBK, cw, ch, b0);
+          tma_load_2d(a_dst + Cfg::kABytes, &maps.b, full_bar(stage), kb * kBK, brow);
         }
+        if (++cb == nkb) {
+          cb = 0;
+          if (++tap == ntaps) { tap = 0; ++seg; }
+          set_tap();
+        }
+        if (++stage == Cfg::kStages) { stage = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
-      uint32_t it = 0, tl = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
-        const WorkItem wi = decode_work(p, w);
-        const int acc = tl & 1;
-        const uint32_t aph = (tl >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
+    // Same structure: warp-uniform loop, one elected lane issues the four UMMAs of a K block and the commit.
+    constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+    uint32_t stage = 0, ph = 0, tl = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
+      const WorkItem wi = decode_work(p, w);
+      const int acc = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+        mbar_wait(full_bar(stage), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = wi.kb0; kb < wi.kb1; ++kb, ++it) {
-          const int stage = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          mbar_wait(full_bar(stage), ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = base + stage * Cfg::kStageBytes;
           const uint64_t a_desc = make_desc_kmajor_sw128(a_addr);
           const uint64_t b_desc = make_desc_kmajor_sw128(a_addr + Cfg::kABytes);
@@ -245,8 +283,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+          if (kb == wi.kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));        // accumulator complete -> epilogue
+        if (++stage == Cfg::kStages) { stage = 0; ph ^= 1; }
       }
     }
   } else {
@@ -256,79 +295,94 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
     const bool leader = (et == 0);
     uint32_t tl = 0;
-    if (p.epi_tma) {
-      // ---------------- TMA epilogue: slot ring, residual prefetch, bias in smem ----------------
+    if (p.epi_vec) {
+      // ---------------- NHWC fp16 epilogue: registers -> 256-bit global stores ----------------
+      // Each epilogue warp owns its TMEM lane quadrant = 32 rows of the tile; a thread owns one row and drains it in
+      // 32-column sub-tiles: tcgen05.ld -> + bias (per-warp smem copy) -> + residual (two 256-bit global loads issued
+      // one sub-tile ahead) -> SiLU / GEGLU gate -> two 256-bit global stores (64 contiguous bytes = 2 full sectors
+      // per row).  No shared-memory staging, no proxy fence, no barrier: the four warps run fully decoupled and the
+      // only waits are the accumulator hand-off and the (prefetched) residual.
       const bool geglu = (p.flags & EPI_GEGLU) != 0;
       const bool silu = (p.flags & EPI_SILU) != 0;
       const bool has_res = p.res != nullptr;
+      const bool has_bias = p.bias != nullptr;
       const int nsub = geglu ? BN / 64 : BN / 32;             // output sub-tiles per tile
       const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
-      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff);
-      const uint32_t slot0 = base + Cfg::kEpiOff;
-      const uint32_t my_row_off = static_cast<uint32_t>(row) * 64u;
-      const uint32_t sw = static_cast<uint32_t>((row >> 1) & 3);
-      uint32_t gsub = 0;                                       // sub-tiles drained so far (slot = gsub % kSlots)
-      // residual prefetch cursor (leader only): runs kLookahead sub-tiles ahead of gsub
-      int pf_w = blockIdx.x, pf_j = 0;
-      uint32_t pf_g = 0;
-      auto prefetch_res = [&]() {
-        if (pf_w >= total_work) return;
-        const WorkItem pw = decode_work(p, pf_w);
-        const int s = pf_g % Cfg::kSlots;
-        mbar_arrive_expect_tx(res_bar(s), Cfg::kSlotBytes);
-        tma_load_2d(slot0 + s * Cfg::kSlotBytes, &maps.r, res_bar(s), pw.nt * out_bn + pf_j * 32, pw.mt * kBM);
-        ++pf_g;
-        if (++pf_j == nsub) { pf_j = 0; pf_w += gridDim.x; }
+      const int n_out = geglu ? p.N / 2 : p.N;
+      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff) + q * (2 * BN);   // this warp's [2][BN]
+      const bool per_batch = p.bias_bstride != 0;
+      __half* const outp = reinterpret_cast<__half*>(p.out);
+      auto load_res = [&](uint32_t* r, int m, int n) {
+        if (m < p.M && n + 32 <= n_out) {
+          const __half* rp = p.res + static_cast<size_t>(m) * p.ldr + n;
+          if (p.epi_vec == 2) {
+            ldg256(rp, r);
+            ldg256(rp + 16, r + 8);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 t = *reinterpret_cast<const uint4*>(rp + 8 * u);
+              r[4 * u] = t.x; r[4 * u + 1] = t.y; r[4 * u + 2] = t.z; r[4 * u + 3] = t.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) r[u] = 0u;
+          if (m < p.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {          // static indices only: r[] must stay in registers
+              if (n + i < n_out) {
+                const uint32_t h = __half_as_ushort(p.res[static_cast<size_t>(m) * p.ldr + n + i]);
+                r[i >> 1] |= h << ((i & 1) * 16);
+              }
+            }
+          }
+        }
       };
-      if (leader && has_res) {
-        for (int i = 0; i < Cfg::kLookahead; ++i) prefetch_res();
-      }
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
-        const int m0 = wi.mt * kBM;
-        const int m = m0 + row;
-        // bias of this tile -> smem (two batch rows: a tile may straddle a batch boundary); issued before the
-        // accumulator wait so the global latency overlaps the mainloop
-        const bool per_batch = p.bias_bstride != 0;
+        const int m0 = wi.mt * kBM + q * 32;                   // first row of this warp
+        const int m = m0 + lane;
+        const int n0 = wi.nt * out_bn;                         // first output column of this tile
+        // bias of this tile -> this warp's smem copy (two batch rows: the 32 rows may straddle a batch boundary);
+        // bias and the first residual sub-tile are requested before the accumulator wait (latency overlaps the MMAs)
         const int b_first = per_batch ? m0 / p.rows_per_batch : 0;
-        int m_last = m0 + kBM - 1;
+        int m_last = m0 + 31;
         if (m_last >= p.M) m_last = p.M - 1;
-        const int b_last = per_batch ? m_last / p.rows_per_batch : 0;
-        const bool bias_smem = p.bias != nullptr && (b_last - b_first) <= 1;
-        float bv[2][(BN + 127) / 128];
-        if (bias_smem) {
+        const int b_last = (per_batch && m_last >= m0) ? m_last / p.rows_per_batch : b_first;
+        if (has_bias) {
+          __syncwarp();                                        // previous tile's bias reads are done
 #pragma unroll
           for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < (BN + 127) / 128; ++c) {
-              const int col = c * 128 + et;
+            for (int c = 0; c < BN / 32; ++c) {
+              const int col = c * 32 + lane;
               const int n = wi.nt * BN + col;
               const int bb = r == 0 ? b_first : b_last;
-              bv[r][c] = (col < BN && n < p.N) ? __ldg(p.bias + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
+              bias_s[r * BN + col] = (n < p.N) ? __ldg(p.bias + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
             }
+          __syncwarp();
         }
+        uint32_t rnext[16];
+        if (has_res) load_res(rnext, m, n0);
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
-        if (bias_smem) {
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < (BN + 127) / 128; ++c) {
-              const int col = c * 128 + et;
-              if (col < BN) bias_s[r * BN + col] = bv[r][c];
-            }
-        }
-        epi_bar_sync();     // bias visible; also orders the previous tile's last slot reads before new writes
+        if (tl == 0 && leader) GEMM_TRACE(5);
+        if (tl == 1 && leader) GEMM_TRACE(11);
         const int my_b = per_batch ? m / p.rows_per_batch : 0;
         const float* my_bias = bias_s + ((my_b > b_first) ? BN : 0);
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int j = 0; j < nsub; ++j, ++gsub) {
-          const int s = gsub % Cfg::kSlots;
-          const uint32_t slot = slot0 + s * Cfg::kSlotBytes + my_row_off;
+        for (int j = 0; j < nsub; ++j) {
           float v[32];
+          uint32_t rcur[16];
+          if (has_res) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) rcur[u] = rnext[u];
+            if (j + 1 < nsub) load_res(rnext, m, n0 + (j + 1) * 32);
+          }
           if (geglu) {
             float gte[32];
             tmem_ld32(taddr + j * 32, v);
@@ -340,10 +394,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = v[i], g = gte[i];
-              if (bias_smem) { a += my_bias[j * 32 + i]; g += my_bias[BN / 2 + j * 32 + i]; }
-              v[i] = a * gelu_erf_f(g);
+            for (int i = 0; i < 32; i += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (has_bias) {
+                ba = *reinterpret_cast<const float4*>(my_bias + j * 32 + i);
+                bg = *reinterpret_cast<const float4*>(my_bias + BN / 2 + j * 32 + i);
+              }
+              v[i] = (v[i] + ba.x) * gelu_erf_f(gte[i] + bg.x);
+              v[i + 1] = (v[i + 1] + ba.y) * gelu_erf_f(gte[i + 1] + bg.y);
+              v[i + 2] = (v[i + 2] + ba.z) * gelu_erf_f(gte[i + 2] + bg.z);
+              v[i + 3] = (v[i + 3] + ba.w) * gelu_erf_f(gte[i + 3] + bg.w);
             }
           } else {
             tmem_ld32(taddr + j * 32, v);
@@ -353,54 +413,52 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            if (bias_smem) {
+            if (has_bias) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += my_bias[j * 32 + i];
-            } else if (p.bias != nullptr && m < p.M) {
-              const float* bp = p.bias + static_cast<size_t>(my_b) * p.bias_bstride + wi.nt * BN + j * 32;
-              for (int i = 0; i < 32; ++i)
-                if (wi.nt * BN + j * 32 + i < p.N) v[i] += __ldg(bp + i);
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bq = *reinterpret_cast<const float4*>(my_bias + j * 32 + i);
+                v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+              }
             }
           }
           if (has_res) {
-            mbar_wait(res_bar(s), (gsub / Cfg::kSlots) & 1);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint32_t r0, r1, r2, r3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                           : "r"(slot + ((static_cast<uint32_t>(u) ^ sw) << 4)));
-              const uint32_t rr[4] = {r0, r1, r2, r3};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[e]));
-                v[u * 8 + 2 * e] += f.x;
-                v[u * 8 + 2 * e + 1] += f.y;
-              }
+            for (int u = 0; u < 16; ++u) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rcur[u]));
+              v[2 * u] += f.x;
+              v[2 * u + 1] += f.y;
             }
           }
           if (silu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
           }
+          const int n = n0 + j * 32;
+          if (m < p.M) {
+            __half* op = outp + static_cast<size_t>(m) * p.ldc + n;
+            if (n + 32 <= n_out) {
+              uint32_t o[16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + ((static_cast<uint32_t>(u) ^ sw) << 4)),
-                         "r"(pack_half2(v[u * 8 + 0], v[u * 8 + 1])), "r"(pack_half2(v[u * 8 + 2], v[u * 8 + 3])),
-                         "r"(pack_half2(v[u * 8 + 4], v[u * 8 + 5])), "r"(pack_half2(v[u * 8 + 6], v[u * 8 + 7]))
-                         : "memory");
-          }
-          fence_proxy_async_shared();
-          epi_bar_sync();
-          if (leader) {
-            tma_store_2d(slot0 + s * Cfg::kSlotBytes, &maps.c, wi.nt * out_bn + j * 32, m0);
-            tma_store_commit();
-            tma_store_wait_read<1>();       // every store but the newest has finished reading its slot
-            if (has_res) prefetch_res();
+              for (int u = 0; u < 16; ++u) o[u] = pack_half2(v[2 * u], v[2 * u + 1]);
+              if (p.epi_vec == 2) {
+                stg256(op, o);
+                stg256(op + 16, o + 8);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  *reinterpret_cast<uint4*>(op + 8 * u) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)            // static indices only: v[] must stay in registers
+                if (n + i < n_out) op[i] = __float2half_rn(v[i]);
+            }
           }
         }
+        if (tl == 0 && leader) GEMM_TRACE(9);
       }
-      if (leader) tma_store_wait_all();
+      if (leader) GEMM_TRACE(6);
+      if (leader) GEMM_TRACE(7);
     } else {
       // ---------------- direct-store epilogue: split-K partials, NCHW outputs ----------------
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
@@ -409,6 +467,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         const uint32_t aph = (tl >> 1) & 1;
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
+        if (tl == 0 && leader) GEMM_TRACE(5);
         const int m = wi.mt * kBM + row;
         const bool row_ok = m < p.M;
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -427,7 +486,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                 for (int j = 0; j < 32; j += 4)
                   *reinterpret_cast<float4*>(pp + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               } else {
-                for (int j = 0; j < 32 && n + j < p.N; ++j) pp[c * 32 + j] = v[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) pp[c * 32 + j] = v[j];
               }
             }
           }
@@ -444,6 +505,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
+      if (leader) GEMM_TRACE(7);
     }
   }
 
@@ -453,6 +515,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 32) GEMM_TRACE(8);
 }
 
 // Split-K finalize: sum fp32 partials over splits in fixed order, then the same epilogue as the fused path.
@@ -475,7 +538,9 @@ __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const GemmPar
           v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
         }
       } else {
-        for (int j = 0; j < 16 && n + j < p.N; ++j) v[j] += pp[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < p.N) v[j] += pp[j];
       }
     }
     epilogue_store16(p, v, m, n);

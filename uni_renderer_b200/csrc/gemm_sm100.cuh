@@ -57,14 +57,13 @@ struct GemmParams {
   const float* aux;          // EPI_AXPBY: x_t, NCHW fp32
   float* aux_out;            // EPI_AXPBY: x_{t-1}, NCHW fp32 (may alias aux)
   int axpby_n0;              // channels < axpby_n0 keep aux unchanged
-  int epi_tma;               // 1: NHWC fp16 output drained through smem slots + TMA store (maps.c / maps.r)
+  int epi_vec;               // NHWC fp16 output through the vector epilogue: 2 = 256-bit, 1 = 128-bit accesses, 0 = off
+  long long* trace;          // debug (unib200_debug_set_trace): [0] = launch counter, then 16 stamps per launch
 };
 
 struct alignas(64) GemmMaps {
   CUtensorMap a[kMaxAMaps];
   CUtensorMap b;
-  CUtensorMap c;   // output  {N_out, M}, box {32, 128}, SWIZZLE_64B (epi_tma)
-  CUtensorMap r;   // residual, same geometry
 };
 
 // host-side launcher (gemm_sm100.cu)
