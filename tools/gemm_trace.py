@@ -10,6 +10,12 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the stamps are compiled in only with -DUNIB_GEMM_TRACE: build that variant here (`python -m uni_renderer_b200.build
+# --trace`, no GPU needed) and it is picked up through UNIB200_LIB
+_TRACE_LIB = os.path.join(ROOT, "uni_renderer_b200", "libunib200_trace.so")
+if not os.path.exists(_TRACE_LIB):
+    raise SystemExit("build the trace variant first: python -m uni_renderer_b200.build --trace")
+os.environ["UNIB200_LIB"] = _TRACE_LIB
 import torch  # noqa: E402
 
 from uni_renderer_b200 import _lib, ops  # noqa: E402

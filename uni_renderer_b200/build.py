@@ -65,5 +65,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines) -> str:
+    """Debug / A-B builds of the same library with extra -D flags -> uni_renderer_b200/libunib200_<tag>.so
+    (loaded with UNIB200_LIB=...).  Used by tools/gemm_trace.py (UNIB_GEMM_TRACE)."""
+    objdir = os.path.join(HERE, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES:
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(o)
+    lib = os.path.join(HERE, f"libunib200_{tag}.so")
+    r = subprocess.run([nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_variant("trace", ["UNIB_GEMM_TRACE"]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True))

@@ -76,11 +76,15 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint64_t p_desc, uint6
 }
 
 // debug stamps: slot layout trace[(who * 16 + j) * 8 + k]
+#ifdef UNIB_ATTN_TRACE
 #define ATTN_TRACE(who, j, k)                                                                                   \
   do {                                                                                                          \
     if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 16)                \
       p.trace[((who) * 16 + (j)) * 8 + (k)] = clock64();                                                        \
   } while (0)
+#else
+#define ATTN_TRACE(who, j, k) do { } while (0)
+#endif
 
 template <int NCH>
 __global__ void __launch_bounds__(320, 1)
@@ -144,76 +148,81 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
 
   if (warp == 8) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (operands stay in uniform registers)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ntile * Cfg::kQBytes);
       for (int t = 0; t < ntile; ++t)
         for (int ch = 0; ch < NCH; ++ch)
           tma_load_4d(base + t * Cfg::kQBytes + ch * 16384, &maps.q, q_full, ch * 64, q_base + t * 128, head, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j % Cfg::kStages;
-        const uint32_t ph = (j / Cfg::kStages) & 1;
-        mbar_wait(kv_empty(st), ph ^ 1);
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(kv_empty(st), ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full(st), Cfg::kStageBytes);
         const uint32_t kdst = kv_smem + st * Cfg::kStageBytes;
+#pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           tma_load_4d(kdst + ch * (BKV * 128), &maps.k, kv_full(st), ch * 64, j * BKV, head, b);
           tma_load_4d(kdst + Cfg::kKBytes + ch * (BKV * 128), &maps.v, kv_full(st), ch * 64, j * BKV, head, b);
         }
       }
+      if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
     }
   } else if (warp == 9) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(128, BKV);
-      const uint32_t idesc_o = make_idesc_f16(128, dpad, 0, 1);   // B (= V) is MN-major
-      const int ks_s = dpad / 16;
-      // operand descriptors of tile t / stage st differ from tile 0 / stage 0 by constants (16-byte units)
-      const uint64_t q_desc0 = make_desc_kmajor_sw128(base);
-      const uint64_t p_desc0 = make_desc_kmajor_sw128(base + Cfg::kPOff);
-      const uint64_t k_desc0 = make_desc_kmajor_sw128(kv_smem);
-      const uint64_t v_desc0 = make_desc_mnmajor_sw128(kv_smem + Cfg::kKBytes, BKV * 128, 1024);
-      constexpr uint64_t kStage16 = Cfg::kStageBytes >> 4;
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
+    // warp-uniform loop; every issue block is executed by one elected lane (always the same one, so the commits
+    // track the MMAs it issued)
+    const uint32_t idesc_s = make_idesc_f16(128, BKV);
+    const uint32_t idesc_o = make_idesc_f16(128, dpad, 0, 1);   // B (= V) is MN-major
+    const int ks_s = dpad / 16;
+    // operand descriptors of tile t / stage st differ from tile 0 / stage 0 by constants (16-byte units)
+    const uint64_t q_desc0 = make_desc_kmajor_sw128(base);
+    const uint64_t p_desc0 = make_desc_kmajor_sw128(base + Cfg::kPOff);
+    const uint64_t k_desc0 = make_desc_kmajor_sw128(kv_smem);
+    const uint64_t v_desc0 = make_desc_mnmajor_sw128(kv_smem + Cfg::kKBytes, BKV * 128, 1024);
+    constexpr uint64_t kStage16 = Cfg::kStageBytes >> 4;
+    mbar_wait(q_full, 0);
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    if (elect_one()) {
       for (int t = 0; t < ntile; ++t) {
         issue_qk_dyn<BKV>(ks_s, tmem_base + t_s_col(t), q_desc0 + t * (Cfg::kQBytes >> 4), k_desc0, idesc_s);
         umma_commit(s_full(t));
       }
-      int st = 0;
-      for (int j = 0; j < nblk; ++j) {
-        const int stn = (st + 1 == Cfg::kStages) ? 0 : st + 1;
+    }
+    int st = 0;
+    uint32_t kv_ph = 0;                        // phase of kv_full(stn) for block j + 1
+    for (int j = 0; j < nblk; ++j) {
+      const int stn = (st + 1 == Cfg::kStages) ? 0 : st + 1;
+      if (stn == 0) kv_ph ^= 1;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (t < ntile) {
-            mbar_wait(p_full(t), j & 1);       // softmax_t(j) has read S_t(j) and written P_t(j)
-            tc_fence_after();
+      for (int t = 0; t < 2; ++t) {
+        if (t < ntile) {
+          mbar_wait(p_full(t), j & 1);       // softmax_t(j) has read S_t(j) and written P_t(j)
+          if (t == 0 && j + 1 < nblk) mbar_wait(kv_full(stn), kv_ph);
+          tc_fence_after();
+          if (elect_one()) {
             ATTN_TRACE(2 + t, j, 0);
             // S_t(j+1) first: the next softmax can start while P_t(j) V(j) is still running
             if (j + 1 < nblk) {
-              if (t == 0) {
-                mbar_wait(kv_full(stn), ((j + 1) / Cfg::kStages) & 1);
-                tc_fence_after();
-              }
-              ATTN_TRACE(2 + t, j, 2);
               issue_qk_dyn<BKV>(ks_s, tmem_base + t_s_col(t), q_desc0 + t * (Cfg::kQBytes >> 4),
                                 k_desc0 + stn * kStage16, idesc_s);
-              ATTN_TRACE(2 + t, j, 3);
               umma_commit(s_full(t));
             }
             ATTN_TRACE(2 + t, j, 4);
             // O_t += P_t V : K loop over the kv rows of this block in steps of 16
             issue_pv<BKV>(tmem_base + t_o_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), v_desc0 + st * kStage16, idesc_o,
                           j == 0);
-            ATTN_TRACE(2 + t, j, 5);
             umma_commit(pv_done(t));                          // P_t buffer + O_t free again
             if (t == ntile - 1) umma_commit(kv_empty(st));   // K(j)/V(j) fully consumed by both tiles
             if (j == nblk - 1) umma_commit(o_ready(t));
             ATTN_TRACE(2 + t, j, 1);
           }
         }
-        st = stn;
       }
+      st = stn;
     }
   } else {
     // =============================== softmax + epilogue (warpgroup t = warp / 4) ===============================
