@@ -32,6 +32,11 @@ int unib200_version(void);
 const char* unib200_last_error(void);                 /* thread-local, valid until the next failing call */
 int unib200_device_info(int* num_sms, int* cc_major, int* cc_minor);
 
+/* Programmatic dependent launch (on by default): every kernel is launched with the programmatic-stream-serialization
+ * attribute and waits (griddepcontrol.wait) before touching global memory, so the prologue of kernel N+1 overlaps the
+ * tail of kernel N inside a stream / CUDA-graph branch.  0 switches it off for launches made afterwards (A/B runs). */
+void unib200_set_pdl(int enabled);
+
 /* ---- programs (recorded op lists; optionally instantiated as a CUDA graph) --------------------------------- */
 unib200_program* unib200_program_create(void);
 void unib200_program_destroy(unib200_program* prog);

@@ -54,7 +54,7 @@ class GnDesc(C.Structure):
 
 # every symbol include/unib200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "unib200_version", "unib200_last_error", "unib200_device_info",
+    "unib200_version", "unib200_last_error", "unib200_device_info", "unib200_set_pdl",
     "unib200_program_create", "unib200_program_destroy", "unib200_program_num_launches", "unib200_program_run",
     "unib200_program_graph_instantiate", "unib200_program_graph_launch", "unib200_program_set_lane",
     "unib200_program_barrier",
@@ -84,6 +84,10 @@ def load() -> C.CDLL:
     lib.unib200_version.restype = ci
     lib.unib200_last_error.restype = C.c_char_p
     lib.unib200_device_info.argtypes = [C.POINTER(ci)] * 3
+    lib.unib200_set_pdl.argtypes = [ci]
+    lib.unib200_set_pdl.restype = None
+    if os.environ.get("UNIB200_PDL") is not None:      # A/B runs: 0 off, 1 on (trigger at CTA end), 2 early trigger
+        lib.unib200_set_pdl(int(os.environ["UNIB200_PDL"]))
     lib.unib200_program_create.restype = vp
     lib.unib200_program_destroy.argtypes = [vp]
     lib.unib200_program_destroy.restype = None

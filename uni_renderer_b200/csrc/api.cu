@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <functional>
 #include <string>
 #include <vector>
@@ -106,8 +108,23 @@ struct unib200_program {
 };
 
 namespace {
+// measurement aid: UNIB200_SKIP_KINDS=<bitmask of UNIB200_OP_*> records no-ops for those op kinds, so the marginal
+// cost of an op class inside the real multi-lane step graph can be read off a bench run (results are garbage)
+int skip_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("UNIB200_SKIP_KINDS");
+    m = e ? atoi(e) : 0;
+  }
+  return m;
+}
+
 int submit(unib200_program* prog, Op op, int launches, void* stream, const char* what, int kind = UNIB200_OP_OTHER,
            double flops = 0.0, double bytes = 0.0, const std::string& desc = std::string()) {
+  if (prog && (skip_mask() & (1 << kind))) {
+    op = [](cudaStream_t) { return cudaSuccess; };
+    launches = 0;
+  }
   if (prog) {
     prog->ops.push_back(std::move(op));
     prog->lane.push_back(prog->cur_lane);
@@ -319,6 +336,8 @@ int unib200_program_graph_launch(unib200_program* prog, void* stream) {
   return 0;
 }
 
+void unib200_set_pdl(int mode) { unib::g_pdl_enabled = mode < 0 ? 0 : mode; }
+
 void unib200_debug_set_trace(void* dev_buf) { g_attn_trace = static_cast<long long*>(dev_buf); }
 
 int unib200_pick_bn(int N, int flags) { return gemm_pick_bn(N, flags); }
@@ -427,6 +446,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   p.aux_out = d->aux_out;
   p.axpby_n0 = d->axpby_first_channel;
   p.trace = g_attn_trace;
+  p.pdl_early = unib::g_pdl_enabled == 2 ? 1 : 0;
   if (!(d->flags & UNIB200_EPI_OUT_NCHW)) {
     if (d->ldc % 8 != 0) return fail("conv_gemm: ldc must be a multiple of 8");
     if (d->res && d->ldr % 8 != 0) return fail("conv_gemm: ldr must be a multiple of 8");
@@ -442,7 +462,11 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     splits = 1;
     if (can_split && tiles * 2 <= sms) {
       splits = sms / tiles;
-      const int max_by_k = total_kb / 4 > 0 ? total_kb / 4 : 1;   // keep >= 4 K blocks per split
+      // a split costs a second launch (finalize) + an fp32 round trip of the tile: only worth it when each split
+      // still has a long K loop (>= 24 K blocks ~ 7 us of mainloop; measured optimum of the step); short-K layers run unsplit and leave the idle
+      // SMs to the other lane of the step graph
+      static const int min_kb = getenv("UNIB200_SPLIT_MIN_KB") ? atoi(getenv("UNIB200_SPLIT_MIN_KB")) : 24;
+      const int max_by_k = total_kb / min_kb > 0 ? total_kb / min_kb : 1;
       if (splits > max_by_k) splits = max_by_k;
       if (splits > 16) splits = 16;
     }
@@ -514,6 +538,7 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
   p.trace = g_attn_trace;
+  p.pdl_early = unib::g_pdl_enabled == 2 ? 1 : 0;
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
   const double bh = static_cast<double>(d->B) * d->heads;
   return submit(prog, std::move(op), 1, stream, "attention", UNIB200_OP_ATTENTION, 4.0 * bh * d->Nq * d->Nk * d->d,

@@ -142,6 +142,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl_early) pdl_launch();
+  pdl_wait();        // PDL: see common.cuh (trigger at the end of the CTA, as in the GEMM kernel)
   // TMEM columns: [S0 | S1 | O0 | O1]
   auto t_s_col = [&](int t) { return static_cast<uint32_t>(t * BKV); };
   auto t_o_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + t * (NCH * 64)); };
@@ -346,6 +348,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  pdl_launch();
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -363,8 +366,7 @@ static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStr
     attr_set = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
-  attention_tcgen05_kernel<NCH><<<grid, 320, Cfg::kSmemBytes, stream>>>(maps, p);
-  return cudaGetLastError();
+  return launch_pdl(attention_tcgen05_kernel<NCH>, grid, dim3(320), Cfg::kSmemBytes, stream, maps, p);
 }
 
 int attention_bkv(int d) { return d <= 64 ? 128 : 64; }

@@ -32,6 +32,17 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute, fires pdl_launch() as soon as its CTA is set up (lets the NEXT kernel of the stream / graph
+// branch get its CTAs resident and run its prologue: barrier init, TMEM allocation, tensor-map prefetch, constant
+// loads) and calls pdl_wait() before its first access to global memory another kernel may have written or may still
+// read.  pdl_wait() returns only when the whole preceding grid has completed and flushed, so correctness never
+// depends on where the trigger sits.  Both are no-ops for a kernel launched without the attribute.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -253,6 +264,24 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// host side: kernel launch with the PDL attribute (switchable for A/B measurements: unib200_set_pdl)
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace unib

@@ -5,6 +5,10 @@
 
 namespace unib {
 
+int g_pdl_enabled = 0;   // measured: no gain inside the two-lane step graph, so off by default
+// launches report through cudaGetLastError() at the call sites below; keep the first launch error sticky
+#define UNIB_CHECK_LAUNCH(expr) do { cudaError_t le_ = (expr); (void)le_; } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: partial (sum, sumsq) per (batch, row-chunk, group).  Each thread owns one 8-channel vector
 // column for the rows it visits (4 independent 128-bit loads in flight), per-channel sums are combined across the
@@ -12,6 +16,8 @@ namespace unib {
 // result is bit-reproducible run to run.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) gn_stats_kernel(GnParams p) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];            // [2][rpb][C]
   const int C = p.C1 + p.C2;
   const int CV = C >> 3;
@@ -79,6 +85,8 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GnParams p) {
 // shared memory and streams rows (4 independent 128-bit loads in flight per thread).  Writes the concatenated
 // [rows, C1+C2] tensor.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];            // scale[C], shift[C], red[8][G][2]
   const int C = p.C1 + p.C2;
   const int cpg = C / p.G;
@@ -166,12 +174,12 @@ cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStrea
   const int rows_per_chunk = (p.HW + chunks - 1) / chunks;
   if (rpb > rows_per_chunk) rpb = rows_per_chunk;
   const int threads = rpb * CV;
-  gn_stats_kernel<<<dim3(chunks, B), threads, 2 * rpb * C * sizeof(float), stream>>>(p);
+  UNIB_CHECK_LAUNCH(launch_pdl(gn_stats_kernel, dim3(dim3(chunks, B)), dim3(threads), 2 * rpb * C * sizeof(float), stream, p));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   int achunks = (4 * num_sms + B - 1) / B;
   if (achunks > p.HW) achunks = p.HW;
-  gn_apply_kernel<<<dim3(achunks, B), 256, (2 * C + 16 * p.G) * sizeof(float), stream>>>(p);
+  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_kernel, dim3(dim3(achunks, B)), dim3(256), (2 * C + 16 * p.G) * sizeof(float), stream, p));
   return cudaGetLastError();
 }
 
@@ -182,6 +190,8 @@ template <int VPL>   // 8-channel vectors per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, int C, float eps) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -242,11 +252,11 @@ cudaError_t launch_layernorm(const __half* x, __half* y, const float* gamma, con
   const int CV = C >> 3;
   const int vpl = (CV + 31) / 32;
   const int blocks = (rows + 7) / 8;
-  if (vpl <= 1) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, C, eps);
-  else if (vpl <= 2) layernorm_kernel<2><<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, C, eps);
-  else if (vpl <= 3) layernorm_kernel<3><<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, C, eps);
-  else if (vpl <= 5) layernorm_kernel<5><<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, C, eps);
-  else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x, y, gamma, beta, rows, C, eps);
+  if (vpl <= 1) UNIB_CHECK_LAUNCH(launch_pdl(layernorm_kernel<1>, dim3(blocks), dim3(256), 0, stream, x, y, gamma, beta, rows, C, eps));
+  else if (vpl <= 2) UNIB_CHECK_LAUNCH(launch_pdl(layernorm_kernel<2>, dim3(blocks), dim3(256), 0, stream, x, y, gamma, beta, rows, C, eps));
+  else if (vpl <= 3) UNIB_CHECK_LAUNCH(launch_pdl(layernorm_kernel<3>, dim3(blocks), dim3(256), 0, stream, x, y, gamma, beta, rows, C, eps));
+  else if (vpl <= 5) UNIB_CHECK_LAUNCH(launch_pdl(layernorm_kernel<5>, dim3(blocks), dim3(256), 0, stream, x, y, gamma, beta, rows, C, eps));
+  else UNIB_CHECK_LAUNCH(launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, stream, x, y, gamma, beta, rows, C, eps));
   return cudaGetLastError();
 }
 
@@ -256,6 +266,8 @@ cudaError_t launch_layernorm(const __half* x, __half* y, const float* gamma, con
 template <typename T>
 __global__ void to_nhwc_kernel(const T* __restrict__ src, __half* __restrict__ dst, int B, int C, int H, int W,
                                long long sb, long long sc, long long sh, long long sw, int Cpad) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const long long total = static_cast<long long>(B) * H * W * Cpad;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -277,15 +289,17 @@ cudaError_t launch_to_nhwc(const void* src, int src_is_f32, __half* dst, int B, 
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (src_is_f32)
-    to_nhwc_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), dst, B, C, H, W, sb, sc, sh, sw, Cpad);
+    UNIB_CHECK_LAUNCH(launch_pdl(to_nhwc_kernel<float>, dim3(blocks), dim3(256), 0, stream, static_cast<const float*>(src), dst, B, C, H, W, sb, sc, sh, sw, Cpad));
   else
-    to_nhwc_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(src), dst, B, C, H, W, sb, sc, sh, sw, Cpad);
+    UNIB_CHECK_LAUNCH(launch_pdl(to_nhwc_kernel<__half>, dim3(blocks), dim3(256), 0, stream, static_cast<const __half*>(src), dst, B, C, H, W, sb, sc, sh, sw, Cpad));
   return cudaGetLastError();
 }
 
 // NHWC fp16 [B*H*W, ld] (first C channels) -> contiguous NCHW fp32/fp16
 template <typename T>
 __global__ void from_nhwc_kernel(const __half* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, int ld) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const long long total = static_cast<long long>(B) * C * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -302,13 +316,15 @@ cudaError_t launch_from_nhwc(const __half* src, void* dst, int dst_is_f32, int B
   const long long total = static_cast<long long>(B) * C * HW;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (dst_is_f32) from_nhwc_kernel<float><<<blocks, 256, 0, stream>>>(src, static_cast<float*>(dst), B, C, HW, ld);
-  else from_nhwc_kernel<__half><<<blocks, 256, 0, stream>>>(src, static_cast<__half*>(dst), B, C, HW, ld);
+  if (dst_is_f32) UNIB_CHECK_LAUNCH(launch_pdl(from_nhwc_kernel<float>, dim3(blocks), dim3(256), 0, stream, src, static_cast<float*>(dst), B, C, HW, ld));
+  else UNIB_CHECK_LAUNCH(launch_pdl(from_nhwc_kernel<__half>, dim3(blocks), dim3(256), 0, stream, src, static_cast<__half*>(dst), B, C, HW, ld));
   return cudaGetLastError();
 }
 
 // nearest-neighbour 2x upsample, NHWC fp16, 128-bit vectors
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int CV) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const long long total = static_cast<long long>(B) * (2 * H) * (2 * W) * CV;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -327,8 +343,8 @@ cudaError_t launch_upsample2x(const __half* src, __half* dst, int B, int H, int 
   const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B,
-                                                H, W, C / 8);
+  UNIB_CHECK_LAUNCH(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), B,
+                                                H, W, C / 8));
   return cudaGetLastError();
 }
 
@@ -337,6 +353,8 @@ cudaError_t launch_upsample2x(const __half* src, __half* dst, int B, int H, int 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void timestep_sinusoid_kernel(const float* __restrict__ t, const int* __restrict__ step_idx, int t_stride,
                                          float* __restrict__ out, int B, int dim) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -351,7 +369,7 @@ __global__ void timestep_sinusoid_kernel(const float* __restrict__ t, const int*
 cudaError_t launch_timestep_sinusoid(const float* t, const int* step_idx, int t_stride, float* out, int B, int dim,
                                      cudaStream_t stream) {
   const int n = B * (dim / 2);
-  timestep_sinusoid_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, step_idx, t_stride, out, B, dim);
+  UNIB_CHECK_LAUNCH(launch_pdl(timestep_sinusoid_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, t, step_idx, t_stride, out, B, dim));
   return cudaGetLastError();
 }
 
@@ -359,6 +377,8 @@ cudaError_t launch_timestep_sinusoid(const float* t, const int* step_idx, int t_
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, const __half* __restrict__ Wt,
                                                    const float* __restrict__ bias, float* __restrict__ y, int B, int K,
                                                    int N, int act_silu) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   extern __shared__ float xs[];      // [B][K]
   for (int i = threadIdx.x; i < B * K; i += blockDim.x) xs[i] = x[i];
   __syncthreads();
@@ -406,8 +426,8 @@ cudaError_t launch_gemv(const float* x, const __half* Wt, const float* bias, flo
     const int bb = (B - b0) < 8 ? (B - b0) : 8;
     const size_t smem = static_cast<size_t>(bb) * K * sizeof(float);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    gemv_kernel<<<(N + 7) / 8, 256, smem, stream>>>(x + static_cast<size_t>(b0) * K, Wt, bias,
-                                                     y + static_cast<size_t>(b0) * N, bb, K, N, act_silu);
+    UNIB_CHECK_LAUNCH(launch_pdl(gemv_kernel, dim3((N + 7) / 8), dim3(256), smem, stream, x + static_cast<size_t>(b0) * K, Wt, bias,
+                                                     y + static_cast<size_t>(b0) * N, bb, K, N, act_silu));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -420,6 +440,8 @@ cudaError_t launch_gemv(const float* x, const __half* Wt, const float* bias, flo
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void axpby_kernel(const float* __restrict__ model_out, const float* __restrict__ x, float* __restrict__ out,
                              const float* __restrict__ coef, const int* __restrict__ step_idx, long long n) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   const float* c = coef + (step_idx ? 2 * static_cast<size_t>(*step_idx) : 0);
   const float a = c[0], bta = c[1];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -431,13 +453,15 @@ cudaError_t launch_axpby(const float* model_out, const float* x, float* out, con
                          long long n, cudaStream_t stream) {
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  axpby_kernel<<<blocks, 256, 0, stream>>>(model_out, x, out, coef, step_idx, n);
+  UNIB_CHECK_LAUNCH(launch_pdl(axpby_kernel, dim3(blocks), dim3(256), 0, stream, model_out, x, out, coef, step_idx, n));
   return cudaGetLastError();
 }
 
 // out = a + b over fp16 vectors (module-level API: UNet skip + externally supplied residual, controlnet.py:1084,1115)
 __global__ void add_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                                long long nvec) {
+  pdl_launch();      // PDL: see common.cuh
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 x = a[i], y = b[i];
@@ -457,14 +481,18 @@ cudaError_t launch_add_f16(const __half* a, const __half* b, __half* out, long l
   const long long nvec = n / 8;
   int blocks = static_cast<int>((nvec + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  add_f16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
-                                             reinterpret_cast<uint4*>(out), nvec);
+  UNIB_CHECK_LAUNCH(launch_pdl(add_f16_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+                                             reinterpret_cast<uint4*>(out), nvec));
   return cudaGetLastError();
 }
 
-__global__ void add_int_kernel(int* p, int v) { *p += v; }
+__global__ void add_int_kernel(int* p, int v) {
+  pdl_launch();
+  pdl_wait();
+  *p += v;
+}
 cudaError_t launch_add_int(int* p, int v, cudaStream_t stream) {
-  add_int_kernel<<<1, 1, 0, stream>>>(p, v);
+  UNIB_CHECK_LAUNCH(launch_pdl(add_int_kernel, dim3(1), dim3(1), 0, stream, p, v));
   return cudaGetLastError();
 }
 

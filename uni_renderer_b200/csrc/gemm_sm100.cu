@@ -195,6 +195,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) GEMM_TRACE(1);
+  // PDL: wait for the previous kernel (producer of our activations / residual / bias, last reader of our output
+  // buffer) to complete; everything above overlapped its tail
+  if (p.pdl_early) pdl_launch();
+  pdl_wait();
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
@@ -511,6 +515,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  // PDL trigger at the END of the CTA's work: a CTA of this kernel owns its SM (shared memory), so an earlier trigger
+  // would only park the next kernel's CTAs on SMs the other graph branch could be using
+  pdl_launch();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -520,6 +527,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 
 // Split-K finalize: sum fp32 partials over splits in fixed order, then the same epilogue as the fused path.
 __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const GemmParams p) {
+  pdl_launch();
+  pdl_wait();
   const int chunks = (p.N + 15) / 16;
   const long long total = static_cast<long long>(p.M) * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -582,15 +591,13 @@ static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_
   }
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total_work < num_sms ? total_work : num_sms;
-  gemm_tcgen05_kernel<BN><<<grid, 192, GemmCfg<BN>::kSmemBytes, stream>>>(maps, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(192), GemmCfg<BN>::kSmemBytes, stream, maps, p);
   if (e != cudaSuccess) return e;
   if (p.splits > 1) {
     const long long total = static_cast<long long>(p.M) * ((p.N + 15) / 16);
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > num_sms * 8) blocks = num_sms * 8;
-    gemm_splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p);
-    e = cudaGetLastError();
+    e = launch_pdl(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, p);
   }
   return e;
 }

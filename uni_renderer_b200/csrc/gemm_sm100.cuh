@@ -58,6 +58,7 @@ struct GemmParams {
   float* aux_out;            // EPI_AXPBY: x_{t-1}, NCHW fp32 (may alias aux)
   int axpby_n0;              // channels < axpby_n0 keep aux unchanged
   int epi_vec;               // NHWC fp16 output through the vector epilogue: 2 = 256-bit, 1 = 128-bit accesses, 0 = off
+  int pdl_early;             // 1: fire the PDL trigger right after CTA setup instead of at the end (unib200_set_pdl(2))
   long long* trace;          // debug (unib200_debug_set_trace): [0] = launch counter, then 16 stamps per launch
 };
 
