@@ -323,9 +323,19 @@ def run_b200(a):
         tot = sum(d["ms"] for d in by.values())
         gm = by["conv_gemm"]
         ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12
+        # DRAM traffic of the same kernel family from the committed ncu capture of one denoising step (profiles/):
+        # per launch, like `achieved`; ncu replays each launch cold-cache, so L2-resident activations count as DRAM
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1b_gemm_traffic.json")
+        if a.mode == "joint" and B == 4 and S == 64 and os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1b_gemm_traffic.json (ncu, cold-cache replay)"
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv / linear family)",
                             "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                            "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": gm["bytes"] / max(gm["launches"], 1),
+                            "algorithmic_flops_per_launch": gm["flops"] / max(gm["launches"], 1),
                             "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                             "launches_per_denoise_step": gm["launches"], "share_of_step": gm["ms"] / tot,
                             "flops_per_denoise_step": gm["flops"]}
