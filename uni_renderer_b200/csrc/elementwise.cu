@@ -3,6 +3,8 @@
 // All NHWC fp16 with 128-bit accesses; statistics in fp32.
 #include "elementwise.cuh"
 
+#include <stdlib.h>
+
 namespace unib {
 
 int g_pdl_enabled = 0;   // measured: no gain inside the two-lane step graph, so off by default
@@ -159,10 +161,211 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
   for (; i < total; i += st) emit(i, load(i));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm (+SiLU): one thread-block CLUSTER per sample.  CTA r of the cluster owns a contiguous slice
+// of the sample's rows: (1) per-group (sum, sumsq) of its slice, reduced in a fixed order in shared memory;
+// (2) cluster barrier, every CTA sums the CS partials of all peers through distributed shared memory (same order
+// everywhere -> bit-identical statistics in every CTA and run to run); (3) normalise + SiLU its own rows, which are
+// still L2-resident from pass (1).  Replaces the stats + apply kernel pair: one launch, one HBM read.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
+  extern __shared__ float sm[];            // [2][rpb][C] reduction scratch, then scale[C] | shift[C]
+  __shared__ float part[2 * 64];           // this CTA's (sum, sumsq) per group -- read by the peers
+  __shared__ float gstat[2 * 64];          // (mean, rstd) per group
+  pdl_launch();
+  pdl_wait();
+  const int C = p.C1 + p.C2;
+  const int CV = C >> 3;
+  const int cpg = C / p.G;
+  const int rpb = blockDim.x / CV;         // rows processed in parallel
+  const int b = blockIdx.y;
+  const uint32_t rank = cluster_ctarank(), cs = cluster_nctarank();
+  const int r0 = static_cast<int>((static_cast<long long>(rank) * p.HW) / cs);
+  const int r1 = static_cast<int>((static_cast<long long>(rank + 1) * p.HW) / cs);
+  float* ssum = sm;
+  float* ssq = sm + rpb * C;
+  if (threadIdx.x < rpb * CV) {
+    const int v = threadIdx.x % CV;
+    const int rsub = threadIdx.x / CV;
+    const int c0 = v * 8;
+    const __half* src;
+    int ld, cc;
+    if (c0 < p.C1) { src = p.x1; ld = p.ld1; cc = c0; } else { src = p.x2; ld = p.ld2; cc = c0 - p.C1; }
+    src += static_cast<size_t>(b) * p.HW * ld + cc;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    auto acc = [&](const uint4& raw) {
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x; s[2 * j + 1] += f.y;
+        q[2 * j] += f.x * f.x; q[2 * j + 1] += f.y * f.y;
+      }
+    };
+    int r = r0 + rsub;
+    for (; r + 3 * rpb < r1; r += 4 * rpb) {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + rpb) * ld);
+      const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * rpb) * ld);
+      const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * rpb) * ld);
+      acc(a0); acc(a1); acc(a2); acc(a3);
+    }
+    for (; r < r1; r += rpb) acc(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ssum[rsub * C + c0 + j] = s[j];
+      ssq[rsub * C + c0 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    for (int r = 0; r < rpb; ++r) { a += ssum[r * C + c]; q2 += ssq[r * C + c]; }
+    ssum[c] = a;
+    ssq[c] = q2;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += ssum[c]; q2 += ssq[c]; }
+    part[2 * g] = a;
+    part[2 * g + 1] = q2;
+  }
+  cluster_sync_all();                      // every CTA's partials are visible cluster-wide
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    const uint32_t la = smem_u32(&part[2 * g]);
+    for (uint32_t r = 0; r < cs; ++r) {
+      a += ld_dsmem_f32(la, r);
+      q2 += ld_dsmem_f32(la + 4, r);
+    }
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * p.HW);
+    const float mu = a * inv_n;
+    const float var = fmaxf(q2 * inv_n - mu * mu, 0.f);
+    gstat[2 * g] = mu;
+    gstat[2 * g + 1] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  float* scale = sm;
+  float* shift = sm + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = gstat[2 * g + 1] * p.gamma[c];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gstat[2 * g] * sc;
+  }
+  __syncthreads();
+  const long long total = static_cast<long long>(r1 - r0) * CV;
+  auto load = [&](long long i) -> uint4 {
+    const int r = r0 + static_cast<int>(i / CV);
+    const int c0 = static_cast<int>(i % CV) * 8;
+    const size_t row = static_cast<size_t>(b) * p.HW + r;
+    const __half* src = (c0 < p.C1) ? p.x1 + row * p.ld1 + c0 : p.x2 + row * p.ld2 + (c0 - p.C1);
+    return *reinterpret_cast<const uint4*>(src);
+  };
+  auto emit = [&](long long i, const uint4& raw) {
+    const int r = r0 + static_cast<int>(i / CV);
+    const int c0 = static_cast<int>(i % CV) * 8;
+    const size_t row = static_cast<size_t>(b) * p.HW + r;
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      float y0 = f.x * scale[c0 + 2 * j] + shift[c0 + 2 * j];
+      float y1 = f.y * scale[c0 + 2 * j + 1] + shift[c0 + 2 * j + 1];
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      o[j] = pack_half2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(p.out + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  long long i = threadIdx.x;
+  const long long st = blockDim.x;
+  for (; i + 3 * st < total; i += 4 * st) {
+    const uint4 a0 = load(i), a1 = load(i + st), a2 = load(i + 2 * st), a3 = load(i + 3 * st);
+    emit(i, a0); emit(i + st, a1); emit(i + 2 * st, a2); emit(i + 3 * st, a3);
+  }
+  for (; i < total; i += st) emit(i, load(i));
+  cluster_sync_all();                      // no CTA may exit while a peer can still read its `part`
+}
+
+// cluster size for a sample of HW rows: as many CTAs as keep >= 8 rows each, at most 16 (non-portable size)
+static int gn_cluster_size(int HW, int max_cs) {
+  int cs = 1;
+  while (cs * 2 <= max_cs && HW / (cs * 2) >= 8) cs *= 2;
+  return cs;
+}
+
+static cudaError_t launch_gn_cluster(const GnParams& p, int B, cudaStream_t stream) {
+  static int max_cs = 0;
+  if (max_cs == 0) {
+    max_cs = 8;
+    if (cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(16, 1);
+      q.blockDim = dim3(512);
+      q.dynamicSmemBytes = 64 * 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gn_cluster_kernel, &q) == cudaSuccess && n > 0) max_cs = 16;
+    }
+    cudaGetLastError();
+  }
+  const int C = p.C1 + p.C2;
+  const int CV = C >> 3;
+  const int rpb = 512 / CV > 0 ? 512 / CV : 1;
+  const size_t smem = static_cast<size_t>(2) * rpb * C * sizeof(float);     // >= 2*C floats of scale/shift
+  const int cs = gn_cluster_size(p.HW, max_cs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, B);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl_enabled ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gn_cluster_kernel, p);
+}
+
 cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStream_t stream) {
   GnParams p = p_in;
   const int C = p.C1 + p.C2;
   if (C % 8 || p.C1 % 8 || C % p.G || (C >> 3) > 512) return cudaErrorInvalidValue;
+  static const bool two_kernel = getenv("UNIB200_GN_TWO_KERNEL") != nullptr;      // A/B: the stats + apply pair
+  if (!two_kernel && p.G <= 64) return launch_gn_cluster(p, B, stream);
   int chunks = (2 * num_sms + B - 1) / B;
   if (chunks > p.HW / 4) chunks = p.HW / 4 > 0 ? p.HW / 4 : 1;
   if (chunks > p.max_chunks) chunks = p.max_chunks;

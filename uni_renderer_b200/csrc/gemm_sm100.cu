@@ -352,10 +352,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         const int n0 = wi.nt * out_bn;                         // first output column of this tile
         // bias of this tile -> this warp's smem copy (two batch rows: the 32 rows may straddle a batch boundary);
         // bias and the first residual sub-tile are requested before the accumulator wait (latency overlaps the MMAs)
-        const int b_first = per_batch ? m0 / p.rows_per_batch : 0;
         int m_last = m0 + 31;
         if (m_last >= p.M) m_last = p.M - 1;
-        const int b_last = (per_batch && m_last >= m0) ? m_last / p.rows_per_batch : b_first;
+        // a warp whose rows all lie beyond M (M < 128) must not index the per-batch bias table out of range
+        const int m_first = m0 < p.M ? m0 : p.M - 1;
+        const int b_first = per_batch ? m_first / p.rows_per_batch : 0;
+        const int b_last = per_batch ? m_last / p.rows_per_batch : b_first;
         if (has_bias) {
           __syncwarp();                                        // previous tile's bias reads are done
 #pragma unroll
