@@ -108,6 +108,17 @@ typedef struct {
                             /* EPI_AXPBY with out != NULL: out receives, NHWC fp16 [M, ldc], the raw prediction   */
                             /* with the clean channels passed through (= cat(latents_mask, mask_pred), the        */
                             /* attribute input of the cycle pass, train/train.py:1393)                            */
+  /* LayerNorm folded into the GEMMs around it (BasicTransformerBlock.norm1/2/3): the GEMM that PRODUCES the
+   * normalised tensor writes per-row partial statistics, the GEMM that CONSUMES LayerNorm(x) takes raw x with
+   * gamma folded into its weights and corrects in the epilogue:
+   *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_wsum[n]) + bias[n],   bias[n] = b[n] + sum_k beta[k] W[n,k]
+   * -- no LayerNorm kernel, no normalised tensor in HBM.                                                          */
+  float* rowstats_out;      /* producer: fp32 [M][ceil(N/BN)][2] (sum, sum of squares) of the stored rows, or NULL */
+  const float* ln_rowstats; /* consumer: the producer's table, [M][ln_parts][2], or NULL                           */
+  int ln_parts;
+  const float* ln_wsum;     /* consumer: fp32 [N], sum_k of the (gamma-folded, fp16-rounded) weight row            */
+  float ln_eps;
+  int ln_C;                 /* channels the statistics were taken over                                             */
 } unib200_gemm_desc;
 
 int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);

@@ -190,6 +190,52 @@ def case_conv_variants():
     return res
 
 
+def case_ln_fold():
+    """LayerNorm folded into the surrounding GEMMs (include/unib200.h): producer GEMM (+bias +residual) writes row
+    statistics, consumer GEMM takes the raw rows with gamma folded into its weights.  Reference: torch fp32
+    layer_norm of the fp16-stored producer output followed by the linear (plain and GEGLU)."""
+    import torch
+    import torch.nn.functional as F
+    from uni_renderer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    res = {}
+    for (M, Cc, N2, geglu) in [(1024, 320, 960, False), (300, 64, 64, False), (256, 1280, 1280, False),
+                               (512, 320, 2560, True), (96, 128, 1024, True)]:
+        a = _mk((M, Cc), g)
+        w1 = _mk((Cc, Cc), g, Cc ** -0.5)
+        b1 = torch.randn(Cc, generator=g, device="cuda")
+        r1 = _mk((M, Cc), g) + 3.0            # non-zero row means exercise the mean correction
+        h = torch.zeros(M, Cc, device="cuda", dtype=torch.half)
+        rs = torch.zeros(M, ops.rowstats_parts(Cc), 2, device="cuda", dtype=torch.float32)
+        ops.conv_gemm(None, [(a, Cc, ops.SEG_1x1)], ops.pack_weight([(w1, ops.SEG_1x1)]), h, M=M, N=Cc, bias=b1, res=r1,
+                      rowstats_out=rs)
+        gamma = 1.0 + 0.3 * torch.randn(Cc, generator=g, device="cuda")
+        beta = 0.2 * torch.randn(Cc, generator=g, device="cuda")
+        w2 = _mk((N2, Cc), g, Cc ** -0.5)
+        b2 = torch.randn(N2, generator=g, device="cuda")
+        flags = 0
+        if geglu:
+            w2p, b2p = ops.pack_geglu(w2.float(), b2)
+            flags = ops.EPI_GEGLU
+        else:
+            w2p, b2p = w2.float(), b2
+        wf, wsum, bias2 = ops.fold_layernorm(w2p, b2p, gamma, beta)
+        n_out = N2 // 2 if geglu else N2
+        out = torch.zeros(M, n_out, device="cuda", dtype=torch.half)
+        ops.conv_gemm(None, [(h, Cc, ops.SEG_1x1)], ops.pack_weight([(wf, ops.SEG_1x1)]), out, M=M, N=N2, bias=bias2,
+                      flags=flags, ln=(rs, wsum, 1e-5, Cc))
+        torch.cuda.synchronize()
+        y = F.layer_norm(h.float(), (Cc,), gamma, beta, 1e-5)
+        ref = y @ w2.float().t() + b2
+        if geglu:
+            ref = ref[:, :N2 // 2] * F.gelu(ref[:, N2 // 2:])
+        res[f"M{M}_C{Cc}_N{N2}_{'geglu' if geglu else 'lin'}"] = _err(out, ref)
+        # the statistics themselves: sum / sum of squares of the stored rows
+        s1 = rs[:, :, 0].sum(1)
+        res[f"M{M}_C{Cc}_rowsum"] = _err(s1, h.float().sum(1))
+    return res
+
+
 def case_norms():
     import torch
     import torch.nn.functional as F

@@ -24,6 +24,14 @@ def test_op_case(case):
 
 
 @gpu
+def test_layernorm_folded_into_gemms():
+    """Looser gate than the plain ops: the reference normalises in fp32 and rounds LayerNorm(x) to fp16 before the
+    GEMM, the fold rounds gamma*W instead -- both are one fp16 rounding of an O(1) operand."""
+    from tests import gpu_probe
+    _assert_ok(gpu_probe.CASES["ln_fold"](), rel_l2=1.5e-3, rel_max=5e-3)
+
+
+@gpu
 def test_gemm_identity_is_exact():
     from tests import gpu_probe
     r = gpu_probe.CASES["gemm_identity"]()

@@ -31,6 +31,8 @@ class GemmDesc(C.Structure):
         ("partial", C.c_void_p), ("partial_bytes", C.c_size_t),
         ("axpby", C.c_void_p), ("axpby_step", C.c_void_p), ("aux", C.c_void_p), ("aux_out", C.c_void_p),
         ("axpby_first_channel", C.c_int),
+        ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_parts", C.c_int), ("ln_wsum", C.c_void_p),
+        ("ln_eps", C.c_float), ("ln_C", C.c_int),
     ]
 
 

@@ -447,6 +447,16 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   p.axpby_n0 = d->axpby_first_channel;
   p.trace = g_attn_trace;
   p.pdl_early = unib::g_pdl_enabled == 2 ? 1 : 0;
+  p.rowstats_out = d->rowstats_out;
+  p.ln_rowstats = d->ln_rowstats;
+  p.ln_wsum = d->ln_wsum;
+  p.ln_parts = d->ln_parts;
+  p.ln_eps = d->ln_eps;
+  p.ln_inv_c = d->ln_C > 0 ? 1.0f / static_cast<float>(d->ln_C) : 0.f;
+  if (d->ln_rowstats && (!d->ln_wsum || d->ln_parts < 1 || d->ln_C < 1))
+    return fail("conv_gemm: ln_rowstats needs ln_wsum, ln_parts >= 1 and ln_C >= 1");
+  if ((d->rowstats_out || d->ln_rowstats) && (d->flags & UNIB200_EPI_OUT_NCHW))
+    return fail("conv_gemm: row statistics / LayerNorm fold need the NHWC fp16 epilogue");
   if (!(d->flags & UNIB200_EPI_OUT_NCHW)) {
     if (d->ldc % 8 != 0) return fail("conv_gemm: ldc must be a multiple of 8");
     if (d->res && d->ldr % 8 != 0) return fail("conv_gemm: ldr must be a multiple of 8");
@@ -457,7 +467,8 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   int splits = d->splits;
   const int tiles = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
-  const bool can_split = d->partial != nullptr && !(d->flags & (UNIB200_EPI_GEGLU));
+  const bool can_split = d->partial != nullptr && !(d->flags & (UNIB200_EPI_GEGLU)) && !d->rowstats_out &&
+                         !d->ln_rowstats;
   if (splits <= 0) {
     splits = 1;
     if (can_split && tiles * 2 <= sms) {

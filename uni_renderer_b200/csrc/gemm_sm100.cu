@@ -19,7 +19,7 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBiasBytes = 4 * 2 * BN * 4;              // per epilogue warp: [2 batch rows][BN] fp32
+  static constexpr int kBiasBytes = 4 * 3 * BN * 4;              // per epilogue warp: bias [2 batch rows][BN] + LayerNorm wsum [BN], fp32
   static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes) / kStageBytes;
 #ifndef UNIB_MAX_STAGES
 #define UNIB_MAX_STAGES 8
@@ -313,7 +313,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       const int nsub = geglu ? BN / 64 : BN / 32;             // output sub-tiles per tile
       const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
       const int n_out = geglu ? p.N / 2 : p.N;
-      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff) + q * (2 * BN);   // this warp's [2][BN]
+      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff) + q * (3 * BN);   // this warp's [2][BN] (+ wsum)
+      float* wsum_s = bias_s + 2 * BN;                                                 // LayerNorm fold: [BN]
+      const bool has_ln = p.ln_rowstats != nullptr;
+      const bool want_stats = p.rowstats_out != nullptr;
       const bool per_batch = p.bias_bstride != 0;
       __half* const outp = reinterpret_cast<__half*>(p.out);
       auto load_res = [&](uint32_t* r, int m, int n) {
@@ -358,19 +361,43 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         const int m_first = m0 < p.M ? m0 : p.M - 1;
         const int b_first = per_batch ? m_first / p.rows_per_batch : 0;
         const int b_last = per_batch ? m_last / p.rows_per_batch : b_first;
-        if (has_bias) {
+        if (has_bias || has_ln) {
           __syncwarp();                                        // previous tile's bias reads are done
+          if (has_bias) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c) {
+                const int col = c * 32 + lane;
+                const int n = wi.nt * BN + col;
+                const int bb = r == 0 ? b_first : b_last;
+                bias_s[r * BN + col] = (n < p.N) ? __ldg(p.bias + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
+              }
+          }
+          if (has_ln) {
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
               const int col = c * 32 + lane;
               const int n = wi.nt * BN + col;
-              const int bb = r == 0 ? b_first : b_last;
-              bias_s[r * BN + col] = (n < p.N) ? __ldg(p.bias + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
+              wsum_s[col] = (n < p.N) ? __ldg(p.ln_wsum + n) : 0.f;
             }
+          }
           __syncwarp();
         }
+        // LayerNorm fold: this row's mean / rstd from the producer's per-N-tile partial sums (fixed order)
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (has_ln && m < p.M) {
+          float s1 = 0.f, s2 = 0.f;
+          const float2* rs = reinterpret_cast<const float2*>(p.ln_rowstats) + static_cast<size_t>(m) * p.ln_parts;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 t = __ldg(rs + i);
+            s1 += t.x;
+            s2 += t.y;
+          }
+          ln_mean = s1 * p.ln_inv_c;
+          ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        }
+        float st_sum = 0.f, st_sq = 0.f;                       // row statistics of this tile's output columns
         uint32_t rnext[16];
         if (has_res) load_res(rnext, m, n0);
         mbar_wait(tfull_bar(acc), aph);
@@ -399,6 +426,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
+            if (has_ln) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                v[i] = ln_rstd * (v[i] - ln_mean * wsum_s[j * 32 + i]);
+                gte[i] = ln_rstd * (gte[i] - ln_mean * wsum_s[BN / 2 + j * 32 + i]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
@@ -418,6 +452,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
+            if (has_ln) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 wq = *reinterpret_cast<const float4*>(wsum_s + j * 32 + i);
+                v[i] = ln_rstd * (v[i] - ln_mean * wq.x);
+                v[i + 1] = ln_rstd * (v[i + 1] - ln_mean * wq.y);
+                v[i + 2] = ln_rstd * (v[i + 2] - ln_mean * wq.z);
+                v[i + 3] = ln_rstd * (v[i + 3] - ln_mean * wq.w);
+              }
             }
             if (has_bias) {
 #pragma unroll
@@ -440,6 +484,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
           }
           const int n = n0 + j * 32;
+          if (want_stats) {
+            if (n + 32 <= n_out) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { st_sum += v[i]; st_sq += v[i] * v[i]; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < n_out) { st_sum += v[i]; st_sq += v[i] * v[i]; }
+            }
+          }
           if (m < p.M) {
             __half* op = outp + static_cast<size_t>(m) * p.ldc + n;
             if (n + 32 <= n_out) {
@@ -461,6 +515,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             }
           }
         }
+        if (want_stats && m < p.M)
+          *reinterpret_cast<float2*>(p.rowstats_out + (static_cast<size_t>(m) * p.n_tiles + wi.nt) * 2) =
+              make_float2(st_sum, st_sq);
         if (tl == 0 && leader) GEMM_TRACE(9);
       }
       if (leader) GEMM_TRACE(6);

@@ -58,6 +58,11 @@ struct GemmParams {
   float* aux_out;            // EPI_AXPBY: x_{t-1}, NCHW fp32 (may alias aux)
   int axpby_n0;              // channels < axpby_n0 keep aux unchanged
   int epi_vec;               // NHWC fp16 output through the vector epilogue: 2 = 256-bit, 1 = 128-bit accesses, 0 = off
+  float* rowstats_out;       // producer of a LayerNorm input: [M][n_tiles][2] (sum, sumsq) of the output rows
+  const float* ln_rowstats;  // consumer of LayerNorm(x): [M][ln_parts][2]; epilogue applies rstd * (acc - mean * wsum)
+  const float* ln_wsum;      // [N]
+  int ln_parts;
+  float ln_eps, ln_inv_c;
   int pdl_early;             // 1: fire the PDL trigger right after CTA setup instead of at the end (unib200_set_pdl(2))
   long long* trace;          // debug (unib200_debug_set_trace): [0] = launch counter, then 16 stamps per launch
 };

@@ -140,21 +140,30 @@ class StreamNet:
             norm(a + ".norm")
             w[a + ".proj_in.w"] = ops.pack_weight([(need(a + ".proj_in.weight"), SEG_1x1)])
             w[a + ".proj_in.b"] = _f32(sd[a + ".proj_in.bias"], dev)
-            for n in ("norm1", "norm2", "norm3"):
-                norm(f"{t}.{n}")
+            # LayerNorm folded into the GEMM that consumes it (include/unib200.h): gamma goes into the weights,
+            # beta into the bias, the mean / rstd correction into the epilogue -- norm1 -> qkv, norm2 -> attn2.to_q,
+            # norm3 -> GEGLU projection.  No LayerNorm kernel runs.
+            def ln(n):
+                return need(f"{t}.{n}.weight").float(), need(f"{t}.{n}.bias").float()
+
             qkv = torch.cat([need(f"{t}.attn1.to_q.weight"), need(f"{t}.attn1.to_k.weight"),
                              need(f"{t}.attn1.to_v.weight")], 0)
-            w[t + ".qkv.w"] = ops.pack_weight([(qkv, SEG_1x1)])
+            wf, wsum, b2 = ops.fold_layernorm(qkv, None, *ln("norm1"))
+            w[t + ".qkv.w"] = ops.pack_weight([(wf, SEG_1x1)])
+            w[t + ".qkv.wsum"], w[t + ".qkv.b"] = wsum, b2
             w[t + ".out1.w"] = ops.pack_weight([(need(f"{t}.attn1.to_out.0.weight"), SEG_1x1)])
             w[t + ".out1.b"] = _f32(sd[f"{t}.attn1.to_out.0.bias"], dev)
-            w[t + ".q2.w"] = ops.pack_weight([(need(f"{t}.attn2.to_q.weight"), SEG_1x1)])
+            wf, wsum, b2 = ops.fold_layernorm(need(f"{t}.attn2.to_q.weight"), None, *ln("norm2"))
+            w[t + ".q2.w"] = ops.pack_weight([(wf, SEG_1x1)])
+            w[t + ".q2.wsum"], w[t + ".q2.b"] = wsum, b2
             kv = torch.cat([need(f"{t}.attn2.to_k.weight"), need(f"{t}.attn2.to_v.weight")], 0)
             w[t + ".kv2.w"] = ops.pack_weight([(kv, SEG_1x1)])
             w[t + ".out2.w"] = ops.pack_weight([(need(f"{t}.attn2.to_out.0.weight"), SEG_1x1)])
             w[t + ".out2.b"] = _f32(sd[f"{t}.attn2.to_out.0.bias"], dev)
             gw, gb = ops.pack_geglu(need(f"{t}.ff.net.0.proj.weight").float(), need(f"{t}.ff.net.0.proj.bias").float())
-            w[t + ".geglu.w"] = ops.pack_weight([(gw, SEG_1x1)])
-            w[t + ".geglu.b"] = gb.float().contiguous()
+            wf, wsum, b2 = ops.fold_layernorm(gw, gb, *ln("norm3"))      # rows already interleaved per N tile
+            w[t + ".geglu.w"] = ops.pack_weight([(wf, SEG_1x1)])
+            w[t + ".geglu.wsum"], w[t + ".geglu.b"] = wsum, b2
             w[t + ".ff2.w"] = ops.pack_weight([(need(f"{t}.ff.net.2.weight"), SEG_1x1)])
             w[t + ".ff2.b"] = _f32(sd[f"{t}.ff.net.2.bias"], dev)
             w[a + ".proj_out.w"] = ops.pack_weight([(need(a + ".proj_out.weight"), SEG_1x1)])
@@ -278,39 +287,41 @@ class StreamNet:
         t = a + ".transformer_blocks.0"
         w = self.w
         g = self._gn(prog, ws, a + ".norm", [x], 1e-6, False)
+        # row statistics of the three LayerNorm inputs (h, h2, h3), written by the GEMMs that produce them
+        parts = ops.rowstats_parts(Cc)
+        rs = [torch.empty(M, parts, 2, device=self.device, dtype=torch.float32) for _ in range(3)]
+        LN_EPS = 1e-5
         h = ws.get(M, Cc)
         ops.conv_gemm(prog, [(g, Cc, SEG_1x1)], w[a + ".proj_in.w"], h, M=M, N=Cc, B=B, bias=w[a + ".proj_in.b"],
-                      partial=ws.partial)
+                      rowstats_out=rs[0])
         ws.put(g)
         # self-attention
-        y = ws.get(M, Cc)
-        ops.layernorm(prog, h, y, w[t + ".norm1.g"], w[t + ".norm1.bt"])
         qkv = ws.get(M, 3 * Cc)
-        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".qkv.w"], qkv, M=M, N=3 * Cc, B=B, partial=ws.partial)
-        ao = y   # reuse
+        ops.conv_gemm(prog, [(h, Cc, SEG_1x1)], w[t + ".qkv.w"], qkv, M=M, N=3 * Cc, B=B, bias=w[t + ".qkv.b"],
+                      ln=(rs[0], w[t + ".qkv.wsum"], LN_EPS, Cc))
+        ao = ws.get(M, Cc)
         ops.attention(prog, qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], ao, B=B, heads=heads, Nq=N, Nk=N, d=d)
         h2 = ws.get(M, Cc)
         ops.conv_gemm(prog, [(ao, Cc, SEG_1x1)], w[t + ".out1.w"], h2, M=M, N=Cc, B=B, bias=w[t + ".out1.b"], res=h,
-                      partial=ws.partial)
+                      rowstats_out=rs[1])
         ws.put(qkv, h)
         # cross-attention on the (precomputed) text keys/values
-        ops.layernorm(prog, h2, y, w[t + ".norm2.g"], w[t + ".norm2.bt"])
         q = ws.get(M, Cc)
-        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".q2.w"], q, M=M, N=Cc, B=B, partial=ws.partial)
-        ops.attention(prog, q, kv[:, :Cc], kv[:, Cc:], y, B=B, heads=heads, Nq=N, Nk=L, d=d)
+        ops.conv_gemm(prog, [(h2, Cc, SEG_1x1)], w[t + ".q2.w"], q, M=M, N=Cc, B=B, bias=w[t + ".q2.b"],
+                      ln=(rs[1], w[t + ".q2.wsum"], LN_EPS, Cc))
+        ops.attention(prog, q, kv[:, :Cc], kv[:, Cc:], ao, B=B, heads=heads, Nq=N, Nk=L, d=d)
         h3 = ws.get(M, Cc)
-        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".out2.w"], h3, M=M, N=Cc, B=B, bias=w[t + ".out2.b"], res=h2,
-                      partial=ws.partial)
+        ops.conv_gemm(prog, [(ao, Cc, SEG_1x1)], w[t + ".out2.w"], h3, M=M, N=Cc, B=B, bias=w[t + ".out2.b"], res=h2,
+                      rowstats_out=rs[2])
         ws.put(q, h2)
         # GEGLU feed-forward
-        ops.layernorm(prog, h3, y, w[t + ".norm3.g"], w[t + ".norm3.bt"])
         ff = ws.get(M, 4 * Cc)
-        ops.conv_gemm(prog, [(y, Cc, SEG_1x1)], w[t + ".geglu.w"], ff, M=M, N=8 * Cc, B=B, bias=w[t + ".geglu.b"],
-                      flags=EPI_GEGLU)
+        ops.conv_gemm(prog, [(h3, Cc, SEG_1x1)], w[t + ".geglu.w"], ff, M=M, N=8 * Cc, B=B, bias=w[t + ".geglu.b"],
+                      flags=EPI_GEGLU, ln=(rs[2], w[t + ".geglu.wsum"], LN_EPS, Cc))
         h4 = ws.get(M, Cc)
         ops.conv_gemm(prog, [(ff, 4 * Cc, SEG_1x1)], w[t + ".ff2.w"], h4, M=M, N=Cc, B=B, bias=w[t + ".ff2.b"], res=h3,
                       partial=ws.partial)
-        ws.put(ff, h3, y)
+        ws.put(ff, h3, ao)
         out = ws.get(M, Cc)
         ops.conv_gemm(prog, [(h4, Cc, SEG_1x1)], w[a + ".proj_out.w"], out, M=M, N=Cc, B=B, bias=w[a + ".proj_out.b"],
                       res=x.t, partial=ws.partial)

@@ -12,7 +12,7 @@ from . import _lib as L
 from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
-           "timestep_sinusoid", "gemv", "axpby", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "device_info",
+           "timestep_sinusoid", "gemv", "axpby", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
            "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
@@ -142,6 +142,25 @@ def pick_bn(N: int, flags: int = 0) -> int:
     return L.load().unib200_pick_bn(N, flags)
 
 
+def rowstats_parts(N: int, flags: int = 0) -> int:
+    """Row-statistics partials a GEMM with N output channels writes per row (one per N tile)."""
+    bn = pick_bn(N, flags)
+    return (N + bn - 1) // bn
+
+
+def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm(x) @ w.T + bias  ==  rstd * (x @ (w * gamma).T - mean * wsum) + bias2  (see include/unib200.h).
+    Returns (w * gamma as fp16-representable fp32, wsum fp32 [N], bias2 fp32 [N]); wsum is taken over the
+    fp16-ROUNDED folded weights, i.e. exactly what the tensor core sums."""
+    w32, g32, b32 = w.detach().float(), gamma.detach().float(), beta.detach().float()
+    wf = (w32 * g32[None, :]).half().float()
+    wsum = wf.sum(dim=1).contiguous()
+    bias2 = (w32 @ b32)
+    if bias is not None:
+        bias2 = bias2 + bias.detach().float()
+    return wf, wsum, bias2.contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     """GEGLU projection [2*inner, C] (+bias): interleave value/gate rows per N-tile so one accumulator tile holds
     both halves of the same output columns (EPI_GEGLU)."""
@@ -167,7 +186,8 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
               flags: int = 0, splits: int = 0, partial: Optional[torch.Tensor] = None,
               axpby: Optional[torch.Tensor] = None, axpby_step: Optional[torch.Tensor] = None,
               aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
-              axpby_first_channel: int = 0, ldc: Optional[int] = None):
+              axpby_first_channel: int = 0, ldc: Optional[int] = None, rowstats_out: Optional[torch.Tensor] = None,
+              ln: Optional[Tuple[torch.Tensor, torch.Tensor, float, int]] = None):
     """segs: (matrix [pixels, >=C] fp16, C, kind).  H = W = 0 selects the plain row-major [M, K] path."""
     lib = L.load()
     d = L.GemmDesc()
@@ -196,9 +216,20 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
         d.partial, d.partial_bytes = partial.data_ptr(), partial.numel() * partial.element_size()
     d.axpby, d.axpby_step, d.aux, d.aux_out = _ptr(axpby), _ptr(axpby_step), _ptr(aux), _ptr(aux_out)
     d.axpby_first_channel = axpby_first_channel
+    if rowstats_out is not None:      # producer of a LayerNorm input: [M, ceil(N / BN), 2] fp32 row statistics
+        assert rowstats_out.dtype == torch.float32 and rowstats_out.is_contiguous()
+        assert rowstats_out.numel() >= M * rowstats_parts(N, flags) * 2
+        d.rowstats_out = rowstats_out.data_ptr()
+    ln_keep = ()
+    if ln is not None:                # consumer of LayerNorm(x): (rowstats [M, parts, 2], wsum [N], eps, C)
+        rs, wsum, eps, Cn = ln
+        assert rs.dtype == torch.float32 and wsum.dtype == torch.float32 and wsum.numel() == N and rs.shape[0] == M
+        d.ln_rowstats, d.ln_parts, d.ln_wsum, d.ln_eps, d.ln_C = rs.data_ptr(), rs.shape[1], wsum.data_ptr(), eps, Cn
+        ln_keep = (rs, wsum)
     L.check(lib.unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
     if prog is not None:
-        prog.keep(*(s[0] for s in segs), weight, out, bias, res, partial, axpby, axpby_step, aux, aux_out)
+        prog.keep(*(s[0] for s in segs), weight, out, bias, res, partial, axpby, axpby_step, aux, aux_out, rowstats_out,
+                  *ln_keep)
 
 
 def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *,
