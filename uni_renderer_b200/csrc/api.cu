@@ -576,7 +576,7 @@ int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* str
   p.max_chunks = mc > 4096 ? 4096 : static_cast<int>(mc);
   const int B = d->B, sms = num_sms();
   Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm(p, B, sms, s); };
-  return submit(prog, std::move(op), 1, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
+  return submit(prog, std::move(op), d->HW <= 256 ? 1 : 2, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
                 4.0 * static_cast<double>(d->B) * d->HW * C,
                 "groupnorm B=" + std::to_string(d->B) + " HW=" + std::to_string(d->HW) + " C=" + std::to_string(p.C1) +
                     "+" + std::to_string(p.C2));
