@@ -428,10 +428,15 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     const uint64_t ktot = static_cast<uint64_t>(total_kb) * 64;
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(d->N)};
     const uint64_t st[1] = {ktot * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    // CTA pairs (cta_group::2: each CTA loads half of the B tile) for the mainloop-bound layers: at least two 128-row
+    // tiles and a long K loop.  Measured (tools/bench_gemm.py): conv3x3 +14..18 %, but short-K 1x1 layers lose ~10 %
+    // to the pair's cluster synchronisation, so those stay on single CTAs.
+    static const int pair_min_kb = getenv("UNIB200_PAIR_MIN_KB") ? atoi(getenv("UNIB200_PAIR_MIN_KB")) : 24;
+    p.cg = (pair_min_kb > 0 && gemm_pair_supported(bn) && d->M > kBM && total_kb >= pair_min_kb) ? 2 : 1;
+    const uint32_t box[2] = {64, static_cast<uint32_t>(bn / p.cg)};
     if (!encode_map(&maps.b, d->weight, 2, dims, st, box, &why)) return fail("conv_gemm B map: " + why);
   }
-  p.m_tiles = (d->M + kBM - 1) / kBM;
+  p.m_tiles = (d->M + kBM * p.cg - 1) / (kBM * p.cg);
   p.n_tiles = (d->N + bn - 1) / bn;
   p.bias = d->bias;
   p.bias_bstride = d->bias_bstride;
@@ -465,7 +470,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     return fail("conv_gemm: EPI_AXPBY needs EPI_OUT_NCHW, axpby, aux and aux_out");
   // split-K: fill the machine when the output has too few tiles (tiny-M layers are weight-bandwidth bound)
   int splits = d->splits;
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * p.cg;       // CTAs one pass over the output keeps busy
   const int sms = num_sms();
   const bool can_split = d->partial != nullptr && !(d->flags & (UNIB200_EPI_GEGLU)) && !d->rowstats_out &&
                          !d->ln_rowstats;

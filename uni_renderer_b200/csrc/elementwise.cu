@@ -168,20 +168,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
 // everywhere -> bit-identical statistics in every CTA and run to run); (3) normalise + SiLU its own rows, which are
 // still L2-resident from pass (1).  Replaces the stats + apply kernel pair: one launch, one HBM read.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
   uint32_t remote;
   float v;

@@ -14,10 +14,13 @@
 
 namespace unib {
 
-template <int BN>
+// CG = CTAs per MMA: 1 = cta_group::1 (tile 128 x BN per CTA); 2 = cta_group::2 (tile 256 x BN per CTA PAIR: each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the per-SM operand ingress per K block drops from
+// 16 KB + BN*128 B to 16 KB + BN*64 B -- the measured limiter of the mainloop)
+template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBiasBytes = 4 * 3 * BN * 4;              // per epilogue warp: bias [2 batch rows][BN] + LayerNorm wsum [BN], fp32
   static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes) / kStageBytes;
@@ -31,6 +34,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M=128 / 32-column epilogue sub-tiles");
+  static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair");
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment for SWIZZLE_128B");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -146,10 +150,12 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader of the CTA pair (issues the MMAs)
+  const int cta = blockIdx.x / CG, ncta = gridDim.x / CG;      // persistent walk: both CTAs of a pair share `cta`
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
@@ -182,16 +188,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 4 * CG);          // pair: the epilogue warps of BOTH CTAs release the leader's MMA warp
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2cta(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();             // peer barriers initialised + TMEM allocated in both CTAs
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) GEMM_TRACE(1);
@@ -208,9 +220,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     // UTMALDG takes them directly); one elected lane issues.  The loop body is a single-thread latency chain that
     // paces the whole mainloop, so everything that only changes per tap / per tile is hoisted out of it.
     uint32_t stage = 0, ph = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = cta; w < total_work; w += ncta) {
       const WorkItem wi = decode_work(p, w);
-      const int p0 = wi.mt * kBM;
+      const int p0 = (wi.mt * CG + static_cast<int>(rank)) * kBM;
       const int w0 = p0 % p.W;
       const int h0 = (p0 / p.W) % p.H;
       const int b0 = p0 / (p.W * p.H);
@@ -245,14 +257,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         ch = h0 + dh;
       };
       set_tap();
-      const int brow = wi.nt * BN;
+      const int brow = wi.nt * BN + static_cast<int>(rank) * (BN / CG);   // pair: this CTA's half of the B tile
       for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
         mbar_wait(empty_bar(stage), ph ^ 1);
         if (elect_one()) {
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_4d(a_dst, amap, full_bar(stage), cb * kBK, cw, ch, b0);
-          tma_load_2d(a_dst + Cfg::kABytes, &maps.b, full_bar(stage), kb * kBK, brow);
+          if (CG == 2) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            const uint32_t full_leader = mapa_u32(full_bar(stage), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_4d_2cta(a_dst, amap, full_leader, cb * kBK, cw, ch, b0);
+            tma_load_2d_2cta(a_dst + Cfg::kABytes, &maps.b, full_leader, kb * kBK, brow);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_4d(a_dst, amap, full_bar(stage), cb * kBK, cw, ch, b0);
+            tma_load_2d(a_dst + Cfg::kABytes, &maps.b, full_bar(stage), kb * kBK, brow);
+          }
         }
         if (++cb == nkb) {
           cb = 0;
@@ -265,36 +285,49 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // Same structure: warp-uniform loop, one elected lane issues the four UMMAs of a K block and the commit.
-    constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+    constexpr uint32_t idesc = make_idesc_f16(kBM * CG, BN);
     uint32_t stage = 0, ph = 0, tl = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
-      const WorkItem wi = decode_work(p, w);
-      const int acc = tl & 1;
-      const uint32_t aph = (tl >> 1) & 1;
-      mbar_wait(tempty_bar(acc), aph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
-        mbar_wait(full_bar(stage), ph);
+    if (rank == 0) {                             // pair: only the leader CTA issues (one UMMA of M = 256 drives both)
+      for (int w = cta; w < total_work; w += ncta, ++tl) {
+        const WorkItem wi = decode_work(p, w);
+        const int acc = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = base + stage * Cfg::kStageBytes;
-          const uint64_t a_desc = make_desc_kmajor_sw128(a_addr);
-          const uint64_t b_desc = make_desc_kmajor_sw128(a_addr + Cfg::kABytes);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
+          mbar_wait(full_bar(stage), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = base + stage * Cfg::kStageBytes;
+            const uint64_t a_desc = make_desc_kmajor_sw128(a_addr);
+            const uint64_t b_desc = make_desc_kmajor_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 B per UMMA_K=16 step inside the 128 B swizzle row (descriptor address is in 16 B units)
-            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 B per UMMA_K=16 step inside the 128 B swizzle row (descriptor address is in 16 B units)
+              if (CG == 2) umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+              else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > wi.kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CG == 2) {
+              umma_commit_2cta(empty_bar(stage), 3);                        // frees the stage in BOTH CTAs
+              if (kb == wi.kb1 - 1) umma_commit_2cta(tfull_bar(acc), 3);    // both CTAs' epilogues
+            } else {
+              umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+              if (kb == wi.kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            }
           }
-          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
-          if (kb == wi.kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          if (++stage == Cfg::kStages) { stage = 0; ph ^= 1; }
         }
-        if (++stage == Cfg::kStages) { stage = 0; ph ^= 1; }
       }
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    // hand the accumulator back to the MMA warp -- which, for a CTA pair, lives in the leader CTA
+    auto release_acc = [&](int a) {
+      if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(a), 0));
+      else mbar_arrive(tempty_bar(a));
+    };
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
     const bool leader = (et == 0);
@@ -346,11 +379,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           }
         }
       };
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
+      for (int w = cta; w < total_work; w += ncta, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
-        const int m0 = wi.mt * kBM + q * 32;                   // first row of this warp
+        const int m0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + q * 32;   // first row of this warp
         const int m = m0 + lane;
         const int n0 = wi.nt * out_bn;                         // first output column of this tile
         // bias of this tile -> this warp's smem copy (two batch rows: the 32 rows may straddle a batch boundary);
@@ -424,7 +457,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             if (j == nsub - 1) {              // accumulator fully read -> release it to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
+              if (lane == 0) release_acc(acc);
             }
             if (has_ln) {
 #pragma unroll
@@ -451,7 +484,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             if (j == nsub - 1) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
+              if (lane == 0) release_acc(acc);
             }
             if (has_ln) {
 #pragma unroll
@@ -524,14 +557,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       if (leader) GEMM_TRACE(7);
     } else {
       // ---------------- direct-store epilogue: split-K partials, NCHW outputs ----------------
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tl) {
+      for (int w = cta; w < total_work; w += ncta, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
         if (tl == 0 && leader) GEMM_TRACE(5);
-        const int m = wi.mt * kBM + row;
+        const int m = (wi.mt * CG + static_cast<int>(rank)) * kBM + row;
         const bool row_ok = m < p.M;
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         if (p.splits > 1) {
@@ -566,20 +599,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) release_acc(acc);
       }
       if (leader) GEMM_TRACE(7);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();       // the peer may still be signalling our barriers / the leader's MMAs read our smem
+  else __syncthreads();
   // PDL trigger at the END of the CTA's work: a CTA of this kernel owns its SM (shared memory), so an earlier trigger
   // would only park the next kernel's CTAs on SMs the other graph branch could be using
   pdl_launch();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
   if (threadIdx.x == 32) GEMM_TRACE(8);
 }
@@ -626,6 +661,8 @@ size_t gemm_smem_bytes(int bn) {
   return 0;
 }
 
+bool gemm_pair_supported(int bn) { return bn == 128 || bn == 160 || bn == 256; }
+
 int gemm_pick_bn(int N, int flags) {
   if (flags & EPI_GEGLU) {                       // value/gate halves must be whole 32-column sub-tiles
     const int cands[3] = {256, 128, 64};
@@ -639,18 +676,39 @@ int gemm_pick_bn(int N, int flags) {
   return N >= 128 ? 128 : (N > 32 ? 64 : 32);
 }
 
-template <int BN>
+template <int BN, int CG>
 static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int total_work = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total_work < num_sms ? total_work : num_sms;
-  cudaError_t e = launch_pdl(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(192), GemmCfg<BN>::kSmemBytes, stream, maps, p);
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;     // work items of one CTA (CG = 1) or one CTA pair
+  const int slots = num_sms / CG;
+  const int grid = CG * (total_work < slots ? total_work : slots);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl_enabled) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, maps, p);
   if (e != cudaSuccess) return e;
   if (p.splits > 1) {
     const long long total = static_cast<long long>(p.M) * ((p.N + 15) / 16);
@@ -662,12 +720,20 @@ static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_
 }
 
 cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int num_sms, cudaStream_t stream) {
+  if (p.cg == 2) {
+    switch (bn) {
+      case 128: return launch_bn<128, 2>(maps, p, num_sms, stream);
+      case 160: return launch_bn<160, 2>(maps, p, num_sms, stream);
+      case 256: return launch_bn<256, 2>(maps, p, num_sms, stream);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (bn) {
-    case 32: return launch_bn<32>(maps, p, num_sms, stream);
-    case 64: return launch_bn<64>(maps, p, num_sms, stream);
-    case 128: return launch_bn<128>(maps, p, num_sms, stream);
-    case 160: return launch_bn<160>(maps, p, num_sms, stream);
-    case 256: return launch_bn<256>(maps, p, num_sms, stream);
+    case 32: return launch_bn<32, 1>(maps, p, num_sms, stream);
+    case 64: return launch_bn<64, 1>(maps, p, num_sms, stream);
+    case 128: return launch_bn<128, 1>(maps, p, num_sms, stream);
+    case 160: return launch_bn<160, 1>(maps, p, num_sms, stream);
+    case 256: return launch_bn<256, 1>(maps, p, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

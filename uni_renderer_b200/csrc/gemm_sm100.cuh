@@ -41,7 +41,8 @@ struct GemmParams {
   ConvSeg seg[kMaxSeg];
   int total_kb;              // sum over segments of ntaps * nkb
   int splits;                // split-K factor (>1 => fp32 partials, finalize kernel applies the epilogue)
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;      // m_tiles counts 128-row tiles (cg = 1) or 256-row PAIR tiles (cg = 2)
+  int cg;                    // CTAs per MMA: 2 = cta_group::2 CTA pairs (cluster of 2 along M)
   // epilogue
   const float* bias;         // [bias_rows][N] fp32 (row b used for rows of batch b when bias_bstride != 0)
   int bias_bstride;
@@ -75,6 +76,7 @@ struct alignas(64) GemmMaps {
 // host-side launcher (gemm_sm100.cu)
 cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int num_sms, cudaStream_t stream);
 int gemm_pick_bn(int N, int flags);
+bool gemm_pair_supported(int bn);
 size_t gemm_smem_bytes(int bn);
 
 }  // namespace unib
