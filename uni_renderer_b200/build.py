@@ -89,6 +89,6 @@ def build_variant(tag: str, defines) -> str:
 
 if __name__ == "__main__":
     if "--trace" in sys.argv:
-        print(build_variant("trace", ["UNIB_GEMM_TRACE"]))
+        print(build_variant("trace", ["UNIB_GEMM_TRACE", "UNIB_ATTN_TRACE"]))
         sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True))

@@ -30,7 +30,7 @@ struct AttnCfg {
   static constexpr int kKvOff = 2 * kQBytes;
   static constexpr int kPOff = kKvOff + kStages * kStageBytes;
   static constexpr int kBarOff = kPOff + 2 * kPBytes;
-  static constexpr int kSmemBytes = kBarOff + 128;         // base is declared 1024-aligned (checked at run time)
+  static constexpr int kSmemBytes = kBarOff + 256;         // base is declared 1024-aligned (checked at run time)
   static constexpr int kTmemCols = 512;                    // 2 x S (BKV) + 2 x O (<= 64 | 128 | 192)
   static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget");
 };
@@ -106,7 +106,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   auto p_full = [&](int t) { return bar_base + 8u * (9 + t); };
   auto o_ready = [&](int t) { return bar_base + 8u * (11 + t); };
   auto pv_done = [&](int t) { return bar_base + 8u * (13 + t); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOff + 120);
+  auto s_free = [&](int t) { return bar_base + 8u * (15 + t); };     // softmax_t holds S_t(j) in registers
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::kBarOff + 248);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +132,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       mbar_init(p_full(s), 128);
       mbar_init(o_ready(s), 1);
       mbar_init(pv_done(s), 1);
+      mbar_init(s_free(s), 128);
     }
     fence_barrier_init();
   }
@@ -199,22 +201,32 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
     for (int j = 0; j < nblk; ++j) {
       const int stn = (st + 1 == Cfg::kStages) ? 0 : st + 1;
       if (stn == 0) kv_ph ^= 1;
+      // (1) S_t(j+1) = Q_t K(j+1)^T as soon as softmax_t has pulled S_t(j) into registers (s_free): the next scores
+      //     are computed WHILE softmax_t(j) exponentiates, so a softmax warpgroup never waits for its tensor-core work
+      if (j + 1 < nblk) {
+        mbar_wait(kv_full(stn), kv_ph);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (t < ntile) {
-          mbar_wait(p_full(t), j & 1);       // softmax_t(j) has read S_t(j) and written P_t(j)
-          if (t == 0 && j + 1 < nblk) mbar_wait(kv_full(stn), kv_ph);
-          tc_fence_after();
-          if (elect_one()) {
-            ATTN_TRACE(2 + t, j, 0);
-            // S_t(j+1) first: the next softmax can start while P_t(j) V(j) is still running
-            if (j + 1 < nblk) {
+        for (int t = 0; t < 2; ++t) {
+          if (t < ntile) {
+            mbar_wait(s_free(t), j & 1);
+            tc_fence_after();
+            if (elect_one()) {
               issue_qk_dyn<BKV>(ks_s, tmem_base + t_s_col(t), q_desc0 + t * (Cfg::kQBytes >> 4),
                                 k_desc0 + stn * kStage16, idesc_s);
               umma_commit(s_full(t));
             }
-            ATTN_TRACE(2 + t, j, 4);
-            // O_t += P_t V : K loop over the kv rows of this block in steps of 16
+          }
+        }
+      }
+      // (2) O_t += P_t(j) V(j) once softmax_t(j) has written P_t(j)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t < ntile) {
+          mbar_wait(p_full(t), j & 1);       // softmax_t(j) has written P_t(j)
+          tc_fence_after();
+          if (elect_one()) {
+            ATTN_TRACE(2 + t, j, 0);
+            // K loop over the kv rows of this block in steps of 16
             issue_pv<BKV>(tmem_base + t_o_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), v_desc0 + st * kStage16, idesc_o,
                           j == 0);
             umma_commit(pv_done(t));                          // P_t buffer + O_t free again
@@ -249,6 +261,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) tmem_ld32(t_s + c * 32, v + c * 32);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free(t));               // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1)
         if (tr) ATTN_TRACE(t, j, 2);
         const int kv_valid = p.Nk - j * BKV;     // columns >= kv_valid are padding (last block only)
         if (kv_valid < BKV) {
@@ -265,11 +279,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
           mx4[3] = fmaxf(mx4[3], v[i + 3]);
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        // P_t V(j-1) was issued AFTER S_t(j): wait for it before O_t is rescaled or the P_t buffer is overwritten
-        if (j > 0) {
-          mbar_wait(pv_done(t), (j - 1) & 1);
-          tc_fence_after();
-        }
+        // P_t V(j-1) must be complete before O_t is rescaled (rare: lazy rescale) or the P_t buffer is overwritten.
+        // The wait is taken as LATE as possible: all exponentials of this block are computed into registers first, so
+        // the tensor core's P V work hides behind the MUFU-bound loop instead of stalling it.
+        bool pv_waited = (j == 0);
         // lazy rescale: move the reference maximum only when some row of this warp grew by more than 2^8
         const bool need = (mx - m_ref) * sl2 > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
@@ -278,6 +291,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
           m_ref = m_new;
           l_run *= alpha;
           if (j > 0) {
+            mbar_wait(pv_done(t), (j - 1) & 1);
+            tc_fence_after();
+            pv_waited = true;
             // P_t V(j-1) is complete (pv_done) and P_t V(j) is not issued before this warpgroup arrives on p_full,
             // so O_t is stable here
 #pragma unroll 1
@@ -295,20 +311,28 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         if (tr) ATTN_TRACE(t, j, 3);
         const float mb = m_ref * sl2;
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[BKV / 2];
+
 #pragma unroll
         for (int u = 0; u < BKV / 8; ++u) {
-          uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = u * 8 + 2 * e;
             const float p0 = fast_exp2(v[i] * sl2 - mb);
             const float p1 = fast_exp2(v[i + 1] * sl2 - mb);
             rs4[e] += p0 + p1;
-            pk[e] = pack_half2(p0, p1);
+            pk[u * 4 + e] = pack_half2(p0, p1);
           }
+        }
+        if (!pv_waited) {                     // warp-uniform
+          mbar_wait(pv_done(t), (j - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int u = 0; u < BKV / 8; ++u) {
           // 16 B unit (u & 7) of this row lands at ((u & 7) ^ (row & 7)) in the 128B-swizzled 64-column chunk u >> 3
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (u >> 3) * 16384 + (((u & 7) ^ sw) << 4)),
-                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       "r"(pk[u * 4 + 0]), "r"(pk[u * 4 + 1]), "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
                        : "memory");
         }
         l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
