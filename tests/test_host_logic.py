@@ -101,3 +101,40 @@ def test_bench_b200_arm_fails_loudly_without_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=240)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_fold_layernorm_matches_torch_cpu():
+    """The host-side algebra of the LayerNorm fold (ops.fold_layernorm, include/unib200.h): with the folded weights,
+    wsum and bias, rstd * (x @ wf.T - mean * wsum) + bias2 equals layer_norm(x) @ w.T + b -- checked in fp64-free
+    plain torch on the CPU (the only difference allowed is the fp16 rounding of the folded weights)."""
+    import torch.nn.functional as F
+    from uni_renderer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for (M, C, N) in [(17, 64, 48), (5, 320, 96)]:
+        x = torch.randn(M, C, generator=g) * 2.0 + 1.5
+        w = torch.randn(N, C, generator=g) * C ** -0.5
+        b = torch.randn(N, generator=g)
+        gamma = 1.0 + 0.3 * torch.randn(C, generator=g)
+        beta = 0.2 * torch.randn(C, generator=g)
+        wf, wsum, bias2 = ops.fold_layernorm(w, b, gamma, beta)
+        assert torch.equal(wf, wf.half().float()), "folded weights must be fp16-representable"
+        mean = x.mean(1, keepdim=True)
+        rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+        got = rstd * (x @ wf.t() - mean * wsum[None]) + bias2[None]
+        ref = F.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
+        torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3)
+        # without the fp16 rounding the identity is exact to fp32 round-off
+        wf_exact = w * gamma[None]
+        got2 = rstd * (x @ wf_exact.t() - mean * wf_exact.sum(1)[None]) + bias2[None]
+        torch.testing.assert_close(got2, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_tile_planning_helpers():
+    """pick_bn / rowstats_parts agree with the packing rules (host-only library calls, no GPU needed)."""
+    from uni_renderer_b200 import ops
+    assert ops.pick_bn(320) == 160 and ops.pick_bn(1280) == 160 and ops.pick_bn(960) == 160
+    assert ops.pick_bn(2560, ops.EPI_GEGLU) == 256
+    assert ops.pick_bn(4) == 32 and ops.pick_bn(28) == 32
+    for n in (32, 64, 128, 320, 640, 1280):
+        bn = ops.pick_bn(n)
+        assert ops.rowstats_parts(n) == (n + bn - 1) // bn
