@@ -297,7 +297,9 @@ def run_b200(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": MODE_CONFIG[a.mode], "mode": a.mode, "per_gpu_batch": B, "global_batch": world * B,
+            "config": {"workload": MODE_CONFIG[a.mode] + (f" (weak scaling: the same shard on each of {world} GPUs)"
+                                                          if world > 1 else ""),
+                       "mode": a.mode, "per_gpu_batch": B, "global_batch": world * B,
                        "latent": S, "denoise_steps": T, "text_tokens": L, "weights": "random-init SD-1.5 shape "
                        "(859.5M + 360.3M + 524.4M params)", "cuda_graph": not a.no_graph,
                        "l2": "every denoising step streams 3.5 GB of weights + activations >> 126 MB L2; no flush needed"},
@@ -309,6 +311,21 @@ def run_b200(a):
             "step_tflops_per_gpu": flops_call * a.steps / (ms_res * 1e-3) / 1e12,
             "step_frac_of_tensor_peak": flops_call * a.steps / (ms_res * 1e-3) / 1e12 / peaks["tflops_sustained"]}
 
+    if rank == 0 and a.mode == "joint" and not a.no_roofline:
+        # BASELINE.json's second figure, "UNet ms/step": the RGB UNet alone (the step of the forward-rendering loop:
+        # UNet encoder + exchange adds + decoder + DDIM update, attribute encoder hoisted) at the same batch, CUDA events
+        uplan = sampler.plan("forward", B, S, L, T)
+        sampler.load_inputs(uplan, d_img, d_attr, d_ehs)
+        sampler.run(uplan, steps=3)
+        torch.cuda.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        sampler.run(uplan, steps=T)
+        u1.record()
+        torch.cuda.synchronize()
+        line["unet_ms_per_step"] = u0.elapsed_time(u1) / T
+        line["unet_ms_per_step_note"] = (f"RGB UNet forward + fused DDIM update, B={B}, {S}x{S} latent, mean of {T} graph "
+                                         "replays (includes the once-per-call setup program)")
     if rank == 0 and not a.no_roofline:
         # per-op device times of ONE denoising step (events around every launch on the launching stream)
         sampler.load_inputs(plan, d_img, d_attr, d_ehs)

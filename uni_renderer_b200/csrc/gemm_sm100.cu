@@ -1,15 +1,16 @@
-// Implicit-GEMM convolution / linear kernel for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (cta_group::1,
-// UMMA 128 x BN x 16, fp16 in / fp32 accumulate in TMEM, double-buffered accumulators) -> tcgen05.ld epilogue.
+// Implicit-GEMM convolution / linear kernel for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (UMMA
+// 128 x BN x 16 per CTA, or 256 x BN x 16 per CTA PAIR with cta_group::2; fp16 in / fp32 accumulate in TMEM,
+// double-buffered accumulators) -> tcgen05.ld epilogue.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
-// Persistent: each CTA walks work items (split, m_tile, n_tile) with stride gridDim.x.
+// Persistent: each CTA (pair) walks work items (split, m_tile, n_tile) with stride gridDim.x (/ 2).
 //
 // Epilogue (NHWC fp16 outputs): each of the four epilogue warps drains its 32 rows of the 128 x BN tile in 32-column
 // sub-tiles straight from TMEM through registers: bias from a per-warp smem copy, the residual (ResNet identity /
 // transformer skip / exchange add) read with 256-bit global loads one sub-tile ahead, SiLU / GEGLU gate in registers,
 // 256-bit global stores (64 contiguous bytes per row and sub-tile = full sectors).  No smem staging, proxy fence or
 // block-wide barrier on the critical path (a TMA-store slot ring measured ~1000 cycles of serial latency per
-// sub-tile and made every small-K GEMM epilogue-bound).  fp32 split-K partials and the tiny NCHW outputs (conv_out + fused scheduler update) use direct
-// per-thread stores.
+// sub-tile and made every small-K GEMM epilogue-bound).  fp32 split-K partials and the tiny NCHW outputs (conv_out +
+// fused scheduler update) use direct per-thread stores.
 #include "gemm_sm100.cuh"
 
 namespace unib {
@@ -147,8 +148,6 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
 #else
 #define GEMM_TRACE(k) do { } while (0)
 #endif
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(192, 1)
