@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--latent", type=int, default=None, help="latent side (default 64; 128 for --mode cycle)")
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-split-batch", action="store_true", help="forward/inverse: one lane instead of two batch halves")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-denoise-steps", type=int, default=2, help="timed CPU denoising steps of the cpu_baseline leg")
@@ -223,7 +224,8 @@ def run_b200(a):
     from dataclasses import replace
     cfgs = (replace(cfg), replace(cfg, in_channels=28), replace(cfg, out_channels=28))
     sds = [random_init_state_dict(k, c, s, dev) for k, c, s in zip(("unet", "attr_enc", "attr_dec"), cfgs, (11, 12, 13))]
-    sampler = DualStreamSampler.from_state_dicts(*sds, *cfgs, device=dev, use_graph=not a.no_graph)
+    sampler = DualStreamSampler.from_state_dicts(*sds, *cfgs, device=dev, use_graph=not a.no_graph,
+                                                 split_batch=not a.no_split_batch)
     del sds
     plan = sampler.plan(a.mode, B, S, L, T)
     torch.cuda.synchronize()

@@ -65,7 +65,7 @@ class DualStreamSampler:
     """
 
     def __init__(self, unet=None, controlnet=None, controldec=None, *, nets: Optional[Sequence[StreamNet]] = None,
-                 prediction_type: str = "epsilon", device=None, use_graph: bool = True):
+                 prediction_type: str = "epsilon", device=None, use_graph: bool = True, split_batch: bool = False):
         if nets is None:
             if unet is None or controlnet is None or controldec is None:
                 raise ValueError("need the three modules or three StreamNets")
@@ -76,6 +76,7 @@ class DualStreamSampler:
             raise RuntimeError("DualStreamSampler runs on CUDA (sm_100a) only")
         self.schedule = DDIMSchedule(prediction_type=prediction_type)
         self.use_graph = use_graph
+        self.split_batch = split_batch
         self.ws = Workspace(self.device)          # lane 0 (RGB stream)
         self.ws1 = Workspace(self.device)         # lane 1 (attribute stream): lanes run concurrently, no shared scratch
         self._plans: Dict[Tuple, _Plan] = {}
@@ -173,10 +174,19 @@ class DualStreamSampler:
             d, m = enc.rec_exchange(setup, ws, skA, midA, [None] * len(skA), None)
             ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
             tpU = temb(unet, step, b["t_img"])
-            skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
-            dskU = [self._add(step, s, r) for s, r in zip(skU, d)]             # controlnet.py:1078-1087
-            dmidU = self._add(step, midU, m)                                    # controlnet.py:1114-1115
-            unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=None, axpby=ax_img)
+            # only one stream is live in this loop; with split_batch the two HALVES of the batch take the two lanes
+            # (samples are independent).  Measured slower on B200 at B=4 (7.05 -> 7.59 ms/step: every weight is
+            # streamed twice and the half-batch tiles are less efficient), so it is off by default.
+            step.barrier()
+            for lane, (b0, b1), wsl in self._batch_lanes(B):
+                step.lane(lane)
+                skU, midU = unet.rec_encoder(step, wsl, _rows(x_img, b0, b1), tpU[b0:b1], _kv_rows(kvU, b0, b1, L), L)
+                dskU = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skU, d)]   # controlnet.py:1078-1087
+                dmidU = self._add(step, midU, _rows(m, b0, b1))                            # controlnet.py:1114-1115
+                unet.rec_decoder(step, wsl, dmidU, dskU, tpU[b0:b1], _kv_rows(kvU, b0, b1, L), L, out_nchw=None,
+                                 axpby=dict(ax_img, latent=b["lat_img"][b0:b1]))
+            step.barrier()
+            step.lane(0)
         else:  # inverse
             # step-invariant: RGB encoder + mid + the decoder-side zero-convs of its raw features
             b["t_zero"] = torch.zeros(1, B, **f32)
@@ -186,10 +196,16 @@ class DualStreamSampler:
             zU, zmidU = dec.rec_exchange(setup, ws, skU, midU, [None] * len(skU), None)
             ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
             tpE, tpD = temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
-            skA, midA = enc.rec_encoder(step, ws, x_attr, tpE, kvE, L)
-            dskA = [self._add(step, s, r) for s, r in zip(skA, zU)]            # controlnet.py:2446-2461
-            dmidA = self._add(step, midA, zmidU)                                # controlnet.py:2476-2477
-            dec.rec_decoder(step, ws, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+            step.barrier()
+            for lane, (b0, b1), wsl in self._batch_lanes(B):       # batch halves on the two lanes, as above
+                step.lane(lane)
+                skA, midA = enc.rec_encoder(step, wsl, _rows(x_attr, b0, b1), tpE[b0:b1], _kv_rows(kvE, b0, b1, L), L)
+                dskA = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skA, zU)]   # controlnet.py:2446-2461
+                dmidA = self._add(step, midA, _rows(zmidU, b0, b1))                         # controlnet.py:2476-2477
+                dec.rec_decoder(step, wsl, dmidA, dskA, tpD[b0:b1], _kv_rows(kvD, b0, b1, L), L, out_nchw=None,
+                                axpby=dict(ax_attr, latent=b["lat_attr"][b0:b1]))
+            step.barrier()
+            step.lane(0)
         ops.add_int(step, b["step"], 1)
 
         plan = _Plan(mode, B, S, L, steps, setup, step, b)
@@ -208,6 +224,12 @@ class DualStreamSampler:
             side.synchronize()
         self._plans[key] = plan
         return plan
+
+    def _batch_lanes(self, B: int):
+        """(lane, (b0, b1), workspace) per batch slice: two halves on two lanes when the batch splits evenly."""
+        if self.split_batch and B >= 2 and B % 2 == 0:
+            return [(0, (0, B // 2), self.ws), (1, (B // 2, B), self.ws1)]
+        return [(0, (0, B), self.ws)]
 
     def _add(self, prog, a: Act, r: Act) -> Act:
         o = Act(torch.empty_like(a.t), a.B, a.H, a.W, a.C)
@@ -303,6 +325,16 @@ class DualStreamSampler:
         _, img, attr = self._sample("cycle", latents_img, latents_attr, prompt_embeds, num_inference_steps,
                                     guidance_scale)
         return img, attr
+
+
+def _rows(a: Act, b0: int, b1: int) -> Act:
+    """Samples [b0, b1) of an activation (a zero-copy row slice: the rows of a sample are contiguous)."""
+    hw = a.H * a.W
+    return Act(a.t[b0 * hw:b1 * hw], b1 - b0, a.H, a.W, a.C)
+
+
+def _kv_rows(kv: Dict[str, torch.Tensor], b0: int, b1: int, L: int) -> Dict[str, torch.Tensor]:
+    return {k: t[b0 * L:b1 * L] for k, t in kv.items()}
 
 
 def all_gather_latents(x: torch.Tensor, group=None) -> torch.Tensor:
