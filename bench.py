@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 4; 2 for --mode cycle)")
     ap.add_argument("--latent", type=int, default=None, help="latent side (default 64; 128 for --mode cycle)")
     ap.add_argument("--denoise-steps", type=int, default=50)
+    ap.add_argument("--scheduler", default="ddim", choices=["ddim", "unipc"],
+                    help="ddim = BASELINE.json's metric; unipc = the scheduler of the reference's shipped eval")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-split-batch", action="store_true", help="forward/inverse: one lane instead of two batch halves")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -227,7 +229,7 @@ def run_b200(a):
     sampler = DualStreamSampler.from_state_dicts(*sds, *cfgs, device=dev, use_graph=not a.no_graph,
                                                  split_batch=not a.no_split_batch)
     del sds
-    plan = sampler.plan(a.mode, B, S, L, T)
+    plan = sampler.plan(a.mode, B, S, L, T, a.scheduler)
     torch.cuda.synchronize()
 
     # synthetic inputs: per-rank seeds so every rank denoises different images (weak scaling: B per GPU is fixed)
@@ -302,7 +304,7 @@ def run_b200(a):
             "config": {"workload": MODE_CONFIG[a.mode] + (f" (weak scaling: the same shard on each of {world} GPUs)"
                                                           if world > 1 else ""),
                        "mode": a.mode, "per_gpu_batch": B, "global_batch": world * B,
-                       "latent": S, "denoise_steps": T, "text_tokens": L, "weights": "random-init SD-1.5 shape "
+                       "latent": S, "denoise_steps": T, "scheduler": a.scheduler, "text_tokens": L, "weights": "random-init SD-1.5 shape "
                        "(859.5M + 360.3M + 524.4M params)", "cuda_graph": not a.no_graph,
                        "l2": "every denoising step streams 3.5 GB of weights + activations >> 126 MB L2; no flush needed"},
             "clocks": clk,

@@ -178,6 +178,14 @@ int unib200_axpby(unib200_program* prog, const float* model_out, const float* x,
                   const int* step_idx, int64_t n, void* stream);
 int unib200_add_int(unib200_program* prog, int* p, int v, void* stream);
 
+/* ---- UniPCMultistepScheduler.step (order 2, bh2, predict-x0; what eval/test_real.py:485-493 attaches to every stream)
+ * as ONE fused pass per stream and step: convert_model_output + corrector + history shift + predictor are linear
+ * combinations with host-tabulated scalars, coef = device [steps][10] (scheduler.py UniPCSchedule), row *step_idx.
+ * sample / last_sample / hist0 / hist1 / model_out: fp32 [B, C, HW]; channels < first_channel are left untouched. */
+int unib200_unipc_step(unib200_program* prog, const float* model_out, float* sample, float* last_sample, float* hist0,
+                       float* hist1, const float* coef, const int* step_idx, int B, int C, int HW, int first_channel,
+                       void* stream);
+
 /* ---- out = a + b over contiguous fp16 (skip + external residual when the three modules are called separately,
  *      models/controlnet.py:1084,1115; the fused step folds these adds into the zero-conv GEMM epilogue) -------- */
 int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* out, int64_t n, void* stream);

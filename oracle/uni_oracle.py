@@ -306,6 +306,131 @@ class DDIM:
         return a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps
 
 
+@dataclass
+class UniPC:
+    """UniPCMultistepScheduler as the shipped eval drives it (eval/test_real.py:485-493: one scheduler per stream,
+    `UniPCMultistepScheduler.from_config(pipeline.scheduler.config)`, 20 steps; step call sites
+    models/pipeline.py:1649,2725-2730).  Restated from the published UniPC algorithm (Zhao et al. 2023, "UniPC: A
+    Unified Predictor-Corrector Framework") in the form diffusers 0.24 implements it: solver_order 2, solver_type
+    "bh2", predict_x0, lower_order_final, no thresholding, sigmas interpolated at the (linspace-spaced) timesteps with
+    the final sigma appended.  PARITY UNPINNED against diffusers itself (not installable here) -- it pins the
+    product's closed-form coefficient tables (uni_renderer_b200/scheduler.py) through an independent formulation:
+    this class runs the tensor algorithm step by step with its model-output history."""
+    num_train_timesteps: int = 1000
+    beta_start: float = 0.00085
+    beta_end: float = 0.012
+    prediction_type: str = "epsilon"
+    solver_order: int = 2
+
+    def __post_init__(self):
+        betas = torch.linspace(self.beta_start ** 0.5, self.beta_end ** 0.5, self.num_train_timesteps,
+                               dtype=torch.float64) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+
+    def set_timesteps(self, n: int):
+        import numpy as np
+        T = self.num_train_timesteps
+        ts = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)       # timestep_spacing "linspace"
+        sig = ((1 - self.alphas_cumprod) / self.alphas_cumprod).sqrt().numpy()
+        s = np.interp(ts, np.arange(T), sig)
+        s_last = float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]).sqrt())
+        self.sigmas = [float(v) for v in s] + [s_last]
+        self.timesteps = [int(t) for t in ts]
+        self.model_outputs = [None] * self.solver_order
+        self.lower_order_nums = 0
+        self.step_index = 0
+        self.last_sample = None
+        self.this_order = 1
+        return self.timesteps
+
+    @staticmethod
+    def _alpha_sigma(sigma: float):
+        alpha = 1.0 / math.sqrt(sigma * sigma + 1.0)
+        return alpha, sigma * alpha
+
+    def _convert(self, model_output, sample):
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[self.step_index])
+        if self.prediction_type == "epsilon":
+            return (sample - sigma_t * model_output) / alpha_t
+        if self.prediction_type == "sample":
+            return model_output
+        if self.prediction_type == "v_prediction":
+            return alpha_t * sample - sigma_t * model_output
+        raise ValueError(self.prediction_type)
+
+    def _bh(self, s_t: float, s_s0: float, s_hist, order: int):
+        """Shared scalar part of the predictor / corrector: returns (alpha_t, sigma_t/sigma_s0, h_phi_1, B_h, rks, R, b)."""
+        alpha_t, sigma_t = self._alpha_sigma(s_t)
+        alpha_s0, sigma_s0 = self._alpha_sigma(s_s0)
+        lam_t, lam_s0 = math.log(alpha_t) - math.log(sigma_t), math.log(alpha_s0) - math.log(sigma_s0)
+        h = lam_t - lam_s0
+        rks = []
+        for s_i in s_hist:
+            a_i, sg_i = self._alpha_sigma(s_i)
+            rks.append(((math.log(a_i) - math.log(sg_i)) - lam_s0) / h)
+        rks.append(1.0)
+        hh = -h                                   # predict_x0
+        h_phi_1 = math.expm1(hh)
+        h_phi_k = h_phi_1 / hh - 1.0
+        B_h = math.expm1(hh)                      # bh2
+        R, b, fact = [], [], 1
+        for i in range(1, order + 1):
+            R.append([rk ** (i - 1) for rk in rks])
+            b.append(h_phi_k * fact / B_h)
+            fact *= i + 1
+            h_phi_k = h_phi_k / hh - 1.0 / fact
+        return alpha_t, sigma_t / sigma_s0, h_phi_1, B_h, rks, R, b
+
+    def _predict(self, sample, order: int):
+        m0 = self.model_outputs[-1]
+        hist = [self.sigmas[self.step_index - i] for i in range(1, order)]
+        alpha_t, ratio, h_phi_1, B_h, rks, R, b = self._bh(self.sigmas[self.step_index + 1], self.sigmas[self.step_index],
+                                                           hist, order)
+        D1s = [(self.model_outputs[-(i + 1)] - m0) / rks[i - 1] for i in range(1, order)]
+        x_t_ = ratio * sample - alpha_t * h_phi_1 * m0
+        if D1s:
+            if order == 2:
+                rhos_p = [0.5]
+            else:
+                rhos_p = torch.linalg.solve(torch.tensor(R, dtype=torch.float64)[:-1, :-1],
+                                            torch.tensor(b, dtype=torch.float64)[:-1]).tolist()
+            pred = sum(r * d for r, d in zip(rhos_p, D1s))
+        else:
+            pred = 0.0
+        return x_t_ - alpha_t * B_h * pred
+
+    def _correct(self, model_t, last_sample, order: int):
+        m0 = self.model_outputs[-1]
+        hist = [self.sigmas[self.step_index - (i + 1)] for i in range(1, order)]
+        alpha_t, ratio, h_phi_1, B_h, rks, R, b = self._bh(self.sigmas[self.step_index], self.sigmas[self.step_index - 1],
+                                                           hist, order)
+        D1s = [(self.model_outputs[-(i + 1)] - m0) / rks[i - 1] for i in range(1, order)]
+        if order == 1:
+            rhos_c = [0.5]
+        else:
+            rhos_c = torch.linalg.solve(torch.tensor(R, dtype=torch.float64),
+                                        torch.tensor(b, dtype=torch.float64)).tolist()
+        x_t_ = ratio * last_sample - alpha_t * h_phi_1 * m0
+        corr = sum(r * d for r, d in zip(rhos_c[:-1], D1s)) if D1s else 0.0
+        return x_t_ - alpha_t * B_h * (corr + rhos_c[-1] * (model_t - m0))
+
+    def step(self, model_output: torch.Tensor, t: int, sample: torch.Tensor) -> torch.Tensor:
+        assert t == self.timesteps[self.step_index], "steps must be taken in schedule order"
+        use_corrector = self.step_index > 0 and self.last_sample is not None
+        x0 = self._convert(model_output, sample)
+        if use_corrector:
+            sample = self._correct(x0, self.last_sample, self.this_order)
+        self.model_outputs = self.model_outputs[1:] + [x0]
+        this_order = min(self.solver_order, len(self.timesteps) - self.step_index)         # lower_order_final
+        self.this_order = min(this_order, self.lower_order_nums + 1)
+        self.last_sample = sample
+        prev = self._predict(sample, self.this_order)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self.step_index += 1
+        return prev
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # random-init state dicts in the reference's key layout (for synthetic benchmarks / tests without the reference)
 # ----------------------------------------------------------------------------------------------------------------

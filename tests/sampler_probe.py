@@ -38,8 +38,11 @@ def tiny_setup(seeds=(11, 12, 13), prediction_type="epsilon", use_graph=True, de
     return sampler, sds, cfgs_o
 
 
-def oracle_step(mode, sds, cfgs, sched, t, x_img, x_attr, ehs):
-    """One denoising step of `mode` exactly as the reference loops execute it (see bench.py cpu_reference_run)."""
+def oracle_step(mode, sds, cfgs, sched, t, x_img, x_attr, ehs, sched_attr=None):
+    """One denoising step of `mode` exactly as the reference loops execute it (see bench.py cpu_reference_run).
+    Multistep schedulers carry history: pass one instance per stream (sched = RGB stream, sched_attr = attributes),
+    like the reference's scheduler_img / scheduler_attr (eval/test_real.py:485-493)."""
+    sa = sched_attr if sched_attr is not None else sched
     with torch.no_grad():
         if mode == "forward":
             d, m, _, _ = uo.attr_encoder_forward(sds[1], cfgs[1], 0, ehs, x_attr)
@@ -47,32 +50,36 @@ def oracle_step(mode, sds, cfgs, sched, t, x_img, x_attr, ehs):
             return sched.step(pred, t, x_img), x_attr
         if mode == "inverse":
             _, attr = uo.dual_stream_step(*sds, *cfgs, x_img, 0, x_attr, t, ehs)
-            return x_img, torch.cat([x_attr[:, :4], sched.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
+            return x_img, torch.cat([x_attr[:, :4], sa.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
         img, attr = uo.dual_stream_step(*sds, *cfgs, x_img, t, x_attr, t, ehs)
         if mode == "cycle":
             x2 = torch.cat([x_attr[:, :4], attr[:, 4:]], 1)
             d, m, _, _ = uo.attr_encoder_forward(sds[1], cfgs[1], 0, ehs, x2)
             img = uo.unet_forward(sds[0], cfgs[0], x_img, t, ehs, d, m)[0]
-        return sched.step(img, t, x_img), torch.cat([x_attr[:, :4], sched.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
+        return sched.step(img, t, x_img), torch.cat([x_attr[:, :4], sa.step(attr[:, 4:], t, x_attr[:, 4:])], 1)
 
 
-def run_mode(mode, B=2, S=16, steps_total=50, n_steps=1, prediction_type="epsilon", use_graph=True, seed=1234):
+def run_mode(mode, B=2, S=16, steps_total=50, n_steps=1, prediction_type="epsilon", use_graph=True, seed=1234,
+             scheduler="ddim"):
     sampler, sds, cfgs = tiny_setup(prediction_type=prediction_type, use_graph=use_graph)
     g = torch.Generator().manual_seed(seed)
     x_img = torch.randn(B, 4, S, S, generator=g)
     x_attr = torch.randn(B, 28, S, S, generator=g)
     ehs = torch.randn(B, 77, cfgs[0].cross_attention_dim, generator=g)
-    plan = sampler.plan(mode, B, S, 77, steps_total)
+    plan = sampler.plan(mode, B, S, 77, steps_total, scheduler)
     sampler.load_inputs(plan, x_img, x_attr, ehs.half())
     sampler.run(plan, steps=n_steps)
     torch.cuda.synchronize()
     got_img, got_attr = plan.bufs["lat_img"].cpu(), plan.bufs["lat_attr"].cpu()
-    sched = uo.DDIM(prediction_type=prediction_type)
+    mk = (lambda: uo.DDIM(prediction_type=prediction_type)) if scheduler == "ddim" else \
+        (lambda: uo.UniPC(prediction_type=prediction_type))
+    sched, sched_a = mk(), mk()
     ts = sched.set_timesteps(steps_total)
+    sched_a.set_timesteps(steps_total)
     ri, ra = x_img, x_attr
     ehs_r = ehs.half().float()          # both sides see the fp16-rounded text embeddings
     for i in range(n_steps):
-        ri, ra = oracle_step(mode, sds, cfgs, sched, ts[i], ri, ra, ehs_r)
+        ri, ra = oracle_step(mode, sds, cfgs, sched, ts[i], ri, ra, ehs_r, sched_a)
     res = {"img": err(got_img, ri), "attr": err(got_attr, ra), "launches_per_step": plan.step.num_launches,
            "mask_untouched": bool(torch.equal(got_attr[:, :4], x_attr[:, :4])),
            "step_counter": int(plan.bufs["step"].item())}

@@ -138,3 +138,37 @@ def test_tile_planning_helpers():
     for n in (32, 64, 128, 320, 640, 1280):
         bn = ops.pick_bn(n)
         assert ops.rowstats_parts(n) == (n + bn - 1) // bn
+
+
+@pytest.mark.parametrize("ptype", ["epsilon", "sample", "v_prediction"])
+@pytest.mark.parametrize("n", [20, 50, 7])
+def test_unipc_tables_match_oracle_stepping(ptype, n):
+    """The closed-form [steps][10] UniPC coefficient table (product) drives the same trajectory as the oracle's
+    tensor-form multistep algorithm with its model-output history (two independent formulations)."""
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.scheduler import UniPCSchedule
+    sch, orc = UniPCSchedule(prediction_type=ptype), uo.UniPC(prediction_type=ptype)
+    ts, rows = sch.table(n)
+    assert ts == orc.set_timesteps(n)
+    if n == 20:
+        assert ts[0] == 999 and ts[1] == 949 and ts[-1] == 50
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 6, 6, generator=g, dtype=torch.float64)
+    S, LS, H0, H1 = x.clone(), torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+    ref = x.clone()
+    for t, c in zip(ts, rows):
+        out = torch.randn(2, 4, 6, 6, generator=g, dtype=torch.float64) * 0.5 + 0.1 * ref     # same net output both sides
+        ref_next = orc.step(out, t, ref)
+        x0 = c[0] * out + c[1] * S
+        Sc = c[2] * LS + c[3] * H0 + c[4] * H1 + c[5] * x0 if c[6] else S
+        S, LS, H1, H0 = c[7] * Sc + c[8] * x0 + c[9] * H0, Sc, H0, x0
+        torch.testing.assert_close(S, ref_next, rtol=1e-9, atol=1e-9)
+        ref = S.clone()
+
+
+def test_unipc_rejects_bad_arguments():
+    from uni_renderer_b200.scheduler import UniPCSchedule
+    with pytest.raises(ValueError):
+        UniPCSchedule(prediction_type="nope")
+    with pytest.raises(ValueError):
+        UniPCSchedule().timesteps(0)

@@ -63,7 +63,7 @@ EXPORTS = [
     "unib200_program_num_ops", "unib200_program_op_info", "unib200_program_op_desc", "unib200_program_profile",
     "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
-    "unib200_axpby", "unib200_add_int", "unib200_add_f16",
+    "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load() -> C.CDLL:
     lib.unib200_axpby.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
     lib.unib200_add_int.argtypes = [vp, vp, ci, vp]
     lib.unib200_add_f16.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.unib200_unipc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     _lib = lib
     return lib
 

@@ -644,6 +644,17 @@ int unib200_axpby(unib200_program* prog, const float* model_out, const float* x,
   return submit(prog, std::move(op), 1, stream, "axpby");
 }
 
+int unib200_unipc_step(unib200_program* prog, const float* model_out, float* sample, float* last_sample, float* hist0,
+                       float* hist1, const float* coef, const int* step_idx, int B, int C, int HW, int first_channel,
+                       void* stream) {
+  if (B <= 0 || C <= 0 || HW <= 0 || first_channel < 0 || first_channel >= C) return fail("unipc_step: bad shape");
+  if (!model_out || !sample || !last_sample || !hist0 || !hist1 || !coef) return fail("unipc_step: null pointer");
+  Op op = [=](cudaStream_t s) {
+    return launch_unipc_step(model_out, sample, last_sample, hist0, hist1, coef, step_idx, B, C, HW, first_channel, s);
+  };
+  return submit(prog, std::move(op), 1, stream, "unipc_step");
+}
+
 int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* out, int64_t n, void* stream) {
   if (n % 8) return fail("add_f16: n must be a multiple of 8");
   Op op = [=](cudaStream_t s) {

@@ -648,6 +648,51 @@ cudaError_t launch_axpby(const float* model_out, const float* x, float* out, con
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// UniPC (order <= 2, bh2, predict-x0) multistep update, one fused pass per stream and step.  Every quantity of the
+// scheduler is a scalar, so corrector + history shift + predictor collapse into linear combinations whose
+// coefficients the host tabulates per step (uni_renderer_b200/scheduler.py UniPCSchedule):
+//   x0  = c[0]*out + c[1]*S                                  (convert_model_output)
+//   S'  = c[6] ? c[2]*LS + c[3]*H0 + c[4]*H1 + c[5]*x0 : S    (corrector, from the second step on)
+//   S  <- c[7]*S' + c[8]*x0 + c[9]*H0;  LS <- S';  H1 <- H0;  H0 <- x0      (predictor + history shift)
+// S = latent state [B, C, HW] fp32 (only channels >= c_first are touched: the clean mask group stays), out = network
+// output [B, C, HW] fp32, LS / H0 / H1 = last corrected sample and the two newest converted outputs.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void unipc_step_kernel(const float* __restrict__ out, float* __restrict__ S, float* __restrict__ LS,
+                                  float* __restrict__ H0, float* __restrict__ H1, const float* __restrict__ coef,
+                                  const int* __restrict__ step_idx, int B, int C, int HW, int c_first) {
+  pdl_launch();
+  pdl_wait();
+  const float* c = coef + (step_idx ? 10 * static_cast<size_t>(*step_idx) : 0);
+  const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5], c7 = c[7], c8 = c[8], c9 = c[9];
+  const bool corr = c[6] != 0.f;
+  const long long per = static_cast<long long>(C - c_first) * HW;
+  const long long total = per * B;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / per;
+    const long long idx = (b * C + c_first) * HW + (i - b * per);
+    const float s = S[idx], h0 = H0[idx], h1 = H1[idx];
+    const float x0 = c0 * out[idx] + c1 * s;
+    const float sc = corr ? c2 * LS[idx] + c3 * h0 + c4 * h1 + c5 * x0 : s;
+    S[idx] = c7 * sc + c8 * x0 + c9 * h0;
+    LS[idx] = sc;
+    H1[idx] = h0;
+    H0[idx] = x0;
+  }
+}
+
+cudaError_t launch_unipc_step(const float* out, float* S, float* LS, float* H0, float* H1, const float* coef,
+                              const int* step_idx, int B, int C, int HW, int c_first, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (C - c_first) * HW;
+  if (total <= 0) return cudaErrorInvalidValue;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  UNIB_CHECK_LAUNCH(launch_pdl(unipc_step_kernel, dim3(blocks), dim3(256), 0, stream, out, S, LS, H0, H1, coef, step_idx,
+                               B, C, HW, c_first));
+  return cudaGetLastError();
+}
+
 // out = a + b over fp16 vectors (module-level API: UNet skip + externally supplied residual, controlnet.py:1084,1115)
 __global__ void add_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                                long long nvec) {

@@ -31,6 +31,8 @@ cudaError_t launch_gemv(const float* x, const __half* Wt, const float* bias, flo
                         int act_silu, cudaStream_t stream);
 cudaError_t launch_axpby(const float* model_out, const float* x, float* out, const float* coef, const int* step_idx,
                          long long n, cudaStream_t stream);
+cudaError_t launch_unipc_step(const float* out, float* S, float* LS, float* H0, float* H1, const float* coef,
+                              const int* step_idx, int B, int C, int HW, int c_first, cudaStream_t stream);
 cudaError_t launch_add_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream);
 cudaError_t launch_add_int(int* p, int v, cudaStream_t stream);
 

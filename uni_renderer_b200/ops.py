@@ -12,7 +12,7 @@ from . import _lib as L
 from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
-           "timestep_sinusoid", "gemv", "axpby", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
+           "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
            "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
@@ -339,6 +339,23 @@ def axpby(prog: Optional[Program], model_out: torch.Tensor, x: torch.Tensor, out
                               _ptr(step_idx), x.numel(), _stream()), "axpby")
     if prog is not None:
         prog.keep(model_out, x, out, coef, step_idx)
+
+
+def unipc_step(prog: Optional[Program], model_out: torch.Tensor, sample: torch.Tensor, last_sample: torch.Tensor,
+               hist0: torch.Tensor, hist1: torch.Tensor, coef: torch.Tensor, step_idx: Optional[torch.Tensor] = None,
+               first_channel: int = 0):
+    """One fused UniPC update of a [B, C, H, W] fp32 latent (include/unib200.h unib200_unipc_step)."""
+    lib = L.load()
+    B, Cn = sample.shape[0], sample.shape[1]
+    HW = sample.numel() // (B * Cn)
+    for t in (model_out, sample, last_sample, hist0, hist1):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.shape == sample.shape
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and coef.shape[-1] == 10
+    L.check(lib.unib200_unipc_step(_h(prog), model_out.data_ptr(), sample.data_ptr(), last_sample.data_ptr(),
+                                   hist0.data_ptr(), hist1.data_ptr(), coef.data_ptr(), _ptr(step_idx), B, Cn, HW,
+                                   first_channel, _stream()), "unipc_step")
+    if prog is not None:
+        prog.keep(model_out, sample, last_sample, hist0, hist1, coef, step_idx)
 
 
 def add_int(prog: Optional[Program], p: torch.Tensor, v: int):

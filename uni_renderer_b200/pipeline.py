@@ -28,7 +28,9 @@ import torch
 
 from . import ops
 from .engine import Act, NetConfig, StreamNet, Workspace, pad_channels
-from .scheduler import DDIMSchedule
+from .scheduler import DDIMSchedule, UniPCSchedule
+
+SCHEDULERS = ("ddim", "unipc")
 
 MODES = ("joint", "forward", "inverse", "cycle")
 MASK_CHANNELS = 4          # the clean mask group in front of the 24 noisy attribute channels (train/train.py:1310)
@@ -46,6 +48,7 @@ class _Plan:
     bufs: Dict[str, torch.Tensor]
     flops_setup: float = 0.0
     flops_step: float = 0.0
+    scheduler: str = "ddim"
 
 
 class DualStreamSampler:
@@ -65,7 +68,8 @@ class DualStreamSampler:
     """
 
     def __init__(self, unet=None, controlnet=None, controldec=None, *, nets: Optional[Sequence[StreamNet]] = None,
-                 prediction_type: str = "epsilon", device=None, use_graph: bool = True, split_batch: bool = False):
+                 prediction_type: str = "epsilon", device=None, use_graph: bool = True, split_batch: bool = False,
+                 scheduler: str = "ddim"):
         if nets is None:
             if unet is None or controlnet is None or controldec is None:
                 raise ValueError("need the three modules or three StreamNets")
@@ -74,7 +78,11 @@ class DualStreamSampler:
         self.device = self.unet.device
         if self.device.type != "cuda":
             raise RuntimeError("DualStreamSampler runs on CUDA (sm_100a) only")
+        if scheduler not in SCHEDULERS:
+            raise ValueError(f"scheduler must be one of {SCHEDULERS}")
+        self.scheduler = scheduler                 # default of the sampling entry points ("ddim": BASELINE; "unipc": eval)
         self.schedule = DDIMSchedule(prediction_type=prediction_type)
+        self.unipc = UniPCSchedule(prediction_type=prediction_type)
         self.use_graph = use_graph
         self.split_batch = split_batch
         self.ws = Workspace(self.device)          # lane 0 (RGB stream)
@@ -91,10 +99,16 @@ class DualStreamSampler:
     # ------------------------------------------------------------------------------------------------------------
     # recording
     # ------------------------------------------------------------------------------------------------------------
-    def plan(self, mode: str, B: int, S: int, L: int = 77, steps: int = 50) -> _Plan:
+    def plan(self, mode: str, B: int, S: int, L: int = 77, steps: int = 50, scheduler: Optional[str] = None) -> _Plan:
         if mode not in MODES:
             raise ValueError(f"mode must be one of {MODES}")
-        key = (mode, B, S, L, steps)
+        scheduler = scheduler or self.scheduler
+        if scheduler not in SCHEDULERS:
+            raise ValueError(f"scheduler must be one of {SCHEDULERS}")
+        if scheduler == "unipc" and mode == "cycle":
+            raise NotImplementedError("the cycle double pass (a training-time construct, train/train.py:1388-1413) is "
+                                      "only wired for the DDIM update")
+        key = (mode, B, S, L, steps, scheduler)
         if key in self._plans:
             return self._plans[key]
         dev, ws, ws1 = self.device, self.ws, self.ws1
@@ -109,8 +123,9 @@ class DualStreamSampler:
         b["step"] = torch.zeros(1, device=dev, dtype=torch.int32)       # device-side step counter
         b["t_img"] = torch.zeros(steps, B, **f32)                       # per-step timestep tables
         b["t_attr"] = torch.zeros(steps, B, **f32)
-        b["coef_img"] = torch.zeros(steps, 2, **f32)                    # (c_out, c_x) per step
-        b["coef_attr"] = torch.zeros(steps, 2, **f32)
+        ncoef = 2 if scheduler == "ddim" else 10
+        b["coef_img"] = torch.zeros(steps, ncoef, **f32)                # DDIM (c_out, c_x) / UniPC 10 scalars per step
+        b["coef_attr"] = torch.zeros(steps, ncoef, **f32)
         x_img = Act(torch.zeros(B * S * S, pad_channels(ci), **f16), B, S, S, pad_channels(ci))
         x_attr = Act(torch.zeros(B * S * S, pad_channels(ca), **f16), B, S, S, pad_channels(ca))
         b["x_img"], b["x_attr"] = x_img.t, x_attr.t
@@ -121,6 +136,23 @@ class DualStreamSampler:
         kvD = dec.rec_kv(setup, ws, b["ehs"], B, L)
         ax_img = {"coef": b["coef_img"], "step": b["step"], "latent": b["lat_img"], "first_channel": 0}
         ax_attr = {"coef": b["coef_attr"], "step": b["step"], "latent": b["lat_attr"], "first_channel": MASK_CHANNELS}
+
+        def decode(net, wsl, mid, skips, tp, kv, ax, tag):
+            """Decoder + scheduler update of one stream: DDIM fused behind conv_out, UniPC as one fused pass on the
+            fp32 prediction (it needs the model-output history, so it cannot live in the conv epilogue)."""
+            if scheduler == "ddim":
+                net.rec_decoder(step, wsl, mid, skips, tp, kv, L, out_nchw=None, axpby=ax)
+                return
+            lat = ax["latent"]
+            for nm in ("pred", "last", "h0", "h1"):
+                b.setdefault(f"{nm}_{tag}", torch.zeros_like(b["lat_img" if tag == "img" else "lat_attr"]))
+            # a batch-half lane passes a row slice of the latent: slice the history buffers the same way
+            off = (lat.data_ptr() - b["lat_img" if tag == "img" else "lat_attr"].data_ptr()) // (lat[0].numel() * 4)
+            view = (lambda t: t[off:off + lat.shape[0]])
+            pred = view(b[f"pred_{tag}"])
+            net.rec_decoder(step, wsl, mid, skips, tp, kv, L, out_nchw=pred)
+            ops.unipc_step(step, pred, lat, view(b[f"last_{tag}"]), view(b[f"h0_{tag}"]), view(b[f"h1_{tag}"]),
+                           ax["coef"], ax["step"], first_channel=ax.get("first_channel", 0))
 
         def temb(net, prog, table, stepped=True):
             return net.rec_temb(prog, ws, table, B, step_idx=b["step"] if stepped else None, t_stride=B)
@@ -141,9 +173,9 @@ class DualStreamSampler:
             step.lane(1)
             dskA, dmidA = dec.rec_exchange(step, ws1, skU, midU, skA, midA)     # skipA + zc_dec(skipU_raw)
             if mode == "joint":
-                dec.rec_decoder(step, ws1, dmidA, dskA, tpD, kvD, L, out_nchw=None, axpby=ax_attr)
+                decode(dec, ws1, dmidA, dskA, tpD, kvD, ax_attr, "attr")
                 step.lane(0)
-                unet.rec_decoder(step, ws, dmidU, dskU, tpU, kvU, L, out_nchw=None, axpby=ax_img)
+                decode(unet, ws, dmidU, dskU, tpU, kvU, ax_img, "img")
                 step.barrier()
             else:
                 step.lane(0)
@@ -183,8 +215,8 @@ class DualStreamSampler:
                 skU, midU = unet.rec_encoder(step, wsl, _rows(x_img, b0, b1), tpU[b0:b1], _kv_rows(kvU, b0, b1, L), L)
                 dskU = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skU, d)]   # controlnet.py:1078-1087
                 dmidU = self._add(step, midU, _rows(m, b0, b1))                            # controlnet.py:1114-1115
-                unet.rec_decoder(step, wsl, dmidU, dskU, tpU[b0:b1], _kv_rows(kvU, b0, b1, L), L, out_nchw=None,
-                                 axpby=dict(ax_img, latent=b["lat_img"][b0:b1]))
+                decode(unet, wsl, dmidU, dskU, tpU[b0:b1], _kv_rows(kvU, b0, b1, L),
+                       dict(ax_img, latent=b["lat_img"][b0:b1]), "img")
             step.barrier()
             step.lane(0)
         else:  # inverse
@@ -202,13 +234,14 @@ class DualStreamSampler:
                 skA, midA = enc.rec_encoder(step, wsl, _rows(x_attr, b0, b1), tpE[b0:b1], _kv_rows(kvE, b0, b1, L), L)
                 dskA = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skA, zU)]   # controlnet.py:2446-2461
                 dmidA = self._add(step, midA, _rows(zmidU, b0, b1))                         # controlnet.py:2476-2477
-                dec.rec_decoder(step, wsl, dmidA, dskA, tpD[b0:b1], _kv_rows(kvD, b0, b1, L), L, out_nchw=None,
-                                axpby=dict(ax_attr, latent=b["lat_attr"][b0:b1]))
+                decode(dec, wsl, dmidA, dskA, tpD[b0:b1], _kv_rows(kvD, b0, b1, L),
+                       dict(ax_attr, latent=b["lat_attr"][b0:b1]), "attr")
             step.barrier()
             step.lane(0)
         ops.add_int(step, b["step"], 1)
 
         plan = _Plan(mode, B, S, L, steps, setup, step, b)
+        plan.scheduler = scheduler
         plan.flops_setup = sum(i[1] for i in setup.op_info())
         plan.flops_step = sum(i[1] for i in step.op_info())
         self._upload_schedule(plan)
@@ -237,7 +270,7 @@ class DualStreamSampler:
         return o
 
     def _upload_schedule(self, plan: _Plan):
-        ts, coefs = self.schedule.table(plan.steps)
+        ts, coefs = (self.schedule if plan.scheduler == "ddim" else self.unipc).table(plan.steps)
         t = torch.tensor(ts, dtype=torch.float32).reshape(-1, 1).expand(plan.steps, plan.B).contiguous()
         c = torch.tensor(coefs, dtype=torch.float64).to(torch.float32)
         b = plan.bufs
@@ -278,7 +311,8 @@ class DualStreamSampler:
     def launches_per_call(self, plan: _Plan) -> int:
         return plan.setup.num_launches + plan.steps * plan.step.num_launches
 
-    def _sample(self, mode, latents_img, latents_attr, prompt_embeds, num_inference_steps, guidance_scale):
+    def _sample(self, mode, latents_img, latents_attr, prompt_embeds, num_inference_steps, guidance_scale,
+                scheduler=None):
         if guidance_scale not in (0, 0.0, None):
             raise NotImplementedError("classifier-free guidance is not supported (every shipped Uni-Renderer caller "
                                       "passes guidance_scale=0, eval/test_real.py:548)")
@@ -286,7 +320,7 @@ class DualStreamSampler:
         if S != S2:
             raise ValueError("square latents only")
         L = prompt_embeds.shape[1]
-        plan = self.plan(mode, B, S, L, num_inference_steps)
+        plan = self.plan(mode, B, S, L, num_inference_steps, scheduler)
         self.load_inputs(plan, latents_img, latents_attr, prompt_embeds)
         self.run(plan)
         dev, dt = latents_img.device, latents_img.dtype
@@ -296,26 +330,26 @@ class DualStreamSampler:
 
     @torch.no_grad()
     def joint_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
-                     guidance_scale: float = 0.0):
+                     guidance_scale: float = 0.0, scheduler: Optional[str] = None):
         """Both streams noisy, same timestep (pipeline_new_d4p.py:1391-1453).  Returns (latents_img, latents_attr)."""
         _, img, attr = self._sample("joint", latents_img, latents_attr, prompt_embeds, num_inference_steps,
-                                    guidance_scale)
+                                    guidance_scale, scheduler)
         return img, attr
 
     @torch.no_grad()
     def forward_render(self, latents_img, attr_latents, prompt_embeds, num_inference_steps: int = 50,
-                       guidance_scale: float = 0.0):
+                       guidance_scale: float = 0.0, scheduler: Optional[str] = None):
         """attributes -> RGB: t_attr = 0, t_img: T -> 0 (pipeline.py:1455,1586-1653).  Returns latents_img."""
         return self._sample("forward", latents_img, attr_latents, prompt_embeds, num_inference_steps,
-                            guidance_scale)[1]
+                            guidance_scale, scheduler)[1]
 
     @torch.no_grad()
     def inverse_render(self, image_latents, latents_attr, prompt_embeds, num_inference_steps: int = 50,
-                       guidance_scale: float = 0.0):
+                       guidance_scale: float = 0.0, scheduler: Optional[str] = None):
         """RGB -> attributes: t_img = 0, t_attr: T -> 0 (pipeline.py:2475,2627-2733).  Returns the 24 attribute
         channels (the clean mask group is sliced off like pipeline.py:2691)."""
         return self._sample("inverse", image_latents, latents_attr, prompt_embeds, num_inference_steps,
-                            guidance_scale)[2][:, MASK_CHANNELS:]
+                            guidance_scale, scheduler)[2][:, MASK_CHANNELS:]
 
     @torch.no_grad()
     def cycle_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
