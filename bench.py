@@ -347,11 +347,13 @@ def run_b200(a):
         # DRAM traffic of the same kernel family from the committed ncu capture of one denoising step (profiles/):
         # per launch, like `achieved`; ncu replays each launch cold-cache, so L2-resident activations count as DRAM
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1b_gemm_traffic.json")
-        if a.mode == "joint" and B == 4 and S == 64 and os.path.exists(tp):
-            with open(tp) as f:
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+        if a.mode == "joint" and B == 4 and S == 64 and cands:
+            with open(cands[-1]) as f:           # newest capture (files are named per round: r1b_, r1c_, ...)
                 tj = json.load(f)
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r1b_gemm_traffic.json (ncu, cold-cache replay)"
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_src = f"profiles/{os.path.basename(cands[-1])} (ncu, cold-cache replay)"
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv / linear family)",
                             "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                             "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
