@@ -68,6 +68,6 @@ for i, (name, B, H, cins, kind, cout, res, geglu) in enumerate(SHAPES):
     e = rows[k]
     gap = int(e[0] - rows[k - 1][8]) if k > 0 else 0
     rel = [int(e[j] - e[0]) if e[j] else -1 for j in range(1, 9)]
-    ext = [int(e[j] - e[0]) if e[j] else -1 for j in (9, 10, 11, 12, 13)]
-    print(f"{name:26s} {gap:6d} " + " ".join(f"{v:6d}" for v in rel) + "   epi0end/acc1/epi1/tma1first/tma1last: " +
+    ext = [int(e[j] - e[0]) if e[j] else -1 for j in (14, 15, 9, 11)]
+    print(f"{name:26s} {gap:6d} " + " ".join(f"{v:6d}" for v in rel) + "   pdlwait/decoded/epi0end/epi1: " +
           " ".join(f"{v:6d}" for v in ext))

@@ -438,6 +438,17 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   }
   p.m_tiles = (d->M + kBM * p.cg - 1) / (kBM * p.cg);
   p.n_tiles = (d->N + bn - 1) / bn;
+  {
+    auto recip = [](unsigned long long dv) { return (1ull << 40) / dv + 1ull; };
+    auto ilog2 = [](int x) { int s = 0; while ((1 << s) < x) ++s; return s; };
+    if (static_cast<long long>(p.m_tiles) * p.n_tiles * 16 >= (1 << 20)) return fail("conv_gemm: too many tiles");
+    p.mul_tiles = recip(static_cast<unsigned long long>(p.m_tiles) * p.n_tiles);
+    p.mul_ntiles = recip(static_cast<unsigned long long>(p.n_tiles));
+    p.w_shift = ilog2(p.W);
+    p.h_shift = ilog2(p.H);
+    const int rpb = p.rows_per_batch;
+    p.rpb_shift = (rpb > 0 && (rpb & (rpb - 1)) == 0) ? ilog2(rpb) : -1;
+  }
   p.bias = d->bias;
   p.bias_bstride = d->bias_bstride;
   p.res = static_cast<const __half*>(d->res);

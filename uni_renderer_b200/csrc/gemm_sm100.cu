@@ -43,15 +43,33 @@ struct GemmCfg {
 struct WorkItem {
   int mt, nt, kb0, kb1;
 };
+// Integer division has no hardware unit: a runtime-divisor `/` costs ~100+ cycles, and the work decode of every tile
+// (three roles) plus the tile-origin decode used to burn ~0.9 us at the head of every launch.  Divisors are fixed per
+// launch, so the host precomputes multiply-shift reciprocals (exact for dividends and divisors < 2^20) and shifts for
+// the power-of-two image dims.
+__device__ __forceinline__ int fast_div(int n, unsigned long long mul) {       // n / d with mul = floor(2^40 / d) + 1
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(n)) * mul) >> 40);
+}
+__device__ __forceinline__ int batch_of_row(const GemmParams& p, int m) {
+  return p.rpb_shift >= 0 ? (m >> p.rpb_shift) : m / p.rows_per_batch;
+}
 __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int w) {
   WorkItem wi;
   const int tiles = p.m_tiles * p.n_tiles;
-  const int split = w / tiles;
-  const int rem = w - split * tiles;
-  wi.mt = rem / p.n_tiles;
+  int split = 0, rem = w;
+  if (p.splits > 1) {
+    split = fast_div(w, p.mul_tiles);
+    rem = w - split * tiles;
+  }
+  wi.mt = fast_div(rem, p.mul_ntiles);
   wi.nt = rem - wi.mt * p.n_tiles;
-  wi.kb0 = static_cast<int>((static_cast<long long>(split) * p.total_kb) / p.splits);
-  wi.kb1 = static_cast<int>((static_cast<long long>(split + 1) * p.total_kb) / p.splits);
+  if (p.splits > 1) {
+    wi.kb0 = static_cast<int>((static_cast<long long>(split) * p.total_kb) / p.splits);
+    wi.kb1 = static_cast<int>((static_cast<long long>(split + 1) * p.total_kb) / p.splits);
+  } else {
+    wi.kb0 = 0;
+    wi.kb1 = p.total_kb;
+  }
   return wi;
 }
 
@@ -60,7 +78,7 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int w) {
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, int m, int n) {
   const int N = p.N;
   if (n >= N) return;
-  const int b = m / p.rows_per_batch;
+  const int b = batch_of_row(p, m);
   if (p.bias != nullptr) {
     const float* bp = p.bias + static_cast<size_t>(b) * p.bias_bstride + n;
     if (n + 16 <= N) {
@@ -210,6 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   // buffer) to complete; everything above overlapped its tail
   if (p.pdl_early) pdl_launch();
   pdl_wait();
+  if (threadIdx.x == 0) GEMM_TRACE(14);
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
@@ -222,11 +241,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     for (int w = cta; w < total_work; w += ncta) {
       const WorkItem wi = decode_work(p, w);
       const int p0 = (wi.mt * CG + static_cast<int>(rank)) * kBM;
-      const int w0 = p0 % p.W;
-      const int h0 = (p0 / p.W) % p.H;
-      const int b0 = p0 / (p.W * p.H);
+      const int w0 = p0 & ((1 << p.w_shift) - 1);                     // W, H are powers of two (linear: W = 2^30)
+      const int h0 = (p0 >> p.w_shift) & ((1 << p.h_shift) - 1);
+      const int b0 = p0 >> (p.w_shift + p.h_shift);
       int seg = 0, tap = 0, cb = 0;
-      {
+      if (wi.kb0 > 0) {                                               // split-K only: locate the first K block
         int k = wi.kb0;
         while (seg < p.nseg) {
           const int per = p.seg[seg].ntaps * p.seg[seg].nkb;
@@ -257,9 +276,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       };
       set_tap();
       const int brow = wi.nt * BN + static_cast<int>(rank) * (BN / CG);   // pair: this CTA's half of the B tile
+#ifdef UNIB_GEMM_TRACE
+      if (w == cta && lane == 0) GEMM_TRACE(15);
+#endif
       for (int kb = wi.kb0; kb < wi.kb1; ++kb) {
         mbar_wait(empty_bar(stage), ph ^ 1);
         if (elect_one()) {
+#ifdef UNIB_GEMM_TRACE
+          if (w == cta && kb == wi.kb0) GEMM_TRACE(2);
+#endif
           const uint32_t a_dst = base + stage * Cfg::kStageBytes;
           if (CG == 2) {
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
@@ -298,6 +323,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           mbar_wait(full_bar(stage), ph);
           tc_fence_after();
           if (elect_one()) {
+#ifdef UNIB_GEMM_TRACE
+            if (w == cta && kb == wi.kb0) GEMM_TRACE(3);
+#endif
             const uint32_t a_addr = base + stage * Cfg::kStageBytes;
             const uint64_t a_desc = make_desc_kmajor_sw128(a_addr);
             const uint64_t b_desc = make_desc_kmajor_sw128(a_addr + Cfg::kABytes);
@@ -391,8 +419,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         if (m_last >= p.M) m_last = p.M - 1;
         // a warp whose rows all lie beyond M (M < 128) must not index the per-batch bias table out of range
         const int m_first = m0 < p.M ? m0 : p.M - 1;
-        const int b_first = per_batch ? m_first / p.rows_per_batch : 0;
-        const int b_last = per_batch ? m_last / p.rows_per_batch : b_first;
+        const int b_first = per_batch ? batch_of_row(p, m_first) : 0;
+        const int b_last = per_batch ? batch_of_row(p, m_last) : b_first;
         if (has_bias || has_ln) {
           __syncwarp();                                        // previous tile's bias reads are done
           if (has_bias) {
@@ -436,7 +464,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         tc_fence_after();
         if (tl == 0 && leader) GEMM_TRACE(5);
         if (tl == 1 && leader) GEMM_TRACE(11);
-        const int my_b = per_batch ? m / p.rows_per_batch : 0;
+        const int my_b = per_batch ? batch_of_row(p, m) : 0;
         const float* my_bias = bias_s + ((my_b > b_first) ? BN : 0);
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1

@@ -41,6 +41,9 @@ struct GemmParams {
   ConvSeg seg[kMaxSeg];
   int total_kb;              // sum over segments of ntaps * nkb
   int splits;                // split-K factor (>1 => fp32 partials, finalize kernel applies the epilogue)
+  unsigned long long mul_tiles, mul_ntiles;   // floor(2^40 / d) + 1 for d = m_tiles * n_tiles, n_tiles (fast_div)
+  int w_shift, h_shift;      // log2 of W, H
+  int rpb_shift;             // log2(rows_per_batch) if that is a power of two, else -1
   int m_tiles, n_tiles;      // m_tiles counts 128-row tiles (cg = 1) or 256-row PAIR tiles (cg = 2)
   int cg;                    // CTAs per MMA: 2 = cta_group::2 CTA pairs (cluster of 2 along M)
   // epilogue
