@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GnParams p) {
 // GroupNorm apply (+ optional SiLU): reduces the chunk partials in a fixed order, builds per-channel scale/shift in
 // shared memory and streams rows (4 independent 128-bit loads in flight per thread).  Writes the concatenated
 // [rows, C1+C2] tensor.
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
+__global__ void __launch_bounds__(512) gn_apply_kernel(GnParams p) {
   pdl_launch();      // PDL: see common.cuh
   pdl_wait();
   extern __shared__ float sm[];            // scale[C], shift[C], red[8][G][2]
@@ -128,37 +128,45 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnParams p) {
   const int CV = C >> 3;
   const int r0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.HW) / gridDim.x);
   const int r1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.HW) / gridDim.x);
-  const long long total = static_cast<long long>(r1 - r0) * CV;
-  auto load = [&](long long i) -> uint4 {
-    const int r = r0 + static_cast<int>(i / CV);
-    const int c0 = static_cast<int>(i % CV) * 8;
-    const size_t row = static_cast<size_t>(b) * p.HW + r;
-    const __half* src = (c0 < p.C1) ? p.x1 + row * p.ld1 + c0 : p.x2 + row * p.ld2 + (c0 - p.C1);
-    return *reinterpret_cast<const uint4*>(src);
-  };
-  auto emit = [&](long long i, const uint4& raw) {
-    const int r = r0 + static_cast<int>(i / CV);
-    const int c0 = static_cast<int>(i % CV) * 8;
-    const size_t row = static_cast<size_t>(b) * p.HW + r;
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    uint32_t o[4];
+  // each thread owns ONE 8-channel vector column (its scale / shift live in registers) and walks rows: no per-element
+  // index division (a runtime-divisor 64-bit `/` and `%` per vector used to dominate this loop)
+  {
+    const int arp = blockDim.x / CV;               // rows in flight per pass
+    const int av = threadIdx.x % CV, arow = threadIdx.x / CV;
+    if (arow < arp) {
+      const int c0 = av * 8;
+      float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      float y0 = f.x * scale[c0 + 2 * j] + shift[c0 + 2 * j];
-      float y1 = f.y * scale[c0 + 2 * j + 1] + shift[c0 + 2 * j + 1];
-      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      o[j] = pack_half2(y0, y1);
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+      const __half* src;
+      int ld;
+      if (c0 < p.C1) { src = p.x1 + c0; ld = p.ld1; } else { src = p.x2 + (c0 - p.C1); ld = p.ld2; }
+      src += static_cast<size_t>(b) * p.HW * ld;
+      __half* dst = p.out + static_cast<size_t>(b) * p.HW * C + c0;
+      auto emit = [&](int r, const uint4& raw) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          float y0 = f.x * sc[2 * j] + sh[2 * j];
+          float y1 = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+          o[j] = pack_half2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      };
+      int r = r0 + arow;
+      for (; r + 3 * arp < r1; r += 4 * arp) {
+        const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld);
+        const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld);
+        const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
+        emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
+      }
+      for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
     }
-    *reinterpret_cast<uint4*>(p.out + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-  };
-  long long i = threadIdx.x;
-  const long long st = blockDim.x;
-  for (; i + 3 * st < total; i += 4 * st) {
-    const uint4 a0 = load(i), a1 = load(i + st), a2 = load(i + 2 * st), a3 = load(i + 3 * st);
-    emit(i, a0); emit(i + st, a1); emit(i + 2 * st, a2); emit(i + 3 * st, a3);
   }
-  for (; i < total; i += st) emit(i, load(i));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -265,37 +273,45 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
     shift[c] = p.beta[c] - gstat[2 * g] * sc;
   }
   __syncthreads();
-  const long long total = static_cast<long long>(r1 - r0) * CV;
-  auto load = [&](long long i) -> uint4 {
-    const int r = r0 + static_cast<int>(i / CV);
-    const int c0 = static_cast<int>(i % CV) * 8;
-    const size_t row = static_cast<size_t>(b) * p.HW + r;
-    const __half* src = (c0 < p.C1) ? p.x1 + row * p.ld1 + c0 : p.x2 + row * p.ld2 + (c0 - p.C1);
-    return *reinterpret_cast<const uint4*>(src);
-  };
-  auto emit = [&](long long i, const uint4& raw) {
-    const int r = r0 + static_cast<int>(i / CV);
-    const int c0 = static_cast<int>(i % CV) * 8;
-    const size_t row = static_cast<size_t>(b) * p.HW + r;
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    uint32_t o[4];
+  // each thread owns ONE 8-channel vector column (its scale / shift live in registers) and walks rows: no per-element
+  // index division (a runtime-divisor 64-bit `/` and `%` per vector used to dominate this loop)
+  {
+    const int arp = blockDim.x / CV;               // rows in flight per pass
+    const int av = threadIdx.x % CV, arow = threadIdx.x / CV;
+    if (arow < arp) {
+      const int c0 = av * 8;
+      float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      float y0 = f.x * scale[c0 + 2 * j] + shift[c0 + 2 * j];
-      float y1 = f.y * scale[c0 + 2 * j + 1] + shift[c0 + 2 * j + 1];
-      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      o[j] = pack_half2(y0, y1);
+      for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+      const __half* src;
+      int ld;
+      if (c0 < p.C1) { src = p.x1 + c0; ld = p.ld1; } else { src = p.x2 + (c0 - p.C1); ld = p.ld2; }
+      src += static_cast<size_t>(b) * p.HW * ld;
+      __half* dst = p.out + static_cast<size_t>(b) * p.HW * C + c0;
+      auto emit = [&](int r, const uint4& raw) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          float y0 = f.x * sc[2 * j] + sh[2 * j];
+          float y1 = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+          if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+          o[j] = pack_half2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      };
+      int r = r0 + arow;
+      for (; r + 3 * arp < r1; r += 4 * arp) {
+        const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld);
+        const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld);
+        const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
+        emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
+      }
+      for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
     }
-    *reinterpret_cast<uint4*>(p.out + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-  };
-  long long i = threadIdx.x;
-  const long long st = blockDim.x;
-  for (; i + 3 * st < total; i += 4 * st) {
-    const uint4 a0 = load(i), a1 = load(i + st), a2 = load(i + 2 * st), a3 = load(i + 3 * st);
-    emit(i, a0); emit(i + st, a1); emit(i + 2 * st, a2); emit(i + 3 * st, a3);
   }
-  for (; i < total; i += st) emit(i, load(i));
   cluster_sync_all();                      // no CTA may exit while a peer can still read its `part`
 }
 
@@ -370,7 +386,7 @@ cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStrea
   if (e != cudaSuccess) return e;
   int achunks = (4 * num_sms + B - 1) / B;
   if (achunks > p.HW) achunks = p.HW;
-  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_kernel, dim3(dim3(achunks, B)), dim3(256), (2 * C + 16 * p.G) * sizeof(float), stream, p));
+  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_kernel, dim3(dim3(achunks, B)), dim3(512), (2 * C + 16 * p.G) * sizeof(float), stream, p));
   return cudaGetLastError();
 }
 
