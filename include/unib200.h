@@ -92,6 +92,8 @@ typedef struct {
   const void* weight;       /* packed fp16 [N, Ktot]                                                              */
   const float* bias;        /* fp32 [N] or [B][N] (bias_bstride = N), may be NULL                                 */
   int bias_bstride;
+  const int* bias_step;     /* optional device counter: the bias table of step s starts at bias + s * bias_step_stride */
+  int64_t bias_step_stride; /* (time-embedding projections tabulated for every step of a sampling loop)             */
   const void* res;          /* optional fp16 residual [M, ldr] added before the activation                        */
   int ldr;
   void* out;                /* fp16 [M, ldc] (or NCHW, see flags)                                                 */

@@ -25,6 +25,7 @@ class GemmDesc(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("nseg", C.c_int),
         ("seg", Seg * 4),
         ("weight", C.c_void_p), ("bias", C.c_void_p), ("bias_bstride", C.c_int),
+        ("bias_step", C.c_void_p), ("bias_step_stride", C.c_int64),
         ("res", C.c_void_p), ("ldr", C.c_int),
         ("out", C.c_void_p), ("ldc", C.c_int),
         ("flags", C.c_int), ("splits", C.c_int),

@@ -451,6 +451,8 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   }
   p.bias = d->bias;
   p.bias_bstride = d->bias_bstride;
+  p.bias_step = d->bias_step;
+  p.bias_step_stride = d->bias_step_stride;
   p.res = static_cast<const __half*>(d->res);
   p.ldr = d->ldr;
   p.out = d->out;

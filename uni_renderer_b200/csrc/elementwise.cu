@@ -386,7 +386,10 @@ cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStrea
   if (e != cudaSuccess) return e;
   int achunks = (4 * num_sms + B - 1) / B;
   if (achunks > p.HW) achunks = p.HW;
-  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_kernel, dim3(dim3(achunks, B)), dim3(512), (2 * C + 16 * p.G) * sizeof(float), stream, p));
+  static const int apply_threads_env = getenv("UNIB200_GN_APPLY_THREADS") ? atoi(getenv("UNIB200_GN_APPLY_THREADS")) : 0;
+  int athreads = apply_threads_env ? apply_threads_env : 256;
+  if (athreads < CV) athreads = 512;            // a block must hold at least one row of 8-channel vectors
+  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_kernel, dim3(dim3(achunks, B)), dim3(athreads), (2 * C + 16 * p.G) * sizeof(float), stream, p));
   return cudaGetLastError();
 }
 

@@ -80,7 +80,8 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
   if (n >= N) return;
   const int b = batch_of_row(p, m);
   if (p.bias != nullptr) {
-    const float* bp = p.bias + static_cast<size_t>(b) * p.bias_bstride + n;
+    const float* bp = p.bias + (p.bias_step ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0) +
+                      static_cast<size_t>(b) * p.bias_bstride + n;
     if (n + 16 <= N) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
@@ -378,6 +379,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       const bool has_ln = p.ln_rowstats != nullptr;
       const bool want_stats = p.rowstats_out != nullptr;
       const bool per_batch = p.bias_bstride != 0;
+      const float* const bias_base = p.bias + ((p.bias != nullptr && p.bias_step != nullptr)
+                                                   ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0);
       __half* const outp = reinterpret_cast<__half*>(p.out);
       auto load_res = [&](uint32_t* r, int m, int n) {
         if (m < p.M && n + 32 <= n_out) {
@@ -431,7 +434,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                 const int col = c * 32 + lane;
                 const int n = wi.nt * BN + col;
                 const int bb = r == 0 ? b_first : b_last;
-                bias_s[r * BN + col] = (n < p.N) ? __ldg(p.bias + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
+                bias_s[r * BN + col] = (n < p.N) ? __ldg(bias_base + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
               }
           }
           if (has_ln) {

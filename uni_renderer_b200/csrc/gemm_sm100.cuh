@@ -49,6 +49,8 @@ struct GemmParams {
   // epilogue
   const float* bias;         // [bias_rows][N] fp32 (row b used for rows of batch b when bias_bstride != 0)
   int bias_bstride;
+  const int* bias_step;      // optional: bias table of step s = bias + s * bias_step_stride (device-side step counter)
+  long long bias_step_stride;
   int rows_per_batch;        // H*W of the OUTPUT (for batch index of a row)
   const __half* res;         // optional residual [M, ldr]
   int ldr;

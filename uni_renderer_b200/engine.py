@@ -61,6 +61,18 @@ class Act:
         return self.t.view(self.B, self.H, self.W, self.t.shape[1])[..., :self.C].permute(0, 3, 1, 2)
 
 
+class Temb:
+    """The [B, sum Cout] table of time-embedding projections the conv1 epilogues index -- either computed for the
+    current call (step is None) or tabulated for EVERY step of a sampling loop (rec_temb_table): then the table of step
+    s starts s * step_stride floats further and the GEMM reads the device-side step counter itself."""
+
+    def __init__(self, t: torch.Tensor, step: Optional[torch.Tensor] = None, step_stride: int = 0):
+        self.t, self.step, self.step_stride = t, step, step_stride
+
+    def __getitem__(self, rows):            # batch slice (the per-step stride is unchanged)
+        return Temb(self.t[rows], self.step, self.step_stride)
+
+
 class Workspace:
     """Per-lane scratch shared by sequentially executed ops + a recycling pool for temporaries."""
 
@@ -230,7 +242,15 @@ class StreamNet:
         ops.gemv(prog, sin, self.w["te1.w"], self.w["te1.b"], e1, silu=True)
         ops.gemv(prog, e1, self.w["te2.w"], self.w["te2.b"], e2, silu=True)     # silu(temb): every consumer applies it
         ops.gemv(prog, e2, self.w["tproj.w"], self.w["tproj.b"], tproj, silu=False)
-        return tproj
+        return Temb(tproj)
+
+    def rec_temb_table(self, prog, t_table: torch.Tensor, step_counter: torch.Tensor) -> Temb:
+        """Time-embedding projections for ALL steps of a loop at once: t_table is [steps, B] (the timesteps are known
+        before the loop starts), the result [steps * B, sum Cout].  Recorded into a program that runs once per plan;
+        the per-step programs then contain no time-embedding kernels at all."""
+        steps, B = t_table.shape
+        full = self.rec_temb(prog, None, t_table.reshape(-1), steps * B)
+        return Temb(full.t[:B], step_counter, B * self.temb_total)
 
     def rec_kv(self, prog, ws: Workspace, ehs: torch.Tensor, B: int, L: int):
         """attn2 to_k/to_v of every transformer block on the text context (step-invariant: ehs is constant over the
@@ -253,7 +273,7 @@ class StreamNet:
                       ws.gn_scratch, B=a.B, HW=a.H * a.W, groups=self.cfg.norm_num_groups, eps=eps, silu=silu)
         return out
 
-    def rec_resnet(self, prog, ws, r: str, srcs: Sequence[Act], tproj: torch.Tensor) -> Act:
+    def rec_resnet(self, prog, ws, r: str, srcs: Sequence[Act], tproj: Temb) -> Act:
         a = srcs[0]
         B, H, W, M = a.B, a.H, a.W, a.M
         Cin = sum(s.C for s in srcs)
@@ -262,7 +282,8 @@ class StreamNet:
         h1 = ws.get(M, Cout)
         off = self.temb_off[r]
         ops.conv_gemm(prog, [(n1, Cin, SEG_3x3)], self.w[r + ".conv1.w"], h1, M=M, N=Cout, B=B, H=H, W=W,
-                      bias=tproj[:, off:off + Cout], bias_bstride=self.temb_total, partial=ws.partial)
+                      bias=tproj.t[:, off:off + Cout], bias_bstride=self.temb_total, bias_step=tproj.step,
+                      bias_step_stride=tproj.step_stride, partial=ws.partial)
         ws.put(n1)
         n2 = self._gn(prog, ws, r + ".norm2", [Act(h1, B, H, W, Cout)], self.cfg.norm_eps, True)
         ws.put(h1)

@@ -182,7 +182,8 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 # ---------------------------------------------------------------------------------------------------------------
 def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, int]], weight: torch.Tensor,
               out: torch.Tensor, *, M: int, N: int, B: int = 0, H: int = 0, W: int = 0,
-              bias: Optional[torch.Tensor] = None, bias_bstride: int = 0, res: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, bias_bstride: int = 0, bias_step: Optional[torch.Tensor] = None,
+              bias_step_stride: int = 0, res: Optional[torch.Tensor] = None,
               flags: int = 0, splits: int = 0, partial: Optional[torch.Tensor] = None,
               axpby: Optional[torch.Tensor] = None, axpby_step: Optional[torch.Tensor] = None,
               aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
@@ -203,6 +204,9 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.stride(-1) == 1
     d.bias, d.bias_bstride = _ptr(bias), bias_bstride
+    if bias_step is not None:
+        assert bias_step.dtype == torch.int32
+        d.bias_step, d.bias_step_stride = bias_step.data_ptr(), bias_step_stride
     if res is not None:
         d.ldr = _check_2d(res, "conv_gemm res")
     d.res = _ptr(res)
@@ -228,7 +232,7 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
         ln_keep = (rs, wsum)
     L.check(lib.unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
     if prog is not None:
-        prog.keep(*(s[0] for s in segs), weight, out, bias, res, partial, axpby, axpby_step, aux, aux_out, rowstats_out,
+        prog.keep(*(s[0] for s in segs), weight, out, bias, bias_step, res, partial, axpby, axpby_step, aux, aux_out, rowstats_out,
                   *ln_keep)
 
 

@@ -49,6 +49,8 @@ class _Plan:
     flops_setup: float = 0.0
     flops_step: float = 0.0
     scheduler: str = "ddim"
+    once: Optional[ops.Program] = None
+    once: Optional[ops.Program] = None
 
 
 class DualStreamSampler:
@@ -85,6 +87,8 @@ class DualStreamSampler:
         self.unipc = UniPCSchedule(prediction_type=prediction_type)
         self.use_graph = use_graph
         self.split_batch = split_batch
+        import os
+        self.temb_table = os.environ.get("UNIB200_TEMB_TABLE", "1") != "0"
         self.ws = Workspace(self.device)          # lane 0 (RGB stream)
         self.ws1 = Workspace(self.device)         # lane 1 (attribute stream): lanes run concurrently, no shared scratch
         self._plans: Dict[Tuple, _Plan] = {}
@@ -154,8 +158,16 @@ class DualStreamSampler:
             ops.unipc_step(step, pred, lat, view(b[f"last_{tag}"]), view(b[f"h0_{tag}"]), view(b[f"h1_{tag}"]),
                            ax["coef"], ax["step"], first_channel=ax.get("first_channel", 0))
 
+        once = ops.Program()      # runs ONCE per plan: everything that only depends on the schedule
+
         def temb(net, prog, table, stepped=True):
-            return net.rec_temb(prog, ws, table, B, step_idx=b["step"] if stepped else None, t_stride=B)
+            """Time-embedding projections: a constant-t table is computed where it is used (setup program); the
+            per-step ones are tabulated for all steps up front (the timesteps of the loop are known in advance)."""
+            if not stepped:
+                return net.rec_temb(prog, ws, table, B)
+            if not self.temb_table:       # A/B: recompute the projections inside every step
+                return net.rec_temb(prog, ws, table, B, step_idx=b["step"], t_stride=B)
+            return net.rec_temb_table(once, table, b["step"])
 
         if mode in ("joint", "cycle"):
             # The RGB stream (lane 0) and the attribute stream (lane 1) only meet at the exchange: two parallel
@@ -242,9 +254,11 @@ class DualStreamSampler:
 
         plan = _Plan(mode, B, S, L, steps, setup, step, b)
         plan.scheduler = scheduler
+        plan.once = once
         plan.flops_setup = sum(i[1] for i in setup.op_info())
         plan.flops_step = sum(i[1] for i in step.op_info())
         self._upload_schedule(plan)
+        once.run()                 # needs the timestep tables uploaded just above
         if self.use_graph:
             # one eager pass first (sets every kernel's function attributes outside capture), then capture on a side
             # stream: the legacy default stream cannot be captured
