@@ -316,7 +316,7 @@ def run_b200(a):
             "step_tflops_per_gpu": flops_call * a.steps / (ms_res * 1e-3) / 1e12,
             "step_frac_of_tensor_peak": flops_call * a.steps / (ms_res * 1e-3) / 1e12 / peaks["tflops_sustained"]}
 
-    if rank == 0 and a.mode == "joint" and not a.no_roofline:
+    if rank == 0 and a.mode == "joint" and not a.no_roofline and T > 5:
         # BASELINE.json's second figure, "UNet ms/step": the RGB UNet alone (the step of the forward-rendering loop:
         # UNet encoder + exchange adds + decoder + DDIM update, attribute encoder hoisted) at the same batch, CUDA events
         uplan = sampler.plan("forward", B, S, L, T)

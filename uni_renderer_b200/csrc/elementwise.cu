@@ -376,7 +376,10 @@ cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStrea
   if (chunks < 1) chunks = 1;
   p.stat_chunks = chunks;
   const int CV = C >> 3;
-  int rpb = 512 / CV;
+  static const int stats_threads_env = getenv("UNIB200_GN_STATS_THREADS") ? atoi(getenv("UNIB200_GN_STATS_THREADS")) : 0;
+  int sthreads = stats_threads_env ? stats_threads_env : 512;
+  if (sthreads < CV) sthreads = 512;
+  int rpb = sthreads / CV;
   if (rpb < 1) rpb = 1;
   const int rows_per_chunk = (p.HW + chunks - 1) / chunks;
   if (rpb > rows_per_chunk) rpb = rows_per_chunk;
