@@ -435,22 +435,35 @@ class StreamNet:
         if taps is None and h is not mid:
             ws.put(h.t)
 
-    def rec_exchange(self, prog, ws, src: Sequence[Act], src_mid: Act, dst: Sequence[Act], dst_mid: Act):
-        """out_i = dst_i + zero_conv_i(src_i): the dual-stream residual exchange (controlnet.py:1754-1775 + :1078-1087
-        for attr->RGB, :2446-2461,2476-2477 for RGB->attr) as ONE 1x1-GEMM per skip with the add in its epilogue."""
+    def _zc(self, name: str, scale: float):
+        """Packed weight + bias of one exchange zero-conv; `conditioning_scale` (controlnet.py:1774-1775 multiplies
+        the 13 zero-conv outputs by it) is folded into both, cached per scale."""
+        if scale == 1.0:
+            return self.w[name + ".w"], self.w[name + ".b"]
+        key = f"{name}@{scale!r}"
+        if key + ".w" not in self.w:
+            self.w[key + ".w"] = (self.w[name + ".w"].float() * scale).half().contiguous()
+            self.w[key + ".b"] = (self.w[name + ".b"] * scale).contiguous()
+        return self.w[key + ".w"], self.w[key + ".b"]
+
+    def rec_exchange(self, prog, ws, src: Sequence[Act], src_mid: Act, dst: Sequence[Act], dst_mid: Act,
+                     scale: float = 1.0):
+        """out_i = dst_i + scale * zero_conv_i(src_i): the dual-stream residual exchange (controlnet.py:1754-1775 +
+        :1078-1087 for attr->RGB, :2446-2461,2476-2477 for RGB->attr) as ONE 1x1-GEMM per skip with the add in its
+        epilogue."""
         zc = self.zc_prefix
         outs = []
         for i, (s, dd) in enumerate(zip(src, dst)):
             o = Act(torch.empty(s.M, s.C, device=self.device, dtype=torch.float16), s.B, s.H, s.W, s.C)
-            ops.conv_gemm(prog, [(s.t, s.C, SEG_1x1)], self.w[f"{zc}_down_blocks.{i}.w"], o.t, M=s.M, N=s.C, B=s.B,
-                          bias=self.w[f"{zc}_down_blocks.{i}.b"], res=dd.t if dd is not None else None,
-                          partial=ws.partial)
+            wz, bz = self._zc(f"{zc}_down_blocks.{i}", scale)
+            ops.conv_gemm(prog, [(s.t, s.C, SEG_1x1)], wz, o.t, M=s.M, N=s.C, B=s.B,
+                          bias=bz, res=dd.t if dd is not None else None, partial=ws.partial)
             outs.append(o)
         m = Act(torch.empty(src_mid.M, src_mid.C, device=self.device, dtype=torch.float16), src_mid.B, src_mid.H,
                 src_mid.W, src_mid.C)
-        ops.conv_gemm(prog, [(src_mid.t, src_mid.C, SEG_1x1)], self.w[f"{zc}_mid_block.w"], m.t, M=m.M, N=m.C, B=m.B,
-                      bias=self.w[f"{zc}_mid_block.b"], res=dst_mid.t if dst_mid is not None else None,
-                      partial=ws.partial)
+        wz, bz = self._zc(f"{zc}_mid_block", scale)
+        ops.conv_gemm(prog, [(src_mid.t, src_mid.C, SEG_1x1)], wz, m.t, M=m.M, N=m.C, B=m.B,
+                      bias=bz, res=dst_mid.t if dst_mid is not None else None, partial=ws.partial)
         return outs, m
 
 

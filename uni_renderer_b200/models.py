@@ -211,6 +211,73 @@ class _NetModule(nn.Module):
         self._invalidate()
         return r
 
+    # -- diffusers-style persistence (train/train.py:905-916,1470-1476 load and save the three networks this way) ----
+    WEIGHTS_NAME = "diffusion_pytorch_model.bin"
+    SAFETENSORS_WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"
+    CONFIG_NAME = "config.json"
+
+    def save_pretrained(self, save_directory: str, safe_serialization: bool = True, **unused):
+        """`<dir>/config.json` + `<dir>/diffusion_pytorch_model.safetensors` (or `.bin`), the layout diffusers'
+        ModelMixin.save_pretrained writes and `from_pretrained` reads."""
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {"_class_name": type(self).__name__, "_diffusers_version": "0.24.0.dev0"}
+        cfg.update({k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.items()})
+        with open(os.path.join(save_directory, self.CONFIG_NAME), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, self.SAFETENSORS_WEIGHTS_NAME), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, self.WEIGHTS_NAME))
+
+    @classmethod
+    def load_config(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, **unused) -> Dict[str, Any]:
+        import json
+        import os
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        path = os.path.join(d, cls.CONFIG_NAME)
+        if not os.path.isfile(path):
+            raise EnvironmentError(f"{path} not found (only local directories are supported: there is no hub access)")
+        with open(path) as f:
+            return json.load(f)
+
+    @classmethod
+    def from_config(cls, config: Dict[str, Any], **overrides):
+        """Construct from a diffusers config dict: keys starting with '_' and keys the constructor does not know are
+        dropped (diffusers' ConfigMixin.extract_init_dict does the same)."""
+        import inspect
+        init_weights = overrides.pop("_init_weights", True)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self", "unused", "_init_weights"}
+        kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in dict(config, **overrides).items()
+              if not k.startswith("_") and k in accepted}
+        return cls(**kw, _init_weights=init_weights)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None,
+                        torch_dtype: Optional[torch.dtype] = None, **unused):
+        """Local-directory subset of diffusers' ModelMixin.from_pretrained (train/train.py:905-916:
+        `UNet2DConditionModel.from_pretrained(path, subfolder="unet")`): config.json -> constructor, then the
+        safetensors / .bin state dict with strict key checking."""
+        import os
+        cfg = cls.load_config(pretrained_model_name_or_path, subfolder=subfolder)
+        m = cls.from_config(cfg, _init_weights=False)
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        st, pt = os.path.join(d, cls.SAFETENSORS_WEIGHTS_NAME), os.path.join(d, cls.WEIGHTS_NAME)
+        if os.path.isfile(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        elif os.path.isfile(pt):
+            sd = torch.load(pt, map_location="cpu", weights_only=True)
+        else:
+            raise EnvironmentError(f"no {cls.SAFETENSORS_WEIGHTS_NAME} or {cls.WEIGHTS_NAME} in {d}")
+        m.load_state_dict(sd, strict=True)
+        if torch_dtype is not None:
+            m = m.to(torch_dtype)
+        return m
+
     def enable_xformers_memory_efficient_attention(self, *a, **k):   # reference callers invoke these; no-ops here
         return None
 
@@ -443,8 +510,8 @@ class AttributeEncoderModel(_NetModule):
             m.load_state_dict(own)
         return m.to(unet.device)
 
-    def _program(self, B, H, W, L):
-        key = (B, H, W, L)
+    def _program(self, B, H, W, L, scale: float = 1.0):
+        key = (B, H, W, L, scale)
         if key in self._progs:
             return self._progs[key]
         net, ws, cfg, dev = self.finalize(), self._ws, self.net_cfg, self._net.device
@@ -458,7 +525,7 @@ class AttributeEncoderModel(_NetModule):
         kv = net.rec_kv(prog, ws, P["ehs"], B, L)
         skips, mid = net.rec_encoder(prog, ws, P["x"], tproj, kv, L)
         P["raw_down"], P["raw_mid"] = skips, mid
-        P["down"], P["mid"] = net.rec_exchange(prog, ws, skips, mid, [None] * len(skips), None)
+        P["down"], P["mid"] = net.rec_exchange(prog, ws, skips, mid, [None] * len(skips), None, scale=scale)
         self._progs[key] = P
         return P
 
@@ -471,11 +538,9 @@ class AttributeEncoderModel(_NetModule):
                      added_cond_kwargs=added_cond_kwargs)
         if cross_attention_kwargs:
             raise NotImplementedError("cross_attention_kwargs are not supported")
-        if float(conditioning_scale) != 1.0:
-            raise NotImplementedError("conditioning_scale != 1.0 is not supported (every shipped caller passes 1.0)")
         B, _, H, W = controlnet_cond.shape
         L = encoder_hidden_states.shape[1]
-        P = self._program(B, H, W, L)
+        P = self._program(B, H, W, L, float(conditioning_scale))      # folded into the 13 zero-convs (:1774-1775)
         P["t"].copy_(self._timesteps(timestep, B, P["t"].device))
         P["ehs"].copy_(encoder_hidden_states.reshape(B * L, -1))
         c = controlnet_cond if controlnet_cond.dtype in (torch.float16, torch.float32) else controlnet_cond.float()
