@@ -68,7 +68,9 @@ int unib200_program_profile(unib200_program* prog, void* stream, int iters, floa
  * nn.Linear of Attention / FeedForward (diffusers leaves called from models/unet_2d_blocks.py:803,1207,2576).
  *   out[m, n] = epilogue( sum over segments/taps/channels  A_seg[pixel(m)+tap, c] * weight[n, k] )
  */
-enum { UNIB200_SEG_1x1 = 0, UNIB200_SEG_3x3 = 1, UNIB200_SEG_3x3_S2 = 2 };
+/* _S2: 3x3 stride 2 pad 1 (Downsample2D of the UNets); _S2P0: 3x3 stride 2 with the input padded by one pixel at the
+ * bottom / right only (diffusers Downsample2D(padding=0) = F.pad(x, (0,1,0,1)) + conv, the AutoencoderKL encoder). */
+enum { UNIB200_SEG_1x1 = 0, UNIB200_SEG_3x3 = 1, UNIB200_SEG_3x3_S2 = 2, UNIB200_SEG_3x3_S2P0 = 3 };
 enum {
   UNIB200_EPI_GEGLU = 1,     /* weight rows interleaved per N-tile: out = (a+ba) * gelu(g+bg); N_out = N/2        */
   UNIB200_EPI_OUT_NCHW = 2,  /* store NCHW (fp16, or fp32 with OUT_F32) instead of NHWC fp16                      */
@@ -191,6 +193,17 @@ int unib200_unipc_step(unib200_program* prog, const float* model_out, float* sam
 /* ---- out = a + b over contiguous fp16 (skip + external residual when the three modules are called separately,
  *      models/controlnet.py:1084,1115; the fused step folds these adds into the zero-conv GEMM epilogue) -------- */
 int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* ---- AutoencoderKL around the loop (models/pipeline.py:1531-1556 encode, :1664,2335-2344 decode)
+ * The VAE's convolutions / GroupNorms / upsampling run on the entry points above.  Its one attention (mid block, a
+ * single head of d = 512, diffusers Attention with residual_connection) does not fit the flash kernel's TMEM layout
+ * and runs as S = Q K^T (unib200_conv_gemm with K as the [N, K] operand), this in-place row softmax
+ * P = softmax(scale * S) over fp16 [rows, ld], and O = P V (unib200_conv_gemm with V^T as the [N, K] operand). */
+int unib200_softmax_rows(unib200_program* prog, void* s_fp16, int rows, int n, int ld, float scale, void* stream);
+/* DiagonalGaussianDistribution of `vae.encode(x).latent_dist`: moments fp32 [B, 2C, HW] (mean | logvar) ->
+ * out fp32 [B, C, HW] = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale; noise == NULL: mode() * scale. */
+int unib200_gaussian_sample(unib200_program* prog, const float* moments, const float* noise, float* out, int B, int C,
+                            int HW, float scale, void* stream);
 
 #ifdef __cplusplus
 }

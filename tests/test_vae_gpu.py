@@ -1,0 +1,48 @@
+"""AutoencoderKL path on the GPU: the ops it adds vs torch fp32 on the same fp16-rounded
+inputs (tight per-op tolerance, as tests/test_ops_gpu.py), and encoder / decoder vs oracle/vae_oracle.py.
+
+Model-level tolerance: fp16 activation storage through ~30 sequential layers; same gate as tests/test_models_gpu.py
+(rel_l2 <= 3e-3, max error <= 1 % of the tensor's max magnitude).  The oracle for this module is PARITY UNPINNED
+against diffusers itself (see its header)."""
+import pytest
+
+gpu = pytest.mark.gpu
+
+
+def _assert_ok(res, rel_l2, rel_max):
+    assert "error" not in res, res
+    for name, r in res.items():
+        assert r["finite"], name
+        assert r["rel_l2"] <= rel_l2, (name, r)
+        assert r["rel_to_max"] <= rel_max, (name, r)
+
+
+@gpu
+@pytest.mark.parametrize("case", ["wide_conv", "s2p0_conv", "attention_by_gemms"])
+def test_vae_gemm_cases(case):
+    from tests import vae_probe
+    _assert_ok(vae_probe.CASES[case](), 6e-4, 2e-3)
+
+
+@gpu
+def test_softmax_rows_and_posterior_sample():
+    from tests import vae_probe
+    res = vae_probe.CASES["softmax_and_sample"]()
+    for k, r in res.items():
+        if k.startswith("softmax"):
+            assert r["finite"] and r["rel_l2"] <= 1e-3 and r["rowsum_err"] <= 2e-3 and r["pad_untouched"], (k, r)
+        else:
+            assert r["finite"] and r["rel_l2"] <= 1e-6, (k, r)
+
+
+@gpu
+@pytest.mark.parametrize("case", ["vae_decode_tiny", "vae_encode_tiny", "vae_sd15_shape"])
+def test_vae_matches_oracle(case):
+    from tests import vae_probe
+    res = vae_probe.CASES[case]()
+    for k, r in res.items():
+        assert r["finite"], (k, r)
+        assert r["rel_l2"] <= 3e-3, (k, r)
+        assert r["rel_to_max"] <= 1e-2, (k, r)
+        if "rerun_bit_exact" in r:
+            assert r["rerun_bit_exact"] and r["fp16_in_dtype"] == "torch.float16", (k, r)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # UNIB200_LIB selects another build of the SAME library (A/B measurements of kernel variants); never a fallback
 LIB_PATH = os.environ.get("UNIB200_LIB") or os.path.join(HERE, "libunib200.so")
 
-SEG_1x1, SEG_3x3, SEG_3x3_S2 = 0, 1, 2
+SEG_1x1, SEG_3x3, SEG_3x3_S2, SEG_3x3_S2P0 = 0, 1, 2, 3
 OP_OTHER, OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM = 0, 1, 2, 3, 4
 OP_NAMES = {OP_OTHER: "other", OP_GEMM: "conv_gemm", OP_ATTENTION: "attention", OP_GROUPNORM: "groupnorm",
             OP_LAYERNORM: "layernorm"}
@@ -65,6 +65,7 @@ EXPORTS = [
     "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
+    "unib200_softmax_rows", "unib200_gaussian_sample",
 ]
 
 _lib = None
@@ -124,6 +125,8 @@ def load() -> C.CDLL:
     lib.unib200_add_int.argtypes = [vp, vp, ci, vp]
     lib.unib200_add_f16.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.unib200_unipc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_softmax_rows.argtypes = [vp, vp, ci, ci, ci, cf, vp]
+    lib.unib200_gaussian_sample.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, vp]
     _lib = lib
     return lib
 

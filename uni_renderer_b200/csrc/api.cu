@@ -371,7 +371,8 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   } else {
     if (d->B * d->H * d->W != d->M) return fail("conv_gemm: M != B*H*W");
     auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
-    if (!pow2(d->W) || !pow2(d->H) || d->W > 128) return fail("conv_gemm: H and W must be powers of two, W <= 128");
+    // W > 128 (VAE resolutions): a 128-pixel tile is then a piece of one image row, box {64, 128, 1, 1}
+    if (!pow2(d->W) || !pow2(d->H)) return fail("conv_gemm: H and W must be powers of two");
     p.W = d->W;
     p.H = d->H;
     p.rows_per_batch = d->H * d->W;
@@ -385,6 +386,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   for (int i = 0; i < d->nseg; ++i) {
     const unib200_seg& s = d->seg[i];
     if (s.C <= 0 || s.ld < s.C || s.ld % 8 != 0) return fail("conv_gemm: bad segment C/ld (ld must be a multiple of 8)");
+    if (s.kind < UNIB200_SEG_1x1 || s.kind > UNIB200_SEG_3x3_S2P0) return fail("conv_gemm: bad segment kind");
     if (linear && s.kind != UNIB200_SEG_1x1) return fail("conv_gemm: linear A only supports 1x1 segments");
     p.seg[i].tmap = nmaps;
     p.seg[i].kind = s.kind;
@@ -398,7 +400,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
       const uint64_t st[3] = {pix, pix * d->M, pix * d->M};
       const uint32_t box[4] = {64, 128, 1, 1};
       if (!encode_map(&maps.a[nmaps++], s.ptr, 4, dims, st, box, &why)) return fail("conv_gemm A map: " + why);
-    } else if (s.kind == UNIB200_SEG_3x3_S2) {
+    } else if (s.kind == UNIB200_SEG_3x3_S2 || s.kind == UNIB200_SEG_3x3_S2P0) {
       if (nmaps + 4 > kMaxAMaps) return fail("conv_gemm: too many tensor maps");
       const int Hi = 2 * d->H, Wi = 2 * d->W;   // source image is twice the output size
       for (int ph = 0; ph < 2; ++ph)
@@ -526,7 +528,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     const int taps = d->seg[i].kind == UNIB200_SEG_1x1 ? 1 : 9;
     kreal += static_cast<double>(taps) * d->seg[i].C;
     // each source pixel is read once algorithmically (a stride-2 conv reads 4x the output pixels)
-    a_bytes += 2.0 * d->seg[i].C * d->M * (d->seg[i].kind == UNIB200_SEG_3x3_S2 ? 4.0 : 1.0);
+    a_bytes += 2.0 * d->seg[i].C * d->M * (d->seg[i].kind >= UNIB200_SEG_3x3_S2 ? 4.0 : 1.0);
   }
   const double n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2.0 : d->N;
   const double flops = 2.0 * d->M * d->N * kreal;
@@ -536,7 +538,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
                      std::to_string(static_cast<long long>(kreal)) + " bn=" + std::to_string(bn) + " splits=" +
                      std::to_string(splits) + " tiles=" + std::to_string(tiles) + " segs=";
   for (int i = 0; i < d->nseg; ++i)
-    desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : "3x3s2:") +
+    desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : d->seg[i].kind == UNIB200_SEG_3x3_S2 ? "3x3s2:" : "3x3s2p0:") +
             std::to_string(d->seg[i].C);
   if (d->flags) desc += " flags=" + std::to_string(d->flags);
   return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes, desc);
@@ -674,6 +676,21 @@ int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* o
     return launch_add_f16(static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(out), n, s);
   };
   return submit(prog, std::move(op), 1, stream, "add_f16");
+}
+
+int unib200_softmax_rows(unib200_program* prog, void* s, int rows, int n, int ld, float scale, void* stream) {
+  if (rows <= 0 || n <= 0 || n % 8 || ld % 8 || ld < n) return fail("softmax_rows: n and ld must be multiples of 8, ld >= n");
+  if (!(scale > 0.f)) return fail("softmax_rows: scale must be positive");
+  if (reinterpret_cast<uintptr_t>(s) & 15) return fail("softmax_rows: matrix must be 16-byte aligned");
+  Op op = [=](cudaStream_t st) { return launch_softmax_rows(static_cast<__half*>(s), rows, n, ld, scale, st); };
+  return submit(prog, std::move(op), 1, stream, "softmax_rows");
+}
+
+int unib200_gaussian_sample(unib200_program* prog, const float* moments, const float* noise, float* out, int B, int C,
+                            int HW, float scale, void* stream) {
+  if (B <= 0 || C <= 0 || HW <= 0 || !moments || !out) return fail("gaussian_sample: bad arguments");
+  Op op = [=](cudaStream_t st) { return launch_gaussian_sample(moments, noise, out, B, C, HW, scale, st); };
+  return submit(prog, std::move(op), 1, stream, "gaussian_sample");
 }
 
 int unib200_add_int(unib200_program* prog, int* p, int v, void* stream) {

@@ -744,6 +744,112 @@ cudaError_t launch_add_f16(const __half* a, const __half* b, __half* out, long l
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row softmax of a materialised fp16 score matrix, in place: P[r, :] = softmax(scale * S[r, :]).  Used only by the
+// single-head d = 512 attention of the AutoencoderKL mid block (one per VAE call), whose head dim does not fit the
+// TMEM layout of the flash kernel: S = Q K^T and O = P V run on the GEMM kernel around this pass.  One block per row,
+// three passes over the row (the 2nd and 3rd hit L1/L2), fp32 statistics, 128-bit accesses.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_256(float v, bool is_max, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : v + w;
+  }
+  __syncthreads();                                   // red[] may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ S, int rows, int n, int ld,
+                                                           float scale_log2e) {
+  pdl_launch();
+  pdl_wait();
+  __shared__ float red[8];
+  const int nv = n >> 3;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    uint4* row = reinterpret_cast<uint4*>(S + static_cast<size_t>(r) * ld);
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+      const uint4 raw = row[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+    mx = block_reduce_256(mx, true, red);
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+      const uint4 raw = row[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        sum += exp2f((f.x - mx) * scale_log2e) + exp2f((f.y - mx) * scale_log2e);
+      }
+    }
+    sum = block_reduce_256(sum, false, red);
+    const float inv = 1.0f / sum;
+    for (int v = threadIdx.x; v < nv; v += 256) {
+      const uint4 raw = row[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        o[j] = pack_half2(exp2f((f.x - mx) * scale_log2e) * inv, exp2f((f.y - mx) * scale_log2e) * inv);
+      }
+      row[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+cudaError_t launch_softmax_rows(__half* S, int rows, int n, int ld, float scale, cudaStream_t stream) {
+  if (rows <= 0 || n <= 0 || n % 8 || ld % 8 || ld < n || !(scale > 0.f)) return cudaErrorInvalidValue;
+  int blocks = rows < 148 * 8 ? rows : 148 * 8;
+  UNIB_CHECK_LAUNCH(launch_pdl(softmax_rows_kernel, dim3(blocks), dim3(256), 0, stream, S, rows, n, ld,
+                               scale * 1.4426950408889634f));
+  return cudaGetLastError();
+}
+
+// DiagonalGaussianDistribution.sample() of the AutoencoderKL posterior: moments = [B, 2C, HW] fp32 (mean | logvar),
+// out = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale; noise == nullptr gives mode() (the mean).
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                       float* __restrict__ out, int B, int C, int HW, float scale) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = static_cast<long long>(B) * C * HW;
+  const long long chw = static_cast<long long>(C) * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / chw, rem = i - b * chw;
+    const float mean = moments[b * 2 * chw + rem];
+    float y = mean;
+    if (noise != nullptr) {
+      const float logvar = fminf(fmaxf(moments[b * 2 * chw + chw + rem], -30.f), 20.f);
+      y = mean + expf(0.5f * logvar) * noise[i];
+    }
+    out[i] = y * scale;
+  }
+}
+
+cudaError_t launch_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW,
+                                   float scale, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (total <= 0) return cudaErrorInvalidValue;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  UNIB_CHECK_LAUNCH(launch_pdl(gaussian_sample_kernel, dim3(blocks), dim3(256), 0, stream, moments, noise, out, B, C, HW,
+                               scale));
+  return cudaGetLastError();
+}
+
 __global__ void add_int_kernel(int* p, int v) {
   pdl_launch();
   pdl_wait();

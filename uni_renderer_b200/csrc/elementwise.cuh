@@ -35,5 +35,8 @@ cudaError_t launch_unipc_step(const float* out, float* S, float* LS, float* H0, 
                               const int* step_idx, int B, int C, int HW, int c_first, cudaStream_t stream);
 cudaError_t launch_add_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream);
 cudaError_t launch_add_int(int* p, int v, cudaStream_t stream);
+cudaError_t launch_softmax_rows(__half* S, int rows, int n, int ld, float scale, cudaStream_t stream);
+cudaError_t launch_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW,
+                                   float scale, cudaStream_t stream);
 
 }  // namespace unib

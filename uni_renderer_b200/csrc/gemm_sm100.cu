@@ -270,6 +270,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           tm += ((dy != 1) ? 2 : 0) + ((dx != 1) ? 1 : 0);
           dh = (dy == 0) ? -1 : 0;
           dw = (dx == 0) ? -1 : 0;
+        } else if (sg.kind == SEG_3x3_S2P0) {
+          const int dy = tap / 3, dx = tap % 3;   // input row = 2*oh + dy (pad bottom/right only) -> parity dy & 1
+          tm += ((dy & 1) ? 2 : 0) + ((dx & 1) ? 1 : 0);
+          dh = dy >> 1;
+          dw = dx >> 1;
         }
         amap = &maps.a[tm];
         cw = w0 + dw;

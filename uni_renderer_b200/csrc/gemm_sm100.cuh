@@ -17,10 +17,10 @@ constexpr int kBK = 64;         // fp16 elements per K block == one 128-byte swi
 constexpr int kMaxSeg = 4;
 constexpr int kMaxAMaps = 6;
 
-enum SegKind : int { SEG_1x1 = 0, SEG_3x3 = 1, SEG_3x3_S2 = 2 };
+enum SegKind : int { SEG_1x1 = 0, SEG_3x3 = 1, SEG_3x3_S2 = 2, SEG_3x3_S2P0 = 3 };
 
 struct ConvSeg {
-  int tmap;   // first A tensor map of this segment (SEG_3x3_S2 uses 4 consecutive parity maps)
+  int tmap;   // first A tensor map of this segment (SEG_3x3_S2 / _S2P0 use 4 consecutive parity maps)
   int kind;   // SegKind
   int nkb;    // channel blocks of 64 per tap
   int ntaps;  // 1 or 9

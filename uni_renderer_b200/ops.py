@@ -9,11 +9,12 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2)
+from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2,
+                   SEG_3x3_S2P0)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
-           "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
-           "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
+           "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "softmax_rows", "gaussian_sample", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
+           "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "SEG_3x3_S2P0", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
 def _stream() -> int:
@@ -360,6 +361,33 @@ def unipc_step(prog: Optional[Program], model_out: torch.Tensor, sample: torch.T
                                    first_channel, _stream()), "unipc_step")
     if prog is not None:
         prog.keep(model_out, sample, last_sample, hist0, hist1, coef, step_idx)
+
+
+def softmax_rows(prog: Optional[Program], s: torch.Tensor, *, rows: int, n: int, scale: float):
+    """In-place P = softmax(scale * S) over the first n columns of each of `rows` rows of an fp16 matrix."""
+    lib = L.load()
+    ld = _check_2d(s, "softmax_rows s")
+    if s.shape[0] < rows or s.shape[1] < n:
+        raise ValueError(f"softmax_rows: matrix {tuple(s.shape)} is smaller than rows={rows}, n={n}")
+    L.check(lib.unib200_softmax_rows(_h(prog), s.data_ptr(), rows, n, ld, float(scale), _stream()), "softmax_rows")
+    if prog is not None:
+        prog.keep(s)
+
+
+def gaussian_sample(prog: Optional[Program], moments: torch.Tensor, noise: Optional[torch.Tensor], out: torch.Tensor, *,
+                    scale: float = 1.0):
+    """out = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale from moments [B, 2C, H, W] fp32; noise None
+    gives the mode (include/unib200.h unib200_gaussian_sample)."""
+    lib = L.load()
+    B, C2, H, W = moments.shape
+    assert moments.dtype == torch.float32 and moments.is_contiguous() and moments.is_cuda and C2 % 2 == 0
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, C2 // 2, H, W)
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == out.shape and noise.is_cuda
+    L.check(lib.unib200_gaussian_sample(_h(prog), moments.data_ptr(), _ptr(noise), out.data_ptr(), B, C2 // 2, H * W,
+                                        float(scale), _stream()), "gaussian_sample")
+    if prog is not None:
+        prog.keep(moments, noise, out)
 
 
 def add_int(prog: Optional[Program], p: torch.Tensor, v: int):
