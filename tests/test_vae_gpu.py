@@ -2,7 +2,8 @@
 inputs (tight per-op tolerance, as tests/test_ops_gpu.py), and encoder / decoder vs oracle/vae_oracle.py.
 
 Model-level tolerance: fp16 activation storage through ~30 sequential layers; same gate as tests/test_models_gpu.py
-(rel_l2 <= 3e-3, max error <= 1 % of the tensor's max magnitude).  The oracle for this module is PARITY UNPINNED
+(max error <= 1 % of the tensor's max magnitude) with rel_l2 <= 4e-3: the decoder is ~40 sequential fp16-stored layers
+plus an fp16 probability matrix (measured on B200: 2.0e-3 tiny, 2.9e-3 at SD-1.x widths; encoder 0.9-1.1e-3).  The oracle for this module is PARITY UNPINNED
 against diffusers itself (see its header)."""
 import pytest
 
@@ -42,7 +43,18 @@ def test_vae_matches_oracle(case):
     res = vae_probe.CASES[case]()
     for k, r in res.items():
         assert r["finite"], (k, r)
-        assert r["rel_l2"] <= 3e-3, (k, r)
+        assert r["rel_l2"] <= 4e-3, (k, r)          # measured 0.9e-3 (encoder) .. 2.9e-3 (SD-1.x-width decoder)
         assert r["rel_to_max"] <= 1e-2, (k, r)
         if "rerun_bit_exact" in r:
             assert r["rerun_bit_exact"] and r["fp16_in_dtype"] == "torch.float16", (k, r)
+
+
+@gpu
+def test_render_pipeline_matches_oracle_chain():
+    """encode -> 2 denoising steps -> decode through RenderPipeline vs the oracle chain on the same seeded noise.
+    Gate: the decoder's own 3e-3 plus the loop's per-step drift (tests/test_sampler_gpu.py: 5e-3 over 3 steps)."""
+    from tests import vae_probe
+    res = vae_probe.CASES["render_pipeline"]()
+    assert res.pop("batched_decode_vs_single")["rel_l2"] <= 5e-4
+    for k, r in res.items():
+        assert r["finite"] and r["rel_l2"] <= 6e-3 and r["rel_to_max"] <= 2e-2, (k, r)

@@ -226,10 +226,75 @@ def case_vae_full_size_timing():
     return out
 
 
+def case_render_pipeline():
+    """Image-to-image calls (uni_renderer_b200.render.RenderPipeline) on the tiny networks: two denoising steps, the
+    same seeded noise on both sides; oracle chain = vae_oracle.encode -> uni_oracle steps + DDIM -> vae_oracle.decode.
+    Also: batched / chunked decode programs agree with one-image-at-a-time calls (not bit for bit: the split-K choice
+    of the small layers depends on the batch)."""
+    import torch
+    from tests import sampler_probe
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.render import RenderPipeline
+    m, vsd, vo = _tiny()
+    sampler, sds, cfgs = sampler_probe.tiny_setup()
+    rp = RenderPipeline(sampler, m)
+    B, S, steps = 2, 64, 2
+    h = S // 4
+    g = torch.Generator().manual_seed(31)
+    imgs = [torch.tanh(torch.randn(B, 3, S, S, generator=g)) for _ in range(7)]
+    ehs = torch.randn(B, 77, cfgs[0].cross_attention_dim, generator=g).half()
+    sf = vo.TINY_VAE.scaling_factor
+    res = {}
+
+    def o_encode(x, noise):
+        with torch.no_grad():
+            return vo.sample_posterior(vo.encode_moments(vsd, vo.TINY_VAE, x), noise) * sf
+
+    def o_loop(mode, x_img, x_attr):
+        sched, sched_a = uo.DDIM(), uo.DDIM()
+        ts = sched.set_timesteps(steps)
+        sched_a.set_timesteps(steps)
+        for i in range(steps):
+            x_img, x_attr = sampler_probe.oracle_step(mode, sds, cfgs, sched, ts[i], x_img, x_attr, ehs.float(), sched_a)
+        return x_img, x_attr
+
+    # inverse rendering: image, masks -> material latents + 5 decoded attribute images
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    out = rp.inverse_rendering(imgs[0], imgs[1], ehs, num_inference_steps=steps, generator=gen)
+    torch.cuda.synchronize()
+    gen.manual_seed(77)
+    n_img, n_msk = (torch.randn(B, 4, h, h, generator=gen, device="cuda").cpu() for _ in range(2))
+    lat = [torch.randn(B, 4, h, h, generator=gen, device="cuda").cpu() for _ in range(6)]
+    l_img, l_msk = o_encode(imgs[0], n_img), o_encode(imgs[1], n_msk)
+    _, xa = o_loop("inverse", l_img, torch.cat([l_msk] + lat, 1))
+    res["inv_material_latents"] = _err(out[0].cpu(), xa[:, 4:8])
+    with torch.no_grad():
+        for i, name in enumerate(("normal", "albedo", "spec_light", "diff_light", "env")):
+            res["inv_" + name] = _err(out[1 + i].cpu(), vo.decode(vsd, vo.TINY_VAE, xa[:, 8 + 4 * i:12 + 4 * i] / sf))
+    # forward rendering: 6 attribute images + material numbers -> RGB image
+    gen.manual_seed(78)
+    rgb = rp.forward_rendering((0.3, 0.8), *imgs[1:7], ehs, num_inference_steps=steps, generator=gen)
+    torch.cuda.synchronize()
+    gen.manual_seed(78)
+    noises = [torch.randn(B, 4, h, h, generator=gen, device="cuda").cpu() for _ in range(7)]
+    ln, la, ls, ld_, le, lm = (o_encode(x, n) for x, n in zip(imgs[1:7], noises[:6]))
+    mat = torch.empty(B, 4, h, h)
+    mat[:, :2], mat[:, 2:] = 0.3 * 2 - 1, 0.8 * 2 - 1
+    xi, _ = o_loop("forward", noises[6], torch.cat((lm, mat, ln, la, ls, ld_, le), 1))
+    with torch.no_grad():
+        res["fwd_rgb"] = _err(rgb.cpu(), vo.decode(vsd, vo.TINY_VAE, xi / sf))
+    # batching is transparent: 3 images in one program == three single calls
+    z = torch.randn(3, 4, h, h, generator=g).cuda()
+    one = torch.cat([m.decode(z[i:i + 1]).sample for i in range(3)], 0)
+    m.max_batch = 2                                   # also exercises the chunked path (2 + 1)
+    res["batched_decode_vs_single"] = _err(m.decode(z).sample, one)
+    return res
+
+
 CASES = {"wide_conv": case_wide_conv, "s2p0_conv": case_s2p0_conv, "softmax_and_sample": case_softmax_and_sample,
          "attention_by_gemms": case_attention_by_gemms, "vae_decode_tiny": case_vae_decode_tiny,
          "vae_encode_tiny": case_vae_encode_tiny, "vae_sd15_shape": case_vae_sd15_shape,
-         "vae_full_size_timing": case_vae_full_size_timing}
+         "vae_full_size_timing": case_vae_full_size_timing, "render_pipeline": case_render_pipeline}
 
 
 if __name__ == "__main__":

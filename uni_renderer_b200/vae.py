@@ -357,6 +357,7 @@ class DiagonalGaussianDistribution:
 class AutoencoderKL(_NetModule):
     """diffusers.AutoencoderKL surface over VaeNet (inference only)."""
     _kind = "vae"
+    max_batch = 8          # images per recorded program; larger batches are processed in chunks of this size
 
     def __init__(self, in_channels: int = 3, out_channels: int = 3, down_block_types=(_DOWN,),
                  up_block_types=(_UP,), block_out_channels=(64,), layers_per_block: int = 1, act_fn: str = "silu",
@@ -447,6 +448,10 @@ class AutoencoderKL(_NetModule):
         fresh tensor (the program's static buffer is copied out), so several encodes can be alive at once."""
         net = self.finalize(x.device if x.is_cuda else None)
         B, _, H, W = x.shape
+        if B > self.max_batch:         # large batches run as chunks of one recorded program (bounded activation memory)
+            parts = [self.encode(x[i:i + self.max_batch]).latent_dist.parameters for i in range(0, B, self.max_batch)]
+            dist = DiagonalGaussianDistribution(torch.cat(parts, 0))
+            return (dist,) if not return_dict else AutoencoderKLOutput(latent_dist=dist)
         P = self._program("enc", B, H, W)
         ops.to_nhwc(None, self._float(x).to(net.device), P["x"].t, P["x"].C)
         P["prog"].run()
@@ -461,6 +466,10 @@ class AutoencoderKL(_NetModule):
         `generator` is accepted and unused, as in diffusers.  Returns a fresh fp32 (or z.dtype) NCHW image."""
         net = self.finalize(z.device if z.is_cuda else None)
         B, _, H, W = z.shape
+        if B > self.max_batch:
+            img = torch.cat([self.decode(z[i:i + self.max_batch], return_dict=False)[0]
+                             for i in range(0, B, self.max_batch)], 0)
+            return (img,) if not return_dict else DecoderOutput(sample=img)
         P = self._program("dec", B, H, W)
         ops.to_nhwc(None, self._float(z).to(net.device), P["z"].t, P["z"].C)
         P["prog"].run()
