@@ -56,6 +56,7 @@ def parse():
                     help="forward/inverse: the two batch halves on two lanes (measured slower at B=4; off by default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the AutoencoderKL side measurement (N=1, 64x64 latents)")
     ap.add_argument("--cpu-denoise-steps", type=int, default=2, help="timed CPU denoising steps of the cpu_baseline leg")
     a = ap.parse_args()
     if a.warmup < 3:
@@ -369,6 +370,14 @@ def run_b200(a):
                 "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
                 "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
             for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+    if rank == 0 and world == 1 and not a.no_vae and S == 64:
+        # the next row of the scope table: the AutoencoderKL that brackets every sampling call of the
+        # reference (models/pipeline.py:1531-1556 encodes, :1664 / :2335-2349 decodes) on the same kernels.  Reported
+        # beside the headline, never inside it: BASELINE.json's metric is the denoising loop on latents.
+        try:
+            line["vae"] = vae_leg(torch, dev, B, S * 8, peaks)
+        except Exception as e:  # noqa: BLE001  (the headline must survive a failure of the side measurement)
+            line["vae"] = {"error": f"{type(e).__name__}: {e}"}
     barrier()
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -380,6 +389,48 @@ def run_b200(a):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def vae_leg(torch, dev, B, image, peaks):
+    """One batched AutoencoderKL decode and encode (SD-1.x widths, random init) at the bench's batch: device ms (CUDA
+    events, 3 warm + 5 timed), algorithmic TFLOP/s and the per-class split of an eager replay."""
+    from uni_renderer_b200 import _lib
+    from uni_renderer_b200 import vae as V
+    cfg = V.VaeConfig()
+    m = V.AutoencoderKL(block_out_channels=cfg.block_out_channels, down_block_types=(V._DOWN,) * 4,
+                        up_block_types=(V._UP,) * 4, layers_per_block=2, norm_num_groups=32, _init_weights=False)
+    m.load_state_dict(V.random_init_vae_state_dict(cfg, 21, dev))
+    m = m.to(dev)
+    g = torch.Generator(device=dev).manual_seed(4)
+    z = torch.randn(B, 4, image // 8, image // 8, generator=g, device=dev)
+    x = torch.tanh(torch.randn(B, 3, image, image, generator=g, device=dev))
+    out = {"config": f"AutoencoderKL SD-1.x widths (83.7M params, random init), batch {B}, {image}x{image} images, fp16 "
+                     "storage / fp32 accumulate", "parity": "tests/test_vae_gpu.py (oracle/vae_oracle.py, parity unpinned)"}
+    for name, key, fn in (("decode", ("dec", B, image // 8, image // 8), lambda: m.decode(z)),
+                          ("encode", ("enc", B, image, image), lambda: m.encode(x))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        P = m._progs[key]["prog"]
+        info, ms_ops = P.op_info(), P.profile(3)
+        by = {}
+        for (kind, fl, by_, nl), t in zip(info, ms_ops):
+            d = by.setdefault(_lib.OP_NAMES[kind], {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += t; d["flops"] += fl; d["launches"] += nl
+        flops = sum(i[1] for i in info)
+        out[name] = {"ms": ms, "images_per_s": B / (ms * 1e-3), "launches": P.num_launches,
+                     "tflops": flops / (ms * 1e-3) / 1e12,
+                     "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                     "by_kind_ms": {k: round(v["ms"], 3) for k, v in by.items()},
+                     "gemm_tflops_eager": round(by["conv_gemm"]["flops"] / (by["conv_gemm"]["ms"] * 1e-3) / 1e12, 1)}
+    return out
 
 
 def main():
