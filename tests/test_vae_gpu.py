@@ -55,6 +55,9 @@ def test_render_pipeline_matches_oracle_chain():
     Gate: the decoder's own 3e-3 plus the loop's per-step drift (tests/test_sampler_gpu.py: 5e-3 over 3 steps)."""
     from tests import vae_probe
     res = vae_probe.CASES["render_pipeline"]()
-    assert res.pop("batched_decode_vs_single")["rel_l2"] <= 5e-4
+    # two fp16 executions of the same decoder whose small layers pick different split-K factors (the choice depends on
+    # the batch): they decorrelate like two independent fp16 roundings of the fp32 result (measured 9.2e-4; each is
+    # 2.0e-3 from the oracle)
+    assert res.pop("batched_decode_vs_single")["rel_l2"] <= 2e-3
     for k, r in res.items():
         assert r["finite"] and r["rel_l2"] <= 6e-3 and r["rel_to_max"] <= 2e-2, (k, r)
