@@ -37,7 +37,7 @@ def test_softmax_rows_and_posterior_sample():
 
 
 @gpu
-@pytest.mark.parametrize("case", ["vae_decode_tiny", "vae_encode_tiny", "vae_sd15_shape"])
+@pytest.mark.parametrize("case", ["vae_decode_tiny", "vae_encode_tiny", "vae_sd15_shape", "vae_sd15_full_size"])
 def test_vae_matches_oracle(case):
     from tests import vae_probe
     res = vae_probe.CASES[case]()

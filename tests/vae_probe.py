@@ -193,6 +193,29 @@ def case_vae_sd15_shape():
                 "moments": _err(mom.cpu(), vo.encode_moments(sd, vo.SD15_VAE, x))}
 
 
+def case_vae_sd15_full_size():
+    """BASELINE size, SD-1.x widths, one image: 64x64 latent -> 512x512 decode and 512x512 -> moments encode against
+    the oracle (1M-row GEMMs, 512-pixel-wide tiles, GroupNorm over 262144 pixels, the 4096-token d = 512 attention)."""
+    import torch
+    from oracle import vae_oracle as vo
+    from uni_renderer_b200 import vae as V
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = vo.random_state_dict(vo.SD15_VAE, 9)
+    m = V.AutoencoderKL(block_out_channels=(128, 256, 512, 512), down_block_types=(V._DOWN,) * 4,
+                        up_block_types=(V._UP,) * 4, layers_per_block=2, norm_num_groups=32)
+    m.load_state_dict(sd)
+    m = m.to("cuda")
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 4, 64, 64, generator=g)
+    x = torch.tanh(torch.randn(1, 3, 512, 512, generator=g))
+    img = m.decode(z.cuda(), return_dict=False)[0]
+    mom = m.encode(x.cuda()).latent_dist.parameters
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        return {"decode_512": _err(img.cpu(), vo.decode(sd, vo.SD15_VAE, z)),
+                "moments_512": _err(mom.cpu(), vo.encode_moments(sd, vo.SD15_VAE, x))}
+
+
 def case_vae_full_size_timing():
     """BASELINE-sized call: B=4, 64x64 latents <-> 512x512 images, SD-1.x VAE widths, random-init weights.  Reports the
     device time of one decode and one encode (CUDA events, 2 warm + 3 timed) -- a first measurement, not a bench."""
@@ -293,7 +316,7 @@ def case_render_pipeline():
 
 CASES = {"wide_conv": case_wide_conv, "s2p0_conv": case_s2p0_conv, "softmax_and_sample": case_softmax_and_sample,
          "attention_by_gemms": case_attention_by_gemms, "vae_decode_tiny": case_vae_decode_tiny,
-         "vae_encode_tiny": case_vae_encode_tiny, "vae_sd15_shape": case_vae_sd15_shape,
+         "vae_encode_tiny": case_vae_encode_tiny, "vae_sd15_shape": case_vae_sd15_shape, "vae_sd15_full_size": case_vae_sd15_full_size,
          "vae_full_size_timing": case_vae_full_size_timing, "render_pipeline": case_render_pipeline}
 
 

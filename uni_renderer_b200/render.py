@@ -29,8 +29,10 @@ ATTR_GROUPS = ("material", "normal", "albedo", "spec_light", "diff_light", "env"
 
 
 class RenderPipeline:
-    def __init__(self, sampler: DualStreamSampler, vae: AutoencoderKL):
-        self.sampler, self.vae = sampler, vae
+    def __init__(self, sampler: DualStreamSampler, vae: AutoencoderKL, prompt_cache=None):
+        """prompt_cache: an optional uni_renderer_b200.text.PromptEmbedCache; with it `prompt_embeds=None` encodes
+        `prompt` (default ' ', what every shipped caller passes) once per process."""
+        self.sampler, self.vae, self.prompt_cache = sampler, vae, prompt_cache
         self.device = sampler.device
         vae.finalize(self.device)
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1)            # pipeline.py:178
@@ -68,9 +70,9 @@ class RenderPipeline:
     # -- the two shipped calls -----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_rendering(self, material_num, normal_image, albedo_image, spec_light_image, diff_light_image, env_image,
-                          masks_image, prompt_embeds, num_inference_steps: int = 50, guidance_scale: float = 0.0,
+                          masks_image, prompt_embeds=None, num_inference_steps: int = 50, guidance_scale: float = 0.0,
                           generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
-                          output_type: str = "pt", scheduler: Optional[str] = None):
+                          output_type: str = "pt", scheduler: Optional[str] = None, prompt: str = " "):
         """attributes -> RGB (mask2image_3mod_albedo).  Images are [B, 3, H, W] tensors in [-1, 1]; material_num is
         (metallic, roughness); returns the decoded image [B, 3, H, W] (or the latents for output_type="latent")."""
         B = normal_image.shape[0]
@@ -84,7 +86,7 @@ class RenderPipeline:
         attr28 = torch.cat((l_masks, l_material, l_normal, l_albedo, l_spec, l_diff, l_env), 1)      # :1583
         if latents is None:
             latents = self._randn((B, 4) + tuple(l_normal.shape[2:]), generator)     # prepare_latents, :705-719
-        ehs = self._embeds(prompt_embeds, B)
+        ehs = self._embeds(prompt_embeds, B, prompt)
         lat = self.sampler.forward_render(latents.to(self.device, torch.float32), attr28, ehs, num_inference_steps,
                                           guidance_scale, scheduler)
         if output_type == "latent":
@@ -92,9 +94,10 @@ class RenderPipeline:
         return self.decode_latents([lat])[0]
 
     @torch.no_grad()
-    def inverse_rendering(self, image, masks, prompt_embeds, num_inference_steps: int = 50, guidance_scale: float = 0.0,
-                          generator: Optional[torch.Generator] = None, latents: Optional[Sequence[torch.Tensor]] = None,
-                          scheduler: Optional[str] = None):
+    def inverse_rendering(self, image, masks, prompt_embeds=None, num_inference_steps: int = 50,
+                          guidance_scale: float = 0.0, generator: Optional[torch.Generator] = None,
+                          latents: Optional[Sequence[torch.Tensor]] = None, scheduler: Optional[str] = None,
+                          prompt: str = " "):
         """RGB -> attributes (image2mask_3mod_albedo).  Returns (material_latents, normal, albedo, spec_light,
         diff_light, env) with the five images decoded to [B, 3, H, W] in [-1, 1] (:2389)."""
         B = image.shape[0]
@@ -104,13 +107,17 @@ class RenderPipeline:
         if len(latents) != len(ATTR_GROUPS):
             raise ValueError(f"need {len(ATTR_GROUPS)} attribute latents ({ATTR_GROUPS})")
         attr28 = torch.cat([l_masks] + [l.to(self.device, torch.float32) for l in latents], 1)
-        ehs = self._embeds(prompt_embeds, B)
+        ehs = self._embeds(prompt_embeds, B, prompt)
         attr24 = self.sampler.inverse_render(l_img, attr28, ehs, num_inference_steps, guidance_scale, scheduler)
         groups = [attr24[:, 4 * i:4 * i + 4] for i in range(len(ATTR_GROUPS))]
         decoded = self.decode_latents(groups[1:])                                    # material stays latent (:2331)
         return (groups[0],) + decoded
 
-    def _embeds(self, prompt_embeds: torch.Tensor, B: int) -> torch.Tensor:
+    def _embeds(self, prompt_embeds: Optional[torch.Tensor], B: int, prompt: str = " ") -> torch.Tensor:
+        if prompt_embeds is None:
+            if self.prompt_cache is None:
+                raise ValueError("pass prompt_embeds, or construct RenderPipeline with a PromptEmbedCache")
+            prompt_embeds = self.prompt_cache.encode(prompt)
         if prompt_embeds.shape[0] == 1 and B > 1:
             prompt_embeds = prompt_embeds.repeat(B, 1, 1)                            # :2109
         if prompt_embeds.shape[0] != B:
