@@ -3,7 +3,9 @@ check the HOST-SIDE wiring of recorded programs (segment order, packed-weight la
 GEMM-softmax-GEMM attention, the quant_conv fold) against the oracle without a GPU.
 
 It is installed by monkeypatching `uni_renderer_b200.ops` inside a test; the product never imports it, and it is not a
-fallback: nothing in uni_renderer_b200/ can reach it.  Kernel-level behaviour is covered by the `-m gpu` tests."""
+fallback: nothing in uni_renderer_b200/ can reach it.  Kernel-level behaviour is covered by the `-m gpu` tests.
+With it the CPU suite runs the REAL recorders (engine.StreamNet, pipeline.DualStreamSampler.plan, vae.VaeNet) of every
+sampling mode and compares the result with the oracle, including a two-process gloo run of the sharded loop."""
 from __future__ import annotations
 
 import torch
@@ -13,6 +15,9 @@ from uni_renderer_b200 import _lib as L
 
 
 class FakeProgram:
+    """Records closures; run() executes them in order (lanes / barriers only order concurrent work on the GPU, and a
+    sequential replay is one valid schedule of the same dependency graph)."""
+
     def __init__(self):
         self.ops = []
         self.has_graph = False
@@ -23,6 +28,25 @@ class FakeProgram:
     def run(self):
         for op in self.ops:
             op()
+
+    def lane(self, n):
+        pass
+
+    def barrier(self):
+        pass
+
+    def instantiate_graph(self):
+        self.has_graph = True
+
+    def launch_graph(self):
+        self.run()
+
+    def op_info(self):
+        return []
+
+    @property
+    def num_ops(self):
+        return len(self.ops)
 
     @property
     def num_launches(self):
@@ -54,15 +78,20 @@ def _taps(x, kind, B, H, W, C):
     return out
 
 
+def _gelu_erf(x):
+    return 0.5 * x * (1.0 + torch.erf(x * 0.7071067811865476))
+
+
 def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_bstride=0, bias_step=None,
               bias_step_stride=0, res=None, flags=0, splits=0, partial=None, axpby=None, axpby_step=None, aux=None,
               aux_out=None, axpby_first_channel=0, ldc=None, rowstats_out=None, ln=None):
-    if flags & ~(L.EPI_OUT_NCHW | L.EPI_OUT_F32 | L.EPI_SILU) or bias_step is not None or ln is not None \
-            or rowstats_out is not None:
-        raise NotImplementedError("emulator: epilogue not modelled")
+    """out = epilogue(sum_k A[m, k] * W[n, k]) with the epilogue order of csrc/gemm_sm100.cu: LayerNorm-fold
+    correction, bias (per batch / per step), GEGLU gate, residual, SiLU, row statistics, store (NHWC fp16, NCHW, or the
+    fused scheduler update)."""
     ktot = sum((1 if k == L.SEG_1x1 else 9) * ((c + 63) // 64 * 64) for _, c, k in segs)
     assert weight.dtype == torch.float16 and tuple(weight.shape) == (N, ktot) and weight.is_contiguous()
     linear = (H == 0 or W == 0)
+    bn = L.load().unib200_pick_bn(N, flags)
 
     def run():
         cols = []
@@ -78,21 +107,116 @@ def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_b
                 cols.append(F.pad(tp, (0, cpad - c)))
         acc = torch.cat(cols, 1) @ weight.float().t()
         rpb = (M // B) if B > 0 else M
+        if ln is not None:                                   # consumer of LayerNorm(x): (rowstats, wsum, eps, C)
+            rs, wsum, eps, Cn = ln
+            s1, s2 = rs[:M, :, 0].sum(1), rs[:M, :, 1].sum(1)
+            mean = s1 / Cn
+            rstd = torch.rsqrt((s2 / Cn - mean * mean).clamp_min(0) + eps)
+            acc = rstd[:, None] * (acc - mean[:, None] * wsum[None, :])
         if bias is not None:
+            step = int(bias_step.item()) if bias_step is not None else 0
             if bias_bstride:
-                acc = acc + bias.reshape(-1, bias_bstride)[:, :N].float().repeat_interleave(rpb, 0)[:M]
+                nb = (M + rpb - 1) // rpb
+                bt = torch.as_strided(bias, (nb, N), (bias_bstride, 1), bias.storage_offset() + step * bias_step_stride)
+                acc = acc + bt.float().repeat_interleave(rpb, 0)[:M]
             else:
-                acc = acc + bias.float()[None, :N]
+                acc = acc + torch.as_strided(bias, (N,), (1,), bias.storage_offset() + step * bias_step_stride).float()
+        n_out = N
+        if flags & L.EPI_GEGLU:                              # per N tile: value columns | gate columns
+            t = acc.reshape(M, N // bn, 2, bn // 2)
+            acc = (t[:, :, 0] * _gelu_erf(t[:, :, 1])).reshape(M, N // 2)
+            n_out = N // 2
         if res is not None:
-            acc = acc + res[:M, :N].float()
+            acc = acc + res[:M, :n_out].float()
         if flags & L.EPI_SILU:
             acc = F.silu(acc)
+        if rowstats_out is not None:                         # consumers add the parts: put the row totals in part 0
+            rv = rowstats_out.reshape(-1)[:M * ((N + bn - 1) // bn) * 2].reshape(M, -1, 2)
+            rv.zero_()
+            rv[:, 0, 0], rv[:, 0, 1] = acc.sum(1), (acc * acc).sum(1)
         if flags & L.EPI_OUT_NCHW:
             nb = M // rpb
-            out.reshape(nb, N, rpb).copy_(acc.reshape(nb, rpb, N).permute(0, 2, 1))
+            pred = acc.reshape(nb, rpb, n_out).permute(0, 2, 1)                     # [nb, N, HW]
+            if flags & L.EPI_AXPBY:
+                row = int(axpby_step.item()) if axpby_step is not None else 0
+                c_out, c_x = axpby.reshape(-1, 2)[row].tolist()
+                x = aux.reshape(nb, n_out, rpb).clone()
+                keep = (torch.arange(n_out) < axpby_first_channel)[None, :, None]
+                if out is not None:
+                    raw = torch.where(keep, x, pred)
+                    out[:M, :n_out].copy_(raw.permute(0, 2, 1).reshape(M, n_out))
+                aux_out.reshape(nb, n_out, rpb).copy_(torch.where(keep, x, c_out * pred + c_x * x))
+            else:
+                out.reshape(nb, n_out, rpb).copy_(pred)
         else:
-            out[:M, :N].copy_(acc)
+            out[:M, :n_out].copy_(acc)
     _submit(prog, run)
+
+
+def attention(prog, q, k, v, out, *, B, heads, Nq, Nk, d, scale=None):
+    sc = float(scale if scale is not None else d ** -0.5)
+
+    def run():
+        for b in range(B):
+            for h in range(heads):
+                qs = q[b * Nq:(b + 1) * Nq, h * d:(h + 1) * d].float()
+                ks = k[b * Nk:(b + 1) * Nk, h * d:(h + 1) * d].float()
+                vs = v[b * Nk:(b + 1) * Nk, h * d:(h + 1) * d].float()
+                out[b * Nq:(b + 1) * Nq, h * d:(h + 1) * d].copy_(torch.softmax(qs @ ks.t() * sc, -1) @ vs)
+    _submit(prog, run)
+
+
+def layernorm(prog, x, y, gamma, beta, eps=1e-5):
+    _submit(prog, lambda: y.copy_(F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps)))
+
+
+def timestep_sinusoid(prog, t, out, *, B, dim, step_idx=None, t_stride=0):
+    def run():
+        import math
+        off = int(step_idx.item()) * t_stride if step_idx is not None else 0
+        tt = t.reshape(-1)[off:off + B].float()
+        half = dim // 2
+        ang = tt[:, None] * torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)[None]
+        out.copy_(torch.cat([torch.cos(ang), torch.sin(ang)], 1))
+    _submit(prog, run)
+
+
+def gemv(prog, x, w, bias, y, *, silu):
+    def run():
+        v = x @ w.float().t()
+        if bias is not None:
+            v = v + bias
+        y.copy_(F.silu(v) if silu else v)
+    _submit(prog, run)
+
+
+def axpby(prog, model_out, x, out, coef, step_idx=None):
+    def run():
+        a, b = coef.reshape(-1, 2)[int(step_idx.item()) if step_idx is not None else 0].tolist()
+        out.copy_(a * model_out + b * x)
+    _submit(prog, run)
+
+
+def unipc_step(prog, model_out, sample, last_sample, hist0, hist1, coef, step_idx=None, first_channel=0):
+    def run():
+        c = coef.reshape(-1, 10)[int(step_idx.item()) if step_idx is not None else 0].tolist()
+        sl = (slice(None), slice(first_channel, None))
+        s, h0, h1 = sample[sl].clone(), hist0[sl].clone(), hist1[sl].clone()
+        x0 = c[0] * model_out[sl] + c[1] * s
+        sc = c[2] * last_sample[sl] + c[3] * h0 + c[4] * h1 + c[5] * x0 if c[6] != 0 else s
+        sample[sl] = c[7] * sc + c[8] * x0 + c[9] * h0
+        last_sample[sl] = sc
+        hist1[sl] = h0
+        hist0[sl] = x0
+    _submit(prog, run)
+
+
+def add_int(prog, p, v):
+    _submit(prog, lambda: p.add_(v))
+
+
+def from_nhwc(prog, src, dst, *, B, Cn, HW):
+    _submit(prog, lambda: dst.copy_(src[:, :Cn].float().reshape(B, HW, Cn).permute(0, 2, 1).reshape(dst.shape)))
 
 
 def groupnorm(prog, x1, C1, x2, C2, gamma, beta, out, scratch, *, B, HW, groups, eps, silu):
@@ -141,9 +265,31 @@ def add_f16(prog, a, b, out):
     _submit(prog, lambda: out.copy_(a.float() + b.float()))
 
 
+EMULATED = ("conv_gemm", "attention", "groupnorm", "layernorm", "upsample2x", "to_nhwc", "from_nhwc", "softmax_rows",
+            "gaussian_sample", "add_f16", "add_int", "timestep_sinusoid", "gemv", "axpby", "unipc_step")
+
+
 def install(monkeypatch):
     """Route uni_renderer_b200.ops through the emulator for the duration of one test."""
     from uni_renderer_b200 import ops
-    for name in ("conv_gemm", "groupnorm", "upsample2x", "to_nhwc", "softmax_rows", "gaussian_sample", "add_f16"):
+    for name in EMULATED:
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "Program", FakeProgram)
+
+
+def cpu_sampler(sds, cfgs, prediction_type="epsilon", scheduler="ddim"):
+    """A DualStreamSampler on the CPU behind the emulator (test only: the constructor's CUDA gate is bypassed by
+    building the object by hand; call install() first)."""
+    from uni_renderer_b200.engine import StreamNet, Workspace
+    from uni_renderer_b200.pipeline import DualStreamSampler
+    from uni_renderer_b200.scheduler import DDIMSchedule, UniPCSchedule
+    s = object.__new__(DualStreamSampler)
+    s.unet, s.enc, s.dec = (StreamNet(k, c, sd, "cpu") for k, c, sd in zip(("unet", "attr_enc", "attr_dec"), cfgs, sds))
+    s.device = torch.device("cpu")
+    s.scheduler = scheduler
+    s.schedule = DDIMSchedule(prediction_type=prediction_type)
+    s.unipc = UniPCSchedule(prediction_type=prediction_type)
+    s.use_graph, s.split_batch, s.temb_table = False, False, True
+    s.ws, s.ws1 = Workspace("cpu"), Workspace("cpu")
+    s._plans = {}
+    return s
