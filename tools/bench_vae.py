@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--image", type=int, default=512)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scheduler", default="ddim", choices=["ddim", "unipc"],
+                    help="unipc + --steps 20 is what the reference's shipped eval runs (eval/test_real.py:485-493)")
     ap.add_argument("--once", action="store_true", help="one decode + one encode and exit (for an ncu launch list)")
     a = ap.parse_args()
     import torch
@@ -100,10 +102,13 @@ def main():
         imgs = [torch.tanh(torch.randn(B, 3, S, S, generator=g, device=dev)) for _ in range(7)]
         ehs = torch.randn(B, 77, 768, generator=g, device=dev).half()
         gen = torch.Generator(device=dev).manual_seed(9)
-        calls = {"inverse_rendering": lambda: rp.inverse_rendering(imgs[0], imgs[1], ehs, a.steps, generator=gen),
-                 "forward_rendering": lambda: rp.forward_rendering((0.3, 0.8), *imgs[1:7], ehs, a.steps, generator=gen)}
-        loops = {"inverse_rendering": lambda: sampler.inverse_render(z, torch.cat([z] * 7, 1), ehs, a.steps),
-                 "forward_rendering": lambda: sampler.forward_render(z, torch.cat([z] * 7, 1), ehs, a.steps)}
+        sch = a.scheduler
+        calls = {"inverse_rendering": lambda: rp.inverse_rendering(imgs[0], imgs[1], ehs, a.steps, generator=gen,
+                                                                   scheduler=sch),
+                 "forward_rendering": lambda: rp.forward_rendering((0.3, 0.8), *imgs[1:7], ehs, a.steps, generator=gen,
+                                                                   scheduler=sch)}
+        loops = {"inverse_rendering": lambda: sampler.inverse_render(z, torch.cat([z] * 7, 1), ehs, a.steps, scheduler=sch),
+                 "forward_rendering": lambda: sampler.forward_render(z, torch.cat([z] * 7, 1), ehs, a.steps, scheduler=sch)}
         for name in calls:
             ms_all = timed(calls[name], k=3, w=2)
             ms_loop = timed(loops[name], k=3, w=1)
@@ -111,7 +116,7 @@ def main():
             fin = all(bool(torch.isfinite(t).all()) for t in (out if isinstance(out, tuple) else (out,)))
             line[name] = {"ms": ms_all, "images_per_s": B / (ms_all * 1e-3), "loop_only_ms": ms_loop,
                           "vae_and_glue_ms": ms_all - ms_loop, "vae_share": (ms_all - ms_loop) / ms_all,
-                          "denoise_steps": a.steps, "scheduler": "ddim", "finite": fin}
+                          "denoise_steps": a.steps, "scheduler": sch, "finite": fin}
     print(json.dumps(line), flush=True)
 
 
