@@ -131,3 +131,53 @@ def test_sharded_loop_world2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count("OK") == 2
+
+
+@pytest.mark.parametrize("name", ["tiny_step_vec_t.pt", "tiny_step_scalar_t.pt"])
+def test_module_forwards_on_emulator_match_reference_golden(monkeypatch, golden_dir, name):
+    """The three drop-in nn.Modules called in the reference's 3-call sequence (train/train.py:1324-1354), their recorded
+    programs executed by the emulator, against the tensors recorded from the REFERENCE's own model files
+    (tests/golden, oracle/make_golden.py): the module-level host wiring (timestep forms, residual ingestion, skip /
+    tap order, return structures) is pinned to the reference in the CPU suite too."""
+    from tests import gpu_model_probe as gp
+    from uni_renderer_b200 import models as M
+    from uni_renderer_b200.engine import StreamNet, Workspace
+    emu.install(monkeypatch)
+
+    def cpu_finalize(self, device=None):            # test only: the product's finalize() refuses non-CUDA devices
+        if self._net is None:
+            self._net = StreamNet(self._kind, self.net_cfg, dict(self.state_dict()), "cpu")
+            self._ws = Workspace("cpu")
+        return self._net
+    monkeypatch.setattr(M._NetModule, "finalize", cpu_finalize)
+    gold = torch.load(os.path.join(golden_dir, name), weights_only=False)
+    gc = gold["config"]
+    (unet, enc, dec), sds, _ = gp.build_modules(gc, device="cpu")
+    for sd, dg in zip(sds, gold["weight_digest"]):
+        if abs(float(sum(v.double().sum() for v in sd.values())) - dg["sum"]) > 1e-6 * max(1.0, abs(dg["abs"])):
+            pytest.skip("torch CPU RNG stream differs from the one that generated the fixtures")
+    B = gc["B"]
+    ti, ta = (gc["t_img"], gc["t_attr"]) if gc["scalar_t"] else (torch.full((B,), gc["t_img"]), torch.full((B,), gc["t_attr"]))
+    x_img, x_attr, ehs = gold["x_img"], gold["x_attr"], gold["ehs"]
+    d, m, raw_a, raw_a_mid = enc(x_img, ta, encoder_hidden_states=ehs, controlnet_cond=x_attr, return_dict=False)
+    img, raw_u, raw_u_mid, taps = unet(x_img, ti, encoder_hidden_states=ehs, down_block_additional_residuals=d,
+                                       mid_block_additional_residual=m, return_dict=False)
+    attr = dec(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=ta, encoder_hidden_states=ehs,
+               down_block_additional_residuals=raw_u, mid_block_additional_residual=raw_u_mid, return_dict=False)
+    assert len(d) == 12 and len(raw_a) == 12 and len(raw_u) == 12 and len(taps) == 13
+    checks = [("unet_sample", img, gold["unet_sample"]), ("dec_sample", attr, gold["dec_sample"]),
+              ("enc_mid", m, gold["enc_mid"]), ("enc_raw_mid", raw_a_mid, gold["enc_raw_mid"]),
+              ("unet_raw_mid", raw_u_mid, gold["unet_raw_mid"])]
+    checks += [(f"enc_down{i}", d[i], gold["enc_down"][i]) for i in range(12)]
+    checks += [(f"enc_raw{i}", raw_a[i], gold["enc_raw_down"][i]) for i in range(12)]
+    checks += [(f"unet_raw{i}", raw_u[i], gold["unet_raw_down"][i]) for i in range(12)]
+    checks += [(f"unet_tap{i}", taps[i], gold["unet_up_taps"][i]) for i in range(13)]
+    for what, got, ref in checks:
+        assert tuple(got.shape) == tuple(ref.shape), what
+        assert _rel(got.float(), ref) < 3e-3, (what, _rel(got.float(), ref))
+    plain = unet(x_img, ti, encoder_hidden_states=ehs).sample
+    assert _rel(plain.float(), gold["unet_sample_plain"]) < 3e-3
+    # conditioning_scale is folded into the 13 zero-convs (models/controlnet.py:1773-1775)
+    d2, m2, _, _ = enc(x_img, ta, encoder_hidden_states=ehs, controlnet_cond=x_attr, conditioning_scale=0.5,
+                       return_dict=False)
+    assert _rel(m2.float(), 0.5 * gold["enc_mid"]) < 3e-3 and _rel(d2[3].float(), 0.5 * gold["enc_down"][3]) < 3e-3
