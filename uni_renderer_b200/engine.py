@@ -15,13 +15,13 @@ GEMM; GEGLU gate in the GEMM epilogue; every transformer residual add in a GEMM 
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import ops
-from .ops import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2, Program)
+from .ops import EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2
 
 
 @dataclass

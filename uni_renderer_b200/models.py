@@ -13,7 +13,7 @@ forward() of the same module with the same input shape); the reference returns f
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, Optional, Tuple
 
 import torch
 from torch import nn

@@ -4,7 +4,7 @@ Every function takes `prog` (a recorded program handle or None for an immediate 
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

@@ -22,7 +22,7 @@ No CPU / eager fallback: constructing a sampler without CUDA or without libunib2
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
@@ -49,7 +49,6 @@ class _Plan:
     flops_setup: float = 0.0
     flops_step: float = 0.0
     scheduler: str = "ddim"
-    once: Optional[ops.Program] = None
     once: Optional[ops.Program] = None
 
 

@@ -20,7 +20,7 @@ No CPU / eager fallback: without CUDA or libunib200.so every call raises.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import torch
 from torch import nn
