@@ -19,6 +19,7 @@ No CPU / eager fallback: without CUDA or libunib200.so every call raises.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple
 
@@ -358,6 +359,7 @@ class AutoencoderKL(_NetModule):
     """diffusers.AutoencoderKL surface over VaeNet (inference only)."""
     _kind = "vae"
     max_batch = 8          # images per recorded program; larger batches are processed in chunks of this size
+    use_graph = os.environ.get("UNIB200_VAE_GRAPH", "1") != "0"     # replay each program as one CUDA graph
 
     def __init__(self, in_channels: int = 3, out_channels: int = 3, down_block_types=(_DOWN,),
                  up_block_types=(_UP,), block_out_channels=(64,), layers_per_block: int = 1, act_fn: str = "silu",
@@ -435,8 +437,21 @@ class AutoencoderKL(_NetModule):
             P["z"] = Act(torch.zeros(B * H * W, cp, device=dev, dtype=torch.float16), B, H, W, cp)
             P["image"] = torch.zeros(B, cfg.out_channels, H * f, W * f, device=dev, dtype=torch.float32)
             net.rec_decoder(P["prog"], ws, P["z"], P["image"])
+        if self.use_graph:
+            # one eager pass first (sets every kernel's function attributes outside capture), then capture on a side
+            # stream -- the legacy default stream cannot be captured (same recipe as DualStreamSampler.plan)
+            P["prog"].run()
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                P["prog"].instantiate_graph()
+            side.synchronize()
         self._progs[key] = P
         return P
+
+    @staticmethod
+    def _replay(P):
+        P["prog"].launch_graph() if P["prog"].has_graph else P["prog"].run()
 
     @staticmethod
     def _float(x: torch.Tensor) -> torch.Tensor:
@@ -454,7 +469,7 @@ class AutoencoderKL(_NetModule):
             return (dist,) if not return_dict else AutoencoderKLOutput(latent_dist=dist)
         P = self._program("enc", B, H, W)
         ops.to_nhwc(None, self._float(x).to(net.device), P["x"].t, P["x"].C)
-        P["prog"].run()
+        self._replay(P)
         dist = DiagonalGaussianDistribution(P["moments"].clone())
         if not return_dict:
             return (dist,)
@@ -472,7 +487,7 @@ class AutoencoderKL(_NetModule):
             return (img,) if not return_dict else DecoderOutput(sample=img)
         P = self._program("dec", B, H, W)
         ops.to_nhwc(None, self._float(z).to(net.device), P["z"].t, P["z"].C)
-        P["prog"].run()
+        self._replay(P)
         img = P["image"].to(z.dtype) if z.dtype in (torch.float16, torch.bfloat16) else P["image"].clone()
         if not return_dict:
             return (img,)
