@@ -181,3 +181,59 @@ def test_module_forwards_on_emulator_match_reference_golden(monkeypatch, golden_
     d2, m2, _, _ = enc(x_img, ta, encoder_hidden_states=ehs, controlnet_cond=x_attr, conditioning_scale=0.5,
                        return_dict=False)
     assert _rel(m2.float(), 0.5 * gold["enc_mid"]) < 3e-3 and _rel(d2[3].float(), 0.5 * gold["enc_down"][3]) < 3e-3
+
+
+def test_render_pipeline_on_emulator_matches_oracle_chain(monkeypatch):
+    """Image-to-image inverse rendering (RenderPipeline: 2 batched encodes -> loop -> 5 batched decodes) on the CPU
+    emulator against vae_oracle.encode -> uni_oracle steps -> vae_oracle.decode with the same seeded generator: pins
+    the noise order (posterior noise of image then masks, then the six attribute latents; models/pipeline.py:2112-2188),
+    the 28-channel layout (:1583) and the decode order (:2335-2349) in the CPU suite."""
+    from oracle import vae_oracle as vo
+    from uni_renderer_b200 import vae as V
+    from uni_renderer_b200.engine import Workspace
+    from uni_renderer_b200.render import RenderPipeline
+    emu.install(monkeypatch)
+    sampler, sds, cfgs = _setup()
+    vsd = vo.random_state_dict(vo.TINY_VAE, 5)
+    vae = V.AutoencoderKL(block_out_channels=(32, 64, 64), down_block_types=(V._DOWN,) * 3, up_block_types=(V._UP,) * 3,
+                          layers_per_block=2, norm_num_groups=8)
+    vae.load_state_dict(vsd)
+    vae.use_graph = False
+
+    def cpu_finalize(self, device=None):            # test only: bypass the CUDA gate of the product
+        if self._net is None:
+            net = object.__new__(V.VaeNet)
+            net.cfg, net.device, net.w = self.vae_cfg, torch.device("cpu"), {}
+            net._pack(V.convert_deprecated_attention_keys(dict(self.state_dict())))
+            self._net, self._ws = net, Workspace("cpu")
+        return self._net
+    monkeypatch.setattr(V.AutoencoderKL, "finalize", cpu_finalize)
+    rp = RenderPipeline(sampler, vae)
+    B, S, steps = 1, 32, 2
+    h = S // 4
+    g = torch.Generator().manual_seed(31)
+    image, masks = (torch.tanh(torch.randn(B, 3, S, S, generator=g)) for _ in range(2))
+    ehs = torch.randn(B, 7, cfgs[0].cross_attention_dim, generator=g).half()
+    gen = torch.Generator().manual_seed(77)
+    out = rp.inverse_rendering(image, masks, ehs, num_inference_steps=steps, generator=gen)
+    assert len(out) == 6 and out[0].shape == (B, 4, h, h) and all(o.shape == (B, 3, S, S) for o in out[1:])
+    gen.manual_seed(77)
+    n_img, n_msk = (torch.randn(B, 4, h, h, generator=gen) for _ in range(2))
+    lat = [torch.randn(B, 4, h, h, generator=gen) for _ in range(6)]
+    sf = vo.TINY_VAE.scaling_factor
+    with torch.no_grad():
+        l_img = vo.sample_posterior(vo.encode_moments(vsd, vo.TINY_VAE, image), n_img) * sf
+        l_msk = vo.sample_posterior(vo.encode_moments(vsd, vo.TINY_VAE, masks), n_msk) * sf
+        sched, sched_a = uo.DDIM(), uo.DDIM()
+        ts = sched.set_timesteps(steps)
+        sched_a.set_timesteps(steps)
+        xi, xa = l_img, torch.cat([l_msk] + lat, 1)
+        for i in range(steps):
+            xi, xa = oracle_step("inverse", sds, cfgs, sched, ts[i], xi, xa, ehs.float(), sched_a)
+        assert _rel(out[0], xa[:, 4:8]) < 5e-3
+        for i in range(5):
+            ref = vo.decode(vsd, vo.TINY_VAE, xa[:, 8 + 4 * i:12 + 4 * i] / sf)
+            assert _rel(out[1 + i], ref) < 6e-3, (i, _rel(out[1 + i], ref))
+    # prompt embeddings come from the cache when none are passed
+    with pytest.raises(ValueError):
+        rp.inverse_rendering(image, masks, None, num_inference_steps=steps)
