@@ -277,7 +277,7 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "Program", FakeProgram)
 
 
-def cpu_sampler(sds, cfgs, prediction_type="epsilon", scheduler="ddim"):
+def cpu_sampler(sds, cfgs, prediction_type="epsilon", scheduler="ddim", split_batch=False, temb_table=True):
     """A DualStreamSampler on the CPU behind the emulator (test only: the constructor's CUDA gate is bypassed by
     building the object by hand; call install() first)."""
     from uni_renderer_b200.engine import StreamNet, Workspace
@@ -289,7 +289,7 @@ def cpu_sampler(sds, cfgs, prediction_type="epsilon", scheduler="ddim"):
     s.scheduler = scheduler
     s.schedule = DDIMSchedule(prediction_type=prediction_type)
     s.unipc = UniPCSchedule(prediction_type=prediction_type)
-    s.use_graph, s.split_batch, s.temb_table = False, False, True
+    s.use_graph, s.split_batch, s.temb_table = False, split_batch, temb_table
     s.ws, s.ws1 = Workspace("cpu"), Workspace("cpu")
     s._plans = {}
     return s

@@ -68,6 +68,29 @@ def test_recorded_loop_matches_oracle(monkeypatch, mode, scheduler, steps):
         assert torch.equal(got_a, x_attr)
 
 
+@pytest.mark.parametrize("mode", ["forward", "inverse"])
+def test_option_paths_agree_with_the_default(monkeypatch, mode):
+    """A/B knobs of the recorder must not change the result: batch halves on two lanes (split_batch: row-sliced
+    activations, K/V, time-embedding rows and latent views) and time embeddings recomputed inside every step
+    (UNIB200_TEMB_TABLE=0) instead of tabulated for the whole loop."""
+    emu.install(monkeypatch)
+    _, sds, cfgs_o = _setup()
+    from uni_renderer_b200.engine import NetConfig
+    nb = NetConfig(block_out_channels=uo.TINY.block_out_channels, num_heads=uo.TINY.num_heads,
+                   cross_attention_dim=uo.TINY.cross_attention_dim, norm_num_groups=uo.TINY.norm_num_groups)
+    cfgs = (replace(nb), replace(nb, in_channels=28), replace(nb, out_channels=28))
+    x_img, x_attr, ehs = _inputs(2, 8, nb.cross_attention_dim)
+    outs = []
+    for kw in ({}, {"split_batch": True}, {"temb_table": False}):
+        s = emu.cpu_sampler(sds, cfgs, **kw)
+        plan = s.plan(mode, 2, 8, ehs.shape[1], 10)
+        s.load_inputs(plan, x_img, x_attr, ehs)
+        s.run(plan, steps=2)
+        outs.append((plan.bufs["lat_img"].clone(), plan.bufs["lat_attr"].clone()))
+    for gi, ga in outs[1:]:
+        assert _rel(gi, outs[0][0]) < 1e-3 and _rel(ga, outs[0][1]) < 1e-3
+
+
 def test_plans_are_cached_and_modes_are_validated(monkeypatch):
     emu.install(monkeypatch)
     sampler, _, cfgs = _setup()
