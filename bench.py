@@ -370,6 +370,10 @@ def run_b200(a):
                 "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
                 "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
             for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+    if rank == 0 and a.mode == "joint" and B == 4 and S == 64 and a.scheduler == "ddim":
+        ref = committed_gpu_pytorch_bar()
+        if ref is not None:
+            line["gpu_pytorch_eager"] = dict(ref, speedup_vs_it=ref["ms_per_denoise_step"] / (ms_res / a.steps / T))
     if rank == 0 and world == 1 and not a.no_vae and S == 64:
         # the next row of the scope table: the AutoencoderKL that brackets every sampling call of the
         # reference (models/pipeline.py:1531-1556 encodes, :1664 / :2335-2349 decodes) on the same kernels.  Reported
@@ -389,6 +393,24 @@ def run_b200(a):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def committed_gpu_pytorch_bar():
+    """SURVEY 8d's "same-box GPU PyTorch" bar: the reference's arithmetic under torch eager fp16 (cuDNN / cuBLAS / SDPA) on
+    a B200 of this pod, measured by tests/torch_eager_probe.py (it executes oracle/, so it cannot run from here) and
+    committed under profiles/.  Quoted with its source -- NOT measured in this run."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_torch_eager_fp16_joint.json")))
+    if not cands:
+        return None
+    try:
+        with open(cands[-1]) as f:
+            d = json.load(f)
+        return {"ms_per_denoise_step": d["ms_per_denoise_step"], "images_per_s": d["images_per_s_50_steps"],
+                "batch": d["batch"], "latent": d["latent"], "torch": d["torch"], "cudnn_benchmark": d["cudnn_benchmark"],
+                "source": f"profiles/{os.path.basename(cands[-1])} (committed measurement, not this run)"}
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def vae_leg(torch, dev, B, image, peaks):
