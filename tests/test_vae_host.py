@@ -142,3 +142,46 @@ def test_fold_quant_conv_is_exact():
     two = F.conv2d(F.conv2d(x, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1),
                    sd["quant_conv.weight"], sd["quant_conv.bias"])
     torch.testing.assert_close(F.conv2d(x, w, b, padding=1), two, rtol=1e-5, atol=1e-5)
+
+
+def test_module_encode_decode_api_on_emulator(monkeypatch):
+    """`vae.encode(x).latent_dist.sample()/.mode()` and `vae.decode(z, return_dict=False)[0]` through the drop-in module
+    (recorded programs executed by the emulator): oracle parity, the chunked path for batches above `max_batch`, the
+    return forms and the dtype rules the reference's call sites rely on (models/pipeline.py:1531, 1664, 2112-2117)."""
+    emu.install(monkeypatch)
+    sd = vo.random_state_dict(vo.TINY_VAE, 5)
+    m = V.AutoencoderKL(**TINY_KW)
+    m.load_state_dict(sd)
+    m.use_graph = False
+
+    def cpu_finalize(self, device=None):            # test only: bypass the CUDA gate of the product
+        if self._net is None:
+            self._net = _cpu_net(dict(self.state_dict()))
+            self._ws = Workspace("cpu")
+        return self._net
+    monkeypatch.setattr(V.AutoencoderKL, "finalize", cpu_finalize)
+    g = torch.Generator().manual_seed(8)
+    x = torch.tanh(torch.randn(3, 3, 32, 32, generator=g))
+    z = torch.randn(3, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        ref_m, ref_img = vo.encode_moments(sd, vo.TINY_VAE, x), vo.decode(sd, vo.TINY_VAE, z)
+    out = m.encode(x)
+    assert isinstance(out, V.AutoencoderKLOutput) and m.encode(x, return_dict=False)[0].parameters.shape == ref_m.shape
+    dist = out.latent_dist
+    assert _rel(dist.parameters, ref_m) < 3e-3 and _rel(dist.mode(), ref_m[:, :4]) < 3e-3
+    assert torch.equal(dist.mean, dist.parameters[:, :4]) and torch.equal(dist.logvar, dist.parameters[:, 4:])
+    g1, g2 = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+    smp = dist.sample(g1)
+    noise = torch.randn(3, 4, 8, 8, generator=g2)
+    assert _rel(smp, vo.sample_posterior(dist.parameters, noise)) < 1e-5
+    img = m.decode(z, return_dict=False)[0]
+    assert img.dtype == torch.float32 and _rel(img, ref_img) < 3e-3
+    assert isinstance(m.decode(z), V.DecoderOutput)
+    # batches above max_batch run as chunks of the recorded program and give the same result
+    m.max_batch = 2
+    assert _rel(m.decode(z).sample, img) < 1e-3 and _rel(m.encode(x).latent_dist.parameters, dist.parameters) < 1e-3
+    assert {k[:2] for k in m._progs} == {("dec", 3), ("dec", 2), ("dec", 1), ("enc", 3), ("enc", 2), ("enc", 1)}
+    with pytest.raises(ValueError):
+        m.decode(torch.zeros(1, 4, 6, 6))             # latent sides must be powers of two
+    full = m(x, sample_posterior=False).sample        # forward(): encode -> mode -> decode
+    assert full.shape == x.shape and torch.isfinite(full).all()
