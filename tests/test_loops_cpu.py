@@ -102,9 +102,11 @@ def test_plans_are_cached_and_modes_are_validated(monkeypatch):
         sampler.plan("cycle", 1, 8, 7, 4, "unipc")
     with pytest.raises(ValueError):
         sampler.load_inputs(p1, torch.zeros(2, 4, 8, 8), torch.zeros(1, 28, 8, 8), torch.zeros(1, 7, 48))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):            # guidance needs the negative embeddings
         sampler.joint_sample(torch.zeros(1, 4, 8, 8), torch.zeros(1, 28, 8, 8), torch.zeros(1, 7, 48).half(), 4,
                              guidance_scale=7.5)
+    with pytest.raises(NotImplementedError):
+        sampler.plan("cycle", 1, 8, 7, 4, cfg=True)
     # step-invariant work is hoisted: forward rendering's step program is shorter than the joint one
     pj, pf = sampler.plan("joint", 1, 8, 7, 4), sampler.plan("forward", 1, 8, 7, 4)
     assert pf.step.num_launches < 0.7 * pj.step.num_launches and pf.setup.num_launches > pj.setup.num_launches
@@ -260,3 +262,44 @@ def test_render_pipeline_on_emulator_matches_oracle_chain(monkeypatch):
     # prompt embeddings come from the cache when none are passed
     with pytest.raises(ValueError):
         rp.inverse_rendering(image, masks, None, num_inference_steps=steps)
+
+
+@pytest.mark.parametrize("mode,scheduler,steps", [("joint", "ddim", 2), ("forward", "ddim", 2), ("inverse", "ddim", 2),
+                                                   ("joint", "unipc", 3), ("inverse", "unipc", 3)])
+def test_cfg_plans_match_the_reference_rules(monkeypatch, mode, scheduler, steps):
+    """Classifier-free guidance (`guidance_scale != 0`, models/pipeline.py:807): doubled batch with
+    cat([negative, positive]) embeddings and the combination rule of each loop (tests/cfg_reference.py), through the
+    public entry points on the emulator."""
+    from tests.cfg_reference import cfg_step
+    emu.install(monkeypatch)
+    sampler, sds, cfgs = _setup()
+    B, S, total, g = 2, 8, 10, 3.0
+    x_img, x_attr, ehs = _inputs(B, S, cfgs[0].cross_attention_dim)
+    neg = torch.randn(1, ehs.shape[1], ehs.shape[2], generator=torch.Generator().manual_seed(5)).half()
+    plan = sampler.plan(mode, B, S, ehs.shape[1], total, scheduler, cfg=True)
+    assert plan.cfg and plan.net_batch == 2 * B and plan.bufs["lat_img"].shape[0] == B
+    sampler.load_inputs(plan, x_img, x_attr, ehs, neg, g)
+    sampler.run(plan, steps=steps)
+    mk = (lambda: uo.DDIM()) if scheduler == "ddim" else (lambda: uo.UniPC())
+    sched, sched_a = mk(), mk()
+    ts = sched.set_timesteps(total)
+    sched_a.set_timesteps(total)
+    ri, ra = x_img, x_attr
+    for i in range(steps):
+        ri, ra = cfg_step(mode, sds, cfgs, sched, ts[i], ri, ra, ehs.float(), neg.float(), g, sched_a)
+    got_i, got_a = plan.bufs["lat_img"], plan.bufs["lat_attr"]
+    assert torch.equal(got_a[:, :4], x_attr[:, :4])
+    if mode != "inverse":
+        assert _rel(got_i, ri) < 5e-3, _rel(got_i, ri)
+    if mode != "forward":
+        assert _rel(got_a, ra) < 5e-3, _rel(got_a, ra)
+    # guidance actually changes the result (the plan without guidance gives something else)
+    p0 = sampler.plan(mode, B, S, ehs.shape[1], total, scheduler)
+    sampler.load_inputs(p0, x_img, x_attr, ehs)
+    sampler.run(p0, steps=steps)
+    tgt = "lat_attr" if mode == "inverse" else "lat_img"
+    assert _rel(p0.bufs[tgt], plan.bufs[tgt]) > 1e-3
+    with pytest.raises(ValueError):
+        sampler.load_inputs(plan, x_img, x_attr, ehs)              # a CFG plan needs the negative embeddings
+    with pytest.raises(ValueError):
+        sampler.load_inputs(p0, x_img, x_attr, ehs, neg, g)

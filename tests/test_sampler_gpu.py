@@ -77,5 +77,5 @@ def test_public_api_host_roundtrip():
     assert torch.isfinite(i1).all() and torch.isfinite(a1).all()
     inv = sampler.inverse_render(x_img, x_attr, ehs, num_inference_steps=2)
     assert inv.shape == (2, 24, 16, 16)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):          # guidance needs the negative embeddings (tests/test_zz_cfg_gpu.py)
         sampler.joint_sample(x_img, x_attr, ehs, guidance_scale=7.5)

@@ -50,6 +50,8 @@ class _Plan:
     flops_step: float = 0.0
     scheduler: str = "ddim"
     once: Optional[ops.Program] = None
+    cfg: bool = False          # classifier-free guidance: the networks run on net_batch = 2 * B samples
+    net_batch: int = 0
 
 
 class DualStreamSampler:
@@ -102,26 +104,35 @@ class DualStreamSampler:
     # ------------------------------------------------------------------------------------------------------------
     # recording
     # ------------------------------------------------------------------------------------------------------------
-    def plan(self, mode: str, B: int, S: int, L: int = 77, steps: int = 50, scheduler: Optional[str] = None) -> _Plan:
+    def plan(self, mode: str, B: int, S: int, L: int = 77, steps: int = 50, scheduler: Optional[str] = None,
+             cfg: bool = False) -> _Plan:
+        """cfg=True records the classifier-free-guidance variant of the loop (`guidance_scale != 0`, models/pipeline.py
+        :807): the networks run on a doubled batch [first half | second half] whose text embeddings are
+        cat([negative, positive]) (:1445), the two halves of each prediction are combined with per-channel-group weights
+        (`_cfg_groups`) and the scheduler update runs on the combined prediction."""
         if mode not in MODES:
             raise ValueError(f"mode must be one of {MODES}")
+        if cfg and mode == "cycle":
+            raise NotImplementedError("the cycle double pass is a training-time construct: no guidance")
         scheduler = scheduler or self.scheduler
         if scheduler not in SCHEDULERS:
             raise ValueError(f"scheduler must be one of {SCHEDULERS}")
         if scheduler == "unipc" and mode == "cycle":
             raise NotImplementedError("the cycle double pass (a training-time construct, train/train.py:1388-1413) is "
                                       "only wired for the DDIM update")
-        key = (mode, B, S, L, steps, scheduler)
+        key = (mode, B, S, L, steps, scheduler, cfg)
         if key in self._plans:
             return self._plans[key]
+        Bs = B                       # samples whose latents are denoised
+        B = 2 * B if cfg else B      # batch the networks see
         dev, ws, ws1 = self.device, self.ws, self.ws1
         unet, enc, dec = self.unet, self.enc, self.dec
         f32 = dict(device=dev, dtype=torch.float32)
         f16 = dict(device=dev, dtype=torch.float16)
         ci, ca = unet.cfg.in_channels, enc.cfg.in_channels
         b: Dict[str, torch.Tensor] = {}
-        b["lat_img"] = torch.zeros(B, ci, S, S, **f32)                 # x_t of the RGB stream (NCHW fp32 state)
-        b["lat_attr"] = torch.zeros(B, ca, S, S, **f32)                # [mask | 6 attribute groups]
+        b["lat_img"] = torch.zeros(Bs, ci, S, S, **f32)                # x_t of the RGB stream (NCHW fp32 state)
+        b["lat_attr"] = torch.zeros(Bs, ca, S, S, **f32)               # [mask | 6 attribute groups]
         b["ehs"] = torch.zeros(B * L, unet.cfg.cross_attention_dim, **f16)
         b["step"] = torch.zeros(1, device=dev, dtype=torch.int32)       # device-side step counter
         b["t_img"] = torch.zeros(steps, B, **f32)                       # per-step timestep tables
@@ -143,6 +154,9 @@ class DualStreamSampler:
         def decode(net, wsl, mid, skips, tp, kv, ax, tag):
             """Decoder + scheduler update of one stream: DDIM fused behind conv_out, UniPC as one fused pass on the
             fp32 prediction (it needs the model-output history, so it cannot live in the conv epilogue)."""
+            if cfg:
+                self._rec_cfg_decode(step, b, net, wsl, mid, skips, tp, kv, L, ax, tag, mode, scheduler, Bs)
+                return
             if scheduler == "ddim":
                 net.rec_decoder(step, wsl, mid, skips, tp, kv, L, out_nchw=None, axpby=ax)
                 return
@@ -168,15 +182,22 @@ class DualStreamSampler:
                 return net.rec_temb(prog, ws, table, B, step_idx=b["step"], t_stride=B)
             return net.rec_temb_table(once, table, b["step"])
 
+        def ingest(prog, lat, x: Act):
+            """fp32 NCHW latent state -> the network's NHWC fp16 input (both halves of the doubled batch under CFG:
+            `torch.cat([latents] * 2)`, models/pipeline.py:1598)."""
+            rows = Bs * S * S
+            for h in range(2 if cfg else 1):
+                ops.to_nhwc(prog, lat, x.t[h * rows:(h + 1) * rows], x.C)
+
         if mode in ("joint", "cycle"):
             # The RGB stream (lane 0) and the attribute stream (lane 1) only meet at the exchange: two parallel
             # branches of the step graph, so the small-M layers of one stream fill the SMs the other leaves idle.
             step.lane(1)
-            ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
+            ingest(step, b["lat_attr"], x_attr)
             tpE, tpD = temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
             skA, midA = enc.rec_encoder(step, ws1, x_attr, tpE, kvE, L)
             step.lane(0)
-            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            ingest(step, b["lat_img"], x_img)
             tpU = temb(unet, step, b["t_img"])
             skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
             step.barrier()
@@ -211,17 +232,17 @@ class DualStreamSampler:
         elif mode == "forward":
             # step-invariant: attribute encoder + its 13 zero-convs (attr28, t_attr = 0, ehs constant)
             b["t_zero"] = torch.zeros(1, B, **f32)
-            ops.to_nhwc(setup, b["lat_attr"], x_attr.t, x_attr.C)
+            ingest(setup, b["lat_attr"], x_attr)
             tpE = temb(enc, setup, b["t_zero"], stepped=False)
             skA, midA = enc.rec_encoder(setup, ws, x_attr, tpE, kvE, L)
             d, m = enc.rec_exchange(setup, ws, skA, midA, [None] * len(skA), None)
-            ops.to_nhwc(step, b["lat_img"], x_img.t, x_img.C)
+            ingest(step, b["lat_img"], x_img)
             tpU = temb(unet, step, b["t_img"])
             # only one stream is live in this loop; with split_batch the two HALVES of the batch take the two lanes
             # (samples are independent).  Measured slower on B200 at B=4 (7.05 -> 7.59 ms/step: every weight is
             # streamed twice and the half-batch tiles are less efficient), so it is off by default.
             step.barrier()
-            for lane, (b0, b1), wsl in self._batch_lanes(B):
+            for lane, (b0, b1), wsl in self._batch_lanes(B, cfg):
                 step.lane(lane)
                 skU, midU = unet.rec_encoder(step, wsl, _rows(x_img, b0, b1), tpU[b0:b1], _kv_rows(kvU, b0, b1, L), L)
                 dskU = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skU, d)]   # controlnet.py:1078-1087
@@ -233,14 +254,14 @@ class DualStreamSampler:
         else:  # inverse
             # step-invariant: RGB encoder + mid + the decoder-side zero-convs of its raw features
             b["t_zero"] = torch.zeros(1, B, **f32)
-            ops.to_nhwc(setup, b["lat_img"], x_img.t, x_img.C)
+            ingest(setup, b["lat_img"], x_img)
             tpU = temb(unet, setup, b["t_zero"], stepped=False)
             skU, midU = unet.rec_encoder(setup, ws, x_img, tpU, kvU, L)
             zU, zmidU = dec.rec_exchange(setup, ws, skU, midU, [None] * len(skU), None)
-            ops.to_nhwc(step, b["lat_attr"], x_attr.t, x_attr.C)
+            ingest(step, b["lat_attr"], x_attr)
             tpE, tpD = temb(enc, step, b["t_attr"]), temb(dec, step, b["t_attr"])
             step.barrier()
-            for lane, (b0, b1), wsl in self._batch_lanes(B):       # batch halves on the two lanes, as above
+            for lane, (b0, b1), wsl in self._batch_lanes(B, cfg):  # batch halves on the two lanes, as above
                 step.lane(lane)
                 skA, midA = enc.rec_encoder(step, wsl, _rows(x_attr, b0, b1), tpE[b0:b1], _kv_rows(kvE, b0, b1, L), L)
                 dskA = [self._add(step, s_, _rows(r, b0, b1)) for s_, r in zip(skA, zU)]   # controlnet.py:2446-2461
@@ -251,7 +272,8 @@ class DualStreamSampler:
             step.lane(0)
         ops.add_int(step, b["step"], 1)
 
-        plan = _Plan(mode, B, S, L, steps, setup, step, b)
+        plan = _Plan(mode, Bs, S, L, steps, setup, step, b)
+        plan.cfg, plan.net_batch = cfg, B
         plan.scheduler = scheduler
         plan.once = once
         plan.flops_setup = sum(i[1] for i in setup.op_info())
@@ -271,11 +293,48 @@ class DualStreamSampler:
         self._plans[key] = plan
         return plan
 
-    def _batch_lanes(self, B: int):
+    def _batch_lanes(self, B: int, cfg: bool = False):
         """(lane, (b0, b1), workspace) per batch slice: two halves on two lanes when the batch splits evenly."""
-        if self.split_batch and B >= 2 and B % 2 == 0:
+        if self.split_batch and not cfg and B >= 2 and B % 2 == 0:
             return [(0, (0, B // 2), self.ws), (1, (B // 2, B), self.ws1)]
         return [(0, (0, B), self.ws)]
+
+    @staticmethod
+    def _cfg_groups(mode: str, tag: str):
+        """(first_channel, last_channel, which) per channel group of a stream's prediction; `which` says how the two
+        halves [first | second] of the doubled batch are combined with guidance scale g:
+          "std"   first + g * (second - first)   joint loop: `uncond, text = chunk(2)` (pipeline_new_d4p.py:1440-1445)
+          "swap"  second + g * (first - second)  forward / inverse rendering name the halves `cond, uncond = chunk(2)`
+                                                 (pipeline.py:1643-1645, 2263-2265) -- mirrored as written
+          "first" first                          inverse rendering keeps `*_pred_cond` for every group but material
+                                                 (pipeline.py:2267-2285)"""
+        if mode == "joint":
+            return [(0, 4, "std")] if tag == "img" else [(MASK_CHANNELS, 28, "std")]
+        if mode == "forward":
+            return [(0, 4, "swap")]
+        return [(MASK_CHANNELS, MASK_CHANNELS + 4, "swap"), (MASK_CHANNELS + 4, 28, "first")]
+
+    def _rec_cfg_decode(self, step, b, net, wsl, mid, skips, tp, kv, L, ax, tag, mode, scheduler, Bs):
+        """Decoder on the doubled batch -> fp32 predictions of both halves -> guided combination -> scheduler update."""
+        lat = ax["latent"]
+        first_channel = ax.get("first_channel", 0)
+        pred2 = b.setdefault(f"pred2_{tag}", torch.zeros((2 * Bs,) + tuple(lat.shape[1:]), device=lat.device,
+                                                         dtype=torch.float32))
+        comb = b.setdefault(f"pred_{tag}", torch.zeros_like(lat))
+        net.rec_decoder(step, wsl, mid, skips, tp, kv, L, out_nchw=pred2)
+        for c0, c1, which in self._cfg_groups(mode, tag):
+            w = b.setdefault(f"cfg_w_{which}", torch.zeros(1, 2, device=lat.device, dtype=torch.float32))
+            for i in range(Bs):                 # a channel group of one sample is one contiguous block
+                ops.axpby(step, pred2[i, c0:c1], pred2[Bs + i, c0:c1], comb[i, c0:c1], w)
+        if scheduler == "ddim":
+            for i in range(Bs):
+                ops.axpby(step, comb[i, first_channel:], lat[i, first_channel:], lat[i, first_channel:], ax["coef"],
+                          ax["step"])
+        else:
+            for nm in ("last", "h0", "h1"):
+                b.setdefault(f"{nm}_{tag}", torch.zeros_like(lat))
+            ops.unipc_step(step, comb, lat, b[f"last_{tag}"], b[f"h0_{tag}"], b[f"h1_{tag}"], ax["coef"], ax["step"],
+                           first_channel=first_channel)
 
     def _add(self, prog, a: Act, r: Act) -> Act:
         o = Act(torch.empty_like(a.t), a.B, a.H, a.W, a.C)
@@ -284,7 +343,7 @@ class DualStreamSampler:
 
     def _upload_schedule(self, plan: _Plan):
         ts, coefs = (self.schedule if plan.scheduler == "ddim" else self.unipc).table(plan.steps)
-        t = torch.tensor(ts, dtype=torch.float32).reshape(-1, 1).expand(plan.steps, plan.B).contiguous()
+        t = torch.tensor(ts, dtype=torch.float32).reshape(-1, 1).expand(plan.steps, plan.net_batch).contiguous()
         c = torch.tensor(coefs, dtype=torch.float64).to(torch.float32)
         b = plan.bufs
         # joint/cycle: both streams walk the same timesteps; forward: t_attr = 0; inverse: t_img = 0 (hoisted)
@@ -296,16 +355,34 @@ class DualStreamSampler:
     # ------------------------------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------------------------------
-    def load_inputs(self, plan: _Plan, latents_img, latents_attr, prompt_embeds):
+    def load_inputs(self, plan: _Plan, latents_img, latents_attr, prompt_embeds, negative_prompt_embeds=None,
+                    guidance_scale: float = 0.0):
         """Copy one batch of inputs (any device / float dtype; pinned host memory makes this an async H2D) into
-        the plan's static buffers."""
+        the plan's static buffers.  A CFG plan also takes the negative embeddings (first half of the doubled batch,
+        `torch.cat([negative_prompt_embeds, prompt_embeds])`, models/pipeline.py:1445) and the guidance scale."""
         b = plan.bufs
+        if plan.cfg:
+            if negative_prompt_embeds is None:
+                raise ValueError("a classifier-free-guidance plan needs negative_prompt_embeds")
+            rows = plan.B * plan.L
+            neg = negative_prompt_embeds
+            if neg.shape[0] == 1 and plan.B > 1:        # the reference only ever builds one negative row (:372-430)
+                neg = neg.expand(plan.B, -1, -1)
+            b["ehs"][:rows].copy_(neg.reshape(rows, -1), non_blocking=True)
+            b["ehs"][rows:].copy_(prompt_embeds.reshape(rows, -1), non_blocking=True)
+            g = float(guidance_scale)
+            for which, w in (("std", (1.0 - g, g)), ("swap", (g, 1.0 - g)), ("first", (1.0, 0.0))):
+                if f"cfg_w_{which}" in b:
+                    b[f"cfg_w_{which}"].copy_(torch.tensor([w], dtype=torch.float32))
+        elif negative_prompt_embeds is not None:
+            raise ValueError("negative_prompt_embeds given to a plan recorded without guidance")
         if tuple(latents_img.shape) != tuple(b["lat_img"].shape) or tuple(latents_attr.shape) != tuple(b["lat_attr"].shape):
             raise ValueError(f"latent shapes {tuple(latents_img.shape)} / {tuple(latents_attr.shape)} do not match "
                              f"the plan {tuple(b['lat_img'].shape)} / {tuple(b['lat_attr'].shape)}")
         b["lat_img"].copy_(latents_img, non_blocking=True)
         b["lat_attr"].copy_(latents_attr, non_blocking=True)
-        b["ehs"].copy_(prompt_embeds.reshape(plan.B * plan.L, -1), non_blocking=True)
+        if not plan.cfg:
+            b["ehs"].copy_(prompt_embeds.reshape(plan.B * plan.L, -1), non_blocking=True)
 
     def run(self, plan: _Plan, steps: Optional[int] = None):
         """setup + `steps` replays of the step program on the current stream (asynchronous)."""
@@ -325,16 +402,18 @@ class DualStreamSampler:
         return plan.setup.num_launches + plan.steps * plan.step.num_launches
 
     def _sample(self, mode, latents_img, latents_attr, prompt_embeds, num_inference_steps, guidance_scale,
-                scheduler=None):
-        if guidance_scale not in (0, 0.0, None):
-            raise NotImplementedError("classifier-free guidance is not supported (every shipped Uni-Renderer caller "
-                                      "passes guidance_scale=0, eval/test_real.py:548)")
+                scheduler=None, negative_prompt_embeds=None):
+        cfg = guidance_scale not in (0, 0.0, None)          # `do_classifier_free_guidance`, models/pipeline.py:807
+        if cfg and negative_prompt_embeds is None:
+            raise ValueError("guidance_scale != 0 needs negative_prompt_embeds (every shipped Uni-Renderer caller passes "
+                             "guidance_scale=0, eval/test_real.py:548)")
         B, _, S, S2 = latents_img.shape
         if S != S2:
             raise ValueError("square latents only")
         L = prompt_embeds.shape[1]
-        plan = self.plan(mode, B, S, L, num_inference_steps, scheduler)
-        self.load_inputs(plan, latents_img, latents_attr, prompt_embeds)
+        plan = self.plan(mode, B, S, L, num_inference_steps, scheduler, cfg=cfg)
+        self.load_inputs(plan, latents_img, latents_attr, prompt_embeds, negative_prompt_embeds if cfg else None,
+                         guidance_scale if cfg else 0.0)
         self.run(plan)
         dev, dt = latents_img.device, latents_img.dtype
         img = plan.bufs["lat_img"].to(device=dev, dtype=dt, non_blocking=False)
@@ -343,26 +422,26 @@ class DualStreamSampler:
 
     @torch.no_grad()
     def joint_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
-                     guidance_scale: float = 0.0, scheduler: Optional[str] = None):
+                     guidance_scale: float = 0.0, scheduler: Optional[str] = None, negative_prompt_embeds=None):
         """Both streams noisy, same timestep (pipeline_new_d4p.py:1391-1453).  Returns (latents_img, latents_attr)."""
         _, img, attr = self._sample("joint", latents_img, latents_attr, prompt_embeds, num_inference_steps,
-                                    guidance_scale, scheduler)
+                                    guidance_scale, scheduler, negative_prompt_embeds)
         return img, attr
 
     @torch.no_grad()
     def forward_render(self, latents_img, attr_latents, prompt_embeds, num_inference_steps: int = 50,
-                       guidance_scale: float = 0.0, scheduler: Optional[str] = None):
+                       guidance_scale: float = 0.0, scheduler: Optional[str] = None, negative_prompt_embeds=None):
         """attributes -> RGB: t_attr = 0, t_img: T -> 0 (pipeline.py:1455,1586-1653).  Returns latents_img."""
         return self._sample("forward", latents_img, attr_latents, prompt_embeds, num_inference_steps,
-                            guidance_scale, scheduler)[1]
+                            guidance_scale, scheduler, negative_prompt_embeds)[1]
 
     @torch.no_grad()
     def inverse_render(self, image_latents, latents_attr, prompt_embeds, num_inference_steps: int = 50,
-                       guidance_scale: float = 0.0, scheduler: Optional[str] = None):
+                       guidance_scale: float = 0.0, scheduler: Optional[str] = None, negative_prompt_embeds=None):
         """RGB -> attributes: t_img = 0, t_attr: T -> 0 (pipeline.py:2475,2627-2733).  Returns the 24 attribute
         channels (the clean mask group is sliced off like pipeline.py:2691)."""
         return self._sample("inverse", image_latents, latents_attr, prompt_embeds, num_inference_steps,
-                            guidance_scale, scheduler)[2][:, MASK_CHANNELS:]
+                            guidance_scale, scheduler, negative_prompt_embeds)[2][:, MASK_CHANNELS:]
 
     @torch.no_grad()
     def cycle_sample(self, latents_img, latents_attr, prompt_embeds, num_inference_steps: int = 50,
