@@ -262,6 +262,12 @@ def test_render_pipeline_on_emulator_matches_oracle_chain(monkeypatch):
     # prompt embeddings come from the cache when none are passed
     with pytest.raises(ValueError):
         rp.inverse_rendering(image, masks, None, num_inference_steps=steps)
+    # guidance passes through to the CFG plan of the loop
+    neg = torch.randn(1, 7, cfgs[0].cross_attention_dim, generator=g).half()
+    gen.manual_seed(77)
+    guided = rp.inverse_rendering(image, masks, ehs, num_inference_steps=steps, generator=gen, guidance_scale=2.0,
+                                  negative_prompt_embeds=neg)
+    assert _rel(guided[0], out[0]) > 1e-3 and _rel(guided[1], out[1]) < 0.5     # material group is guided (:2263)
 
 
 @pytest.mark.parametrize("mode,scheduler,steps", [("joint", "ddim", 2), ("forward", "ddim", 2), ("inverse", "ddim", 2),

@@ -72,7 +72,8 @@ class RenderPipeline:
     def forward_rendering(self, material_num, normal_image, albedo_image, spec_light_image, diff_light_image, env_image,
                           masks_image, prompt_embeds=None, num_inference_steps: int = 50, guidance_scale: float = 0.0,
                           generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
-                          output_type: str = "pt", scheduler: Optional[str] = None, prompt: str = " "):
+                          output_type: str = "pt", scheduler: Optional[str] = None, prompt: str = " ",
+                          negative_prompt_embeds: Optional[torch.Tensor] = None):
         """attributes -> RGB (mask2image_3mod_albedo).  Images are [B, 3, H, W] tensors in [-1, 1]; material_num is
         (metallic, roughness); returns the decoded image [B, 3, H, W] (or the latents for output_type="latent")."""
         B = normal_image.shape[0]
@@ -88,7 +89,7 @@ class RenderPipeline:
             latents = self._randn((B, 4) + tuple(l_normal.shape[2:]), generator)     # prepare_latents, :705-719
         ehs = self._embeds(prompt_embeds, B, prompt)
         lat = self.sampler.forward_render(latents.to(self.device, torch.float32), attr28, ehs, num_inference_steps,
-                                          guidance_scale, scheduler)
+                                          guidance_scale, scheduler, negative_prompt_embeds)
         if output_type == "latent":
             return lat
         return self.decode_latents([lat])[0]
@@ -97,7 +98,7 @@ class RenderPipeline:
     def inverse_rendering(self, image, masks, prompt_embeds=None, num_inference_steps: int = 50,
                           guidance_scale: float = 0.0, generator: Optional[torch.Generator] = None,
                           latents: Optional[Sequence[torch.Tensor]] = None, scheduler: Optional[str] = None,
-                          prompt: str = " "):
+                          prompt: str = " ", negative_prompt_embeds: Optional[torch.Tensor] = None):
         """RGB -> attributes (image2mask_3mod_albedo).  Returns (material_latents, normal, albedo, spec_light,
         diff_light, env) with the five images decoded to [B, 3, H, W] in [-1, 1] (:2389)."""
         B = image.shape[0]
@@ -108,7 +109,8 @@ class RenderPipeline:
             raise ValueError(f"need {len(ATTR_GROUPS)} attribute latents ({ATTR_GROUPS})")
         attr28 = torch.cat([l_masks] + [l.to(self.device, torch.float32) for l in latents], 1)
         ehs = self._embeds(prompt_embeds, B, prompt)
-        attr24 = self.sampler.inverse_render(l_img, attr28, ehs, num_inference_steps, guidance_scale, scheduler)
+        attr24 = self.sampler.inverse_render(l_img, attr28, ehs, num_inference_steps, guidance_scale, scheduler,
+                                             negative_prompt_embeds)
         groups = [attr24[:, 4 * i:4 * i + 4] for i in range(len(ATTR_GROUPS))]
         decoded = self.decode_latents(groups[1:])                                    # material stays latent (:2331)
         return (groups[0],) + decoded
