@@ -32,9 +32,11 @@ int unib200_version(void);
 const char* unib200_last_error(void);                 /* thread-local, valid until the next failing call */
 int unib200_device_info(int* num_sms, int* cc_major, int* cc_minor);
 
-/* Programmatic dependent launch (on by default): every kernel is launched with the programmatic-stream-serialization
- * attribute and waits (griddepcontrol.wait) before touching global memory, so the prologue of kernel N+1 overlaps the
- * tail of kernel N inside a stream / CUDA-graph branch.  0 switches it off for launches made afterwards (A/B runs). */
+/* Programmatic dependent launch (OFF by default: measured as no gain inside the two-lane step graph):
+ * when enabled (1 = trigger at CTA end, 2 = early trigger) every kernel is launched with the
+ * programmatic-stream-serialization attribute and waits (griddepcontrol.wait) before touching global memory, so the
+ * prologue of kernel N+1 overlaps the tail of kernel N inside a stream / CUDA-graph branch.  Applies to launches made
+ * after the call (A/B runs; env UNIB200_PDL in the Python binding). */
 void unib200_set_pdl(int enabled);
 
 /* ---- programs (recorded op lists; optionally instantiated as a CUDA graph) --------------------------------- */
