@@ -258,19 +258,32 @@ class DDIM:
     beta_end: float = 0.012
     steps_offset: int = 1
     prediction_type: str = "epsilon"
+    timestep_spacing: str = "leading"
+    beta_schedule: str = "scaled_linear"
     alphas_cumprod: torch.Tensor = field(init=False)
     timesteps: List[int] = field(init=False, default_factory=list)
     num_inference_steps: int = 0
 
     def __post_init__(self):
-        betas = torch.linspace(self.beta_start ** 0.5, self.beta_end ** 0.5, self.num_train_timesteps,
-                               dtype=torch.float32) ** 2
+        if self.beta_schedule == "scaled_linear":
+            betas = torch.linspace(self.beta_start ** 0.5, self.beta_end ** 0.5, self.num_train_timesteps,
+                                   dtype=torch.float32) ** 2
+        else:
+            betas = torch.linspace(self.beta_start, self.beta_end, self.num_train_timesteps, dtype=torch.float32)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
 
     def set_timesteps(self, n: int):
+        """DDIMScheduler.set_timesteps of diffusers 0.24 for the three `timestep_spacing` values."""
+        import numpy as np
         self.num_inference_steps = n
-        ratio = self.num_train_timesteps // n
-        self.timesteps = [int(i * ratio) + self.steps_offset for i in range(n)][::-1]
+        T = self.num_train_timesteps
+        if self.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].copy().astype(np.int64) + self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)).astype(np.int64) - 1
+        else:
+            ts = np.linspace(0, T - 1, n).round()[::-1].copy().astype(np.int64)
+        self.timesteps = [int(t) for t in ts]
         return self.timesteps
 
     def coefficients(self, t: int) -> Tuple[float, float]:
@@ -321,16 +334,28 @@ class UniPC:
     beta_end: float = 0.012
     prediction_type: str = "epsilon"
     solver_order: int = 2
+    timestep_spacing: str = "linspace"
+    steps_offset: int = 0
+    solver_type: str = "bh2"
+    beta_schedule: str = "scaled_linear"
 
     def __post_init__(self):
-        betas = torch.linspace(self.beta_start ** 0.5, self.beta_end ** 0.5, self.num_train_timesteps,
-                               dtype=torch.float64) ** 2
+        if self.beta_schedule == "scaled_linear":
+            betas = torch.linspace(self.beta_start ** 0.5, self.beta_end ** 0.5, self.num_train_timesteps,
+                                   dtype=torch.float64) ** 2
+        else:
+            betas = torch.linspace(self.beta_start, self.beta_end, self.num_train_timesteps, dtype=torch.float64)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
 
     def set_timesteps(self, n: int):
         import numpy as np
         T = self.num_train_timesteps
-        ts = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)       # timestep_spacing "linspace"
+        if self.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":       # what from_config(SD-1.x scheduler config) inherits
+            ts = (np.arange(0, n + 1) * (T // (n + 1))).round()[::-1][:-1].copy().astype(np.int64) + self.steps_offset
+        else:
+            ts = np.arange(T, 0, -T / n).round().copy().astype(np.int64) - 1
         sig = ((1 - self.alphas_cumprod) / self.alphas_cumprod).sqrt().numpy()
         s = np.interp(ts, np.arange(T), sig)
         s_last = float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]).sqrt())
@@ -372,7 +397,7 @@ class UniPC:
         hh = -h                                   # predict_x0
         h_phi_1 = math.expm1(hh)
         h_phi_k = h_phi_1 / hh - 1.0
-        B_h = math.expm1(hh)                      # bh2
+        B_h = math.expm1(hh) if self.solver_type == "bh2" else hh
         R, b, fact = [], [], 1
         for i in range(1, order + 1):
             R.append([rk ** (i - 1) for rk in rks])

@@ -20,7 +20,9 @@ def err(got, ref):
     got, ref = got.float().cpu(), ref.float().cpu()
     d = (got - ref).abs()
     return {"max_abs": round(d.max().item(), 6), "rel_l2": round((d.norm() / (ref.norm() + 1e-12)).item(), 6),
-            "ref_absmax": round(ref.abs().max().item(), 4)}
+            "ref_absmax": round(ref.abs().max().item(), 4),
+            # north_star's elementwise criterion (rtol 1e-3 / atol 1e-4): fraction of elements that meet it
+            "allclose_frac": round((d <= 1e-4 + 1e-3 * ref.abs()).float().mean().item(), 4)}
 
 
 def build_modules(gc, device="cuda"):

@@ -60,7 +60,10 @@ def oracle_step(mode, sds, cfgs, sched, t, x_img, x_attr, ehs, sched_attr=None):
 
 
 def run_mode(mode, B=2, S=16, steps_total=50, n_steps=1, prediction_type="epsilon", use_graph=True, seed=1234,
-             scheduler="ddim"):
+             scheduler="ddim", start_index=0):
+    """start_index: first step of the walk to replay (e.g. 48 of 50 = t 21, a LATE step where c_out dominates the
+    update).  Single DDIM steps also report the error of the recovered network PREDICTION, pred = (x_prev - c_x x) /
+    c_out ("img_pred" / "attr_pred"): the latent itself hides the prediction error behind |c_out| ~ 0.02-0.16."""
     sampler, sds, cfgs = tiny_setup(prediction_type=prediction_type, use_graph=use_graph)
     g = torch.Generator().manual_seed(seed)
     x_img = torch.randn(B, 4, S, S, generator=g)
@@ -68,7 +71,14 @@ def run_mode(mode, B=2, S=16, steps_total=50, n_steps=1, prediction_type="epsilo
     ehs = torch.randn(B, 77, cfgs[0].cross_attention_dim, generator=g)
     plan = sampler.plan(mode, B, S, 77, steps_total, scheduler)
     sampler.load_inputs(plan, x_img, x_attr, ehs.half())
-    sampler.run(plan, steps=n_steps)
+    if start_index == 0:
+        sampler.run(plan, steps=n_steps)
+    else:                                    # same as run(), from a later point of the schedule (multistep: DDIM only)
+        assert scheduler == "ddim"
+        plan.bufs["step"].fill_(start_index)
+        plan.setup.run()
+        for _ in range(n_steps):
+            plan.step.launch_graph() if use_graph else plan.step.run()
     torch.cuda.synchronize()
     got_img, got_attr = plan.bufs["lat_img"].cpu(), plan.bufs["lat_attr"].cpu()
     mk = (lambda: uo.DDIM(prediction_type=prediction_type)) if scheduler == "ddim" else \
@@ -78,11 +88,18 @@ def run_mode(mode, B=2, S=16, steps_total=50, n_steps=1, prediction_type="epsilo
     sched_a.set_timesteps(steps_total)
     ri, ra = x_img, x_attr
     ehs_r = ehs.half().float()          # both sides see the fp16-rounded text embeddings
-    for i in range(n_steps):
+    for i in range(start_index, start_index + n_steps):
         ri, ra = oracle_step(mode, sds, cfgs, sched, ts[i], ri, ra, ehs_r, sched_a)
     res = {"img": err(got_img, ri), "attr": err(got_attr, ra), "launches_per_step": plan.step.num_launches,
            "mask_untouched": bool(torch.equal(got_attr[:, :4], x_attr[:, :4])),
-           "step_counter": int(plan.bufs["step"].item())}
+           "step_counter": int(plan.bufs["step"].item()) - start_index, "t": ts[start_index]}
+    if n_steps == 1 and scheduler == "ddim":
+        c_out, c_x = sched.coefficients(ts[start_index])
+        rec = lambda x_prev, x: (x_prev.double() - c_x * x.double()) / c_out      # noqa: E731
+        if mode != "inverse":
+            res["img_pred"] = err(rec(got_img, x_img), rec(ri, x_img))
+        if mode != "forward":
+            res["attr_pred"] = err(rec(got_attr[:, 4:], x_attr[:, 4:]), rec(ra[:, 4:], x_attr[:, 4:]))
     return res
 
 

@@ -172,3 +172,93 @@ def test_unipc_rejects_bad_arguments():
         UniPCSchedule(prediction_type="nope")
     with pytest.raises(ValueError):
         UniPCSchedule().timesteps(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scheduler configuration honoured from the caller's scheduler objects (eval/test_real.py:485-493)
+# ---------------------------------------------------------------------------------------------------------------
+SD1X_SCHEDULER_CONFIG = dict(_class_name="PNDMScheduler", beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                             num_train_timesteps=1000, set_alpha_to_one=False, skip_prk_steps=True, steps_offset=1,
+                             clip_sample=False, trained_betas=None)          # scheduler_config.json of SD-1.x checkpoints
+
+
+@pytest.mark.parametrize("spacing,offset,solver", [("leading", 1, "bh2"), ("trailing", 0, "bh2"), ("linspace", 0, "bh1")])
+def test_unipc_tables_follow_the_scheduler_config(spacing, offset, solver):
+    """`UniPCMultistepScheduler.from_config(pipeline.scheduler.config)` inherits the SD-1.x base config: "leading"
+    spacing with steps_offset 1 (941, 894, ... for 20 steps -- not the class default linspace 999, 949, ...)."""
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.scheduler import UniPCMultistepScheduler, UniPCSchedule
+    holder = UniPCMultistepScheduler.from_config(dict(SD1X_SCHEDULER_CONFIG, timestep_spacing=spacing, steps_offset=offset),
+                                                 solver_type=solver)
+    sch = UniPCSchedule.from_config(holder.config)
+    assert (sch.timestep_spacing, sch.steps_offset, sch.solver_type, sch.beta_schedule) == (spacing, offset, solver,
+                                                                                             "scaled_linear")
+    orc = uo.UniPC(timestep_spacing=spacing, steps_offset=offset, solver_type=solver)
+    n = 20
+    ts, rows = sch.table(n)
+    assert ts == orc.set_timesteps(n)
+    if spacing == "leading":
+        assert ts[:2] == [941, 894] and ts[-1] == 48
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 5, 5, generator=g, dtype=torch.float64)
+    S, LS, H0, H1, ref = x.clone(), torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x), x.clone()
+    for t, c in zip(ts, rows):
+        out = torch.randn(1, 4, 5, 5, generator=g, dtype=torch.float64) * 0.5 + 0.1 * ref
+        ref_next = orc.step(out, t, ref)
+        x0 = c[0] * out + c[1] * S
+        Sc = c[2] * LS + c[3] * H0 + c[4] * H1 + c[5] * x0 if c[6] else S
+        S, LS, H1, H0 = c[7] * Sc + c[8] * x0 + c[9] * H0, Sc, H0, x0
+        torch.testing.assert_close(S, ref_next, rtol=1e-9, atol=1e-9)
+        ref = S.clone()
+
+
+def test_timestep_lists_match_numpy_for_every_step_count():
+    """The UniPC "linspace" list must round half-way cases like numpy (n = 30 contains 499, not 500)."""
+    import numpy as np
+    from uni_renderer_b200.scheduler import DDIMSchedule, UniPCSchedule
+    u, d = UniPCSchedule(), DDIMSchedule()
+    for n in range(1, 999):
+        assert u.timesteps(n) == np.linspace(0, 999, n + 1).round()[::-1][:-1].astype(np.int64).tolist()
+    assert 499 in u.timesteps(30) and 500 not in u.timesteps(30)
+    for n in (1, 7, 20, 50, 1000):
+        assert d.timesteps(n) == [(i * (1000 // n)) + 1 for i in range(n)][::-1]
+    dl = DDIMSchedule(timestep_spacing="trailing", steps_offset=0)
+    assert dl.timesteps(50)[0] == 999 and dl.timesteps(50)[-1] == 19
+
+
+def test_ddim_from_config_and_unsupported_options():
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.scheduler import DDIMSchedule, DDIMScheduler, UniPCSchedule
+    holder = DDIMScheduler.from_config(SD1X_SCHEDULER_CONFIG)
+    assert holder.config.steps_offset == 1 and holder.config.clip_sample is False and "skip_prk_steps" not in holder.config
+    sch = DDIMSchedule.from_config(holder.config)
+    assert sch.signature() == DDIMSchedule().signature()             # == the SD-1.x defaults the bench uses
+    orc = uo.DDIM()
+    assert sch.timesteps(50) == orc.set_timesteps(50)
+    for t in (981, 501, 1):
+        a, b = sch.coefficients(t, 50), orc.coefficients(t)
+        assert abs(a[0] - b[0]) < 1e-6 and abs(a[1] - b[1]) < 1e-6
+    tr = DDIMSchedule.from_config(dict(holder.config, timestep_spacing="trailing"))
+    otr = uo.DDIM(timestep_spacing="trailing")
+    assert tr.timesteps(20) == otr.set_timesteps(20)
+    with pytest.raises(NotImplementedError):
+        DDIMSchedule.from_config(dict(holder.config, clip_sample=True))        # diffusers' own DDIM default
+    with pytest.raises(NotImplementedError):
+        UniPCSchedule.from_config(dict(SD1X_SCHEDULER_CONFIG, solver_order=3))
+    with pytest.raises(NotImplementedError):
+        UniPCSchedule.from_config(dict(SD1X_SCHEDULER_CONFIG, use_karras_sigmas=True))
+    with pytest.raises(NotImplementedError):
+        DDIMSchedule.from_config(dict(holder.config, beta_schedule="sigmoid"))
+
+
+def test_pipeline_from_pretrained_loads_the_scheduler_config(tmp_path):
+    """`pipeline.scheduler.config` must exist after from_pretrained: the eval builds every per-stream scheduler from it."""
+    import json
+    from uni_renderer_b200.scheduler import UniPCMultistepScheduler, UniPCSchedule, load_scheduler_config
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(SD1X_SCHEDULER_CONFIG))
+    base = load_scheduler_config(str(tmp_path / "scheduler"))
+    assert type(base).__name__ == "PNDMScheduler" and base.config.steps_offset == 1
+    per_stream = UniPCMultistepScheduler.from_config(base.config)
+    assert per_stream.config.timestep_spacing == "leading" and per_stream.config.solver_order == 2
+    assert UniPCSchedule.from_config(per_stream.config).timesteps(20)[0] == 941

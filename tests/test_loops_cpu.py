@@ -240,7 +240,7 @@ def test_render_pipeline_on_emulator_matches_oracle_chain(monkeypatch):
     image, masks = (torch.tanh(torch.randn(B, 3, S, S, generator=g)) for _ in range(2))
     ehs = torch.randn(B, 7, cfgs[0].cross_attention_dim, generator=g).half()
     gen = torch.Generator().manual_seed(77)
-    out = rp.inverse_rendering(image, masks, ehs, num_inference_steps=steps, generator=gen)
+    out = rp.inverse_rendering(image, masks, ehs, num_inference_steps=steps, generator=gen, posterior_generator=gen)
     assert len(out) == 6 and out[0].shape == (B, 4, h, h) and all(o.shape == (B, 3, S, S) for o in out[1:])
     gen.manual_seed(77)
     n_img, n_msk = (torch.randn(B, 4, h, h, generator=gen) for _ in range(2))
@@ -266,7 +266,7 @@ def test_render_pipeline_on_emulator_matches_oracle_chain(monkeypatch):
     neg = torch.randn(1, 7, cfgs[0].cross_attention_dim, generator=g).half()
     gen.manual_seed(77)
     guided = rp.inverse_rendering(image, masks, ehs, num_inference_steps=steps, generator=gen, guidance_scale=2.0,
-                                  negative_prompt_embeds=neg)
+                                  negative_prompt_embeds=neg, posterior_generator=gen)
     assert _rel(guided[0], out[0]) > 1e-3 and _rel(guided[1], out[1]) < 0.5     # material group is guided (:2263)
 
 

@@ -125,3 +125,20 @@ def test_timestep_forms():
     assert f(torch.tensor([1, 2]), 2, "cpu").tolist() == [1.0, 2.0]
     with pytest.raises(ValueError):
         f(torch.tensor([1, 2, 3]), 2, "cpu")
+
+
+def test_remaining_module_methods_raise_clear_errors_instead_of_attribute_errors():
+    """models/controlnet.py:591-779: attn_processors / set_attn_processor / set_default_attn_processor /
+    set_attention_slice / enable_freeu / disable_freeu exist on the reference modules; here the switches that would
+    change the fused kernels raise NotImplementedError, the ones that restore the default are no-ops."""
+    for m in (_tiny_unet(), M.AttributeEncoderModel(in_channels=28, **TINY),
+              M.AttributeDecoderModel(out_channels=28, up_block_types=M._SD_UP, **TINY)):
+        assert m.attn_processors == {}
+        assert m.set_default_attn_processor() is None and m.disable_freeu() is None
+        assert m.enable_xformers_memory_efficient_attention() is None
+        with pytest.raises(NotImplementedError):
+            m.set_attn_processor(object())
+        with pytest.raises(NotImplementedError):
+            m.set_attention_slice("auto")
+        with pytest.raises(NotImplementedError):
+            m.enable_freeu(s1=0.9, s2=0.2, b1=1.2, b2=1.4)

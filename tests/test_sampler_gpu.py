@@ -1,9 +1,12 @@
 """Parity of the fused sampling loops on the GPU (through the C ABI) against the CPU oracle, teacher-forced per step.
 
-Tolerance: the latents are fp32 state, the networks run with fp16 storage / fp32 accumulation, so one step's update
-differs from the fp32 oracle by the network's fp16 error (rel_l2 ~1e-3 on the prediction, see test_models_gpu.py)
-scaled by |c_out| <= ~0.1 at the timesteps used here -> rel_l2 <= 2e-3 on the updated latent is a loose but safe gate;
-the 3-step runs compound that and are gated at 5e-3."""
+Tolerance: the latents are fp32 state, the networks run with fp16 storage / fp32 accumulation.  x_prev = c_x x + c_out
+pred with |c_out| ~ 0.16 at t = 981 (0.02 at t = 21), so an error on the LATENT hides the network error by that factor:
+single DDIM steps are therefore gated on the recovered PREDICTION (pred = (x_prev - c_x x) / c_out) at the model-level
+gate of test_models_gpu.py (rel_l2 <= 3e-3; measured ~1e-3), at the first AND at a late timestep, and the latent itself
+at <= 3e-4.  Multi-step / UniPC runs (no closed-form recovery) keep a latent gate."""
+PRED_GATE = 3e-3
+LATENT_GATE = 3e-4
 import pytest
 
 gpu = pytest.mark.gpu
@@ -15,10 +18,27 @@ def test_one_step_matches_oracle(mode):
     from tests import sampler_probe
     r = sampler_probe.run_mode(mode, n_steps=1)
     assert r["img"]["finite"] and r["attr"]["finite"]
-    assert r["img"]["rel_l2"] <= 2e-3, r
-    assert r["attr"]["rel_l2"] <= 2e-3, r
+    assert r["img"]["rel_l2"] <= LATENT_GATE, r
+    assert r["attr"]["rel_l2"] <= LATENT_GATE, r
+    for k in ("img_pred", "attr_pred"):
+        if k in r:
+            assert r[k]["rel_l2"] <= PRED_GATE, (k, r)
+    assert ("img_pred" in r) == (mode != "inverse") and ("attr_pred" in r) == (mode != "forward")
     assert r["mask_untouched"], "the clean mask channels must never be updated (pipeline.py:2691)"
     assert r["step_counter"] == 1
+
+
+@gpu
+@pytest.mark.parametrize("mode", ["joint", "forward", "inverse"])
+def test_late_timestep_step_matches_oracle(mode):
+    """Step 48 of 50 (t = 21): alpha_bar ~ 0.98, the update is dominated by the network prediction."""
+    from tests import sampler_probe
+    r = sampler_probe.run_mode(mode, n_steps=1, start_index=48)
+    assert r["t"] == 21 and r["step_counter"] == 1 and r["mask_untouched"]
+    for k in ("img_pred", "attr_pred"):
+        if k in r:
+            assert r[k]["rel_l2"] <= PRED_GATE, (k, r)
+    assert r["img"]["rel_l2"] <= LATENT_GATE and r["attr"]["rel_l2"] <= LATENT_GATE, r
 
 
 @gpu
@@ -26,6 +46,7 @@ def test_one_step_matches_oracle(mode):
 def test_prediction_types(ptype):
     from tests import sampler_probe
     r = sampler_probe.run_mode("joint", n_steps=1, prediction_type=ptype)
+    assert r["img_pred"]["rel_l2"] <= PRED_GATE and r["attr_pred"]["rel_l2"] <= PRED_GATE, r
     assert r["img"]["rel_l2"] <= 3e-3 and r["attr"]["rel_l2"] <= 3e-3, r
 
 
@@ -73,6 +94,14 @@ def test_public_api_host_roundtrip():
     i1, a1 = sampler.joint_sample(x_img, x_attr, ehs, num_inference_steps=4)
     i2, a2 = sampler.joint_sample(x_img, x_attr, ehs, num_inference_steps=4)
     assert i1.device.type == "cpu" and i1.dtype == torch.float32 and i1.shape == x_img.shape
+    # device-resident fp32 inputs: the results must be COPIES of the plan's static state, not aliases of it (a second
+    # call with other noise must not rewrite the first call's result)
+    xi_d, xa_d, e_d = x_img.cuda(), x_attr.cuda(), ehs.cuda()
+    d1, da1 = sampler.joint_sample(xi_d, xa_d, e_d, num_inference_steps=4)
+    keep = d1.clone()
+    d2, _ = sampler.joint_sample(xi_d + 1.0, xa_d, e_d, num_inference_steps=4)
+    assert d1.data_ptr() != d2.data_ptr() and torch.equal(d1, keep) and not torch.equal(d1, d2)
+    assert torch.equal(d1.cpu(), i1) and torch.equal(da1.cpu(), a1)
     assert torch.equal(i1, i2) and torch.equal(a1, a2)
     assert torch.isfinite(i1).all() and torch.isfinite(a1).all()
     inv = sampler.inverse_render(x_img, x_attr, ehs, num_inference_steps=2)

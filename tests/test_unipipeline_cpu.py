@@ -86,6 +86,7 @@ def test_real_image2mask_call_as_the_shipped_eval_makes_it(monkeypatch):
     pipe.enable_xformers_memory_efficient_attention()
     ehs = torch.randn(1, 7, 48, generator=torch.Generator().manual_seed(3)).half()
     g = torch.Generator().manual_seed(42)
+    torch.manual_seed(1)        # the VAE posterior noise comes from the global RNG, as in the reference
     material, normal, albedo, spec, diff, env = pipe.real_image2mask_3mod_albedo(
         " ", _pil(1), _pil(2), guidance_scale=0.0, height=32, width=32, num_inference_steps=3, generator=g,
         prompt_embeds=ehs)
@@ -96,11 +97,13 @@ def test_real_image2mask_call_as_the_shipped_eval_makes_it(monkeypatch):
     x, m = UP.preprocess_image(_pil(1), 32, 32), UP.preprocess_image(_pil(2), 32, 32)
     assert x.shape == (1, 3, 32, 32) and -1.0 <= float(x.min()) and float(x.max()) <= 1.0
     g.manual_seed(42)
+    torch.manual_seed(1)
     ref = pipe._render.inverse_rendering(x, m, ehs, 3, 0.0, g, scheduler="unipc")
     assert torch.equal(ref[0], material)
     assert np.array_equal(np.asarray(UP.postprocess_image(ref[2], "pil")[0]), np.asarray(albedo[0]))
     # output_type variants and the tensor-input alias
     g.manual_seed(42)
+    torch.manual_seed(1)
     out_pt = pipe.image2mask_3mod_albedo(" ", (x + 1) / 2, (m + 1) / 2, guidance_scale=0.0, num_inference_steps=3,
                                          generator=g, prompt_embeds=ehs, output_type="pt", height=32, width=32)
     assert torch.equal(out_pt[0], material) and out_pt[1].shape == (1, 3, 32, 32) and float(out_pt[1].min()) >= 0.0
@@ -131,3 +134,32 @@ def test_mask2image_call(monkeypatch):
     with pytest.raises(NotImplementedError):
         UP.UniRendererPipeline(vae=pipe.vae, unet=pipe.unet, controlnet=pipe.controlnet, controldec=pipe.controldec,
                                safety_checker=object())
+
+
+def test_assigned_scheduler_config_drives_the_timestep_table(monkeypatch):
+    """The eval's `UniPCMultistepScheduler.from_config(pipeline.scheduler.config)` inherits "leading" spacing and
+    steps_offset 1 from the SD-1.x base config: the fused loop must walk 941, 894, ... -- and an unsupported option must
+    raise instead of being ignored."""
+    from uni_renderer_b200 import scheduler as S
+    from tests.test_host_logic import SD1X_SCHEDULER_CONFIG
+    pipe = _build(monkeypatch)
+    base = S.PNDMScheduler.from_config(SD1X_SCHEDULER_CONFIG)
+    pipe.scheduler_img = S.UniPCMultistepScheduler.from_config(base.config)
+    ehs = torch.randn(1, 7, 48, generator=torch.Generator().manual_seed(3)).half()
+    imgs = [_pil(10 + i) for i in range(6)]
+    pipe.mask2image_3mod_albedo(" ", np.array([0.3, 0.8]), *imgs, height=32, width=32, num_inference_steps=4,
+                                guidance_scale=0.0, generator=torch.Generator().manual_seed(7), prompt_embeds=ehs,
+                                output_type="latent")
+    plans = [p for p in pipe._sampler._plans.values() if p.scheduler == "unipc"]
+    assert len(plans) == 1 and plans[0].timesteps == S.UniPCSchedule.from_config(pipe.scheduler_img.config).timesteps(4)
+    assert plans[0].timesteps[0] == 801            # leading: 200 * 4 + 1   (linspace would start at 999)
+    # the class-default scheduler (linspace) records a second plan, it does not silently reuse the first
+    pipe.scheduler_img = S.UniPCMultistepScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    pipe.mask2image_3mod_albedo(" ", np.array([0.3, 0.8]), *imgs, height=32, width=32, num_inference_steps=4,
+                                guidance_scale=0.0, generator=torch.Generator().manual_seed(7), prompt_embeds=ehs,
+                                output_type="latent")
+    assert sorted(p.timesteps[0] for p in pipe._sampler._plans.values() if p.scheduler == "unipc") == [801, 999]
+    pipe.scheduler_img = S.UniPCMultistepScheduler(solver_order=3)
+    with pytest.raises(NotImplementedError):
+        pipe.mask2image_3mod_albedo(" ", np.array([0.3, 0.8]), *imgs, height=32, width=32, num_inference_steps=4,
+                                    guidance_scale=0.0, prompt_embeds=ehs)

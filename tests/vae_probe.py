@@ -283,7 +283,8 @@ def case_render_pipeline():
 
     # inverse rendering: image, masks -> material latents + 5 decoded attribute images
     gen = torch.Generator(device="cuda").manual_seed(77)
-    out = rp.inverse_rendering(imgs[0], imgs[1], ehs, num_inference_steps=steps, generator=gen)
+    out = rp.inverse_rendering(imgs[0], imgs[1], ehs, num_inference_steps=steps, generator=gen,
+                               posterior_generator=gen)
     torch.cuda.synchronize()
     gen.manual_seed(77)
     n_img, n_msk = (torch.randn(B, 4, h, h, generator=gen, device="cuda").cpu() for _ in range(2))
@@ -296,7 +297,8 @@ def case_render_pipeline():
             res["inv_" + name] = _err(out[1 + i].cpu(), vo.decode(vsd, vo.TINY_VAE, xa[:, 8 + 4 * i:12 + 4 * i] / sf))
     # forward rendering: 6 attribute images + material numbers -> RGB image
     gen.manual_seed(78)
-    rgb = rp.forward_rendering((0.3, 0.8), *imgs[1:7], ehs, num_inference_steps=steps, generator=gen)
+    rgb = rp.forward_rendering((0.3, 0.8), *imgs[1:7], ehs, num_inference_steps=steps, generator=gen,
+                               posterior_generator=gen)
     torch.cuda.synchronize()
     gen.manual_seed(78)
     noises = [torch.randn(B, 4, h, h, generator=gen, device="cuda").cpu() for _ in range(7)]

@@ -69,5 +69,6 @@ for i, (name, B, H, cins, kind, cout, res, geglu) in enumerate(SHAPES):
     gap = int(e[0] - rows[k - 1][8]) if k > 0 else 0
     rel = [int(e[j] - e[0]) if e[j] else -1 for j in range(1, 9)]
     ext = [int(e[j] - e[0]) if e[j] else -1 for j in (14, 15, 9, 11)]
+    sub = [int(e[j] - e[0]) if e[j] else -1 for j in (4, 10, 12, 13)]
     print(f"{name:26s} {gap:6d} " + " ".join(f"{v:6d}" for v in rel) + "   pdlwait/decoded/epi0end/epi1: " +
-          " ".join(f"{v:6d}" for v in ext))
+          " ".join(f"{v:6d}" for v in ext) + "   sub-tile 1 top/ld/math/stored: " + " ".join(f"{v:6d}" for v in sub))

@@ -8,8 +8,9 @@
 namespace unib {
 
 int g_pdl_enabled = 0;   // measured: no gain inside the two-lane step graph, so off by default
-// launches report through cudaGetLastError() at the call sites below; keep the first launch error sticky
-#define UNIB_CHECK_LAUNCH(expr) do { cudaError_t le_ = (expr); (void)le_; } while (0)
+// every launcher below returns cudaError_t: a failed launch returns ITS error code at once (cudaLaunchKernelEx errors
+// under stream capture are not always sticky, so cudaGetLastError() alone could miss them)
+#define UNIB_CHECK_LAUNCH(expr) do { cudaError_t le_ = (expr); if (le_ != cudaSuccess) return le_; } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: partial (sum, sumsq) per (batch, row-chunk, group).  Each thread owns one 8-channel vector

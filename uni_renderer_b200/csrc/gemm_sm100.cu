@@ -479,6 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         for (int j = 0; j < nsub; ++j) {
           float v[32];
           uint32_t rcur[16];
+          if (tl == 0 && leader && j == 1) GEMM_TRACE(4);
           if (has_res) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) rcur[u] = rnext[u];
@@ -516,6 +517,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           } else {
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
+            if (tl == 0 && leader && j == 1) GEMM_TRACE(10);
             if (j == nsub - 1) {
               tc_fence_before();
               __syncwarp();
@@ -552,6 +554,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
           }
           const int n = n0 + j * 32;
+          if (tl == 0 && leader && j == 1) GEMM_TRACE(12);
           if (want_stats) {
             if (n + 32 <= n_out) {
 #pragma unroll
@@ -582,6 +585,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
                 if (n + i < n_out) op[i] = __float2half_rn(v[i]);
             }
           }
+          if (tl == 0 && leader && j == 1) GEMM_TRACE(13);
         }
         if (want_stats && m < p.M)
           *reinterpret_cast<float2*>(p.rowstats_out + (static_cast<size_t>(m) * p.n_tiles + wi.nt) * 2) =

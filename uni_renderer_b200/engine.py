@@ -115,7 +115,9 @@ class StreamNet:
     # ------------------------------------------------------------------------------------------------------------
     def _pack(self, sd):
         dev, cfg, w = self.device, self.cfg, self.w
-        need = lambda k: sd[k].detach().to(dev)    # noqa: E731
+        # packing runs where the state dict lives (host tensors are packed on the host and uploaded once; device
+        # tensors -- the synthetic benchmarks -- are packed on the device); everything ends up on `dev` below
+        need = lambda k: sd[k].detach()    # noqa: E731
 
         def conv3(name, kind=SEG_3x3):
             w[name + ".w"] = ops.pack_weight([(need(name + ".weight"), kind)])
@@ -138,7 +140,7 @@ class StreamNet:
             self.temb_off[r] = off
             off += cout
             tw.append(need(r + ".time_emb_proj.weight"))
-            tb.append(sd[r + ".time_emb_proj.bias"].detach().to(dev).float() + sd[r + ".conv1.bias"].detach().to(dev).float())
+            tb.append(sd[r + ".time_emb_proj.bias"].detach().float() + sd[r + ".conv1.bias"].detach().float())
             norm(r + ".norm1")
             norm(r + ".norm2")
             w[r + ".conv1.w"] = ops.pack_weight([(need(r + ".conv1.weight"), SEG_3x3)])
@@ -199,10 +201,12 @@ class StreamNet:
             self.zc_prefix = zc
         self._sd_conv2 = {}
         for r in self.resnets:      # conv2 (+ fused shortcut) is packed lazily: the split of the shortcut's input
-            self._sd_conv2[r] = (need(r + ".conv2.weight"), sd[r + ".conv2.bias"].detach().to(dev).float(),
+            self._sd_conv2[r] = (need(r + ".conv2.weight"), sd[r + ".conv2.bias"].detach().float(),
                                  need(r + ".conv_shortcut.weight") if r + ".conv_shortcut.weight" in sd else None,
-                                 sd[r + ".conv_shortcut.bias"].detach().to(dev).float()
+                                 sd[r + ".conv_shortcut.bias"].detach().float()
                                  if r + ".conv_shortcut.bias" in sd else None)
+        for k in list(w):
+            w[k] = w[k].to(dev)
 
     def _conv2_packed(self, r: str, src_channels: Sequence[int]):
         """conv2 3x3 followed by the 1x1 shortcut segments over the (possibly two-source) block input."""
@@ -218,8 +222,8 @@ class StreamNet:
                     c0 += c
                 assert c0 == wsc.shape[1]
                 bias = b2 + bsc
-            self.w[key] = ops.pack_weight(parts)
-            self.w[r + ".conv2.b"] = bias.contiguous()
+            self.w[key] = ops.pack_weight(parts).to(self.device)
+            self.w[r + ".conv2.b"] = bias.contiguous().to(self.device)
             self.w[r + ".has_sc"] = torch.tensor(int(wsc is not None))
         return self.w[key], self.w[r + ".conv2.b"], bool(self.w[r + ".has_sc"].item())
 

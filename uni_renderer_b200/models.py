@@ -281,6 +281,33 @@ class _NetModule(nn.Module):
     def enable_xformers_memory_efficient_attention(self, *a, **k):   # reference callers invoke these; no-ops here
         return None
 
+    # -- the rest of the reference's module surface (models/controlnet.py:629 set_attn_processor, :680
+    #    set_attention_slice, :649 set_default_attn_processor, :749 enable_freeu, :773 disable_freeu, :591
+    #    attn_processors): the attention and the skip path are fixed fused kernels here, so the switches that would
+    #    change them raise a clear error instead of an AttributeError; the ones that restore the default are no-ops.
+    @property
+    def attn_processors(self) -> Dict[str, Any]:
+        return {}
+
+    def set_attn_processor(self, processor, _remove_lora: bool = False):
+        raise NotImplementedError("set_attn_processor: attention runs in the fused tcgen05 kernel of uni_renderer_b200; "
+                                  "custom attention processors (LoRA, added-KV, sliced) are not supported")
+
+    def set_default_attn_processor(self):
+        return None
+
+    def set_attention_slice(self, slice_size):
+        raise NotImplementedError("set_attention_slice: the fused attention kernel never materialises the score matrix, "
+                                  "slicing is neither needed nor supported")
+
+    def enable_freeu(self, s1, s2, b1, b2):
+        raise NotImplementedError("enable_freeu: FreeU rescales the skip / backbone features inside the up blocks "
+                                  "(models/unet_2d_blocks.py:2522-2544); no shipped Uni-Renderer caller enables it and "
+                                  "the fused decoder does not implement it")
+
+    def disable_freeu(self):
+        return None
+
     def enable_gradient_checkpointing(self):
         raise NotImplementedError("uni_renderer_b200 is an inference path: training/backward is out of scope")
 

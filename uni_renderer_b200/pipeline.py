@@ -52,6 +52,8 @@ class _Plan:
     once: Optional[ops.Program] = None
     cfg: bool = False          # classifier-free guidance: the networks run on net_batch = 2 * B samples
     net_batch: int = 0
+    schedule: object = None    # the DDIMSchedule / UniPCSchedule whose tables were uploaded
+    timesteps: Optional[list] = None
 
 
 class DualStreamSampler:
@@ -72,7 +74,8 @@ class DualStreamSampler:
 
     def __init__(self, unet=None, controlnet=None, controldec=None, *, nets: Optional[Sequence[StreamNet]] = None,
                  prediction_type: str = "epsilon", device=None, use_graph: bool = True, split_batch: bool = False,
-                 scheduler: str = "ddim"):
+                 scheduler: str = "ddim", ddim_schedule: Optional[DDIMSchedule] = None,
+                 unipc_schedule: Optional[UniPCSchedule] = None):
         if nets is None:
             if unet is None or controlnet is None or controldec is None:
                 raise ValueError("need the three modules or three StreamNets")
@@ -84,8 +87,10 @@ class DualStreamSampler:
         if scheduler not in SCHEDULERS:
             raise ValueError(f"scheduler must be one of {SCHEDULERS}")
         self.scheduler = scheduler                 # default of the sampling entry points ("ddim": BASELINE; "unipc": eval)
-        self.schedule = DDIMSchedule(prediction_type=prediction_type)
-        self.unipc = UniPCSchedule(prediction_type=prediction_type)
+        # the tables default to the SD-1.x scheduler config; `set_schedules` installs the ones built from the scheduler
+        # objects a caller assigned (UniRendererPipeline does that from their `.config`)
+        self.schedule = ddim_schedule or DDIMSchedule(prediction_type=prediction_type)
+        self.unipc = unipc_schedule or UniPCSchedule(prediction_type=prediction_type)
         self.use_graph = use_graph
         self.split_batch = split_batch
         import os
@@ -93,6 +98,14 @@ class DualStreamSampler:
         self.ws = Workspace(self.device)          # lane 0 (RGB stream)
         self.ws1 = Workspace(self.device)         # lane 1 (attribute stream): lanes run concurrently, no shared scratch
         self._plans: Dict[Tuple, _Plan] = {}
+
+    def set_schedules(self, ddim: Optional[DDIMSchedule] = None, unipc: Optional[UniPCSchedule] = None):
+        """Install other timestep / coefficient tables (plans are keyed by the tables' signature, so plans recorded for
+        the previous schedule stay valid and are reused if it comes back)."""
+        if ddim is not None:
+            self.schedule = ddim
+        if unipc is not None:
+            self.unipc = unipc
 
     @classmethod
     def from_state_dicts(cls, sd_unet, sd_enc, sd_dec, cfg_unet: NetConfig, cfg_enc: NetConfig, cfg_dec: NetConfig,
@@ -120,7 +133,8 @@ class DualStreamSampler:
         if scheduler == "unipc" and mode == "cycle":
             raise NotImplementedError("the cycle double pass (a training-time construct, train/train.py:1388-1413) is "
                                       "only wired for the DDIM update")
-        key = (mode, B, S, L, steps, scheduler, cfg)
+        sched_obj = self.schedule if scheduler == "ddim" else self.unipc
+        key = (mode, B, S, L, steps, scheduler, cfg, sched_obj.signature())
         if key in self._plans:
             return self._plans[key]
         Bs = B                       # samples whose latents are denoised
@@ -275,6 +289,7 @@ class DualStreamSampler:
         plan = _Plan(mode, Bs, S, L, steps, setup, step, b)
         plan.cfg, plan.net_batch = cfg, B
         plan.scheduler = scheduler
+        plan.schedule = sched_obj
         plan.once = once
         plan.flops_setup = sum(i[1] for i in setup.op_info())
         plan.flops_step = sum(i[1] for i in step.op_info())
@@ -342,7 +357,8 @@ class DualStreamSampler:
         return o
 
     def _upload_schedule(self, plan: _Plan):
-        ts, coefs = (self.schedule if plan.scheduler == "ddim" else self.unipc).table(plan.steps)
+        ts, coefs = plan.schedule.table(plan.steps)
+        plan.timesteps = list(ts)
         t = torch.tensor(ts, dtype=torch.float32).reshape(-1, 1).expand(plan.steps, plan.net_batch).contiguous()
         c = torch.tensor(coefs, dtype=torch.float64).to(torch.float32)
         b = plan.bufs
@@ -403,7 +419,10 @@ class DualStreamSampler:
 
     def _sample(self, mode, latents_img, latents_attr, prompt_embeds, num_inference_steps, guidance_scale,
                 scheduler=None, negative_prompt_embeds=None):
-        cfg = guidance_scale not in (0, 0.0, None)          # `do_classifier_free_guidance`, models/pipeline.py:807
+        # `do_classifier_free_guidance`: `guidance_scale != 0` in models/pipeline.py:807 (forward / inverse rendering),
+        # but `guidance_scale > 1` in the joint loop's pipeline (models/pipeline_new_d4p.py:808-809)
+        g = 0.0 if guidance_scale is None else float(guidance_scale)
+        cfg = (g > 1.0) if mode in ("joint", "cycle") else (g != 0.0)
         if cfg and negative_prompt_embeds is None:
             raise ValueError("guidance_scale != 0 needs negative_prompt_embeds (every shipped Uni-Renderer caller passes "
                              "guidance_scale=0, eval/test_real.py:548)")
@@ -415,9 +434,11 @@ class DualStreamSampler:
         self.load_inputs(plan, latents_img, latents_attr, prompt_embeds, negative_prompt_embeds if cfg else None,
                          guidance_scale if cfg else 0.0)
         self.run(plan)
+        # always COPIES: the plan's latent buffers are static state that the next call with the same plan overwrites
+        # (a same-device fp32 `.to()` would hand the caller an alias of them)
         dev, dt = latents_img.device, latents_img.dtype
-        img = plan.bufs["lat_img"].to(device=dev, dtype=dt, non_blocking=False)
-        attr = plan.bufs["lat_attr"].to(device=dev, dtype=dt, non_blocking=False)
+        img = plan.bufs["lat_img"].to(device=dev, dtype=dt, non_blocking=False, copy=True)
+        attr = plan.bufs["lat_attr"].to(device=dev, dtype=dt, non_blocking=False, copy=True)
         return plan, img, attr
 
     @torch.no_grad()

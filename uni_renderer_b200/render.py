@@ -13,8 +13,11 @@ Tensor-level mirror of the two calls the shipped eval makes on the reference pip
       spec_light, diff_light, env images) like :2389
 
 B200-first differences (results identical for the same noise): the encodes of one call run as ONE batched program
-(6B / 2B images), the five decodes as one 5B-latent program, and the loop is the fused CUDA-graph sampler.  Noise is
-drawn per encode / per latent group in the reference's order, so a seeded generator is consumed identically.
+(6B / 2B images), the five decodes as one 5B-latent program, and the loop is the fused CUDA-graph sampler.
+RNG use follows the reference: `generator` feeds ONLY the `prepare_latents` draws (models/pipeline.py:705-719,
+2119-2188); the VAE posterior noise of `latent_dist.sample()` is drawn WITHOUT a generator there (:1531-1556,
+2113-2116), i.e. from the device's global RNG -- here too, one draw per encoded image in the reference's order
+(`posterior_generator` exists for reproducible tests only).
 """
 from __future__ import annotations
 
@@ -46,7 +49,8 @@ class RenderPipeline:
     def encode_images(self, images: Sequence[torch.Tensor], generator: Optional[torch.Generator] = None,
                       sample: bool = True) -> Tuple[torch.Tensor, ...]:
         """`vae.encode(x).latent_dist.sample() * scaling_factor` for several [B, 3, H, W] images in [-1, 1] as one
-        batched encoder program; the posterior noise of each image is drawn separately, in order."""
+        batched encoder program; the posterior noise of each image is drawn separately, in order (generator None =
+        the device's global RNG, which is what the reference's `latent_dist.sample()` uses)."""
         from . import ops
         n, B = len(images), images[0].shape[0]
         x = torch.cat([i.to(self.device) for i in images], 0)
@@ -73,13 +77,15 @@ class RenderPipeline:
                           masks_image, prompt_embeds=None, num_inference_steps: int = 50, guidance_scale: float = 0.0,
                           generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
                           output_type: str = "pt", scheduler: Optional[str] = None, prompt: str = " ",
-                          negative_prompt_embeds: Optional[torch.Tensor] = None):
+                          negative_prompt_embeds: Optional[torch.Tensor] = None,
+                          posterior_generator: Optional[torch.Generator] = None):
         """attributes -> RGB (mask2image_3mod_albedo).  Images are [B, 3, H, W] tensors in [-1, 1]; material_num is
         (metallic, roughness); returns the decoded image [B, 3, H, W] (or the latents for output_type="latent")."""
         B = normal_image.shape[0]
         # encode order of the reference: normal, albedo, spec_light, diff_light, env, masks (:1531-1556)
         l_normal, l_albedo, l_spec, l_diff, l_env, l_masks = self.encode_images(
-            [normal_image, albedo_image, spec_light_image, diff_light_image, env_image, masks_image], generator)
+            [normal_image, albedo_image, spec_light_image, diff_light_image, env_image, masks_image],
+            posterior_generator)
         metallic, roughness = float(material_num[0]), float(material_num[1])
         l_material = torch.empty_like(l_normal)
         l_material[:, :2] = metallic * 2 - 1.0                                       # :1534-1541
@@ -98,11 +104,12 @@ class RenderPipeline:
     def inverse_rendering(self, image, masks, prompt_embeds=None, num_inference_steps: int = 50,
                           guidance_scale: float = 0.0, generator: Optional[torch.Generator] = None,
                           latents: Optional[Sequence[torch.Tensor]] = None, scheduler: Optional[str] = None,
-                          prompt: str = " ", negative_prompt_embeds: Optional[torch.Tensor] = None):
+                          prompt: str = " ", negative_prompt_embeds: Optional[torch.Tensor] = None,
+                          posterior_generator: Optional[torch.Generator] = None):
         """RGB -> attributes (image2mask_3mod_albedo).  Returns (material_latents, normal, albedo, spec_light,
         diff_light, env) with the five images decoded to [B, 3, H, W] in [-1, 1] (:2389)."""
         B = image.shape[0]
-        l_img, l_masks = self.encode_images([image, masks], generator)               # :2112-2117
+        l_img, l_masks = self.encode_images([image, masks], posterior_generator)     # :2112-2117
         if latents is None:                                                          # six draws, :2119-2188
             latents = [self._randn(tuple(l_img.shape), generator) for _ in ATTR_GROUPS]
         if len(latents) != len(ATTR_GROUPS):

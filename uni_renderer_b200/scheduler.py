@@ -18,6 +18,47 @@ from dataclasses import dataclass, field
 from typing import List, Tuple
 
 PREDICTION_TYPES = ("epsilon", "sample", "v_prediction")
+TIMESTEP_SPACINGS = ("leading", "trailing", "linspace")
+
+
+def _cfg_get(cfg, key, default=None):
+    """Read `key` from a diffusers scheduler config (FrozenDict / plain dict / attribute object)."""
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def alphas_cumprod_table(num_train_timesteps: int, beta_start: float, beta_end: float, beta_schedule: str) -> List[float]:
+    """float64 cumulative product of (1 - beta_t) for the beta schedules diffusers' DDIM / UniPC schedulers accept."""
+    n = num_train_timesteps
+    if beta_schedule == "scaled_linear":
+        s0, s1 = math.sqrt(beta_start), math.sqrt(beta_end)
+        betas = [(s0 + (s1 - s0) * i / (n - 1)) ** 2 for i in range(n)]
+    elif beta_schedule == "linear":
+        betas = [beta_start + (beta_end - beta_start) * i / (n - 1) for i in range(n)]
+    elif beta_schedule == "squaredcos_cap_v2":
+        bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2    # noqa: E731
+        betas = [min(1.0 - bar((i + 1) / n) / bar(i / n), 0.999) for i in range(n)]
+    else:
+        raise NotImplementedError(f"beta_schedule {beta_schedule!r} is not supported")
+    acc, out = 1.0, []
+    for b in betas:
+        acc *= 1.0 - b
+        out.append(acc)
+    return out
+
+
+def _reject_config(cfg, name: str, allowed: dict):
+    """Raise on every scheduler option whose value the coefficient tables do not reproduce."""
+    for key, ok in allowed.items():
+        v = _cfg_get(cfg, key, ok[0])
+        if isinstance(v, list):
+            v = tuple(v)
+        if v not in ok:
+            raise NotImplementedError(f"{name}: config option {key}={v!r} is not supported on the B200 path "
+                                      f"(supported: {ok})")
 
 
 @dataclass
@@ -28,28 +69,55 @@ class DDIMSchedule:
     steps_offset: int = 1
     prediction_type: str = "epsilon"
     set_alpha_to_one: bool = False
+    beta_schedule: str = "scaled_linear"
+    timestep_spacing: str = "leading"
     alphas_cumprod: List[float] = field(init=False, repr=False)
 
     def __post_init__(self):
         if self.prediction_type not in PREDICTION_TYPES:
             raise ValueError(f"prediction_type must be one of {PREDICTION_TYPES}, got {self.prediction_type!r}")
-        n = self.num_train_timesteps
-        s0, s1 = math.sqrt(self.beta_start), math.sqrt(self.beta_end)
-        # betas = linspace(sqrt(b0), sqrt(b1), n)^2 evaluated like torch's fp32 linspace/cumprod would be too lossy to
-        # reproduce bit-for-bit on the host; keep the table in float64 and round once when it is uploaded.
-        acc, out = 1.0, []
-        for i in range(n):
-            b = (s0 + (s1 - s0) * i / (n - 1)) ** 2
-            acc *= 1.0 - b
-            out.append(acc)
-        self.alphas_cumprod = out
+        if self.timestep_spacing not in TIMESTEP_SPACINGS:
+            raise ValueError(f"timestep_spacing must be one of {TIMESTEP_SPACINGS}, got {self.timestep_spacing!r}")
+        # torch's fp32 linspace/cumprod would be too lossy to reproduce bit-for-bit on the host; keep the table in
+        # float64 and round once when it is uploaded.
+        self.alphas_cumprod = alphas_cumprod_table(self.num_train_timesteps, self.beta_start, self.beta_end,
+                                                   self.beta_schedule)
+
+    @classmethod
+    def from_config(cls, config, prediction_type: str = None) -> "DDIMSchedule":
+        """Build the tables from a diffusers DDIMScheduler's `.config` (the object a caller assigned to
+        `pipeline.scheduler_*`): betas, timestep spacing, offset, prediction type.  Options that would change the
+        update rule (clip_sample, thresholding, trained_betas, rescale_betas_zero_snr) raise."""
+        _reject_config(config, "DDIMScheduler", {"clip_sample": (False,), "thresholding": (False,),
+                                                  "trained_betas": (None,), "rescale_betas_zero_snr": (False,)})
+        return cls(num_train_timesteps=int(_cfg_get(config, "num_train_timesteps", 1000)),
+                   beta_start=float(_cfg_get(config, "beta_start", 0.00085)),
+                   beta_end=float(_cfg_get(config, "beta_end", 0.012)),
+                   steps_offset=int(_cfg_get(config, "steps_offset", 0)),
+                   prediction_type=prediction_type or _cfg_get(config, "prediction_type", "epsilon"),
+                   set_alpha_to_one=bool(_cfg_get(config, "set_alpha_to_one", True)),
+                   beta_schedule=_cfg_get(config, "beta_schedule", "linear"),
+                   timestep_spacing=_cfg_get(config, "timestep_spacing", "leading"))
+
+    def signature(self) -> Tuple:
+        return ("ddim", self.num_train_timesteps, self.beta_start, self.beta_end, self.steps_offset,
+                self.prediction_type, self.set_alpha_to_one, self.beta_schedule, self.timestep_spacing)
 
     def timesteps(self, num_inference_steps: int) -> List[int]:
-        """timestep_spacing="leading": (arange(n) * (T // n))[::-1] + steps_offset."""
-        if not 0 < num_inference_steps <= self.num_train_timesteps:
+        """diffusers DDIMScheduler.set_timesteps: "leading" (arange(n) * (T // n))[::-1] + steps_offset; "trailing"
+        round(arange(T, 0, -T / n)) - 1; "linspace" round(linspace(0, T - 1, n))[::-1] (numpy arithmetic, so half-way
+        cases round exactly like diffusers)."""
+        import numpy as np
+        T, n = self.num_train_timesteps, num_inference_steps
+        if not 0 < n <= T:
             raise ValueError("num_inference_steps must be in [1, num_train_timesteps]")
-        ratio = self.num_train_timesteps // num_inference_steps
-        return [i * ratio + self.steps_offset for i in range(num_inference_steps)][::-1]
+        if self.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.int64) + self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)).astype(np.int64) - 1
+        else:
+            ts = np.linspace(0, T - 1, n).round()[::-1].astype(np.int64)
+        return [int(t) for t in ts]
 
     def coefficients(self, t: int, num_inference_steps: int) -> Tuple[float, float]:
         """(c_out, c_x) of the eta=0 update at timestep t."""
@@ -84,25 +152,61 @@ class UniPCSchedule:
     beta_start: float = 0.00085
     beta_end: float = 0.012
     prediction_type: str = "epsilon"
+    beta_schedule: str = "scaled_linear"
+    timestep_spacing: str = "linspace"
+    steps_offset: int = 0
+    solver_type: str = "bh2"
     alphas_cumprod: List[float] = field(init=False, repr=False)
 
     def __post_init__(self):
         if self.prediction_type not in PREDICTION_TYPES:
             raise ValueError(f"prediction_type must be one of {PREDICTION_TYPES}, got {self.prediction_type!r}")
-        n = self.num_train_timesteps
-        s0, s1 = math.sqrt(self.beta_start), math.sqrt(self.beta_end)
-        acc, out = 1.0, []
-        for i in range(n):
-            acc *= 1.0 - (s0 + (s1 - s0) * i / (n - 1)) ** 2
-            out.append(acc)
-        self.alphas_cumprod = out
+        if self.timestep_spacing not in TIMESTEP_SPACINGS:
+            raise ValueError(f"timestep_spacing must be one of {TIMESTEP_SPACINGS}, got {self.timestep_spacing!r}")
+        if self.solver_type not in ("bh1", "bh2"):
+            raise ValueError(f"solver_type must be bh1 or bh2, got {self.solver_type!r}")
+        self.alphas_cumprod = alphas_cumprod_table(self.num_train_timesteps, self.beta_start, self.beta_end,
+                                                   self.beta_schedule)
+
+    @classmethod
+    def from_config(cls, config, prediction_type: str = None) -> "UniPCSchedule":
+        """Build the tables from a diffusers UniPCMultistepScheduler's `.config`.  The shipped eval creates it with
+        `UniPCMultistepScheduler.from_config(pipeline.scheduler.config)` (eval/test_real.py:485-493), which INHERITS the
+        base scheduler's betas, `timestep_spacing` and `steps_offset` (SD-1.x: "leading", offset 1) -- all honoured
+        here.  The closed-form tables cover solver_order 2 with predict_x0 and lower_order_final (the class defaults);
+        anything else raises."""
+        _reject_config(config, "UniPCMultistepScheduler",
+                       {"solver_order": (2,), "predict_x0": (True,), "lower_order_final": (True,),
+                        "thresholding": (False,), "use_karras_sigmas": (False,), "trained_betas": (None,),
+                        "disable_corrector": ((), None), "solver_p": (None,)})
+        return cls(num_train_timesteps=int(_cfg_get(config, "num_train_timesteps", 1000)),
+                   beta_start=float(_cfg_get(config, "beta_start", 0.0001)),
+                   beta_end=float(_cfg_get(config, "beta_end", 0.02)),
+                   prediction_type=prediction_type or _cfg_get(config, "prediction_type", "epsilon"),
+                   beta_schedule=_cfg_get(config, "beta_schedule", "linear"),
+                   timestep_spacing=_cfg_get(config, "timestep_spacing", "linspace"),
+                   steps_offset=int(_cfg_get(config, "steps_offset", 0)),
+                   solver_type=_cfg_get(config, "solver_type", "bh2"))
+
+    def signature(self) -> Tuple:
+        return ("unipc", self.num_train_timesteps, self.beta_start, self.beta_end, self.prediction_type,
+                self.beta_schedule, self.timestep_spacing, self.steps_offset, self.solver_type)
 
     def timesteps(self, num_inference_steps: int) -> List[int]:
-        """timestep_spacing="linspace": round(linspace(0, T-1, n+1))[::-1][:-1] (round half to even, like numpy)."""
-        if not 0 < num_inference_steps < self.num_train_timesteps:
-            raise ValueError("num_inference_steps must be in [1, num_train_timesteps)")
+        """diffusers 0.24 UniPCMultistepScheduler.set_timesteps, in numpy arithmetic (so half-way cases of the linspace
+        round exactly like diffusers): "linspace" round(linspace(0, T-1, n+1))[::-1][:-1]; "leading"
+        round(arange(n+1) * (T // (n+1)))[::-1][:-1] + steps_offset; "trailing" round(arange(T, 0, -T/n)) - 1."""
+        import numpy as np
         T, n = self.num_train_timesteps, num_inference_steps
-        return [int(round((T - 1) * i / n)) for i in range(n + 1)][::-1][:-1]
+        if not 0 < n < T:
+            raise ValueError("num_inference_steps must be in [1, num_train_timesteps)")
+        if self.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            ts = (np.arange(0, n + 1) * (T // (n + 1))).round()[::-1][:-1].copy().astype(np.int64) + self.steps_offset
+        else:
+            ts = np.arange(T, 0, -T / n).round().copy().astype(np.int64) - 1
+        return [int(t) for t in ts]
 
     def _lambdas(self, ts: List[int]):
         """(alpha, sigma, lambda = log alpha - log sigma) at each timestep of the walk + the appended final sigma."""
@@ -115,11 +219,11 @@ class UniPCSchedule:
         return out
 
     @staticmethod
-    def _phis(h: float):
-        """bh2 / predict_x0 scalars for step size h: (h_phi_1, B_h, b_1, b_2)."""
+    def _phis(h: float, bh2: bool = True):
+        """bh2 (B_h = expm1(-h)) or bh1 (B_h = -h) / predict_x0 scalars for step size h: (h_phi_1, B_h, b_1, b_2)."""
         hh = -h
         h_phi_1 = math.expm1(hh)
-        B_h = h_phi_1
+        B_h = h_phi_1 if bh2 else hh
         phi_k = h_phi_1 / hh - 1.0
         b1 = phi_k / B_h
         phi_k2 = phi_k / hh - 0.5
@@ -146,7 +250,7 @@ class UniPCSchedule:
             if i > 0:
                 a_s0, s_s0, lam_s0 = als[i - 1]
                 h = lam_i - lam_s0
-                h_phi_1, B_h, b1, b2 = self._phis(h)
+                h_phi_1, B_h, b1, b2 = self._phis(h, self.solver_type == "bh2")
                 k_ls = s_i / s_s0
                 k_h0 = -a_i * h_phi_1
                 if prev_order == 1:
@@ -166,7 +270,7 @@ class UniPCSchedule:
             order = min(2, n - i, lower_order_nums + 1)
             a_t, s_t, lam_t = als[i + 1]
             h = lam_t - lam_i
-            h_phi_1, B_h, _, _ = self._phis(h)
+            h_phi_1, B_h, _, _ = self._phis(h, self.solver_type == "bh2")
             p_s = s_t / s_i
             p_new = -a_t * h_phi_1
             p_old = 0.0
@@ -179,3 +283,72 @@ class UniPCSchedule:
             if lower_order_nums < 2:
                 lower_order_nums += 1
         return ts, rows
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# config holders with the diffusers class names: what `UniRendererPipeline.from_pretrained` puts in `pipeline.scheduler`
+# so that the shipped eval's `UniPCMultistepScheduler.from_config(pipeline.scheduler.config)` line has a `.config` to read
+# (eval/test_real.py:485-493).  They carry configuration only -- the stepping itself is the fused kernels' job.
+# ----------------------------------------------------------------------------------------------------------------
+class SchedulerConfig(dict):
+    """dict with attribute access (diffusers' FrozenDict behaves like this)."""
+
+    def __getattr__(self, key):
+        try:
+            return self[key]
+        except KeyError as e:
+            raise AttributeError(key) from e
+
+
+class _SchedulerHolder:
+    _defaults: dict = {}
+
+    def __init__(self, **kwargs):
+        self.config = SchedulerConfig(dict(self._defaults, **kwargs))
+
+    @classmethod
+    def from_config(cls, config, **overrides):
+        """diffusers' SchedulerMixin.from_config: keep the keys this class knows, override, default the rest."""
+        src = dict(config) if isinstance(config, dict) else {k: getattr(config, k) for k in dir(config)
+                                                             if not k.startswith("_")}
+        kw = {k: v for k, v in src.items() if k in cls._defaults}
+        kw.update(overrides)
+        return cls(**kw)
+
+
+class DDIMScheduler(_SchedulerHolder):
+    _defaults = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
+                     prediction_type="epsilon", thresholding=False, timestep_spacing="leading",
+                     rescale_betas_zero_snr=False)
+
+
+class UniPCMultistepScheduler(_SchedulerHolder):
+    _defaults = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, solver_order=2, prediction_type="epsilon", thresholding=False,
+                     predict_x0=True, solver_type="bh2", lower_order_final=True, disable_corrector=[],
+                     solver_p=None, use_karras_sigmas=False, timestep_spacing="linspace", steps_offset=0)
+
+
+class PNDMScheduler(_SchedulerHolder):
+    """The scheduler class SD-1.x checkpoints ship (scheduler/scheduler_config.json): a config source only."""
+    _defaults = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, skip_prk_steps=False, set_alpha_to_one=False, prediction_type="epsilon",
+                     timestep_spacing="leading", steps_offset=0, clip_sample=False)
+
+
+def load_scheduler_config(directory: str):
+    """`<dir>/scheduler_config.json` -> a config holder named after its `_class_name` (unknown classes keep every key)."""
+    import json
+    import os
+    path = os.path.join(directory, "scheduler_config.json")
+    with open(path) as f:
+        cfg = json.load(f)
+    name = cfg.get("_class_name", "")
+    known = {"DDIMScheduler": DDIMScheduler, "UniPCMultistepScheduler": UniPCMultistepScheduler,
+             "PNDMScheduler": PNDMScheduler}
+    kw = {k: v for k, v in cfg.items() if not k.startswith("_")}
+    if name in known:
+        return known[name](**{k: v for k, v in kw.items() if k in known[name]._defaults})
+    holder = type(name or "Scheduler", (_SchedulerHolder,), {"_defaults": dict(kw)})
+    return holder()

@@ -14,8 +14,10 @@ toggles, :1368 mask2image_3mod_albedo, :1990 image2mask_3mod_albedo, :2391 real_
 body on `RenderPipeline` (batched VAE programs + the fused CUDA-graph loops).  What stays host Python exactly as in the
 reference: PIL / numpy pre- and post-processing (diffusers' VaeImageProcessor semantics: RGB, Lanczos resize, [0, 1]
 -> [-1, 1]; `(x / 2 + 0.5).clamp(0, 1)` back) and the text encoder, which runs once per distinct prompt
-(`PromptEmbedCache`).  The per-stream scheduler attributes the callers assign are honoured by KIND: UniPC or DDIM with
-their `config.prediction_type`; anything else raises.
+(`PromptEmbedCache`).  The per-stream scheduler attributes the callers assign are honoured through their `.config`: the
+timestep / coefficient tables of the fused loops are rebuilt from `beta_*`, `beta_schedule`, `timestep_spacing`,
+`steps_offset`, `prediction_type` (and `solver_type` for UniPC); a scheduler class other than DDIM / UniPC, or an option
+the tables do not reproduce (`clip_sample`, `thresholding`, `solver_order != 2`, Karras sigmas ...), raises.
 """
 from __future__ import annotations
 
@@ -25,6 +27,7 @@ import torch
 
 from .pipeline import DualStreamSampler
 from .render import RenderPipeline
+from .scheduler import DDIMSchedule, UniPCSchedule, load_scheduler_config
 from .text import PromptEmbedCache
 
 _STREAM_SCHEDULERS = ("scheduler_img", "scheduler_attr", "scheduler_material", "scheduler_albedo", "scheduler_normal",
@@ -46,6 +49,18 @@ def _prediction_type(obj) -> str:
     if pt is None and isinstance(cfg, dict):
         pt = cfg.get("prediction_type")
     return pt or getattr(obj, "prediction_type", None) or "epsilon"
+
+
+def _schedule_from(obj, kind: str):
+    """The coefficient-table object for an assigned scheduler: built from its `.config` when it has one (diffusers
+    objects, the holders of scheduler.py), else the SD-1.x defaults with the object's prediction type."""
+    cls = UniPCSchedule if kind == "unipc" else DDIMSchedule
+    cfg = getattr(obj, "config", None)
+    has_keys = cfg is not None and any((k in cfg) if isinstance(cfg, dict) else hasattr(cfg, k)
+                                       for k in ("beta_start", "timestep_spacing", "num_train_timesteps"))
+    if has_keys:
+        return cls.from_config(cfg, prediction_type=_prediction_type(obj))
+    return cls(prediction_type=_prediction_type(obj))
 
 
 def preprocess_image(image, height: int, width: int) -> torch.Tensor:
@@ -120,6 +135,11 @@ class UniRendererPipeline:
             if comps[name] is None and pretrained_model_name_or_path is not None \
                     and os.path.isdir(os.path.join(pretrained_model_name_or_path, name)):
                 comps[name] = klass.from_pretrained(pretrained_model_name_or_path, subfolder=name)
+        # `pipeline.scheduler.config` is what the eval derives every per-stream scheduler from (test_real.py:485-493)
+        if comps["scheduler"] is None and pretrained_model_name_or_path is not None:
+            sdir = os.path.join(pretrained_model_name_or_path, "scheduler")
+            if os.path.isfile(os.path.join(sdir, "scheduler_config.json")):
+                comps["scheduler"] = load_scheduler_config(sdir)
         return cls(**comps)
 
     # -- toggles the reference's callers invoke ------------------------------------------------------------------
@@ -156,10 +176,14 @@ class UniRendererPipeline:
         if any(s is None for s in scheds):
             raise ValueError(f"assign {', '.join(sched_names)} before sampling (eval/test_real.py:485-493)")
         kinds = {_scheduler_kind(s) for s in scheds}
-        ptypes = {_prediction_type(s) for s in scheds}
-        if len(kinds) != 1 or len(ptypes) != 1:
+        if len(kinds) != 1:
             raise NotImplementedError("the per-stream schedulers of one call must share kind and prediction_type")
-        kind, ptype = kinds.pop(), ptypes.pop()
+        kind = kinds.pop()
+        tables = [_schedule_from(s, kind) for s in scheds]
+        if len({t.signature() for t in tables}) != 1:
+            raise NotImplementedError("the per-stream schedulers of one call must share kind, prediction_type and "
+                                      "configuration (the fused loop walks ONE timestep table)")
+        ptype = tables[0].prediction_type
         if self._render is None or self._render_key != ptype:
             if self._sampler is None or self._render_key != ptype:
                 self._sampler = DualStreamSampler(self.unet, self.controlnet, self.controldec, prediction_type=ptype)
@@ -168,6 +192,7 @@ class UniRendererPipeline:
                 cache = PromptEmbedCache(self.tokenizer, self.text_encoder, device=self._sampler.device)
             self._render = RenderPipeline(self._sampler, self.vae, prompt_cache=cache)
             self._render_key = ptype
+        self._sampler.set_schedules(**{"unipc" if kind == "unipc" else "ddim": tables[0]})
         return self._render, kind
 
     def _embeds(self, rp: RenderPipeline, prompt, prompt_embeds, negative_prompt, negative_prompt_embeds, guidance_scale):
