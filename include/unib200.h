@@ -119,7 +119,7 @@ typedef struct {
    * gamma folded into its weights and corrects in the epilogue:
    *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_wsum[n]) + bias[n],   bias[n] = b[n] + sum_k beta[k] W[n,k]
    * -- no LayerNorm kernel, no normalised tensor in HBM.                                                          */
-  float* rowstats_out;      /* producer: fp32 [M][ceil(N/BN)][2] (sum, sum of squares) of the stored rows, or NULL */
+  float* rowstats_out;      /* producer: fp32 [M][2*ceil(N/BN)][2] (sum, sum of squares) of the stored rows, or NULL */
   const float* ln_rowstats; /* consumer: the producer's table, [M][ln_parts][2], or NULL                           */
   int ln_parts;
   const float* ln_wsum;     /* consumer: fp32 [N], sum_k of the (gamma-folded, fp16-rounded) weight row            */

@@ -131,7 +131,7 @@ def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_b
         if flags & L.EPI_SILU:
             acc = F.silu(acc)
         if rowstats_out is not None:                         # consumers add the parts: put the row totals in part 0
-            rv = rowstats_out.reshape(-1)[:M * ((N + bn - 1) // bn) * 2].reshape(M, -1, 2)
+            rv = rowstats_out.reshape(-1)[:M * 2 * ((N + bn - 1) // bn) * 2].reshape(M, -1, 2)
             rv.zero_()
             rv[:, 0, 0], rv[:, 0, 1] = acc.sum(1), (acc * acc).sum(1)
         if flags & L.EPI_OUT_NCHW:

@@ -434,7 +434,8 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     // tiles and a long K loop.  Measured (tools/bench_gemm.py): conv3x3 +14..18 %, but short-K 1x1 layers lose ~10 %
     // to the pair's cluster synchronisation, so those stay on single CTAs.
     static const int pair_min_kb = getenv("UNIB200_PAIR_MIN_KB") ? atoi(getenv("UNIB200_PAIR_MIN_KB")) : 24;
-    p.cg = (pair_min_kb > 0 && gemm_pair_supported(bn) && d->M > kBM && total_kb >= pair_min_kb) ? 2 : 1;
+    p.cg = (pair_min_kb > 0 && gemm_pair_supported(bn) && d->M > kBM && total_kb >= pair_min_kb &&
+            !(d->flags & UNIB200_EPI_GEGLU)) ? 2 : 1;
     const uint32_t box[2] = {64, static_cast<uint32_t>(bn / p.cg)};
     if (!encode_map(&maps.b, d->weight, 2, dims, st, box, &why)) return fail("conv_gemm B map: " + why);
   }
@@ -513,15 +514,27 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   }
   p.splits = splits;
   p.partial = d->partial;
-  // NHWC fp16 outputs leave through the register -> vector-store epilogue; 256-bit accesses when rows are 32 B aligned
-  p.epi_vec = 0;
-  if (!(d->flags & UNIB200_EPI_OUT_NCHW) && splits == 1 && d->out != nullptr) {
+  // epilogue mode (csrc/gemm_sm100.cu GemmMode): the register -> 256-bit-store epilogue needs an NHWC fp16 output whose
+  // rows are 32 B aligned and whose width is a multiple of 32; everything else takes the direct-store epilogue
+  {
     auto al32 = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0; };
-    p.epi_vec = (al32(d->out, d->ldc) && (!d->res || al32(d->res, d->ldr))) ? 2 : 1;
-    if ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->res && (reinterpret_cast<uintptr_t>(d->res) & 15)))
+    const int n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2 : d->N;
+    const bool vec_ok = !(d->flags & (UNIB200_EPI_OUT_NCHW | UNIB200_EPI_SILU)) && splits == 1 && d->out != nullptr &&
+                        n_out % 32 == 0 && d->N % 32 == 0 && al32(d->out, d->ldc) && (!d->res || al32(d->res, d->ldr));
+    if (d->flags & UNIB200_EPI_GEGLU) {
+      if (!vec_ok || d->res) return fail("conv_gemm: GEGLU needs an aligned NHWC fp16 output (N / 2 a multiple of 32), no "
+                                         "residual, no split-K / NCHW");
+      p.mode = 1;
+    } else {
+      p.mode = vec_ok ? 0 : 2;
+    }
+    if (p.mode == 2 && (d->rowstats_out || d->ln_rowstats))
+      return fail("conv_gemm: row statistics / LayerNorm fold need the vector epilogue (aligned NHWC fp16 output, N a "
+                  "multiple of 32)");
+    if (p.mode == 2 && !(d->flags & UNIB200_EPI_OUT_NCHW) &&
+        ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->res && (reinterpret_cast<uintptr_t>(d->res) & 15))))
       return fail("conv_gemm: out / res must be 16-byte aligned");
   }
-  if ((d->flags & UNIB200_EPI_GEGLU) && !p.epi_vec) return fail("conv_gemm: GEGLU cannot be combined with split-K / NCHW");
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   double kreal = 0.0, a_bytes = 0.0;
   for (int i = 0; i < d->nseg; ++i) {

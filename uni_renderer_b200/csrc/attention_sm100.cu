@@ -17,6 +17,12 @@
 
 #include <stdlib.h>
 
+// measured on B200 (tools/ab_attn.sh, 4096 x 4096 tokens, d = 40): 0 -> 241.9 us, 1 -> 251.6, 2 -> 248.6, 3 -> 241.1,
+// 5 -> 230.5, 7 -> 219.5, 9 -> 249.4, 11 -> 245.1; at d = 80 (BKV = 64) variant 0 stays the fastest (25.6 vs 27.1 us)
+#ifndef UNIB_ATTN_DEFAULT_VARIANT
+#define UNIB_ATTN_DEFAULT_VARIANT 7
+#endif
+
 namespace unib {
 
 template <int NCH>
@@ -86,7 +92,15 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint64_t p_desc, uint6
 #define ATTN_TRACE(who, j, k) do { } while (0)
 #endif
 
-template <int NCH>
+// VAR (softmax variant bits; A/B-measured on B200):
+//   1  packed fp32 pairs: the scale/subtract runs as FFMA2, the row sums as FADD2, the row maximum as FMNMX3
+//      (halves the issue slots of the non-MUFU work of the exponential loop)
+//   2  one-time stagger: warpgroup 1 starts its first block when warpgroup 0 is half-way through its exponentials, so
+//      the two tiles alternate on the MUFU unit instead of running their exponential phases in lockstep
+//   4  every 4th pair of exponentials on the FMA pipe (exp2_poly_x2);  8  every 2nd pair
+constexpr int kAttnPacked = 1, kAttnStagger = 2, kAttnPoly4 = 4, kAttnPoly2 = 8;
+
+template <int NCH, int VAR>
 __global__ void __launch_bounds__(320, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH>;
@@ -251,6 +265,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       float m_ref = -INFINITY, l_run = 0.f;
       const uint32_t p_row = base + Cfg::kPOff + t * Cfg::kPBytes + row * 128;
       const int sw = row & 7;
+      if ((VAR & kAttnStagger) && t == 1) named_bar_sync(1, 256);    // ntile == 2 here: tile 0's warpgroup arrives (j = 0)
       for (int j = 0; j < nblk; ++j) {
         const bool tr = (lane == 0 && qd == 0);
         if (tr) ATTN_TRACE(t, j, 0);
@@ -271,12 +286,24 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
             if (i >= kv_valid) v[i] = -INFINITY;
         }
         float mx4[4] = {v[0], v[1], v[2], v[3]};              // 4 independent chains (FMNMX latency, not issue, bounds)
+        if (VAR & kAttnPacked) {
 #pragma unroll
-        for (int i = 4; i < BKV; i += 4) {
-          mx4[0] = fmaxf(mx4[0], v[i]);
-          mx4[1] = fmaxf(mx4[1], v[i + 1]);
-          mx4[2] = fmaxf(mx4[2], v[i + 2]);
-          mx4[3] = fmaxf(mx4[3], v[i + 3]);
+          for (int i = 4; i + 8 <= BKV; i += 8) {               // FMNMX3: two new elements per instruction
+            mx4[0] = fmax3(mx4[0], v[i], v[i + 1]);
+            mx4[1] = fmax3(mx4[1], v[i + 2], v[i + 3]);
+            mx4[2] = fmax3(mx4[2], v[i + 4], v[i + 5]);
+            mx4[3] = fmax3(mx4[3], v[i + 6], v[i + 7]);
+          }
+          mx4[0] = fmax3(mx4[0], v[BKV - 4], v[BKV - 3]);
+          mx4[1] = fmax3(mx4[1], v[BKV - 2], v[BKV - 1]);
+        } else {
+#pragma unroll
+          for (int i = 4; i < BKV; i += 4) {
+            mx4[0] = fmaxf(mx4[0], v[i]);
+            mx4[1] = fmaxf(mx4[1], v[i + 1]);
+            mx4[2] = fmaxf(mx4[2], v[i + 2]);
+            mx4[3] = fmaxf(mx4[3], v[i + 3]);
+          }
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // P_t V(j-1) must be complete before O_t is rescaled (rare: lazy rescale) or the P_t buffer is overwritten.
@@ -313,15 +340,47 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[BKV / 2];
 
+        if (VAR & (kAttnPacked | kAttnPoly4 | kAttnPoly2)) {
+          const f32x2_t sl2_2 = pack_f32x2(sl2, sl2), nmb_2 = pack_f32x2(-mb, -mb);
+          f32x2_t rs2[4] = {0ull, 0ull, 0ull, 0ull};             // (0.f, 0.f) pairs
 #pragma unroll
-        for (int u = 0; u < BKV / 8; ++u) {
+          for (int u = 0; u < BKV / 8; ++u) {
+            if ((VAR & kAttnStagger) && j == 0 && t == 0 && ntile == 2 && u == BKV / 16)
+              named_bar_arrive(1, 256);                         // half-way through tile 0's first block: release tile 1
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = u * 8 + 2 * e;
+              float x0, x1, p0, p1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(v[i], v[i + 1]), sl2_2, nmb_2), x0, x1);
+              const bool poly = ((VAR & kAttnPoly2) && (e & 1)) || ((VAR & kAttnPoly4) && e == 3);
+              if (poly) {
+                exp2_poly_x2(x0, x1, p0, p1);
+              } else {
+                p0 = fast_exp2(x0);
+                p1 = fast_exp2(x1);
+              }
+              rs2[e] = add_f32x2(rs2[e], pack_f32x2(p0, p1));
+              pk[u * 4 + e] = pack_half2(p0, p1);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int i = u * 8 + 2 * e;
-            const float p0 = fast_exp2(v[i] * sl2 - mb);
-            const float p1 = fast_exp2(v[i + 1] * sl2 - mb);
-            rs4[e] += p0 + p1;
-            pk[u * 4 + e] = pack_half2(p0, p1);
+            float a, b2;
+            unpack_f32x2(rs2[e], a, b2);
+            rs4[e] = a + b2;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < BKV / 8; ++u) {
+            if ((VAR & kAttnStagger) && j == 0 && t == 0 && ntile == 2 && u == BKV / 16) named_bar_arrive(1, 256);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = u * 8 + 2 * e;
+              const float p0 = fast_exp2(v[i] * sl2 - mb);
+              const float p1 = fast_exp2(v[i + 1] * sl2 - mb);
+              rs4[e] += p0 + p1;
+              pk[u * 4 + e] = pack_half2(p0, p1);
+            }
           }
         }
         if (!pv_waited) {                     // warp-uniform
@@ -379,27 +438,49 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   }
 }
 
-template <int NCH>
+template <int NCH, int VAR>
 static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = AttnCfg<NCH>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
-  return launch_pdl(attention_tcgen05_kernel<NCH>, grid, dim3(320), Cfg::kSmemBytes, stream, maps, p);
+  return launch_pdl(attention_tcgen05_kernel<NCH, VAR>, grid, dim3(320), Cfg::kSmemBytes, stream, maps, p);
 }
 
 int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
 
+// softmax variant (bits above): the default is the measured optimum; UNIB200_ATTN_VARIANT overrides it for A/B runs
+static int attention_variant(int nch) {
+  static const int v = getenv("UNIB200_ATTN_VARIANT") ? atoi(getenv("UNIB200_ATTN_VARIANT")) : -1;
+  if (v >= 0) return v;
+  return nch == 1 ? UNIB_ATTN_DEFAULT_VARIANT : 0;
+}
+
+template <int NCH>
+static cudaError_t launch_var(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
+  switch (attention_variant(NCH)) {
+    case 0: return launch_cfg<NCH, 0>(maps, p, stream);
+    case 1: return launch_cfg<NCH, 1>(maps, p, stream);
+    case 2: return launch_cfg<NCH, 2>(maps, p, stream);
+    case 3: return launch_cfg<NCH, 3>(maps, p, stream);
+    case 5: return launch_cfg<NCH, 5>(maps, p, stream);
+    case 7: return launch_cfg<NCH, 7>(maps, p, stream);
+    case 9: return launch_cfg<NCH, 9>(maps, p, stream);
+    case 11: return launch_cfg<NCH, 11>(maps, p, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_attention(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
   if (p.d % 8 != 0 || p.d > 192 || p.d < 8) return cudaErrorInvalidValue;
-  if (p.d <= 64) return launch_cfg<1>(maps, p, stream);
-  if (p.d <= 128) return launch_cfg<2>(maps, p, stream);
-  return launch_cfg<3>(maps, p, stream);
+  if (p.d <= 64) return launch_var<1>(maps, p, stream);
+  if (p.d <= 128) return launch_var<2>(maps, p, stream);
+  return launch_var<3>(maps, p, stream);
 }
 
 }  // namespace unib

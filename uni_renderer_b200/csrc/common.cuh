@@ -327,6 +327,68 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 process two fp32 lanes per issue slot) and 3-input max (FMNMX3)
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma_f32x2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t sub_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add_rm_f32x2(f32x2_t a, f32x2_t b) {      // round toward -inf
+  f32x2_t r;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a PAIR of x <= ~8 on the FMA pipe (Cody-Waite: floor via a round-down magic add, degree-3 minimax polynomial
+// of 2^f on [0, 1) with max relative error 8.6e-5 -- below the fp16 resolution of P -- exponent inserted by an integer
+// add).  Offloads part of the softmax exponentials from the MUFU unit (16 ex2/clk/SM), which bounds attention at head
+// dim 40.  Inputs are clamped to >= -126 (the exponent insert would wrap below).
+__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const f32x2_t x = pack_f32x2(x0, x1);
+  const f32x2_t magic = pack_f32x2(12582912.0f, 12582912.0f);                // 1.5 * 2^23
+  const f32x2_t r = add_rm_f32x2(x, magic);                                  // low mantissa bits = floor(x)
+  const f32x2_t f = sub_f32x2(x, sub_f32x2(r, magic));                       // x - floor(x) in [0, 1)
+  f32x2_t q = fma_f32x2(pack_f32x2(0.07706618f, 0.07706618f), f, pack_f32x2(0.22764593f, 0.22764593f));
+  q = fma_f32x2(q, f, pack_f32x2(0.69511658f, 0.69511658f));
+  q = fma_f32x2(q, f, pack_f32x2(1.0f, 1.0f));
+  float q0, q1, r0, r1;
+  unpack_f32x2(q, q0, q1);
+  unpack_f32x2(r, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

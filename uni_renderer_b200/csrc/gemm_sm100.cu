@@ -1,11 +1,11 @@
 // Implicit-GEMM convolution / linear kernel for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (UMMA
 // 128 x BN x 16 per CTA, or 256 x BN x 16 per CTA PAIR with cta_group::2; fp16 in / fp32 accumulate in TMEM,
 // double-buffered accumulators) -> tcgen05.ld epilogue.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.
 // Persistent: each CTA (pair) walks work items (split, m_tile, n_tile) with stride gridDim.x (/ 2).
 //
-// Epilogue (NHWC fp16 outputs): each of the four epilogue warps drains its 32 rows of the 128 x BN tile in 32-column
-// sub-tiles straight from TMEM through registers: bias from a per-warp smem copy, the residual (ResNet identity /
+// Epilogue (NHWC fp16 outputs): the eight epilogue warps (two per TMEM lane quadrant = 32 rows of the 128 x BN tile,
+// splitting its 32-column sub-tiles) drain the accumulator straight from TMEM through registers: bias from a per-warp smem copy, the residual (ResNet identity /
 // transformer skip / exchange add) read with 256-bit global loads one sub-tile ahead, SiLU / GEGLU gate in registers,
 // 256-bit global stores (64 contiguous bytes per row and sub-tile = full sectors).  No smem staging, proxy fence or
 // block-wide barrier on the critical path (a TMA-store slot ring measured ~1000 cycles of serial latency per
@@ -23,7 +23,11 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBiasBytes = 4 * 3 * BN * 4;              // per epilogue warp: bias [2 batch rows][BN] + LayerNorm wsum [BN], fp32
+  // per epilogue warp (8): bias [2 batch rows] + LayerNorm wsum [1] for ITS half of the tile's 32-column sub-tiles, fp32
+  // (GEGLU keeps value and gate columns: 2 x the slots of its BN / 64 output sub-tiles)
+  static constexpr int kVecFloats = 3 * (((BN / 32 + 1) / 2) * 32);
+  static constexpr int kGegluFloats = 6 * (((BN / 64 + 1) / 2) * 32);
+  static constexpr int kBiasBytes = 8 * 4 * (kVecFloats > kGegluFloats ? kVecFloats : kGegluFloats);
   static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes) / kStageBytes;
 #ifndef UNIB_MAX_STAGES
 #define UNIB_MAX_STAGES 8
@@ -168,8 +172,20 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float* v, 
 #define GEMM_TRACE(k) do { } while (0)
 #endif
 
-template <int BN, int CG>
-__global__ void __launch_bounds__(192, 1)
+// Epilogue modes (compile-time, so that each kernel's hot epilogue loop is short straight-line code: the one-kernel
+// version with run-time flags spent 34 % of its issue slots on instruction-cache misses, ncu stall_no_inst):
+//   MODE_VEC     NHWC fp16 output through registers -> 256-bit global stores; N a multiple of 32, rows 32 B aligned;
+//                bias / residual / LayerNorm fold / row statistics are short run-time-optional blocks
+//   MODE_GEGLU   value * gelu(gate) of the two halves of the tile, otherwise as MODE_VEC
+//   MODE_DIRECT  everything else through per-thread scalar / 128-bit stores: split-K fp32 partials, NCHW outputs and
+//                the fused scheduler update, SiLU, odd N, unaligned rows
+enum GemmMode : int { MODE_VEC = 0, MODE_GEGLU = 1, MODE_DIRECT = 2 };
+
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quadrant: they split the tile's column sub-tiles
+constexpr int kGemmThreads = (2 + kEpiWarps) * 32;
+
+template <int BN, int CG, int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader of the CTA pair (issues the MMAs)
@@ -206,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * CG);          // pair: the epilogue warps of BOTH CTAs release the leader's MMA warp
+      mbar_init(tempty_bar(a), kEpiWarps * CG);  // pair: the epilogue warps of BOTH CTAs release the leader's MMA warp
     }
     fence_barrier_init();
   }
@@ -354,75 +370,57 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..9) ===============================
+    // Eight warps: warp w may access TMEM lane quadrant w & 3 (hardware rule), so two warps share each quadrant = 32
+    // rows of the tile and split its 32-column sub-tiles between them (even / odd, flipped every tile so that odd
+    // sub-tile counts balance).  Two epilogue warps per scheduler also hide each other's TMEM / global latencies.
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int hw = (warp - 2) >> 2;         // which half of the sub-tiles (before the per-tile flip)
+    const int ew = warp - 2;                // 0..7
     // hand the accumulator back to the MMA warp -- which, for a CTA pair, lives in the leader CTA
     auto release_acc = [&](int a) {
       if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(a), 0));
       else mbar_arrive(tempty_bar(a));
     };
-    const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
-    const bool leader = (et == 0);
+    const bool leader = (threadIdx.x == 64);
     uint32_t tl = 0;
-    if (p.epi_vec) {
+    if (MODE == MODE_VEC || MODE == MODE_GEGLU) {
       // ---------------- NHWC fp16 epilogue: registers -> 256-bit global stores ----------------
-      // Each epilogue warp owns its TMEM lane quadrant = 32 rows of the tile; a thread owns one row and drains it in
-      // 32-column sub-tiles: tcgen05.ld -> + bias (per-warp smem copy) -> + residual (two 256-bit global loads issued
-      // one sub-tile ahead) -> SiLU / GEGLU gate -> two 256-bit global stores (64 contiguous bytes = 2 full sectors
-      // per row).  No shared-memory staging, no proxy fence, no barrier: the four warps run fully decoupled and the
-      // only waits are the accumulator hand-off and the (prefetched) residual.
-      const bool geglu = (p.flags & EPI_GEGLU) != 0;
-      const bool silu = (p.flags & EPI_SILU) != 0;
-      const bool has_res = p.res != nullptr;
+      // A thread owns one row of the tile and drains its warp's sub-tiles: tcgen05.ld (32 fp32 columns) -> LayerNorm
+      // fold -> + bias (per-warp smem copy) -> + residual (two 256-bit global loads issued one sub-tile ahead) ->
+      // [GEGLU gate] -> two 256-bit global stores (64 contiguous bytes = 2 full sectors per row).  No shared-memory
+      // staging, no proxy fence, no block-wide barrier: the warps run fully decoupled.
+      constexpr bool geglu = (MODE == MODE_GEGLU);
+      constexpr int nsub = geglu ? BN / 64 : BN / 32;           // output sub-tiles per tile
+      constexpr int nmine = (nsub + 1) / 2;                     // at most this many per warp
+      constexpr int out_bn = geglu ? BN / 2 : BN;               // output columns per tile
+      constexpr int kWarpFloats = (geglu ? 3 * 2 : 3) * nmine * 32;
+      static_assert(kEpiWarps * kWarpFloats * 4 <= Cfg::kBiasBytes, "per-warp bias copies must fit");
+      const bool has_res = !geglu && p.res != nullptr;
       const bool has_bias = p.bias != nullptr;
-      const int nsub = geglu ? BN / 64 : BN / 32;             // output sub-tiles per tile
-      const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
       const int n_out = geglu ? p.N / 2 : p.N;
-      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff) + q * (3 * BN);   // this warp's [2][BN] (+ wsum)
-      float* wsum_s = bias_s + 2 * BN;                                                 // LayerNorm fold: [BN]
+      // this warp's bias copy: [2 batch rows][slots][32] (+ LayerNorm wsum [slots][32]); slot = local sub-tile index;
+      // GEGLU keeps value and gate columns in two consecutive slots
+      constexpr int kSlots = geglu ? 2 * nmine : nmine;
+      float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBiasOff) + ew * kWarpFloats;
+      float* wsum_s = bias_s + 2 * kSlots * 32;
       const bool has_ln = p.ln_rowstats != nullptr;
-      const bool want_stats = p.rowstats_out != nullptr;
+      const bool want_stats = !geglu && p.rowstats_out != nullptr;
       const bool per_batch = p.bias_bstride != 0;
       const float* const bias_base = p.bias + ((p.bias != nullptr && p.bias_step != nullptr)
                                                    ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0);
       __half* const outp = reinterpret_cast<__half*>(p.out);
-      auto load_res = [&](uint32_t* r, int m, int n) {
-        if (m < p.M && n + 32 <= n_out) {
-          const __half* rp = p.res + static_cast<size_t>(m) * p.ldr + n;
-          if (p.epi_vec == 2) {
-            ldg256(rp, r);
-            ldg256(rp + 16, r + 8);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 t = *reinterpret_cast<const uint4*>(rp + 8 * u);
-              r[4 * u] = t.x; r[4 * u + 1] = t.y; r[4 * u + 2] = t.z; r[4 * u + 3] = t.w;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) r[u] = 0u;
-          if (m < p.M) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {          // static indices only: r[] must stay in registers
-              if (n + i < n_out) {
-                const uint32_t h = __half_as_ushort(p.res[static_cast<size_t>(m) * p.ldr + n + i]);
-                r[i >> 1] |= h << ((i & 1) * 16);
-              }
-            }
-          }
-        }
-      };
       for (int w = cta; w < total_work; w += ncta, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
+        const int h = (hw + static_cast<int>(tl)) & 1;         // my sub-tiles: h, h + 2, ...
         const int m0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + q * 32;   // first row of this warp
         const int m = m0 + lane;
+        const bool row_ok = m < p.M;
         const int n0 = wi.nt * out_bn;                         // first output column of this tile
-        // bias of this tile -> this warp's smem copy (two batch rows: the 32 rows may straddle a batch boundary);
-        // bias and the first residual sub-tile are requested before the accumulator wait (latency overlaps the MMAs)
+        // bias of my sub-tiles -> smem (two batch rows: the 32 rows may straddle a batch boundary); bias and the first
+        // residual sub-tile are requested before the accumulator wait (latency overlaps the MMAs)
         int m_last = m0 + 31;
         if (m_last >= p.M) m_last = p.M - 1;
         // a warp whose rows all lie beyond M (M < 128) must not index the per-batch bias table out of range
@@ -431,30 +429,25 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         const int b_last = per_batch ? batch_of_row(p, m_last) : b_first;
         if (has_bias || has_ln) {
           __syncwarp();                                        // previous tile's bias reads are done
-          if (has_bias) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int c = 0; c < BN / 32; ++c) {
-                const int col = c * 32 + lane;
-                const int n = wi.nt * BN + col;
-                const int bb = r == 0 ? b_first : b_last;
-                bias_s[r * BN + col] = (n < p.N) ? __ldg(bias_base + static_cast<size_t>(bb) * p.bias_bstride + n) : 0.f;
-              }
-          }
-          if (has_ln) {
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-              const int col = c * 32 + lane;
-              const int n = wi.nt * BN + col;
-              wsum_s[col] = (n < p.N) ? __ldg(p.ln_wsum + n) : 0.f;
+          for (int s = 0; s < kSlots; ++s) {
+            // tile column of slot s, lane: plain -> sub-tile h + 2 s; GEGLU -> value (s even) / gate (s odd) column
+            const int jj = geglu ? (s >> 1) : s;
+            const int j = h + 2 * jj;
+            const int col = (geglu && (s & 1) ? BN / 2 : 0) + j * 32 + lane;
+            const int n = wi.nt * BN + col;
+            const bool ok = j < nsub && n < p.N;
+            if (has_bias) {
+              bias_s[s * 32 + lane] = ok ? __ldg(bias_base + static_cast<size_t>(b_first) * p.bias_bstride + n) : 0.f;
+              bias_s[(kSlots + s) * 32 + lane] = ok ? __ldg(bias_base + static_cast<size_t>(b_last) * p.bias_bstride + n) : 0.f;
             }
+            if (has_ln) wsum_s[s * 32 + lane] = ok ? __ldg(p.ln_wsum + n) : 0.f;
           }
           __syncwarp();
         }
         // LayerNorm fold: this row's mean / rstd from the producer's per-N-tile partial sums (fixed order)
         float ln_mean = 0.f, ln_rstd = 1.f;
-        if (has_ln && m < p.M) {
+        if (has_ln && row_ok) {
           float s1 = 0.f, s2 = 0.f;
           const float2* rs = reinterpret_cast<const float2*>(p.ln_rowstats) + static_cast<size_t>(m) * p.ln_parts;
           for (int i = 0; i < p.ln_parts; ++i) {
@@ -465,49 +458,65 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           ln_mean = s1 * p.ln_inv_c;
           ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
         }
-        float st_sum = 0.f, st_sq = 0.f;                       // row statistics of this tile's output columns
+        float st_sum = 0.f, st_sq = 0.f;                       // row statistics of my output columns
         uint32_t rnext[16];
-        if (has_res) load_res(rnext, m, n0);
+        const __half* const res_row = p.res + static_cast<size_t>(m) * p.ldr + n0;
+        if (has_res && row_ok && h < nsub) {
+          ldg256(res_row + h * 32, rnext);
+          ldg256(res_row + h * 32 + 16, rnext + 8);
+        }
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
         if (tl == 0 && leader) GEMM_TRACE(5);
         if (tl == 1 && leader) GEMM_TRACE(11);
         const int my_b = per_batch ? batch_of_row(p, m) : 0;
-        const float* my_bias = bias_s + ((my_b > b_first) ? BN : 0);
+        const float* my_bias = bias_s + ((my_b > b_first) ? kSlots * 32 : 0);
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        int jlast = h;                                         // my last sub-tile (releases the accumulator)
+        while (jlast + 2 < nsub) jlast += 2;
+        if (h >= nsub) {                                       // no work this tile (BN = 32): just release
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(acc);
+        }
 #pragma unroll 1
-        for (int j = 0; j < nsub; ++j) {
+        for (int j = h, jj = 0; j < nsub; j += 2, ++jj) {
           float v[32];
           uint32_t rcur[16];
-          if (tl == 0 && leader && j == 1) GEMM_TRACE(4);
+          if (tl == 0 && leader && jj == 1) GEMM_TRACE(4);
           if (has_res) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) rcur[u] = rnext[u];
-            if (j + 1 < nsub) load_res(rnext, m, n0 + (j + 1) * 32);
+            if (j + 2 < nsub && row_ok) {
+              ldg256(res_row + (j + 2) * 32, rnext);
+              ldg256(res_row + (j + 2) * 32 + 16, rnext + 8);
+            }
           }
           if (geglu) {
             float gte[32];
             tmem_ld32(taddr + j * 32, v);
             tmem_ld32(taddr + BN / 2 + j * 32, gte);
             tmem_ld_wait();
-            if (j == nsub - 1) {              // accumulator fully read -> release it to the MMA warp
+            if (j == jlast) {                 // my part of the accumulator is read -> release it to the MMA warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) release_acc(acc);
             }
+            const float* wv = wsum_s + (2 * jj) * 32;
+            const float* bv = my_bias + (2 * jj) * 32;
             if (has_ln) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                v[i] = ln_rstd * (v[i] - ln_mean * wsum_s[j * 32 + i]);
-                gte[i] = ln_rstd * (gte[i] - ln_mean * wsum_s[BN / 2 + j * 32 + i]);
+                v[i] = ln_rstd * (v[i] - ln_mean * wv[i]);
+                gte[i] = ln_rstd * (gte[i] - ln_mean * wv[32 + i]);
               }
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
               if (has_bias) {
-                ba = *reinterpret_cast<const float4*>(my_bias + j * 32 + i);
-                bg = *reinterpret_cast<const float4*>(my_bias + BN / 2 + j * 32 + i);
+                ba = *reinterpret_cast<const float4*>(bv + i);
+                bg = *reinterpret_cast<const float4*>(bv + 32 + i);
               }
               v[i] = (v[i] + ba.x) * gelu_erf_f(gte[i] + bg.x);
               v[i + 1] = (v[i + 1] + ba.y) * gelu_erf_f(gte[i + 1] + bg.y);
@@ -517,8 +526,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           } else {
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
-            if (tl == 0 && leader && j == 1) GEMM_TRACE(10);
-            if (j == nsub - 1) {
+            if (tl == 0 && leader && jj == 1) GEMM_TRACE(10);
+            if (j == jlast) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) release_acc(acc);
@@ -526,7 +535,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             if (has_ln) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 wq = *reinterpret_cast<const float4*>(wsum_s + j * 32 + i);
+                const float4 wq = *reinterpret_cast<const float4*>(wsum_s + jj * 32 + i);
                 v[i] = ln_rstd * (v[i] - ln_mean * wq.x);
                 v[i + 1] = ln_rstd * (v[i + 1] - ln_mean * wq.y);
                 v[i + 2] = ln_rstd * (v[i + 2] - ln_mean * wq.z);
@@ -536,81 +545,60 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             if (has_bias) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 bq = *reinterpret_cast<const float4*>(my_bias + j * 32 + i);
+                const float4 bq = *reinterpret_cast<const float4*>(my_bias + jj * 32 + i);
                 v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
               }
             }
-          }
-          if (has_res) {
+            if (has_res) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rcur[u]));
-              v[2 * u] += f.x;
-              v[2 * u + 1] += f.y;
-            }
-          }
-          if (silu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-          }
-          const int n = n0 + j * 32;
-          if (tl == 0 && leader && j == 1) GEMM_TRACE(12);
-          if (want_stats) {
-            if (n + 32 <= n_out) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) { st_sum += v[i]; st_sq += v[i] * v[i]; }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n + i < n_out) { st_sum += v[i]; st_sq += v[i] * v[i]; }
-            }
-          }
-          if (m < p.M) {
-            __half* op = outp + static_cast<size_t>(m) * p.ldc + n;
-            if (n + 32 <= n_out) {
-              uint32_t o[16];
-#pragma unroll
-              for (int u = 0; u < 16; ++u) o[u] = pack_half2(v[2 * u], v[2 * u + 1]);
-              if (p.epi_vec == 2) {
-                stg256(op, o);
-                stg256(op + 16, o + 8);
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  *reinterpret_cast<uint4*>(op + 8 * u) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+              for (int u = 0; u < 16; ++u) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rcur[u]));
+                v[2 * u] += f.x;
+                v[2 * u + 1] += f.y;
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)            // static indices only: v[] must stay in registers
-                if (n + i < n_out) op[i] = __float2half_rn(v[i]);
             }
           }
-          if (tl == 0 && leader && j == 1) GEMM_TRACE(13);
+          if (tl == 0 && leader && jj == 1) GEMM_TRACE(12);
+          if (want_stats) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { st_sum += v[i]; st_sq += v[i] * v[i]; }
+          }
+          if (row_ok) {
+            __half* op = outp + static_cast<size_t>(m) * p.ldc + n0 + j * 32;
+            uint32_t o[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) o[u] = pack_half2(v[2 * u], v[2 * u + 1]);
+            stg256(op, o);
+            stg256(op + 16, o + 8);
+          }
+          if (tl == 0 && leader && jj == 1) GEMM_TRACE(13);
         }
-        if (want_stats && m < p.M)
-          *reinterpret_cast<float2*>(p.rowstats_out + (static_cast<size_t>(m) * p.n_tiles + wi.nt) * 2) =
+        // two partials per row and N tile (one per warp of the quadrant pair), summed by the consumer in fixed order
+        if (want_stats && row_ok)
+          *reinterpret_cast<float2*>(p.rowstats_out + (static_cast<size_t>(m) * (2 * p.n_tiles) + 2 * wi.nt + h) * 2) =
               make_float2(st_sum, st_sq);
         if (tl == 0 && leader) GEMM_TRACE(9);
       }
       if (leader) GEMM_TRACE(6);
       if (leader) GEMM_TRACE(7);
     } else {
-      // ---------------- direct-store epilogue: split-K partials, NCHW outputs ----------------
+      // ---------------- direct-store epilogue: split-K partials, NCHW outputs, generic shapes ----------------
       for (int w = cta; w < total_work; w += ncta, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
+        const int h = (hw + static_cast<int>(tl)) & 1;
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
         if (tl == 0 && leader) GEMM_TRACE(5);
-        const int m = (wi.mt * CG + static_cast<int>(rank)) * kBM + row;
+        const int m = (wi.mt * CG + static_cast<int>(rank)) * kBM + q * 32 + lane;
         const bool row_ok = m < p.M;
         const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         if (p.splits > 1) {
           const int split = w / (p.m_tiles * p.n_tiles);
           float* pp = p.partial + (static_cast<size_t>(split) * p.M + m) * p.N + wi.nt * BN;
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
+          for (int c = h; c < BN / 32; c += 2) {
             float v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
@@ -629,7 +617,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           }
         } else {
 #pragma unroll 1
-          for (int c = 0; c < BN / 16; ++c) {
+          for (int c = h; c < BN / 16; c += 2) {
             float v[16];
             tmem_ld16(taddr + c * 16, v);
             tmem_ld_wait();
@@ -715,12 +703,12 @@ int gemm_pick_bn(int N, int flags) {
   return N >= 128 ? 128 : (N > 32 ? 64 : 32);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int MODE>
 static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -730,7 +718,7 @@ static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_
   const int grid = CG * (total_work < slots ? total_work : slots);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -747,7 +735,7 @@ static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, maps, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, MODE>, maps, p);
   if (e != cudaSuccess) return e;
   if (p.splits > 1) {
     const long long total = static_cast<long long>(p.M) * ((p.N + 15) / 16);
@@ -758,21 +746,39 @@ static cudaError_t launch_bn(const GemmMaps& maps, const GemmParams& p, int num_
   return e;
 }
 
+template <int BN, int CG>
+static cudaError_t launch_mode(const GemmMaps& maps, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  switch (p.mode) {
+    case MODE_VEC: return launch_bn<BN, CG, MODE_VEC>(maps, p, num_sms, stream);
+    case MODE_DIRECT: return launch_bn<BN, CG, MODE_DIRECT>(maps, p, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int num_sms, cudaStream_t stream) {
+  if (p.mode == MODE_GEGLU) {                    // GEGLU projections: K = C is short, single CTAs only
+    if (p.cg != 1) return cudaErrorInvalidValue;
+    switch (bn) {
+      case 64: return launch_bn<64, 1, MODE_GEGLU>(maps, p, num_sms, stream);
+      case 128: return launch_bn<128, 1, MODE_GEGLU>(maps, p, num_sms, stream);
+      case 256: return launch_bn<256, 1, MODE_GEGLU>(maps, p, num_sms, stream);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (p.cg == 2) {
     switch (bn) {
-      case 128: return launch_bn<128, 2>(maps, p, num_sms, stream);
-      case 160: return launch_bn<160, 2>(maps, p, num_sms, stream);
-      case 256: return launch_bn<256, 2>(maps, p, num_sms, stream);
+      case 128: return launch_mode<128, 2>(maps, p, num_sms, stream);
+      case 160: return launch_mode<160, 2>(maps, p, num_sms, stream);
+      case 256: return launch_mode<256, 2>(maps, p, num_sms, stream);
     }
     return cudaErrorInvalidValue;
   }
   switch (bn) {
-    case 32: return launch_bn<32, 1>(maps, p, num_sms, stream);
-    case 64: return launch_bn<64, 1>(maps, p, num_sms, stream);
-    case 128: return launch_bn<128, 1>(maps, p, num_sms, stream);
-    case 160: return launch_bn<160, 1>(maps, p, num_sms, stream);
-    case 256: return launch_bn<256, 1>(maps, p, num_sms, stream);
+    case 32: return launch_mode<32, 1>(maps, p, num_sms, stream);
+    case 64: return launch_mode<64, 1>(maps, p, num_sms, stream);
+    case 128: return launch_mode<128, 1>(maps, p, num_sms, stream);
+    case 160: return launch_mode<160, 1>(maps, p, num_sms, stream);
+    case 256: return launch_mode<256, 1>(maps, p, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

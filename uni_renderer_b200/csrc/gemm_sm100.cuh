@@ -63,8 +63,8 @@ struct GemmParams {
   const float* aux;          // EPI_AXPBY: x_t, NCHW fp32
   float* aux_out;            // EPI_AXPBY: x_{t-1}, NCHW fp32 (may alias aux)
   int axpby_n0;              // channels < axpby_n0 keep aux unchanged
-  int epi_vec;               // NHWC fp16 output through the vector epilogue: 2 = 256-bit, 1 = 128-bit accesses, 0 = off
-  float* rowstats_out;       // producer of a LayerNorm input: [M][n_tiles][2] (sum, sumsq) of the output rows
+  int mode;                  // GemmMode (gemm_sm100.cu): 0 vector NHWC fp16 epilogue, 1 GEGLU, 2 direct stores
+  float* rowstats_out;       // producer of a LayerNorm input: [M][2 * n_tiles][2] (sum, sumsq) of the output rows
   const float* ln_rowstats;  // consumer of LayerNorm(x): [M][ln_parts][2]; epilogue applies rstd * (acc - mean * wsum)
   const float* ln_wsum;      // [N]
   int ln_parts;

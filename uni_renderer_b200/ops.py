@@ -144,9 +144,10 @@ def pick_bn(N: int, flags: int = 0) -> int:
 
 
 def rowstats_parts(N: int, flags: int = 0) -> int:
-    """Row-statistics partials a GEMM with N output channels writes per row (one per N tile)."""
+    """Row-statistics partials a GEMM with N output channels writes per row: two per N tile (the two epilogue warps
+    that share a row of the tile each sum their own column sub-tiles, csrc/gemm_sm100.cu)."""
     bn = pick_bn(N, flags)
-    return (N + bn - 1) // bn
+    return 2 * ((N + bn - 1) // bn)
 
 
 def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
@@ -221,7 +222,7 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
         d.partial, d.partial_bytes = partial.data_ptr(), partial.numel() * partial.element_size()
     d.axpby, d.axpby_step, d.aux, d.aux_out = _ptr(axpby), _ptr(axpby_step), _ptr(aux), _ptr(aux_out)
     d.axpby_first_channel = axpby_first_channel
-    if rowstats_out is not None:      # producer of a LayerNorm input: [M, ceil(N / BN), 2] fp32 row statistics
+    if rowstats_out is not None:      # producer of a LayerNorm input: [M, 2 * ceil(N / BN), 2] fp32 row statistics
         assert rowstats_out.dtype == torch.float32 and rowstats_out.is_contiguous()
         assert rowstats_out.numel() >= M * rowstats_parts(N, flags) * 2
         d.rowstats_out = rowstats_out.data_ptr()
