@@ -4,8 +4,11 @@ native GroupNorm / LayerNorm -- i.e. how the reference itself runs on this GPU (
 modules under fp16 weights with diffusers' AttnProcessor2_0 = F.scaled_dot_product_attention).  Times the joint
 dual-stream denoising step of BASELINE configs[1] (B = 4, 64x64 latents, SD-1.5 widths, random init) with CUDA events.
 
-Checker-side measurement (it executes oracle/): lives under tests/, never imported by the product or by bench.py.
-    python tests/torch_eager_probe.py [--batch 4] [--latent 64] [--steps 5] [--warmup 3] [--tiny --device cpu]
+TEST / BASELINE INFRASTRUCTURE (it executes oracle/): never imported by the product.  bench.py runs it as a
+SUBPROCESS in its `gpu_pytorch_eager` baseline leg (outside every timed region of the B200 arm), with and without
+cuDNN autotuning / channels_last, and quotes the best.
+    python oracle/torch_eager.py [--batch 4] [--latent 64] [--steps 5] [--warmup 3] [--cudnn-benchmark]
+                                 [--channels-last] [--tiny --device cpu]
 Prints one JSON line."""
 import argparse
 import json
@@ -27,6 +30,7 @@ def main():
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--tiny", action="store_true", help="tiny widths (CPU dry run of this script)")
     ap.add_argument("--cudnn-benchmark", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="NHWC activations and conv weights (cuDNN's fast layout)")
     a = ap.parse_args()
     import torch
     import torch.nn.functional as F
@@ -42,6 +46,12 @@ def main():
     cfgs_p = (replace(nb), replace(nb, in_channels=28), replace(nb, out_channels=28))
     cfgs = (replace(base_o), replace(base_o, in_channels=28), replace(base_o, out_channels=28))
     sds = [random_init_state_dict(k, c, s, dev, dtype=dt) for k, c, s in zip(("unet", "attr_enc", "attr_dec"), cfgs_p, (11, 12, 13))]
+
+    if a.channels_last:
+        for sd in sds:
+            for k, v in sd.items():
+                if v.dim() == 4:
+                    sd[k] = v.contiguous(memory_format=torch.channels_last)
 
     sin0 = uo.timestep_sinusoid
     uo.timestep_sinusoid = lambda t, dim: sin0(t.detach().float().cpu(), dim).to(device=dev, dtype=dt)
@@ -59,6 +69,9 @@ def main():
     g = torch.Generator().manual_seed(1234)
     x_img = torch.randn(B, 4, S, S, generator=g).to(dev, dt)
     x_attr = torch.randn(B, 28, S, S, generator=g).to(dev, dt)
+    if a.channels_last:
+        x_img = x_img.contiguous(memory_format=torch.channels_last)
+        x_attr = x_attr.contiguous(memory_format=torch.channels_last)
     ehs = torch.randn(B, 77, base_o.cross_attention_dim, generator=g).to(dev, dt)
     sched = uo.DDIM()
     ts = sched.set_timesteps(50)
@@ -91,7 +104,8 @@ def main():
         "what": "torch eager fp16 (cuDNN / cuBLAS / SDPA) execution of the reference's joint dual-stream denoising step",
         "device": torch.cuda.get_device_name(0) if dev.type == "cuda" else "cpu", "torch": torch.__version__,
         "dtype": str(dt), "batch": B, "latent": S, "widths": list(base_o.block_out_channels),
-        "cudnn_benchmark": bool(a.cudnn_benchmark), "steps": a.steps, "warmup": a.warmup,
+        "cudnn_benchmark": bool(a.cudnn_benchmark), "channels_last": bool(a.channels_last), "steps": a.steps,
+        "warmup": a.warmup,
         "ms_per_denoise_step": ms, "images_per_s_50_steps": B / (50 * ms * 1e-3),
         "finite": bool(torch.isfinite(x_img.float()).all() and torch.isfinite(x_attr.float()).all())}), flush=True)
 
