@@ -72,7 +72,8 @@ int unib200_program_profile(unib200_program* prog, void* stream, int iters, floa
  */
 /* _S2: 3x3 stride 2 pad 1 (Downsample2D of the UNets); _S2P0: 3x3 stride 2 with the input padded by one pixel at the
  * bottom / right only (diffusers Downsample2D(padding=0) = F.pad(x, (0,1,0,1)) + conv, the AutoencoderKL encoder). */
-enum { UNIB200_SEG_1x1 = 0, UNIB200_SEG_3x3 = 1, UNIB200_SEG_3x3_S2 = 2, UNIB200_SEG_3x3_S2P0 = 3 };
+enum { UNIB200_SEG_1x1 = 0, UNIB200_SEG_3x3 = 1, UNIB200_SEG_3x3_S2 = 2, UNIB200_SEG_3x3_S2P0 = 3,
+       UNIB200_SEG_UP2x2 = 4 /* nearest-2x upsample folded into the following 3x3 conv, see unib200_gemm_desc */ };
 enum {
   UNIB200_EPI_GEGLU = 1,     /* weight rows interleaved per N-tile: out = (a+ba) * gelu(g+bg); N_out = N/2        */
   UNIB200_EPI_OUT_NCHW = 2,  /* store NCHW (fp16, or fp32 with OUT_F32) instead of NHWC fp16                      */
@@ -125,6 +126,21 @@ typedef struct {
   const float* ln_wsum;     /* consumer: fp32 [N], sum_k of the (gamma-folded, fp16-rounded) weight row            */
   float ln_eps;
   int ln_C;                 /* channels the statistics were taken over                                             */
+  /* UNIB200_SEG_UP2x2 (single segment): Upsample2D = F.interpolate(scale 2, "nearest") + conv3x3 (models/
+   * unet_2d_blocks.py:2588,2701) as ONE GEMM over the LOW-resolution input: output pixel (2h+py, 2w+px) only sees the
+   * 2 x 2 input pixels (h-1+py+ty, w-1+px+tx), so each of the 4 output parities is a 2x2 conv whose weights are sums
+   * of the 3x3 taps (packed on the host: N = 4 * Cout rows ordered [parity][Cout], K = [4 taps][ceil(C/64)*64]).
+   * M, B, H, W describe the INPUT; out is the fp16 [B * 2H * 2W, ldc] high-resolution image; bias has Cout entries.
+   * 2.25x fewer MACs than convolving the materialised upsampled tensor, which is never written.  Needs the vector
+   * epilogue and Cout a power-of-two multiple of the N tile; no residual, no split-K.                                 */
+  /* GroupNorm statistics fused into the epilogue of the GEMM that PRODUCES a GroupNorm input (ResnetBlock2D norm1 /
+   * norm2, Transformer2DModel.norm, conv_norm_out): per (block of gn_rows rows, micro-group of gn_gran channels) the
+   * sum and the sum of squares of the output; unib200_groupnorm with part1 / part2 set consumes them, so a GroupNorm
+   * is ONE launch that reads its input once.  Needs the vector epilogue (no split-K), N % gn_gran == 0, gn_gran even
+   * and dividing the N tile, gn_rows in {32, 64, 128} dividing the rows of one sample.                              */
+  float* gn_part;           /* fp32 [M / gn_rows][N / gn_gran][2], or NULL                                         */
+  int gn_gran;
+  int gn_rows;
 } unib200_gemm_desc;
 
 int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);
@@ -159,6 +175,11 @@ typedef struct {
   int silu;
   float* scratch;            /* fp32 scratch, scratch_floats >= B * chunks * groups * 2 for some chunks >= 1       */
   size_t scratch_floats;
+  /* statistics already produced by the GEMM epilogues that wrote x1 / x2 (unib200_gemm_desc.gn_part): when part1 is
+   * set (and part2 whenever x2 is), no statistics pass runs -- one launch, one read of the input                     */
+  const float* part1;        /* [B * HW / part_rows][C1 / part_gran][2]                                            */
+  const float* part2;        /* [B * HW / part_rows][C2 / part_gran][2]                                            */
+  int part_gran, part_rows;
 } unib200_gn_desc;
 int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* desc, void* stream);
 

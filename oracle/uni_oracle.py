@@ -164,10 +164,13 @@ def mid_block(sd: SD, cfg: NetConfig, sample, temb, ehs):
     return resnet_block(sd, "mid_block.resnets.1", sample, temb, cfg)
 
 
-def up_blocks(sd: SD, cfg: NetConfig, sample, skips: Sequence[torch.Tensor], temb, ehs):
+def up_blocks(sd: SD, cfg: NetConfig, sample, skips: Sequence[torch.Tensor], temb, ehs, up_additional=None):
     """CrossAttnUpBlock2D.forward (:2508-2590) / UpBlock2D.forward (:2643-2704) chain; returns (sample, taps)
-    where taps mirrors the reference's modified per-resnet outputs (:2584,2697)."""
+    where taps mirrors the reference's modified per-resnet outputs (:2584,2697).  `up_additional` (12 tensors, decoder
+    layer order) selects the UpResBlock2D / CrossAttnUpResBlock2D variants (models/unet_2d_blocks.py:2706-2822,
+    2237-2415): `hidden_states += up_additional_states` after every layer (:2814, :2408)."""
     skips = list(skips)
+    up_additional = list(up_additional) if up_additional is not None else None
     taps = [sample]
     nb = len(cfg.block_out_channels)
     for i in range(nb):
@@ -176,6 +179,8 @@ def up_blocks(sd: SD, cfg: NetConfig, sample, skips: Sequence[torch.Tensor], tem
             sample = resnet_block(sd, f"up_blocks.{i}.resnets.{j}", sample, temb, cfg)
             if cfg.up_has_attn[i]:
                 sample = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", sample, ehs, cfg)
+            if up_additional is not None:
+                sample = sample + up_additional.pop(0)
             taps.append(sample)
         if i != nb - 1:
             sample = F.interpolate(sample, scale_factor=2.0, mode="nearest")
@@ -224,15 +229,18 @@ def attr_encoder_forward(sd: SD, cfg: NetConfig, timestep, ehs, controlnet_cond,
 
 
 def attr_decoder_forward(sd: SD, cfg: NetConfig, sample, down_block_res_samples, timestep, ehs,
-                         down_block_additional_residuals=None, mid_block_additional_residual=None):
-    """AttributeDecoderModel.forward(return_dict=False) -- models/controlnet.py:2342-2527."""
+                         down_block_additional_residuals=None, mid_block_additional_residual=None,
+                         up_block_additional_residuals=None):
+    """AttributeDecoderModel.forward(return_dict=False) -- models/controlnet.py:2342-2527.  With
+    `up_block_additional_residuals` the up blocks are the UpRes variants (the class defaults, :1794-1797; the live forward
+    has their extra argument commented out at :2486-2510, so this restates the BLOCK semantics of SURVEY row a8)."""
     temb = time_embedding(sd, cfg, timestep, None)
     skips = list(down_block_res_samples)
     if down_block_additional_residuals is not None:    # :2446-2461
         skips = [s + _conv(sd, f"control_down_blocks.{i}", r)
                  for i, (s, r) in enumerate(zip(skips, down_block_additional_residuals))]
     sample = sample + _conv(sd, "control_mid_block", mid_block_additional_residual)   # :2476-2477
-    h, _ = up_blocks(sd, cfg, sample, skips, temb, ehs)
+    h, _ = up_blocks(sd, cfg, sample, skips, temb, ehs, up_block_additional_residuals)
     return out_head(sd, cfg, h)
 
 

@@ -84,16 +84,45 @@ def _gelu_erf(x):
 
 def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_bstride=0, bias_step=None,
               bias_step_stride=0, res=None, flags=0, splits=0, partial=None, axpby=None, axpby_step=None, aux=None,
-              aux_out=None, axpby_first_channel=0, ldc=None, rowstats_out=None, ln=None):
+              aux_out=None, axpby_first_channel=0, ldc=None, rowstats_out=None, ln=None, gn=None):
     """out = epilogue(sum_k A[m, k] * W[n, k]) with the epilogue order of csrc/gemm_sm100.cu: LayerNorm-fold
     correction, bias (per batch / per step), GEGLU gate, residual, SiLU, row statistics, store (NHWC fp16, NCHW, or the
     fused scheduler update)."""
-    ktot = sum((1 if k == L.SEG_1x1 else 9) * ((c + 63) // 64 * 64) for _, c, k in segs)
+    ktot = sum((1 if k == L.SEG_1x1 else 4 if k == L.SEG_UP2x2 else 9) * ((c + 63) // 64 * 64) for _, c, k in segs)
     assert weight.dtype == torch.float16 and tuple(weight.shape) == (N, ktot) and weight.is_contiguous()
     linear = (H == 0 or W == 0)
     bn = L.load().unib200_pick_bn(N, flags)
 
+    def run_up():
+        """SEG_UP2x2 (include/unib200.h): four parity 2x2 convs over the low-resolution input, rows scattered to the
+        high-resolution output; statistics blocks are (low-res 128-row tile, parity)."""
+        (t, c, _), = segs
+        cout, cpad = N // 4, (c + 63) // 64 * 64
+        assert flags == 0 and res is None and not bias_bstride and cout % bn == 0
+        xp = F.pad(t[:, :c].float().reshape(B, H, W, c), (0, 0, 1, 1, 1, 1))
+        img = torch.zeros(B, 2 * H, 2 * W, cout)
+        for par in range(4):
+            py, px = par >> 1, par & 1
+            cols = []
+            for ty in range(2):
+                for tx in range(2):
+                    dh, dw = ty - 1 + py, tx - 1 + px
+                    cols.append(F.pad(xp[:, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W].reshape(B * H * W, c), (0, cpad - c)))
+            acc = torch.cat(cols, 1) @ weight[par * cout:(par + 1) * cout].float().t()
+            if bias is not None:
+                acc = acc + bias.float()
+            img[:, py::2, px::2] = acc.reshape(B, H, W, cout)
+            if gn is not None:
+                part, gran, rows = gn
+                assert rows == 128 and M % 128 == 0
+                tt = acc.reshape(M // 128, 128, cout // gran, gran)
+                part.reshape(-1)[:(M // 128) * 4 * (cout // gran) * 2].reshape(M // 128, 4, cout // gran, 2)[:, par].copy_(
+                    torch.stack([tt.sum((1, 3)), (tt * tt).sum((1, 3))], -1))
+        out[:4 * M, :cout].copy_(img.reshape(4 * M, cout))
+
     def run():
+        if segs[0][2] == L.SEG_UP2x2:
+            return run_up()
         cols = []
         for t, c, kind in segs:
             assert t.dtype == torch.float16 and t.stride(1) == 1
@@ -130,6 +159,12 @@ def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_b
             acc = acc + res[:M, :n_out].float()
         if flags & L.EPI_SILU:
             acc = F.silu(acc)
+        if gn is not None:                                   # GroupNorm statistics of the output (fp32, pre-rounding)
+            part, gran, rows = gn
+            assert not (flags & (L.EPI_GEGLU | L.EPI_OUT_NCHW)) and M % rows == 0 and N % gran == 0 and bn % gran == 0
+            t = acc.reshape(M // rows, rows, N // gran, gran)
+            part.reshape(-1)[:(M // rows) * (N // gran) * 2].reshape(M // rows, N // gran, 2).copy_(
+                torch.stack([t.sum((1, 3)), (t * t).sum((1, 3))], -1))
         if rowstats_out is not None:                         # consumers add the parts: put the row totals in part 0
             rv = rowstats_out.reshape(-1)[:M * 2 * ((N + bn - 1) // bn) * 2].reshape(M, -1, 2)
             rv.zero_()
@@ -219,13 +254,29 @@ def from_nhwc(prog, src, dst, *, B, Cn, HW):
     _submit(prog, lambda: dst.copy_(src[:, :Cn].float().reshape(B, HW, Cn).permute(0, 2, 1).reshape(dst.shape)))
 
 
-def groupnorm(prog, x1, C1, x2, C2, gamma, beta, out, scratch, *, B, HW, groups, eps, silu):
+def groupnorm(prog, x1, C1, x2, C2, gamma, beta, out, scratch, *, B, HW, groups, eps, silu, parts=None):
     def run():
         x = x1[:, :C1].float()
         if x2 is not None:
             x = torch.cat([x, x2[:, :C2].float()], 1)
         C = x.shape[1]
-        y = F.group_norm(x.reshape(B, HW, C).permute(0, 2, 1), groups, gamma, beta, eps)
+        if parts is not None:
+            # statistics from the producers' epilogue partials ([B*HW / rows][C_i / gran][2]), exactly as
+            # gn_apply_parts_kernel combines them: proves the host wiring hands the right tables to the right norm
+            p1, p2, gran, rows = parts
+            nrb = HW // rows
+            mg = p1.reshape(-1)[:B * nrb * (C1 // gran) * 2].reshape(B, nrb, C1 // gran, 2).sum(1)
+            if x2 is not None:
+                mg = torch.cat([mg, p2.reshape(-1)[:B * nrb * (C2 // gran) * 2].reshape(B, nrb, C2 // gran, 2).sum(1)], 1)
+            cpg = C // groups
+            gs = mg.reshape(B, groups, cpg // gran, 2).sum(2)                 # [B, G, 2]
+            mean = gs[..., 0] / (cpg * HW)
+            rstd = torch.rsqrt((gs[..., 1] / (cpg * HW) - mean * mean).clamp_min(0) + eps)
+            xg = x.reshape(B, HW, groups, cpg)
+            y = ((xg - mean[:, None, :, None]) * rstd[:, None, :, None]).reshape(B, HW, C) * gamma + beta
+            y = y.permute(0, 2, 1)
+        else:
+            y = F.group_norm(x.reshape(B, HW, C).permute(0, 2, 1), groups, gamma, beta, eps)
         if silu:
             y = F.silu(y)
         out.copy_(y.permute(0, 2, 1).reshape(B * HW, C))

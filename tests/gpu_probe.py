@@ -270,6 +270,112 @@ def case_norms():
     return res
 
 
+def case_gn_fused():
+    """GroupNorm statistics emitted by the GEMM epilogue (conv_gemm(gn=...)) + the single-launch apply that consumes them:
+    the partial tables against torch sums of the fp32 result, and the normalised output against torch's GroupNorm of the
+    STORED fp16 tensor(s) -- single source, two sources with another group size, 64- and 32-row blocks, a 3x3 conv
+    producer (CTA pairs) and a 1x1 producer with residual."""
+    import torch
+    import torch.nn.functional as F
+    from uni_renderer_b200 import ops
+    from uni_renderer_b200.ops import SEG_1x1, SEG_3x3
+    g = torch.Generator(device="cuda").manual_seed(14)
+    res = {}
+    scratch = torch.empty(1 << 20, device="cuda", dtype=torch.float32)
+
+    def producer(B, H, Cin, Cout, kind, gran, rows, with_res):
+        M = B * H * H
+        x = _mk((M, Cin), g)
+        wt = torch.randn(Cout, Cin, *((1, 1) if kind == SEG_1x1 else (3, 3)), generator=g, device="cuda") * (
+            (Cin * (1 if kind == SEG_1x1 else 9)) ** -0.5)
+        bias = torch.randn(Cout, generator=g, device="cuda")
+        r = _mk((M, Cout), g) if with_res else None
+        out = torch.zeros(M, Cout, device="cuda", dtype=torch.half)
+        part = torch.full((M // rows, Cout // gran, 2), float("nan"), device="cuda")
+        ops.conv_gemm(None, [(x, Cin, kind)], ops.pack_weight([(wt, kind)]), out, M=M, N=Cout, B=B,
+                      H=0 if kind == SEG_1x1 else H, W=0 if kind == SEG_1x1 else H, bias=bias, res=r,
+                      gn=(part, gran, rows))
+        torch.cuda.synchronize()
+        xi = x.float().reshape(B, H, H, Cin).permute(0, 3, 1, 2)
+        ref = F.conv2d(xi, wt.half().float(), bias, padding=0 if kind == SEG_1x1 else 1).permute(0, 2, 3, 1).reshape(M, Cout)
+        if with_res:
+            ref = ref + r.float()
+        t = ref.reshape(M // rows, rows, Cout // gran, gran)
+        ref_part = torch.stack([t.sum((1, 3)), (t * t).sum((1, 3))], -1)
+        return out, part, ref, ref_part
+
+    cases = [("c3_320_32x32", 2, 32, 320, 320, SEG_3x3, 10, 128, False),
+             ("p1_640_32x32_res", 2, 32, 640, 640, SEG_1x1, 10, 128, True),
+             ("c3_64_8x8_rows64", 4, 8, 32, 64, SEG_3x3, 4, 64, False),
+             ("p1_128_rows32", 3, 8, 64, 128, SEG_1x1, 4, 32, True)]
+    outs = {}
+    for name, B, H, Cin, Cout, kind, gran, rows, wr in cases:
+        out, part, ref, ref_part = producer(B, H, Cin, Cout, kind, gran, rows, wr)
+        res[name + "_out"] = _err(out, ref)
+        res[name + "_part"] = _err(part, ref_part)
+        outs[name] = (out, part, B, H * H, Cout, gran, rows)
+        # single-source GroupNorm from the partials
+        G = 32 if Cout % 320 == 0 else 8
+        gamma = torch.randn(Cout, generator=g, device="cuda")
+        beta = torch.randn(Cout, generator=g, device="cuda")
+        y = torch.zeros(B * H * H, Cout, device="cuda", dtype=torch.half)
+        ops.groupnorm(None, out, Cout, None, 0, gamma, beta, y, scratch, B=B, HW=H * H, groups=G, eps=1e-5, silu=True,
+                      parts=(part, None, gran, rows))
+        torch.cuda.synchronize()
+        xr = out.float().reshape(B, H * H, Cout).permute(0, 2, 1)
+        refy = F.silu(F.group_norm(xr, G, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(B * H * H, Cout)
+        res[name + "_gn"] = _err(y, refy)
+    # two sources, group size 30 = 3 micro-groups of 10, the group at the seam straddles both tables
+    o1, p1, B, HW, C1, gran, rows = outs["p1_640_32x32_res"]
+    o2, p2 = outs["c3_320_32x32"][:2]
+    Cc = C1 + 320
+    gamma = torch.randn(Cc, generator=g, device="cuda")
+    beta = torch.randn(Cc, generator=g, device="cuda")
+    y = torch.zeros(B * HW, Cc, device="cuda", dtype=torch.half)
+    ops.groupnorm(None, o1, C1, o2, 320, gamma, beta, y, scratch, B=B, HW=HW, groups=32, eps=1e-5, silu=True,
+                  parts=(p1, p2, gran, rows))
+    torch.cuda.synchronize()
+    xr = torch.cat([o1, o2], 1).float().reshape(B, HW, Cc).permute(0, 2, 1)
+    refy = F.silu(F.group_norm(xr, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(B * HW, Cc)
+    res["two_source_640+320_gn"] = _err(y, refy)
+    return res
+
+
+def case_upfold():
+    """SEG_UP2x2: nearest-2x upsample + conv3x3 as four parity 2x2 convs on the low-resolution input, against torch's
+    F.interpolate + conv2d with the ORIGINAL weights (the parity weights are fp32 sums of 1-4 taps rounded once to fp16,
+    so the reference uses fp16-rounded single taps and the gate allows that one extra rounding), plus the GroupNorm
+    statistics of the scattered output."""
+    import torch
+    import torch.nn.functional as F
+    from uni_renderer_b200 import ops
+    from uni_renderer_b200.ops import SEG_UP2x2
+    g = torch.Generator(device="cuda").manual_seed(15)
+    res = {}
+    for name, B, H, C, Cout, gran in [("up_1280_16to32", 2, 16, 1280, 1280, 10), ("up_640_32to64", 1, 32, 640, 640, 10),
+                                      ("up_128_8to16", 3, 8, 128, 128, 4)]:
+        M = B * H * H
+        x = _mk((M, C), g)
+        wt = torch.randn(Cout, C, 3, 3, generator=g, device="cuda") * (9 * C) ** -0.5
+        bias = torch.randn(Cout, generator=g, device="cuda")
+        out = torch.zeros(4 * M, Cout, device="cuda", dtype=torch.half)
+        use_gn = (H * H) % 128 == 0
+        part = torch.full((4 * M // 128, Cout // gran, 2), float("nan"), device="cuda") if use_gn else None
+        ops.conv_gemm(None, [(x, C, SEG_UP2x2)], ops.pack_upsample_conv(wt), out, M=M, N=4 * Cout, B=B, H=H, W=H, bias=bias,
+                      gn=(part, gran, 128) if use_gn else None)
+        torch.cuda.synchronize()
+        xi = F.interpolate(x.float().reshape(B, H, H, C).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+        ref = F.conv2d(xi, wt.half().float(), bias, padding=1).permute(0, 2, 3, 1).reshape(4 * M, Cout)
+        res[name] = _err(out, ref)
+        if use_gn:
+            # per sample, micro-group totals must equal torch's (block order inside a sample is the kernel's business)
+            nb = 4 * H * H // 128
+            got = part.reshape(B, nb, Cout // gran, 2).sum(1)
+            t = ref.reshape(B, 4 * H * H, Cout // gran, gran)
+            res[name + "_part"] = _err(got, torch.stack([t.sum((1, 3)), (t * t).sum((1, 3))], -1))
+    return res
+
+
 def _attn_case(B, heads, Nq, Nk, d, g, fused_qkv):
     import torch
     from uni_renderer_b200 import ops

@@ -309,3 +309,49 @@ def test_cfg_plans_match_the_reference_rules(monkeypatch, mode, scheduler, steps
         sampler.load_inputs(plan, x_img, x_attr, ehs)              # a CFG plan needs the negative embeddings
     with pytest.raises(ValueError):
         sampler.load_inputs(p0, x_img, x_attr, ehs, neg, g)
+
+
+@pytest.mark.parametrize("mode", ["joint", "forward"])
+def test_groupnorm_statistics_fused_into_gemm_epilogues(monkeypatch, mode):
+    """North-star item "GroupNorm fused into the epilogue": with the fusion forced on at every size the kernels allow,
+    every GEMM that produces a GroupNorm input also writes (row block, micro-group) statistics, and the GroupNorm of a
+    single source AND of a two-source concat (decoder: h | exchanged skip, other group size) normalises with the sums of
+    those tables -- the emulator computes the statistics ONLY from the tables, so a table handed to the wrong norm, a
+    wrong granularity or a missing producer shows up as a mismatch with the oracle."""
+    emu.install(monkeypatch)
+    sampler, sds, cfgs = _setup()
+    for net in (sampler.unet, sampler.enc, sampler.dec):
+        assert net.gn_gran == 4                          # gcd of the tiny config's group sizes (32 / 8, 64 / 8, 128 / 8)
+        net.gn_force = True
+    B, S, total = 2, 16, 10                              # 16x16, 8x8 fuse (HW % 32 == 0); 4x4 and 2x2 fall back
+    seen = {"fused": 0, "plain": 0, "producers": 0}
+    from uni_renderer_b200 import ops
+    real_gn, real_gemm = ops.groupnorm, ops.conv_gemm
+
+    def spy_gn(*a, **k):
+        seen["fused" if k.get("parts") is not None else "plain"] += 1
+        if k.get("parts") is not None and a[3] is not None:
+            seen["two_source"] = seen.get("two_source", 0) + 1
+        return real_gn(*a, **k)
+
+    def spy_gemm(*a, **k):
+        seen["producers"] += k.get("gn") is not None
+        return real_gemm(*a, **k)
+    monkeypatch.setattr(ops, "groupnorm", spy_gn)
+    monkeypatch.setattr(ops, "conv_gemm", spy_gemm)
+    x_img, x_attr, ehs = _inputs(B, S, cfgs[0].cross_attention_dim)
+    plan = sampler.plan(mode, B, S, ehs.shape[1], total, "ddim")
+    sampler.load_inputs(plan, x_img, x_attr, ehs)
+    sampler.run(plan, steps=2)
+    assert seen["fused"] > 20 and seen["plain"] > 0 and seen["producers"] >= seen["fused"]
+    if mode == "joint":
+        assert seen.get("two_source", 0) >= 6            # decoder concat norms at 16x16 and 8x8, both streams
+    sched, sched_a = uo.DDIM(), uo.DDIM()
+    ts = sched.set_timesteps(total)
+    sched_a.set_timesteps(total)
+    ri, ra = x_img, x_attr
+    for i in range(2):
+        ri, ra = oracle_step(mode, sds, cfgs, sched, ts[i], ri, ra, ehs.float(), sched_a)
+    assert _rel(plan.bufs["lat_img"], ri) < 5e-3
+    if mode == "joint":
+        assert _rel(plan.bufs["lat_attr"], ra) < 5e-3

@@ -16,7 +16,7 @@ def _assert_ok(res, rel_l2=5e-4, rel_max=1.5e-3):
 
 
 @gpu
-@pytest.mark.parametrize("case", ["gemm_linear", "conv3x3", "conv_variants", "norms", "attention_d40",
+@pytest.mark.parametrize("case", ["gemm_linear", "conv3x3", "conv_variants", "norms", "gn_fused", "upfold", "attention_d40",
                                   "attention_d80", "attention_d160", "misc"])
 def test_op_case(case):
     from tests import gpu_probe

@@ -108,3 +108,17 @@ def test_public_api_host_roundtrip():
     assert inv.shape == (2, 24, 16, 16)
     with pytest.raises(ValueError):          # guidance needs the negative embeddings (tests/test_zz_cfg_gpu.py)
         sampler.joint_sample(x_img, x_attr, ehs, guidance_scale=7.5)
+
+
+@gpu
+@pytest.mark.parametrize("mode", ["joint", "inverse"])
+def test_fused_groupnorm_statistics_forced_on_tiny_config(mode, monkeypatch):
+    """UNIB200_GN_FUSED=force: the GroupNorm statistics come from the GEMM epilogues at every size the kernels allow (the
+    default only fuses samples of more than 256 pixels, i.e. never on the tiny config) -- same oracle, same gates."""
+    monkeypatch.setenv("UNIB200_GN_FUSED", "force")
+    from tests import sampler_probe
+    r = sampler_probe.run_mode(mode, n_steps=1)
+    assert r["img"]["rel_l2"] <= LATENT_GATE and r["attr"]["rel_l2"] <= LATENT_GATE, r
+    for k in ("img_pred", "attr_pred"):
+        if k in r:
+            assert r[k]["rel_l2"] <= PRED_GATE, (k, r)

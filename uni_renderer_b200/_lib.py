@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # UNIB200_LIB selects another build of the SAME library (A/B measurements of kernel variants); never a fallback
 LIB_PATH = os.environ.get("UNIB200_LIB") or os.path.join(HERE, "libunib200.so")
 
-SEG_1x1, SEG_3x3, SEG_3x3_S2, SEG_3x3_S2P0 = 0, 1, 2, 3
+SEG_1x1, SEG_3x3, SEG_3x3_S2, SEG_3x3_S2P0, SEG_UP2x2 = 0, 1, 2, 3, 4
 OP_OTHER, OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM = 0, 1, 2, 3, 4
 OP_NAMES = {OP_OTHER: "other", OP_GEMM: "conv_gemm", OP_ATTENTION: "attention", OP_GROUPNORM: "groupnorm",
             OP_LAYERNORM: "layernorm"}
@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("axpby_first_channel", C.c_int),
         ("rowstats_out", C.c_void_p), ("ln_rowstats", C.c_void_p), ("ln_parts", C.c_int), ("ln_wsum", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_C", C.c_int),
+        ("gn_part", C.c_void_p), ("gn_gran", C.c_int), ("gn_rows", C.c_int),
     ]
 
 
@@ -52,6 +53,7 @@ class GnDesc(C.Structure):
         ("B", C.c_int), ("HW", C.c_int), ("groups", C.c_int), ("eps", C.c_float),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p), ("silu", C.c_int),
         ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t),
+        ("part1", C.c_void_p), ("part2", C.c_void_p), ("part_gran", C.c_int), ("part_rows", C.c_int),
     ]
 
 

@@ -345,7 +345,7 @@ int unib200_pick_bn(int N, int flags) { return gemm_pick_bn(N, flags); }
 size_t unib200_packed_k(int nseg, const unib200_seg* seg) {
   size_t k = 0;
   for (int i = 0; i < nseg; ++i) {
-    const int taps = seg[i].kind == UNIB200_SEG_1x1 ? 1 : 9;
+    const int taps = seg[i].kind == UNIB200_SEG_1x1 ? 1 : seg[i].kind == UNIB200_SEG_UP2x2 ? 4 : 9;
     k += static_cast<size_t>(taps) * ((seg[i].C + 63) / 64) * 64;
   }
   return k;
@@ -386,12 +386,13 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   for (int i = 0; i < d->nseg; ++i) {
     const unib200_seg& s = d->seg[i];
     if (s.C <= 0 || s.ld < s.C || s.ld % 8 != 0) return fail("conv_gemm: bad segment C/ld (ld must be a multiple of 8)");
-    if (s.kind < UNIB200_SEG_1x1 || s.kind > UNIB200_SEG_3x3_S2P0) return fail("conv_gemm: bad segment kind");
+    if (s.kind < UNIB200_SEG_1x1 || s.kind > UNIB200_SEG_UP2x2) return fail("conv_gemm: bad segment kind");
+    if (s.kind == UNIB200_SEG_UP2x2 && d->nseg != 1) return fail("conv_gemm: SEG_UP2x2 must be the only segment");
     if (linear && s.kind != UNIB200_SEG_1x1) return fail("conv_gemm: linear A only supports 1x1 segments");
     p.seg[i].tmap = nmaps;
     p.seg[i].kind = s.kind;
     p.seg[i].nkb = (s.C + 63) / 64;
-    p.seg[i].ntaps = s.kind == UNIB200_SEG_1x1 ? 1 : 9;
+    p.seg[i].ntaps = s.kind == UNIB200_SEG_1x1 ? 1 : s.kind == UNIB200_SEG_UP2x2 ? 4 : 9;
     total_kb += p.seg[i].ntaps * p.seg[i].nkb;
     const uint64_t pix = static_cast<uint64_t>(s.ld) * 2;
     if (linear) {
@@ -452,6 +453,20 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     const int rpb = p.rows_per_batch;
     p.rpb_shift = (rpb > 0 && (rpb & (rpb - 1)) == 0) ? ilog2(rpb) : -1;
   }
+  p.up_shift = -1;
+  const bool up = d->seg[0].kind == UNIB200_SEG_UP2x2;
+  if (up) {
+    const int cout = d->N / 4;
+    const int tpp = cout / bn;                       // N tiles per output parity
+    if (d->N % 4 || cout % bn || tpp < 1 || (tpp & (tpp - 1)))
+      return fail("conv_gemm: SEG_UP2x2 needs N = 4 * Cout with Cout a power-of-two multiple of the N tile");
+    if (d->res || d->rowstats_out || d->ln_rowstats || d->flags != 0)
+      return fail("conv_gemm: SEG_UP2x2 supports bias (and GroupNorm statistics) only");
+    if (d->gn_part && d->gn_rows != 128) return fail("conv_gemm: SEG_UP2x2 GroupNorm statistics need gn_rows = 128");
+    p.up_cout = cout;
+    p.up_shift = 0;
+    while ((1 << p.up_shift) < tpp) ++p.up_shift;
+  }
   p.bias = d->bias;
   p.bias_bstride = d->bias_bstride;
   p.bias_step = d->bias_step;
@@ -489,7 +504,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   const int tiles = p.m_tiles * p.n_tiles * p.cg;       // CTAs one pass over the output keeps busy
   const int sms = num_sms();
   const bool can_split = d->partial != nullptr && !(d->flags & (UNIB200_EPI_GEGLU)) && !d->rowstats_out &&
-                         !d->ln_rowstats;
+                         !d->ln_rowstats && !d->gn_part && !up;
   if (splits <= 0) {
     splits = 1;
     if (can_split && tiles * 2 <= sms) {
@@ -528,9 +543,20 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     } else {
       p.mode = vec_ok ? 0 : 2;
     }
-    if (p.mode == 2 && (d->rowstats_out || d->ln_rowstats))
-      return fail("conv_gemm: row statistics / LayerNorm fold need the vector epilogue (aligned NHWC fp16 output, N a "
-                  "multiple of 32)");
+    if (p.mode == 2 && (d->rowstats_out || d->ln_rowstats || d->gn_part))
+      return fail("conv_gemm: row statistics / LayerNorm fold / GroupNorm statistics need the vector epilogue (aligned "
+                  "NHWC fp16 output, N a multiple of 32, no split-K)");
+    if (up && p.mode != 0) return fail("conv_gemm: SEG_UP2x2 needs the vector epilogue (aligned NHWC fp16 output)");
+    if (d->gn_part) {
+      if (p.mode != 0) return fail("conv_gemm: GroupNorm statistics cannot be combined with GEGLU");
+      if (d->gn_gran < 2 || d->gn_gran % 2 || bn % d->gn_gran || d->N % d->gn_gran || (up && (d->N / 4) % d->gn_gran))
+        return fail("conv_gemm: gn_gran must be even and divide both N and the N tile");
+      if ((d->gn_rows != 32 && d->gn_rows != 64 && d->gn_rows != 128) || d->M % d->gn_rows)
+        return fail("conv_gemm: gn_rows must be 32, 64 or 128 and divide M");
+      p.gn_part = d->gn_part;
+      p.gn_gran = d->gn_gran;
+      p.gn_rows = d->gn_rows;
+    }
     if (p.mode == 2 && !(d->flags & UNIB200_EPI_OUT_NCHW) &&
         ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->res && (reinterpret_cast<uintptr_t>(d->res) & 15))))
       return fail("conv_gemm: out / res must be 16-byte aligned");
@@ -538,10 +564,11 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   double kreal = 0.0, a_bytes = 0.0;
   for (int i = 0; i < d->nseg; ++i) {
-    const int taps = d->seg[i].kind == UNIB200_SEG_1x1 ? 1 : 9;
+    const int taps = d->seg[i].kind == UNIB200_SEG_1x1 ? 1 : d->seg[i].kind == UNIB200_SEG_UP2x2 ? 4 : 9;
     kreal += static_cast<double>(taps) * d->seg[i].C;
     // each source pixel is read once algorithmically (a stride-2 conv reads 4x the output pixels)
-    a_bytes += 2.0 * d->seg[i].C * d->M * (d->seg[i].kind >= UNIB200_SEG_3x3_S2 ? 4.0 : 1.0);
+    a_bytes += 2.0 * d->seg[i].C * d->M *
+               ((d->seg[i].kind == UNIB200_SEG_3x3_S2 || d->seg[i].kind == UNIB200_SEG_3x3_S2P0) ? 4.0 : 1.0);
   }
   const double n_out = (d->flags & UNIB200_EPI_GEGLU) ? d->N / 2.0 : d->N;
   const double flops = 2.0 * d->M * d->N * kreal;
@@ -551,7 +578,7 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
                      std::to_string(static_cast<long long>(kreal)) + " bn=" + std::to_string(bn) + " splits=" +
                      std::to_string(splits) + " tiles=" + std::to_string(tiles) + " segs=";
   for (int i = 0; i < d->nseg; ++i)
-    desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : d->seg[i].kind == UNIB200_SEG_3x3_S2 ? "3x3s2:" : "3x3s2p0:") +
+    desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : d->seg[i].kind == UNIB200_SEG_3x3_S2 ? "3x3s2:" : d->seg[i].kind == UNIB200_SEG_UP2x2 ? "up2x2:" : "3x3s2p0:") +
             std::to_string(d->seg[i].C);
   if (d->flags) desc += " flags=" + std::to_string(d->flags);
   return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes, desc);
@@ -603,11 +630,25 @@ int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* str
   if (C % 8 || p.C1 % 8 || d->groups <= 0 || C % d->groups || C / 8 > 512 || d->ld1 % 8 ||
       (d->x2 && d->ld2 % 8))
     return fail("groupnorm: unsupported channel configuration");
+  const int B = d->B, sms = num_sms();
+  if (d->part1) {
+    // statistics come from the producing GEMMs' epilogues: one apply launch
+    const int g = d->part_gran, R = d->part_rows;
+    if (d->x2 && !d->part2) return fail("groupnorm: part2 is required when x2 and part1 are given");
+    if (g < 2 || p.C1 % g || p.C2 % g || (C / d->groups) % g || R < 1 || d->HW % R)
+      return fail("groupnorm: part_gran must divide C1, C2 and the group size; part_rows must divide HW");
+    if (C / g > 1024) return fail("groupnorm: too many micro-groups");
+    p.part1 = d->part1; p.part2 = d->part2; p.part_gran = g; p.part_rows = R;
+    Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm_parts(p, B, sms, s); };
+    return submit(prog, std::move(op), 1, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
+                  4.0 * static_cast<double>(d->B) * d->HW * C,
+                  "groupnorm(fused stats) B=" + std::to_string(d->B) + " HW=" + std::to_string(d->HW) + " C=" +
+                      std::to_string(p.C1) + "+" + std::to_string(p.C2));
+  }
   const size_t per_chunk = static_cast<size_t>(d->B) * d->groups * 2;
   const size_t mc = per_chunk ? d->scratch_floats / per_chunk : 0;
   if (mc < 1 || !d->scratch) return fail("groupnorm: scratch too small");
   p.max_chunks = mc > 4096 ? 4096 : static_cast<int>(mc);
-  const int B = d->B, sms = num_sms();
   Op op = [p, B, sms](cudaStream_t s) { return launch_groupnorm(p, B, sms, s); };
   return submit(prog, std::move(op), d->HW <= 256 ? 1 : 2, stream, "groupnorm", UNIB200_OP_GROUPNORM, 0.0,
                 4.0 * static_cast<double>(d->B) * d->HW * C,

@@ -316,6 +316,115 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
   cluster_sync_all();                      // no CTA may exit while a peer can still read its `part`
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU) whose statistics were produced by the epilogues of the GEMMs that wrote the input(s)
+// (GemmParams::gn_part): every CTA sums the (row block, micro-group) partials of its sample in a fixed order -- a few
+// KB -- builds per-channel scale / shift and streams its rows.  ONE launch and ONE read of the input per GroupNorm.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) gn_apply_parts_kernel(GnParams p) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float sm[];            // scale[C], shift[C], mg[(C / gran)][2], gstat[G][2]
+  const int C = p.C1 + p.C2;
+  const int cpg = C / p.G;
+  const int gran = p.part_gran;
+  const int nmg = C / gran, nmg1 = p.C1 / gran, nmg2 = p.C2 / gran;
+  float* scale = sm;
+  float* shift = sm + C;
+  float* mgs = sm + 2 * C;
+  float* gstat = mgs + 2 * nmg;
+  const int b = blockIdx.y;
+  const int nrb = p.HW / p.part_rows;      // row blocks of one sample
+  for (int t = threadIdx.x; t < 2 * nmg; t += blockDim.x) {
+    const int st = t & 1, mg = t >> 1;
+    const float* src;
+    int stride;
+    if (mg < nmg1) { src = p.part1 + (static_cast<size_t>(b) * nrb * nmg1 + mg) * 2 + st; stride = 2 * nmg1; }
+    else { src = p.part2 + (static_cast<size_t>(b) * nrb * nmg2 + (mg - nmg1)) * 2 + st; stride = 2 * nmg2; }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // four interleaved chains, combined in a fixed order
+    int r = 0;
+    for (; r + 3 < nrb; r += 4) {
+      a0 += __ldg(src + static_cast<size_t>(r) * stride);
+      a1 += __ldg(src + static_cast<size_t>(r + 1) * stride);
+      a2 += __ldg(src + static_cast<size_t>(r + 2) * stride);
+      a3 += __ldg(src + static_cast<size_t>(r + 3) * stride);
+    }
+    for (; r < nrb; ++r) a0 += __ldg(src + static_cast<size_t>(r) * stride);
+    mgs[t] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  const int mpg = cpg / gran;              // micro-groups per group
+  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    float a = 0.f, q2 = 0.f;
+    for (int i = g * mpg; i < (g + 1) * mpg; ++i) { a += mgs[2 * i]; q2 += mgs[2 * i + 1]; }
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * p.HW);
+    const float mu = a * inv_n;
+    const float var = fmaxf(q2 * inv_n - mu * mu, 0.f);
+    gstat[2 * g] = mu;
+    gstat[2 * g + 1] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = gstat[2 * g + 1] * p.gamma[c];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gstat[2 * g] * sc;
+  }
+  __syncthreads();
+  const int CV = C >> 3;
+  const int r0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.HW) / gridDim.x);
+  const int r1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.HW) / gridDim.x);
+  const int arp = blockDim.x / CV;               // rows in flight per pass
+  const int av = threadIdx.x % CV, arow = threadIdx.x / CV;
+  if (arow < arp) {
+    const int c0 = av * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+    const __half* src;
+    int ld;
+    if (c0 < p.C1) { src = p.x1 + c0; ld = p.ld1; } else { src = p.x2 + (c0 - p.C1); ld = p.ld2; }
+    src += static_cast<size_t>(b) * p.HW * ld;
+    __half* dst = p.out + static_cast<size_t>(b) * p.HW * C + c0;
+    auto emit = [&](int r, const uint4& raw) {
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        float y0 = f.x * sc[2 * j] + sh[2 * j];
+        float y1 = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+        if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        o[j] = pack_half2(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    int r = r0 + arow;
+    for (; r + 3 * arp < r1; r += 4 * arp) {
+      const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+      const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld);
+      const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld);
+      const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
+      emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
+    }
+    for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+  }
+}
+
+cudaError_t launch_groupnorm_parts(const GnParams& p, int B, int num_sms, cudaStream_t stream) {
+  const int C = p.C1 + p.C2;
+  if (C % 8 || p.C1 % 8 || C % p.G || (C >> 3) > 512 || p.part1 == nullptr) return cudaErrorInvalidValue;
+  const int CV = C >> 3;
+  int achunks = (4 * num_sms + B - 1) / B;
+  if (achunks > p.HW) achunks = p.HW;
+  static const int apply_threads_env = getenv("UNIB200_GN_APPLY_THREADS") ? atoi(getenv("UNIB200_GN_APPLY_THREADS")) : 0;
+  int athreads = apply_threads_env ? apply_threads_env : 256;
+  if (athreads < CV) athreads = 512;            // a block must hold at least one row of 8-channel vectors
+  const size_t smem = (2 * C + 2 * (C / p.part_gran) + 2 * p.G) * sizeof(float);
+  UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_parts_kernel, dim3(dim3(achunks, B)), dim3(athreads), smem, stream, p));
+  return cudaGetLastError();
+}
+
 // cluster size for a sample of HW rows: as many CTAs as keep >= 8 rows each, at most 16 (non-portable size)
 static int gn_cluster_size(int HW, int max_cs) {
   int cs = 1;

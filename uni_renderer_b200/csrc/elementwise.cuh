@@ -15,9 +15,13 @@ struct GnParams {
   float* partial;                       // [B][max_chunks][G][2] fp32 scratch
   int max_chunks;
   int stat_chunks;                      // filled in by the launcher
+  // statistics from the producing GEMMs' epilogues (GemmParams::gn_part): [B*HW / part_rows][C{1,2} / part_gran][2]
+  const float* part1; const float* part2;
+  int part_gran, part_rows;
 };
 
 cudaError_t launch_groupnorm(const GnParams& p, int B, int num_sms, cudaStream_t stream);
+cudaError_t launch_groupnorm_parts(const GnParams& p, int B, int num_sms, cudaStream_t stream);
 cudaError_t launch_layernorm(const __half* x, __half* y, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t stream);
 cudaError_t launch_to_nhwc(const void* src, int src_is_f32, __half* dst, int B, int C, int H, int W, long long sb,

@@ -28,13 +28,16 @@ struct GemmCfg {
   static constexpr int kVecFloats = 3 * (((BN / 32 + 1) / 2) * 32);
   static constexpr int kGegluFloats = 6 * (((BN / 64 + 1) / 2) * 32);
   static constexpr int kBiasBytes = 8 * 4 * (kVecFloats > kGegluFloats ? kVecFloats : kGegluFloats);
-  static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes) / kStageBytes;
+  // GroupNorm statistics fused into the epilogue: pair partials of one tile, [2 tile parities][4 lane quadrants][BN]
+  static constexpr int kStatBytes = 2 * 4 * BN * 4;
+  static constexpr int kStagesFit = (232448 - 1024 - 512 - kBiasBytes - kStatBytes) / kStageBytes;
 #ifndef UNIB_MAX_STAGES
 #define UNIB_MAX_STAGES 8
 #endif
   static constexpr int kStages = kStagesFit > UNIB_MAX_STAGES ? UNIB_MAX_STAGES : kStagesFit;
   static constexpr int kBiasOff = kStages * kStageBytes;
-  static constexpr int kBarOff = kBiasOff + kBiasBytes;
+  static constexpr int kStatOff = kBiasOff + kBiasBytes;
+  static constexpr int kBarOff = kStatOff + kStatBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kBarOff + kNumBars * 8 + 16 + 1024;
@@ -273,6 +276,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       }
       int nkb = 1, ntaps = 1, cw = w0, ch = h0;
       const CUtensorMap* amap = &maps.a[0];
+      const int par = p.up_shift >= 0 ? (wi.nt >> p.up_shift) : 0;    // SEG_UP2x2: output parity (py, px) of this N tile
       auto set_tap = [&]() {                   // geometry of (seg, tap): tensor map + shifted tile origin
         const ConvSeg sg = p.seg[seg < p.nseg ? seg : 0];
         nkb = sg.nkb;
@@ -291,6 +295,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           tm += ((dy & 1) ? 2 : 0) + ((dx & 1) ? 1 : 0);
           dh = dy >> 1;
           dw = dx >> 1;
+        } else if (sg.kind == SEG_UP2x2) {
+          // nearest-2x + conv3x3 for output pixel (2h + py, 2w + px): the 3 x 3 taps on the upsampled image touch only
+          // the 2 x 2 low-resolution pixels (h - 1 + py + ty, w - 1 + px + tx); their weights are pre-summed on the host
+          dh = (tap >> 1) - 1 + (par >> 1);
+          dw = (tap & 1) - 1 + (par & 1);
         }
         amap = &maps.a[tm];
         cw = w0 + dw;
@@ -406,6 +415,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       float* wsum_s = bias_s + 2 * kSlots * 32;
       const bool has_ln = p.ln_rowstats != nullptr;
       const bool want_stats = !geglu && p.rowstats_out != nullptr;
+      // GroupNorm statistics of the output for the GroupNorm that consumes it (north_star: "GroupNorm ... fused into
+      // the epilogue"): per sub-tile every thread forms 16 column-pair sums and sums of squares of its row, a
+      // transposing butterfly (31 shuffles) reduces them over the warp's 32 rows so that lane i ends up with value i,
+      // the values go to shared memory, and once per tile the eight warps combine quadrants and pairs into
+      // (row block, micro-group of gn_gran channels) partials in global memory -- fixed order, no atomics.
+      const bool want_gn = !geglu && p.gn_part != nullptr;
+      float* const stat_s = reinterpret_cast<float*>(smem + Cfg::kStatOff);
+      const int et = threadIdx.x - 64;                          // 0..255 within the epilogue group
       const bool per_batch = p.bias_bstride != 0;
       const float* const bias_base = p.bias + ((p.bias != nullptr && p.bias_step != nullptr)
                                                    ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0);
@@ -418,7 +435,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         const int m0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + q * 32;   // first row of this warp
         const int m = m0 + lane;
         const bool row_ok = m < p.M;
-        const int n0 = wi.nt * out_bn;                         // first output column of this tile
+        int n0 = wi.nt * out_bn;                               // first output column of this tile
+        int nb0 = wi.nt * BN;                                  // first bias / weight column of this tile
+        size_t orow = static_cast<size_t>(m);                  // output row of this thread
+        int gn_blk_mul = 1, gn_blk_add = 0;
+        if (!geglu && p.up_shift >= 0) {                       // SEG_UP2x2: scatter to the high-resolution image
+          const int par = wi.nt >> p.up_shift;
+          n0 -= par * p.up_cout;
+          nb0 = n0;
+          const int ww = m & ((1 << p.w_shift) - 1), hh = (m >> p.w_shift) & ((1 << p.h_shift) - 1);
+          const int bb = m >> (p.w_shift + p.h_shift);
+          orow = ((static_cast<size_t>(bb) << (p.h_shift + 1)) + 2 * hh + (par >> 1)) * (2u << p.w_shift) + 2 * ww + (par & 1);
+          gn_blk_mul = 4;                                      // statistics: row block = (low-res tile, parity)
+          gn_blk_add = par;
+        }
         // bias of my sub-tiles -> smem (two batch rows: the 32 rows may straddle a batch boundary); bias and the first
         // residual sub-tile are requested before the accumulator wait (latency overlaps the MMAs)
         int m_last = m0 + 31;
@@ -435,8 +465,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             const int jj = geglu ? (s >> 1) : s;
             const int j = h + 2 * jj;
             const int col = (geglu && (s & 1) ? BN / 2 : 0) + j * 32 + lane;
-            const int n = wi.nt * BN + col;
-            const bool ok = j < nsub && n < p.N;
+            const int n = nb0 + col;
+            const bool ok = j < nsub && wi.nt * BN + col < p.N;
             if (has_bias) {
               bias_s[s * 32 + lane] = ok ? __ldg(bias_base + static_cast<size_t>(b_first) * p.bias_bstride + n) : 0.f;
               bias_s[(kSlots + s) * 32 + lane] = ok ? __ldg(bias_base + static_cast<size_t>(b_last) * p.bias_bstride + n) : 0.f;
@@ -563,8 +593,32 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) { st_sum += v[i]; st_sq += v[i] * v[i]; }
           }
+          if (!geglu && want_gn) {
+            float x[32];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float a = row_ok ? v[2 * u] : 0.f, b = row_ok ? v[2 * u + 1] : 0.f;
+              x[u] = a + b;
+              x[16 + u] = a * a + b * b;
+            }
+            // transposing butterfly: after the round with offset `off` a lane keeps the half of its values whose index
+            // bit equals its own lane bit, summed over the lane pair -> finally lane i holds sum over rows of x[i]
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+              const int off = 16 >> r, n = 32 >> r;
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < n / 2; ++i) {
+                const float keep = up ? x[i + n / 2] : x[i];
+                const float send = up ? x[i] : x[i + n / 2];
+                x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            // lane < 16: sum of pair `lane`; lane >= 16: sum of squares of pair `lane - 16`
+            stat_s[((tl & 1) * 4 + q) * BN + (j * 16 + (lane & 15)) * 2 + (lane >> 4)] = x[0];
+          }
           if (row_ok) {
-            __half* op = outp + static_cast<size_t>(m) * p.ldc + n0 + j * 32;
+            __half* op = outp + orow * p.ldc + n0 + j * 32;
             uint32_t o[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) o[u] = pack_half2(v[2 * u], v[2 * u + 1]);
@@ -577,6 +631,25 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         if (want_stats && row_ok)
           *reinterpret_cast<float2*>(p.rowstats_out + (static_cast<size_t>(m) * (2 * p.n_tiles) + 2 * wi.nt + h) * 2) =
               make_float2(st_sum, st_sq);
+        if (!geglu && want_gn) {
+          named_bar_sync(2, kEpiWarps * 32);                   // the tile's pair partials are complete in stat_s
+          const float* sb = stat_s + (tl & 1) * 4 * BN;
+          const int ng = BN / p.gn_gran, qpb = p.gn_rows >> 5;  // micro-groups per tile, quadrants per row block
+          const int nout = (4 / qpb) * ng * 2;
+          const int ngN = p.N / p.gn_gran;
+          for (int o = et; o < nout; o += kEpiWarps * 32) {
+            const int st = o & 1, mg = (o >> 1) % ng, rb = (o >> 1) / ng;
+            float acc = 0.f;
+            for (int qq = rb * qpb; qq < (rb + 1) * qpb; ++qq)
+              for (int pp = 0; pp < (p.gn_gran >> 1); ++pp) acc += sb[qq * BN + (mg * (p.gn_gran >> 1) + pp) * 2 + st];
+            const int row0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + rb * p.gn_rows;
+            const int gmg = n0 / p.gn_gran + mg;
+            if (row0 < p.M && wi.nt * ng + mg < ngN)
+              p.gn_part[(static_cast<size_t>(row0 / p.gn_rows * gn_blk_mul + gn_blk_add) * (gn_blk_mul == 4 ? p.up_cout / p.gn_gran : ngN) + gmg) * 2 + st] = acc;
+          }
+          // the other parity buffer is written during the next tile; this one is rewritten two tiles from now, after
+          // every thread has passed the next tile's barrier
+        }
         if (tl == 0 && leader) GEMM_TRACE(9);
       }
       if (leader) GEMM_TRACE(6);

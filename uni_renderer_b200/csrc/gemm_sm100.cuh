@@ -17,7 +17,7 @@ constexpr int kBK = 64;         // fp16 elements per K block == one 128-byte swi
 constexpr int kMaxSeg = 4;
 constexpr int kMaxAMaps = 6;
 
-enum SegKind : int { SEG_1x1 = 0, SEG_3x3 = 1, SEG_3x3_S2 = 2, SEG_3x3_S2P0 = 3 };
+enum SegKind : int { SEG_1x1 = 0, SEG_3x3 = 1, SEG_3x3_S2 = 2, SEG_3x3_S2P0 = 3, SEG_UP2x2 = 4 };
 
 struct ConvSeg {
   int tmap;   // first A tensor map of this segment (SEG_3x3_S2 / _S2P0 use 4 consecutive parity maps)
@@ -69,6 +69,14 @@ struct GemmParams {
   const float* ln_wsum;      // [N]
   int ln_parts;
   float ln_eps, ln_inv_c;
+  // nearest-2x upsample folded into the following 3x3 conv (SEG_UP2x2): the N dimension is [4 output parities][Cout],
+  // a tile's parity is nt >> up_shift; rows are LOW-resolution pixels and the epilogue scatters them to the
+  // high-resolution image.  up_shift < 0: off.
+  int up_shift;
+  int up_cout;
+  float* gn_part;            // GroupNorm statistics of the output: [M / gn_rows][N / gn_gran][2] (sum, sumsq), or null
+  int gn_gran;               // channels per micro-group (even, divides the N tile and N)
+  int gn_rows;               // rows per partial block: 32, 64 or 128 (divides the rows of one sample)
   int pdl_early;             // 1: fire the PDL trigger right after CTA setup instead of at the end (unib200_set_pdl(2))
   long long* trace;          // debug (unib200_debug_set_trace): [0] = launch counter, then 16 stamps per launch
 };

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .ops import EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2
+from .ops import EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2, SEG_UP2x2
 
 
 @dataclass
@@ -51,6 +51,7 @@ class Act:
     H: int
     W: int
     C: int
+    gn: Optional[tuple] = None      # (part, gran, rows): GroupNorm statistics written by the producing GEMM's epilogue
 
     @property
     def M(self) -> int:
@@ -109,6 +110,18 @@ class StreamNet:
         self.has_decoder = kind in ("unet", "attr_dec")
         self.w: Dict[str, torch.Tensor] = {}
         self._pack(sd)
+        # GroupNorm statistics fused into the producing GEMMs' epilogues: micro-groups of `gn_gran` channels, the gcd
+        # of every group size a tensor of this network can meet (single source C / G, or (C + C') / G behind a concat)
+        import math
+        import os
+        g = 0
+        for c in cfg.block_out_channels:
+            g = math.gcd(g, c // cfg.norm_num_groups)
+        self.gn_gran = g if (g >= 2 and g % 2 == 0 and all(c % cfg.norm_num_groups == 0 for c in cfg.block_out_channels)
+                             and os.environ.get("UNIB200_GN_FUSED", "1") != "0") else 0
+        self._sms = None
+        self.gn_min_hw = 256
+        self.gn_force = os.environ.get("UNIB200_GN_FUSED") == "force"    # tests: fuse at every size the kernels allow
 
     # ------------------------------------------------------------------------------------------------------------
     # weight ingest: diffusers state-dict layout -> packed K-major fp16 + fp32 vectors
@@ -188,8 +201,17 @@ class StreamNet:
             for i in range(len(cfg.block_out_channels) - 1):
                 conv3(f"down_blocks.{i}.downsamplers.0.conv", SEG_3x3_S2)
         if self.has_decoder:
+            import os
+            self.upfold = os.environ.get("UNIB200_UPFOLD", "1") != "0"
             for i in range(len(cfg.block_out_channels) - 1):
-                conv3(f"up_blocks.{i}.upsamplers.0.conv")
+                n = f"up_blocks.{i}.upsamplers.0.conv"
+                cout = sd[n + ".weight"].shape[0]
+                if self.upfold and ops.upfold_supported(cout):
+                    # nearest-2x folded into the conv: four parity 2x2 convs on the low-resolution input (SEG_UP2x2)
+                    w[n + ".wup"] = ops.pack_upsample_conv(need(n + ".weight"))
+                    w[n + ".b"] = _f32(sd[n + ".bias"], dev)
+                else:
+                    conv3(n)
             norm("conv_norm_out")
             conv3("conv_out")
         zc = {"attr_enc": "controlnet", "attr_dec": "control"}.get(self.kind)
@@ -268,16 +290,50 @@ class StreamNet:
             kv[a] = out
         return kv
 
+    def gn_plan(self, M: int, N: int, B: int, HW: int) -> Optional[tuple]:
+        """(part, gran, rows) for a GEMM [M, N] whose output feeds a GroupNorm, or None when the statistics cannot be
+        fused: small samples (<= 256 pixels: the single-launch cluster GroupNorm already reads them from L2 and their
+        GEMMs are split-K), GEMMs that would be split-K (too few tiles), shapes the micro-groups do not divide."""
+        if not self.gn_gran or HW % 32 or M != B * HW or (HW <= self.gn_min_hw and not self.gn_force):
+            return None
+        gran = self.gn_gran
+        bn = ops.pick_bn(N)
+        if N % gran or bn % gran or N % 32:
+            return None
+        if self._sms is None:
+            self._sms = ops.device_info()[0] if self.device.type == "cuda" else 148
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        if tiles * 2 <= self._sms and not self.gn_force:   # csrc/api.cu would pick split-K (fp32 partials, no fused epilogue)
+            return None
+        rows = 128 if HW % 128 == 0 else (64 if HW % 64 == 0 else 32)
+        part = torch.empty(M // rows, N // gran, 2, device=self.device, dtype=torch.float32)
+        return (part, gran, rows)
+
     def _gn(self, prog, ws, name, srcs: Sequence[Act], eps, silu) -> torch.Tensor:
         a = srcs[0]
         b = srcs[1] if len(srcs) > 1 else None
         Ct = a.C + (b.C if b else 0)
         out = ws.get(a.M, Ct)
+        parts = None
+        if a.gn is not None and (b is None or (b.gn is not None and b.gn[1:] == a.gn[1:])) \
+                and (Ct // self.cfg.norm_num_groups) % a.gn[1] == 0 and a.C % a.gn[1] == 0:
+            parts = (a.gn[0], b.gn[0] if b else None, a.gn[1], a.gn[2])
         ops.groupnorm(prog, a.t, a.C, b.t if b else None, b.C if b else 0, self.w[name + ".g"], self.w[name + ".bt"], out,
-                      ws.gn_scratch, B=a.B, HW=a.H * a.W, groups=self.cfg.norm_num_groups, eps=eps, silu=silu)
+                      ws.gn_scratch, B=a.B, HW=a.H * a.W, groups=self.cfg.norm_num_groups, eps=eps, silu=silu,
+                      parts=parts)
         return out
 
-    def rec_resnet(self, prog, ws, r: str, srcs: Sequence[Act], tproj: Temb) -> Act:
+    def _with_identity(self, key: str, wname: str, C: int) -> torch.Tensor:
+        """Packed weight `wname` followed by a C x C identity 1x1 segment: a second residual rides through the GEMM as
+        an extra K segment (products with 1.0 are exact in the fp32 accumulator), so `h += up_additional_states`
+        (UpRes blocks, unet_2d_blocks.py:2408,2814) needs no kernel of its own even where the epilogue's residual
+        input is already taken."""
+        if key not in self.w:
+            eye = ops.pack_weight([(torch.eye(C, device=self.w[wname].device), SEG_1x1)])
+            self.w[key] = torch.cat([self.w[wname], eye.to(self.w[wname].device)], 1).contiguous()
+        return self.w[key]
+
+    def rec_resnet(self, prog, ws, r: str, srcs: Sequence[Act], tproj: Temb, extra_res: Optional[Act] = None) -> Act:
         a = srcs[0]
         B, H, W, M = a.B, a.H, a.W, a.M
         Cin = sum(s.C for s in srcs)
@@ -285,11 +341,12 @@ class StreamNet:
         n1 = self._gn(prog, ws, r + ".norm1", srcs, self.cfg.norm_eps, True)
         h1 = ws.get(M, Cout)
         off = self.temb_off[r]
+        gn1 = self.gn_plan(M, Cout, B, H * W)
         ops.conv_gemm(prog, [(n1, Cin, SEG_3x3)], self.w[r + ".conv1.w"], h1, M=M, N=Cout, B=B, H=H, W=W,
                       bias=tproj.t[:, off:off + Cout], bias_bstride=self.temb_total, bias_step=tproj.step,
-                      bias_step_stride=tproj.step_stride, partial=ws.partial)
+                      bias_step_stride=tproj.step_stride, partial=None if gn1 else ws.partial, gn=gn1)
         ws.put(n1)
-        n2 = self._gn(prog, ws, r + ".norm2", [Act(h1, B, H, W, Cout)], self.cfg.norm_eps, True)
+        n2 = self._gn(prog, ws, r + ".norm2", [Act(h1, B, H, W, Cout, gn1)], self.cfg.norm_eps, True)
         ws.put(h1)
         w2, b2, has_sc = self._conv2_packed(r, [s.C for s in srcs])
         out = ws.get(M, Cout)
@@ -300,11 +357,19 @@ class StreamNet:
         else:
             assert len(srcs) == 1 and Cin == Cout
             res = a.t
-        ops.conv_gemm(prog, segs, w2, out, M=M, N=Cout, B=B, H=H, W=W, bias=b2, res=res, partial=ws.partial)
+        if extra_res is not None:              # UpResBlock2D: `hidden_states += up_additional_states` (:2814)
+            if res is None:
+                res = extra_res.t
+            else:
+                w2 = self._with_identity(r + ".conv2.w+I", r + ".conv2.w", Cout)
+                segs.append((extra_res.t, Cout, SEG_1x1))
+        gn2 = self.gn_plan(M, Cout, B, H * W)
+        ops.conv_gemm(prog, segs, w2, out, M=M, N=Cout, B=B, H=H, W=W, bias=b2, res=res,
+                      partial=None if gn2 else ws.partial, gn=gn2)
         ws.put(n2)
-        return Act(out, B, H, W, Cout)
+        return Act(out, B, H, W, Cout, gn2)
 
-    def rec_transformer(self, prog, ws, a: str, x: Act, kv: torch.Tensor, L: int) -> Act:
+    def rec_transformer(self, prog, ws, a: str, x: Act, kv: torch.Tensor, L: int, extra_res: Optional[Act] = None) -> Act:
         cfg = self.cfg
         B, H, W, M, Cc = x.B, x.H, x.W, x.M, x.C
         heads, d = cfg.num_heads, x.C // cfg.num_heads
@@ -348,19 +413,25 @@ class StreamNet:
                       partial=ws.partial)
         ws.put(ff, h3, ao)
         out = ws.get(M, Cc)
-        ops.conv_gemm(prog, [(h4, Cc, SEG_1x1)], w[a + ".proj_out.w"], out, M=M, N=Cc, B=B, bias=w[a + ".proj_out.b"],
-                      res=x.t, partial=ws.partial)
+        gno = self.gn_plan(M, Cc, B, H * W)
+        po_segs, po_w = [(h4, Cc, SEG_1x1)], w[a + ".proj_out.w"]
+        if extra_res is not None:              # CrossAttnUpResBlock2D: `hidden_states += up_additional_states` (:2408)
+            po_segs.append((extra_res.t, Cc, SEG_1x1))
+            po_w = self._with_identity(a + ".proj_out.w+I", a + ".proj_out.w", Cc)
+        ops.conv_gemm(prog, po_segs, po_w, out, M=M, N=Cc, B=B, bias=w[a + ".proj_out.b"],
+                      res=x.t, partial=None if gno else ws.partial, gn=gno)
         ws.put(h4)
-        return Act(out, B, H, W, Cc)
+        return Act(out, B, H, W, Cc, gno)
 
     def rec_encoder(self, prog, ws, x_in: Act, tproj, kv, L: int):
         """conv_in + down blocks + mid block.  Returns (skips[12], mid).  Skip buffers are never recycled."""
         cfg = self.cfg
         B, H, W = x_in.B, x_in.H, x_in.W
         c0 = cfg.block_out_channels[0]
-        h = Act(torch.empty(x_in.M, c0, device=self.device, dtype=torch.float16), B, H, W, c0)
+        h = Act(torch.empty(x_in.M, c0, device=self.device, dtype=torch.float16), B, H, W, c0,
+                self.gn_plan(x_in.M, c0, B, H * W))
         ops.conv_gemm(prog, [(x_in.t, x_in.C, SEG_3x3)], self.w["conv_in.w"], h.t, M=h.M, N=c0, B=B, H=H, W=W,
-                      bias=self.w["conv_in.b"])
+                      bias=self.w["conv_in.b"], gn=h.gn)
         skips = [h]
         nb = len(cfg.block_out_channels)
         for i in range(nb):
@@ -376,8 +447,9 @@ class StreamNet:
             if i != nb - 1:
                 n = f"down_blocks.{i}.downsamplers.0.conv"
                 o = Act(torch.empty(h.M // 4, h.C, device=self.device, dtype=torch.float16), B, h.H // 2, h.W // 2, h.C)
+                o.gn = self.gn_plan(o.M, o.C, B, o.H * o.W)
                 ops.conv_gemm(prog, [(h.t, h.C, SEG_3x3_S2)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=B, H=o.H, W=o.W,
-                              bias=self.w[n + ".b"], partial=ws.partial)
+                              bias=self.w[n + ".b"], partial=None if o.gn else ws.partial, gn=o.gn)
                 h = o
                 skips.append(h)
         r0 = self.rec_resnet(prog, ws, "mid_block.resnets.0", [h], tproj)
@@ -389,12 +461,14 @@ class StreamNet:
         return skips, mid
 
     def rec_decoder(self, prog, ws, mid: Act, skips: Sequence[Act], tproj, kv, L: int, *, out_nchw: torch.Tensor,
-                    taps: Optional[list] = None, axpby: Optional[dict] = None):
+                    taps: Optional[list] = None, axpby: Optional[dict] = None,
+                    up_additional: Optional[Sequence[Act]] = None):
         """up blocks + conv_norm_out/SiLU/conv_out.  `skips` are the 12 (already exchanged) skip tensors; they are
         consumed from the end (controlnet.py:1124-1125).  The prediction is written NCHW fp32 into `out_nchw`, or,
         with `axpby`, the scheduler update is applied in the conv_out epilogue (latent updated in place)."""
         cfg = self.cfg
         skips = list(skips)
+        extra = list(up_additional) if up_additional is not None else None      # UpRes blocks: one per decoder layer
         h = mid
         if taps is not None:
             taps.append(h)
@@ -402,12 +476,14 @@ class StreamNet:
         for i in range(nb):
             for j in range(cfg.layers_per_block + 1):
                 s = skips.pop()
-                r = self.rec_resnet(prog, ws, f"up_blocks.{i}.resnets.{j}", [h, s], tproj)
+                ex = extra.pop(0) if extra is not None else None
+                r = self.rec_resnet(prog, ws, f"up_blocks.{i}.resnets.{j}", [h, s], tproj,
+                                    extra_res=None if cfg.up_has_attn[i] else ex)
                 if h is not mid and taps is None:
                     ws.put(h.t)
                 if cfg.up_has_attn[i]:
                     a = f"up_blocks.{i}.attentions.{j}"
-                    h = self.rec_transformer(prog, ws, a, r, kv[a], L)
+                    h = self.rec_transformer(prog, ws, a, r, kv[a], L, extra_res=ex)
                     ws.put(r.t)
                 else:
                     h = r
@@ -415,12 +491,23 @@ class StreamNet:
                     taps.append(h)
             if i != nb - 1:
                 n = f"up_blocks.{i}.upsamplers.0.conv"
-                up = ws.get(h.M * 4, h.C)
-                ops.upsample2x(prog, h.t, up, B=h.B, H=h.H, W=h.W, Cn=h.C)
                 o = Act(ws.get(h.M * 4, h.C), h.B, h.H * 2, h.W * 2, h.C)
-                ops.conv_gemm(prog, [(up, h.C, SEG_3x3)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=o.B, H=o.H, W=o.W,
-                              bias=self.w[n + ".b"], partial=ws.partial)
-                ws.put(up)
+                if n + ".wup" in self.w:
+                    # Upsample2D (unet_2d_blocks.py:2588,2701) as ONE GEMM over the low-resolution tensor: the upsampled
+                    # tensor is never materialised and the conv costs 4/9 of the MACs
+                    gnu = self.gn_plan(o.M, o.C, o.B, o.H * o.W)
+                    if gnu is not None and (gnu[2] != 128 or (h.H * h.W) % 128):
+                        gnu = None
+                    o.gn = gnu
+                    ops.conv_gemm(prog, [(h.t, h.C, SEG_UP2x2)], self.w[n + ".wup"], o.t, M=h.M, N=4 * o.C, B=h.B, H=h.H,
+                                  W=h.W, bias=self.w[n + ".b"], gn=gnu)
+                else:
+                    up = ws.get(h.M * 4, h.C)
+                    ops.upsample2x(prog, h.t, up, B=h.B, H=h.H, W=h.W, Cn=h.C)
+                    o.gn = self.gn_plan(o.M, o.C, o.B, o.H * o.W)
+                    ops.conv_gemm(prog, [(up, h.C, SEG_3x3)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=o.B, H=o.H, W=o.W,
+                                  bias=self.w[n + ".b"], partial=None if o.gn else ws.partial, gn=o.gn)
+                    ws.put(up)
                 if taps is None:
                     ws.put(h.t)
                 h = o
@@ -459,9 +546,11 @@ class StreamNet:
         outs = []
         for i, (s, dd) in enumerate(zip(src, dst)):
             o = Act(torch.empty(s.M, s.C, device=self.device, dtype=torch.float16), s.B, s.H, s.W, s.C)
+            # with a residual the output is a decoder skip (second source of a concat GroupNorm): emit its statistics
+            o.gn = self.gn_plan(s.M, s.C, s.B, s.H * s.W) if dd is not None else None
             wz, bz = self._zc(f"{zc}_down_blocks.{i}", scale)
             ops.conv_gemm(prog, [(s.t, s.C, SEG_1x1)], wz, o.t, M=s.M, N=s.C, B=s.B,
-                          bias=bz, res=dd.t if dd is not None else None, partial=ws.partial)
+                          bias=bz, res=dd.t if dd is not None else None, partial=None if o.gn else ws.partial, gn=o.gn)
             outs.append(o)
         m = Act(torch.empty(src_mid.M, src_mid.C, device=self.device, dtype=torch.float16), src_mid.B, src_mid.H,
                 src_mid.W, src_mid.C)

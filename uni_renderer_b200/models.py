@@ -23,6 +23,9 @@ from .engine import Act, NetConfig, StreamNet, Workspace, pad_channels
 
 _SD_DOWN = ("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D")
 _SD_UP = ("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D")
+# the class defaults of AttributeDecoderModel (models/controlnet.py:1794-1797): same parameters as _SD_UP, but every layer
+# adds an extra residual (`hidden_states += up_additional_states`, models/unet_2d_blocks.py:2408,2814 -- SURVEY row a8)
+_SD_UPRES = ("UpResBlock2D", "CrossAttnUpResBlock2D", "CrossAttnUpResBlock2D", "CrossAttnUpResBlock2D")
 
 
 @dataclass
@@ -350,9 +353,8 @@ def _net_config(in_channels, out_channels, block_out_channels, layers_per_block,
                 cross_attention_dim, norm_num_groups, norm_eps, down_block_types, up_block_types, **other) -> NetConfig:
     if tuple(down_block_types) != _SD_DOWN[:len(block_out_channels)] and tuple(down_block_types) != _SD_DOWN:
         raise ValueError(f"unsupported down_block_types {down_block_types}")
-    if tuple(up_block_types) != _SD_UP:
-        raise ValueError(f"unsupported up_block_types {up_block_types} (AttributeDecoderModel's UpRes defaults cannot "
-                         "run their own forward in the reference either; use the from_unet() types)")
+    if tuple(up_block_types) not in (_SD_UP, _SD_UPRES):
+        raise ValueError(f"unsupported up_block_types {up_block_types}")
     if not isinstance(attention_head_dim, int) or not isinstance(layers_per_block, int):
         raise ValueError("per-block attention_head_dim / layers_per_block tuples are not supported")
     if norm_num_groups is None:

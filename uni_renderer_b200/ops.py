@@ -10,11 +10,11 @@ import torch
 
 from . import _lib as L
 from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2,
-                   SEG_3x3_S2P0)
+                   SEG_3x3_S2P0, SEG_UP2x2)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
            "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "softmax_rows", "gaussian_sample", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
-           "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "SEG_3x3_S2P0", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
+           "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "SEG_3x3_S2P0", "SEG_UP2x2", "pack_upsample_conv", "upfold_supported", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
 def _stream() -> int:
@@ -138,6 +138,38 @@ def pack_weight(parts: Sequence[Tuple[torch.Tensor, int]], device=None) -> torch
     return out.to(device) if device is not None else out
 
 
+_UP_TAPS = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}     # (parity, 2x2 tap) -> 3x3 taps it sums
+
+
+def pack_upsample_conv(w: torch.Tensor) -> torch.Tensor:
+    """Upsample2D = nearest-2x + conv3x3 [O, I, 3, 3] as four 2x2 convs on the LOW-resolution input (SEG_UP2x2,
+    include/unib200.h): output pixel (2h+py, 2w+px) sees input pixels (h-1+py+ty, w-1+px+tx), ty, tx in {0, 1}; its
+    weights are the sums of the 3x3 taps that land on the same input pixel.  Returns fp16 [4 * O, 4 * ceil(I/64)*64],
+    rows ordered [parity py*2+px][O], K ordered [tap ty*2+tx][channel].  The sums are formed in fp32 and rounded ONCE."""
+    w = w.detach().float()
+    O, I, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    Ipad = (I + 63) // 64 * 64
+    out = torch.zeros(4, O, 4, Ipad, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    acc = 0
+                    for dy in _UP_TAPS[(py, ty)]:
+                        for dx in _UP_TAPS[(px, tx)]:
+                            acc = acc + w[:, :, dy, dx]
+                    out[py * 2 + px, :, ty * 2 + tx, :I] = acc
+    return out.reshape(4 * O, 4 * Ipad).to(torch.float16).contiguous()
+
+
+def upfold_supported(cout: int) -> bool:
+    """SEG_UP2x2 needs Cout to be a power-of-two multiple of the N tile the kernel picks for N = 4 * Cout."""
+    bn = pick_bn(4 * cout)
+    t = cout // bn if bn and cout % bn == 0 else 0
+    return t >= 1 and (t & (t - 1)) == 0 and cout % 32 == 0
+
+
 def pick_bn(N: int, flags: int = 0) -> int:
     """N-tile width the kernel uses for this (N, flags) -- asked from the library so packing always agrees."""
     return L.load().unib200_pick_bn(N, flags)
@@ -190,8 +222,10 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
               axpby: Optional[torch.Tensor] = None, axpby_step: Optional[torch.Tensor] = None,
               aux: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None,
               axpby_first_channel: int = 0, ldc: Optional[int] = None, rowstats_out: Optional[torch.Tensor] = None,
-              ln: Optional[Tuple[torch.Tensor, torch.Tensor, float, int]] = None):
-    """segs: (matrix [pixels, >=C] fp16, C, kind).  H = W = 0 selects the plain row-major [M, K] path."""
+              ln: Optional[Tuple[torch.Tensor, torch.Tensor, float, int]] = None,
+              gn: Optional[Tuple[torch.Tensor, int, int]] = None):
+    """segs: (matrix [pixels, >=C] fp16, C, kind).  H = W = 0 selects the plain row-major [M, K] path.
+    gn = (part fp32 [M / rows, N / gran, 2], gran, rows): also emit the GroupNorm statistics of the output."""
     lib = L.load()
     d = L.GemmDesc()
     d.M, d.N, d.B, d.H, d.W, d.nseg = M, N, B, H, W, len(segs)
@@ -199,7 +233,7 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
     for i, (t, c, kind) in enumerate(segs):
         ld = _check_2d(t, f"conv_gemm seg {i}")
         d.seg[i].ptr, d.seg[i].C, d.seg[i].ld, d.seg[i].kind = t.data_ptr(), c, ld, kind
-        ktot += (1 if kind == SEG_1x1 else 9) * ((c + 63) // 64 * 64)
+        ktot += (1 if kind == SEG_1x1 else 4 if kind == SEG_UP2x2 else 9) * ((c + 63) // 64 * 64)
     if weight.dtype != torch.float16 or tuple(weight.shape) != (N, ktot) or not weight.is_contiguous():
         raise ValueError(f"conv_gemm: packed weight must be contiguous fp16 [{N}, {ktot}], got {tuple(weight.shape)}")
     d.weight = weight.data_ptr()
@@ -232,10 +266,14 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
         assert rs.dtype == torch.float32 and wsum.dtype == torch.float32 and wsum.numel() == N and rs.shape[0] == M
         d.ln_rowstats, d.ln_parts, d.ln_wsum, d.ln_eps, d.ln_C = rs.data_ptr(), rs.shape[1], wsum.data_ptr(), eps, Cn
         ln_keep = (rs, wsum)
+    if gn is not None:
+        part, gran, rows = gn
+        assert part.dtype == torch.float32 and part.is_contiguous() and part.numel() >= (M // rows) * (N // gran) * 2
+        d.gn_part, d.gn_gran, d.gn_rows = part.data_ptr(), gran, rows
     L.check(lib.unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
     if prog is not None:
         prog.keep(*(s[0] for s in segs), weight, out, bias, bias_step, res, partial, axpby, axpby_step, aux, aux_out, rowstats_out,
-                  *ln_keep)
+                  *ln_keep, gn[0] if gn is not None else None)
 
 
 def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *,
@@ -255,9 +293,16 @@ def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torc
 
 def groupnorm(prog: Optional[Program], x1: torch.Tensor, C1: int, x2: Optional[torch.Tensor], C2: int,
               gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, scratch: torch.Tensor, *, B: int, HW: int,
-              groups: int, eps: float, silu: bool):
+              groups: int, eps: float, silu: bool,
+              parts: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], int, int]] = None):
+    """parts = (part1, part2 | None, gran, rows): statistics already written by the epilogues of the GEMMs that produced
+    x1 / x2 (conv_gemm(..., gn=...)) -- then this is ONE apply launch."""
     lib = L.load()
     g = L.GnDesc()
+    if parts is not None:
+        p1, p2, gran, rows = parts
+        assert p1.dtype == torch.float32 and (x2 is None or p2 is not None)
+        g.part1, g.part2, g.part_gran, g.part_rows = p1.data_ptr(), _ptr(p2), gran, rows
     g.x1, g.ld1, g.C1 = x1.data_ptr(), _check_2d(x1, "groupnorm x1"), C1
     if x2 is not None:
         g.x2, g.ld2, g.C2 = x2.data_ptr(), _check_2d(x2, "groupnorm x2"), C2
@@ -268,7 +313,7 @@ def groupnorm(prog: Optional[Program], x1: torch.Tensor, C1: int, x2: Optional[t
     g.scratch, g.scratch_floats = scratch.data_ptr(), scratch.numel()
     L.check(lib.unib200_groupnorm(_h(prog), C.byref(g), _stream()), "groupnorm")
     if prog is not None:
-        prog.keep(x1, x2, gamma, beta, out, scratch)
+        prog.keep(x1, x2, gamma, beta, out, scratch, *(parts[:2] if parts is not None else ()))
 
 
 def layernorm(prog: Optional[Program], x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
