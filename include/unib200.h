@@ -228,6 +228,47 @@ int unib200_softmax_rows(unib200_program* prog, void* s_fp16, int rows, int n, i
 int unib200_gaussian_sample(unib200_program* prog, const float* moments, const float* noise, float* out, int B, int C,
                             int HW, float scale, void* stream);
 
+/* ---- step-level context -----------------------------------------------------------------
+ * A context owns what one dual-stream sampler needs at run time -- recorded programs (ownership passes to it), device
+ * buffers it allocated or was handed, weights uploaded into it -- so that, once a plan exists, a denoising step, a
+ * per-network forward or the WHOLE sampling loop is one C call with plain pointers: no Python, no torch in the loop.
+ * (Recording the programs = the layer wiring of models/controlnet.py + unet_2d_blocks.py stays in the host layer,
+ * uni_renderer_b200/engine.py + pipeline.py, which calls the op entry points above.)
+ * Replaces, at the reference's boundary: the three module forwards (models/controlnet.py:781,1657,2342) ->
+ * unib200_ctx_run(ctx, "unet" | "attr_enc" | "attr_dec"); one loop body (models/pipeline_new_d4p.py:1391-1453,
+ * models/pipeline.py:1586-1653, 2627-2733) -> unib200_dual_step; the whole `for t in timesteps` loop ->
+ * unib200_sample_loop.  One thread at a time per context; asynchronous w.r.t. the host like every other entry point. */
+typedef struct unib200_ctx unib200_ctx;
+typedef struct {
+  int use_graph;            /* replay the step program as a CUDA graph when it has been instantiated (default 1)       */
+  int reserved[7];
+} unib200_config;
+enum { UNIB200_F16 = 0, UNIB200_F32 = 1, UNIB200_I32 = 2 };
+unib200_ctx* unib200_create(int device, const unib200_config* cfg);            /* cfg may be NULL                      */
+void unib200_destroy(unib200_ctx* ctx);                                        /* frees programs, buffers, weights     */
+/* copy a tensor (host or device memory) into context-owned device memory under `key`; the caller keeps `src` */
+int unib200_load_weight(unib200_ctx* ctx, const char* key, const void* src, int dtype, const int64_t* shape, int ndim);
+int unib200_alloc(unib200_ctx* ctx, const char* key, size_t bytes, int zero);  /* named context-owned device buffer    */
+int unib200_bind(unib200_ctx* ctx, const char* key, void* dev_ptr, size_t bytes);   /* borrow a caller-owned buffer   */
+void* unib200_buffer(unib200_ctx* ctx, const char* key, size_t* bytes);        /* device pointer of `key`, or NULL      */
+/* hand a recorded program to the context under a name; "once" (schedule tables, runs at attach time of a loop),
+ * "setup" (step-invariant work, once per call) and "step" (one denoising step) drive the loop entry points */
+int unib200_ctx_attach(unib200_ctx* ctx, const char* name, unib200_program* prog);
+int unib200_ctx_run(unib200_ctx* ctx, const char* name, void* stream);
+int unib200_unet_forward(unib200_ctx* ctx, void* stream);                      /* = unib200_ctx_run(ctx, "unet")       */
+int unib200_attr_enc_forward(unib200_ctx* ctx, void* stream);
+int unib200_attr_dec_forward(unib200_ctx* ctx, void* stream);
+/* ONE denoising step of the attached "step" program (both streams, exchange, scheduler updates; the device-side step
+ * counter advances) */
+int unib200_dual_step(unib200_ctx* ctx, void* stream);
+/* the whole loop: copies the inputs (host or device pointers; NULL = keep the buffer's content) into the buffers bound
+ * as "lat_img" / "lat_attr" / "ehs", zeroes "step", runs "setup" and n_steps x "step", and copies the final latents out
+ * (NULL = leave them in the bound buffers) -- everything enqueued on `stream`. */
+int unib200_sample_loop(unib200_ctx* ctx, int n_steps, const void* lat_img, const void* lat_attr, const void* ehs,
+                        void* out_lat_img, void* out_lat_attr, void* stream);
+/* The sharded loop's one collective, ncclAllGather of the final latents, is issued by the host layer through
+ * torch.distributed (pipeline.all_gather_latents): this library does not link NCCL. */
+
 #ifdef __cplusplus
 }
 #endif

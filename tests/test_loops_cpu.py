@@ -355,3 +355,56 @@ def test_groupnorm_statistics_fused_into_gemm_epilogues(monkeypatch, mode):
     assert _rel(plan.bufs["lat_img"], ri) < 5e-3
     if mode == "joint":
         assert _rel(plan.bufs["lat_attr"], ra) < 5e-3
+
+
+def test_upres_decoder_blocks_add_the_extra_residual_per_layer(monkeypatch):
+    """UpResBlock2D / CrossAttnUpResBlock2D (`hidden_states += up_additional_states` after every decoder
+    layer, models/unet_2d_blocks.py:2408,2814) through the drop-in AttributeDecoderModel with its class-default
+    up_block_types, on the emulator against the oracle.  The add rides through the layer's last GEMM (epilogue residual,
+    or an identity K segment where that input is taken) -- no kernel of its own.  With the plain up blocks the argument
+    is ignored with a warning, exactly like the reference's live forward (models/controlnet.py:2464-2510)."""
+    from tests import gpu_model_probe as gp
+    from uni_renderer_b200 import models as M
+    from uni_renderer_b200.engine import StreamNet, Workspace
+    emu.install(monkeypatch)
+
+    def cpu_finalize(self, device=None):
+        if self._net is None:
+            self._net = StreamNet(self._kind, self.net_cfg, dict(self.state_dict()), "cpu")
+            self._ws = Workspace("cpu")
+        return self._net
+    monkeypatch.setattr(M._NetModule, "finalize", cpu_finalize)
+    gc = dict(block_out_channels=uo.TINY.block_out_channels, num_heads=uo.TINY.num_heads,
+              cross_attention_dim=uo.TINY.cross_attention_dim, norm_num_groups=uo.TINY.norm_num_groups, seeds=(11, 12, 13))
+    (unet, enc, dec_plain), sds, cfgs = gp.build_modules(gc, device="cpu")
+    kw = dict(block_out_channels=tuple(gc["block_out_channels"]), attention_head_dim=gc["num_heads"],
+              cross_attention_dim=gc["cross_attention_dim"], norm_num_groups=gc["norm_num_groups"])
+    dec = M.AttributeDecoderModel(out_channels=28, _init_weights=False, **kw)            # UpRes defaults
+    dec.load_state_dict(sds[2])
+    B, S = 2, 8
+    x_img, x_attr, ehs = _inputs(B, S, cfgs[0].cross_attention_dim)
+    ehs = ehs.float()
+    t = 501
+    d, m, raw_a, raw_a_mid = enc(x_img, t, encoder_hidden_states=ehs, controlnet_cond=x_attr, return_dict=False)
+    _, raw_u, raw_u_mid, taps = unet(x_img, t, encoder_hidden_states=ehs, down_block_additional_residuals=d,
+                                     mid_block_additional_residual=m, return_dict=False)
+    g = torch.Generator().manual_seed(9)
+    ups = [0.5 * torch.randn(tp.shape, generator=g) for tp in taps[1:]]                  # one per decoder layer
+    got = dec(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=t, encoder_hidden_states=ehs,
+              down_block_additional_residuals=raw_u, up_block_additional_residuals=ups,
+              mid_block_additional_residual=raw_u_mid, return_dict=False)
+    f = lambda ts: [x.float() for x in ts]       # noqa: E731
+    with torch.no_grad():
+        ref = uo.attr_decoder_forward(sds[2], cfgs[2], raw_a_mid.float(), f(raw_a), t, ehs, f(raw_u), raw_u_mid.float(),
+                                      up_block_additional_residuals=[u.half().float() for u in ups])
+        ref_plain = uo.attr_decoder_forward(sds[2], cfgs[2], raw_a_mid.float(), f(raw_a), t, ehs, f(raw_u),
+                                            raw_u_mid.float())
+    assert _rel(got.float(), ref) < 3e-3 and _rel(ref_plain, ref) > 0.05
+    with pytest.raises(ValueError):
+        dec(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=t, encoder_hidden_states=ehs,
+            down_block_additional_residuals=raw_u, mid_block_additional_residual=raw_u_mid, return_dict=False)
+    with pytest.warns(UserWarning):
+        ign = dec_plain(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=t, encoder_hidden_states=ehs,
+                        down_block_additional_residuals=raw_u, up_block_additional_residuals=ups,
+                        mid_block_additional_residual=raw_u_mid, return_dict=False)
+    assert _rel(ign.float(), ref_plain) < 3e-3

@@ -89,3 +89,41 @@ def test_sd15_shape_step_matches_reference_checksums():
         assert abs(o.std().item() - ref["std"]) <= 5e-3 * ref["std"]
     assert abs(raw_u_mid.float().norm().item() - gold["raw_u_mid_l2"]) <= 5e-3 * gold["raw_u_mid_l2"]
     assert abs(raw_a_mid.float().norm().item() - gold["raw_a_mid_l2"]) <= 5e-3 * gold["raw_a_mid_l2"]
+
+
+@gpu
+def test_upres_decoder_blocks_on_gpu():
+    """SURVEY row a8 on the GPU: the class-default UpRes up blocks of AttributeDecoderModel (extra residual after every
+    decoder layer) against the oracle; tiny widths, two resolutions of attention blocks + the attention-free block."""
+    import torch
+    from oracle import uni_oracle as uo
+    from tests import gpu_model_probe as gp
+    from uni_renderer_b200 import models as M
+    gc = dict(block_out_channels=uo.TINY.block_out_channels, num_heads=uo.TINY.num_heads,
+              cross_attention_dim=uo.TINY.cross_attention_dim, norm_num_groups=uo.TINY.norm_num_groups, seeds=(11, 12, 13))
+    (unet, enc, _), sds, cfgs = gp.build_modules(gc)
+    dec = M.AttributeDecoderModel(out_channels=28, _init_weights=False, block_out_channels=tuple(gc["block_out_channels"]),
+                                  attention_head_dim=gc["num_heads"], cross_attention_dim=gc["cross_attention_dim"],
+                                  norm_num_groups=gc["norm_num_groups"])
+    assert dec.net_cfg.up_res
+    dec.load_state_dict(sds[2])
+    dec.to("cuda")
+    g = torch.Generator().manual_seed(1234)
+    B, S, t = 2, 16, 501
+    x_img, x_attr = torch.randn(B, 4, S, S, generator=g).cuda(), torch.randn(B, 28, S, S, generator=g).cuda()
+    ehs = torch.randn(B, 77, cfgs[0].cross_attention_dim, generator=g).cuda()
+    d, m, raw_a, raw_a_mid = enc(x_img, t, encoder_hidden_states=ehs, controlnet_cond=x_attr, return_dict=False)
+    _, raw_u, raw_u_mid, taps = unet(x_img, t, encoder_hidden_states=ehs, down_block_additional_residuals=d,
+                                     mid_block_additional_residual=m, return_dict=False)
+    ups = [0.5 * torch.randn(tp.shape, generator=g).cuda() for tp in taps[1:]]
+    got = dec(sample=raw_a_mid, down_block_res_samples=raw_a, timestep=t, encoder_hidden_states=ehs,
+              down_block_additional_residuals=raw_u, up_block_additional_residuals=ups,
+              mid_block_additional_residual=raw_u_mid, return_dict=False)
+    torch.cuda.synchronize()
+    c = lambda x: x.float().cpu()          # noqa: E731
+    with torch.no_grad():
+        ref = uo.attr_decoder_forward(sds[2], cfgs[2], c(raw_a_mid), [c(x) for x in raw_a], t, c(ehs).half().float(),
+                                      [c(x) for x in raw_u], c(raw_u_mid),
+                                      up_block_additional_residuals=[c(u).half().float() for u in ups])
+    r = gp.err(got, ref)
+    assert r["rel_l2"] <= 3e-3, r

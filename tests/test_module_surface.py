@@ -52,8 +52,12 @@ def test_constructor_rejects_what_the_path_does_not_implement():
         _tiny_unet(use_linear_projection=True)
     with pytest.raises(ValueError):
         _tiny_unet(down_block_types=("DownBlock2D",) * 4)
-    with pytest.raises(ValueError):                # the decoder's UpRes defaults cannot run in the reference either
-        M.AttributeDecoderModel(out_channels=28, **TINY)
+    # the decoder's class-default UpRes up blocks (models/controlnet.py:1794-1797) are constructible: SURVEY row a8
+    d = M.AttributeDecoderModel(out_channels=28, **TINY)
+    assert d.config.up_block_types == M._SD_UPRES and d.net_cfg.up_res
+    assert set(d.state_dict()) == set(M.AttributeDecoderModel(out_channels=28, up_block_types=M._SD_UP, **TINY).state_dict())
+    with pytest.raises(ValueError):
+        M.AttributeDecoderModel(out_channels=28, up_block_types=("UpBlock2D",) * 4, **TINY)
 
 
 def test_from_unet_copies_the_shared_trunk_and_zeroes_the_exchange():

@@ -68,6 +68,9 @@ EXPORTS = [
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
     "unib200_softmax_rows", "unib200_gaussian_sample",
+    "unib200_create", "unib200_destroy", "unib200_load_weight", "unib200_alloc", "unib200_bind", "unib200_buffer",
+    "unib200_ctx_attach", "unib200_ctx_run", "unib200_unet_forward", "unib200_attr_enc_forward",
+    "unib200_attr_dec_forward", "unib200_dual_step", "unib200_sample_loop",
 ]
 
 _lib = None
@@ -129,6 +132,20 @@ def load() -> C.CDLL:
     lib.unib200_unipc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.unib200_softmax_rows.argtypes = [vp, vp, ci, ci, ci, cf, vp]
     lib.unib200_gaussian_sample.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, vp]
+    lib.unib200_create.argtypes = [ci, vp]
+    lib.unib200_create.restype = vp
+    lib.unib200_destroy.argtypes = [vp]
+    lib.unib200_destroy.restype = None
+    lib.unib200_load_weight.argtypes = [vp, C.c_char_p, vp, ci, C.POINTER(i64), ci]
+    lib.unib200_alloc.argtypes = [vp, C.c_char_p, C.c_size_t, ci]
+    lib.unib200_bind.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.unib200_buffer.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t)]
+    lib.unib200_buffer.restype = vp
+    lib.unib200_ctx_attach.argtypes = [vp, C.c_char_p, vp]
+    lib.unib200_ctx_run.argtypes = [vp, C.c_char_p, vp]
+    for fn in (lib.unib200_unet_forward, lib.unib200_attr_enc_forward, lib.unib200_attr_dec_forward, lib.unib200_dual_step):
+        fn.argtypes = [vp, vp]
+    lib.unib200_sample_loop.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

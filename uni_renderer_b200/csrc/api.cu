@@ -351,13 +351,25 @@ size_t unib200_packed_k(int nseg, const unib200_seg* seg) {
   return k;
 }
 
-int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* stream) {
+}  // extern "C"
+
+namespace {
+struct PreparedGemm {
+  GemmMaps maps;
+  GemmParams p;
+  int bn = 0, launches = 1;
+  double flops = 0.0, bytes = 0.0;
+  std::string desc;
+};
+
+// validation, tensor maps, tiling / split-K / epilogue-mode planning of one conv_gemm descriptor
+int prepare_gemm(const unib200_gemm_desc* d, PreparedGemm* out) {
   if (!d) return fail("null desc");
   if (d->M <= 0 || d->N <= 0 || d->nseg < 1 || d->nseg > kMaxSeg) return fail("conv_gemm: bad M/N/nseg");
   const bool linear = (d->H == 0 || d->W == 0);
-  GemmMaps maps;
+  GemmMaps& maps = out->maps;
   memset(&maps, 0, sizeof(maps));
-  GemmParams p;
+  GemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   p.M = d->M;
   p.N = d->N;
@@ -561,7 +573,6 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
         ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->res && (reinterpret_cast<uintptr_t>(d->res) & 15))))
       return fail("conv_gemm: out / res must be 16-byte aligned");
   }
-  Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   double kreal = 0.0, a_bytes = 0.0;
   for (int i = 0; i < d->nseg; ++i) {
     const int taps = d->seg[i].kind == UNIB200_SEG_1x1 ? 1 : d->seg[i].kind == UNIB200_SEG_UP2x2 ? 4 : 9;
@@ -581,7 +592,69 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
     desc += std::string(i ? "+" : "") + (d->seg[i].kind == UNIB200_SEG_1x1 ? "1x1:" : d->seg[i].kind == UNIB200_SEG_3x3 ? "3x3:" : d->seg[i].kind == UNIB200_SEG_3x3_S2 ? "3x3s2:" : d->seg[i].kind == UNIB200_SEG_UP2x2 ? "up2x2:" : "3x3s2p0:") +
             std::to_string(d->seg[i].C);
   if (d->flags) desc += " flags=" + std::to_string(d->flags);
-  return submit(prog, std::move(op), splits > 1 ? 2 : 1, stream, "conv_gemm", UNIB200_OP_GEMM, flops, bytes, desc);
+  out->bn = bn;
+  out->launches = splits > 1 ? 2 : 1;
+  out->flops = flops;
+  out->bytes = bytes;
+  out->desc = desc;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* stream) {
+  PreparedGemm g;
+  int rc = prepare_gemm(d, &g);
+  if (rc != 0) return rc;
+  const int sms = num_sms();
+  const int bn = g.bn;
+  const GemmMaps maps = g.maps;
+  const GemmParams p = g.p;
+  Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
+  return submit(prog, std::move(op), g.launches, stream, "conv_gemm", UNIB200_OP_GEMM, g.flops, g.bytes, g.desc);
+}
+
+// G = 2 grouped launch: two GEMMs of identical shape (M, N, one 1x1 / linear segment of the same C, same flags) in ONE
+// kernel -- the two directions of the dual-stream residual exchange at one skip site (models/controlnet.py:1078-1087 and
+// :2446-2461 read the same pair of co-located tensors): out0 = res0 + W0 a0 + b0, out1 = res1 + W1 a1 + b1.
+int unib200_conv_gemm_dual(unib200_program* prog, const unib200_gemm_desc* d0, const unib200_gemm_desc* d1, void* stream) {
+  PreparedGemm g0, g1;
+  int rc = prepare_gemm(d0, &g0);
+  if (rc != 0) return rc;
+  if ((rc = prepare_gemm(d1, &g1)) != 0) return rc;
+  if (d0->M != d1->M || d0->N != d1->N || d0->nseg != 1 || d1->nseg != 1 || d0->seg[0].C != d1->seg[0].C ||
+      d0->seg[0].kind != UNIB200_SEG_1x1 || d1->seg[0].kind != UNIB200_SEG_1x1 || d0->flags != 0 || d1->flags != 0 ||
+      d0->H != d1->H || d0->W != d1->W || d0->B != d1->B)
+    return fail("conv_gemm_dual: the two problems must have the same shape, one 1x1 segment and no flags");
+  if (g0.p.mode != 0 || g1.p.mode != 0 || g0.p.splits != 1 || g1.p.splits != 1 || g0.p.cg != g1.p.cg || g0.bn != g1.bn)
+    return fail("conv_gemm_dual: both problems need the vector epilogue (aligned NHWC fp16 output, no split-K)");
+  if (d0->bias_step || d1->bias_step || d0->bias_bstride || d1->bias_bstride || d0->rowstats_out || d1->rowstats_out ||
+      d0->ln_rowstats || d1->ln_rowstats || !d0->bias != !d1->bias || !d0->res != !d1->res || d0->ldc != d1->ldc ||
+      d0->ldr != d1->ldr || !d0->gn_part != !d1->gn_part || d0->gn_gran != d1->gn_gran || d0->gn_rows != d1->gn_rows)
+    return fail("conv_gemm_dual: epilogue options of the two problems must match (plain bias / residual / GroupNorm "
+                "statistics only)");
+  GemmMaps maps = g0.maps;
+  maps.a[1] = g1.maps.a[0];
+  maps.b2 = g1.maps.b;
+  GemmParams p = g0.p;
+  p.dual = 1;
+  p.mt_single = g0.p.m_tiles;
+  p.m_tiles = 2 * g0.p.m_tiles;
+  {
+    auto recip = [](unsigned long long dv) { return (1ull << 40) / dv + 1ull; };
+    if (static_cast<long long>(p.m_tiles) * p.n_tiles * 16 >= (1 << 20)) return fail("conv_gemm_dual: too many tiles");
+    p.mul_tiles = recip(static_cast<unsigned long long>(p.m_tiles) * p.n_tiles);
+  }
+  p.bias2 = g1.p.bias;
+  p.res2 = g1.p.res;
+  p.out2 = g1.p.out;
+  p.gn_part2 = g1.p.gn_part;
+  const int sms = num_sms();
+  const int bn = g0.bn;
+  Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
+  return submit(prog, std::move(op), 1, stream, "conv_gemm_dual", UNIB200_OP_GEMM, g0.flops + g1.flops, g0.bytes + g1.bytes,
+                "dual " + g0.desc);
 }
 
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* stream) {
@@ -745,6 +818,139 @@ int unib200_gaussian_sample(unib200_program* prog, const float* moments, const f
   if (B <= 0 || C <= 0 || HW <= 0 || !moments || !out) return fail("gaussian_sample: bad arguments");
   Op op = [=](cudaStream_t st) { return launch_gaussian_sample(moments, noise, out, B, C, HW, scale, st); };
   return submit(prog, std::move(op), 1, stream, "gaussian_sample");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// step-level context
+// ---------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+#include <map>
+
+struct unib200_ctx {
+  struct Buf { void* ptr = nullptr; size_t bytes = 0; bool owned = false; };
+  int device = 0;
+  int use_graph = 1;
+  std::map<std::string, Buf> bufs;
+  std::map<std::string, unib200_program*> progs;
+};
+
+namespace {
+unib200_ctx::Buf* ctx_buf(unib200_ctx* c, const char* key) {
+  auto it = c->bufs.find(key);
+  return it == c->bufs.end() ? nullptr : &it->second;
+}
+int ctx_put(unib200_ctx* c, const char* key, void* ptr, size_t bytes, bool owned) {
+  unib200_ctx::Buf& b = c->bufs[key];
+  if (b.owned && b.ptr) cudaFree(b.ptr);
+  b.ptr = ptr; b.bytes = bytes; b.owned = owned;
+  return 0;
+}
+int ctx_replay(unib200_ctx* c, const char* name, void* stream, bool allow_graph) {
+  auto it = c->progs.find(name);
+  if (it == c->progs.end()) return fail(std::string("context has no program named '") + name + "'");
+  unib200_program* p = it->second;
+  if (allow_graph && c->use_graph && p->exec) return unib200_program_graph_launch(p, stream);
+  return unib200_program_run(p, stream);
+}
+}  // namespace
+
+extern "C" {
+
+unib200_ctx* unib200_create(int device, const unib200_config* cfg) {
+  if (cudaSetDevice(device) != cudaSuccess) { fail("unib200_create: cudaSetDevice failed"); return nullptr; }
+  unib200_ctx* c = new (std::nothrow) unib200_ctx();
+  if (!c) return nullptr;
+  c->device = device;
+  c->use_graph = cfg ? cfg->use_graph : 1;
+  return c;
+}
+
+void unib200_destroy(unib200_ctx* c) {
+  if (!c) return;
+  for (auto& kv : c->progs) unib200_program_destroy(kv.second);
+  for (auto& kv : c->bufs)
+    if (kv.second.owned && kv.second.ptr) cudaFree(kv.second.ptr);
+  delete c;
+}
+
+int unib200_alloc(unib200_ctx* c, const char* key, size_t bytes, int zero) {
+  if (!c || !key || bytes == 0) return fail("unib200_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail_cuda("unib200_alloc", e);
+  if (zero && (e = cudaMemset(p, 0, bytes)) != cudaSuccess) { cudaFree(p); return fail_cuda("unib200_alloc (memset)", e); }
+  return ctx_put(c, key, p, bytes, true);
+}
+
+int unib200_bind(unib200_ctx* c, const char* key, void* dev_ptr, size_t bytes) {
+  if (!c || !key || !dev_ptr) return fail("unib200_bind: bad arguments");
+  return ctx_put(c, key, dev_ptr, bytes, false);
+}
+
+void* unib200_buffer(unib200_ctx* c, const char* key, size_t* bytes) {
+  unib200_ctx::Buf* b = (c && key) ? ctx_buf(c, key) : nullptr;
+  if (bytes) *bytes = b ? b->bytes : 0;
+  return b ? b->ptr : nullptr;
+}
+
+int unib200_load_weight(unib200_ctx* c, const char* key, const void* src, int dtype, const int64_t* shape, int ndim) {
+  if (!c || !key || !src || !shape || ndim < 1 || ndim > 8) return fail("unib200_load_weight: bad arguments");
+  const size_t es = dtype == UNIB200_F16 ? 2 : (dtype == UNIB200_F32 || dtype == UNIB200_I32) ? 4 : 0;
+  if (!es) return fail("unib200_load_weight: dtype must be UNIB200_F16 / _F32 / _I32");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] <= 0) return fail("unib200_load_weight: non-positive dimension");
+    n *= static_cast<size_t>(shape[i]);
+  }
+  int rc = unib200_alloc(c, key, n * es, 0);
+  if (rc != 0) return rc;
+  cudaError_t e = cudaMemcpy(ctx_buf(c, key)->ptr, src, n * es, cudaMemcpyDefault);     // host or device source
+  if (e != cudaSuccess) return fail_cuda("unib200_load_weight (copy)", e);
+  return 0;
+}
+
+int unib200_ctx_attach(unib200_ctx* c, const char* name, unib200_program* prog) {
+  if (!c || !name || !prog) return fail("unib200_ctx_attach: bad arguments");
+  auto it = c->progs.find(name);
+  if (it != c->progs.end() && it->second != prog) unib200_program_destroy(it->second);
+  c->progs[name] = prog;
+  return 0;
+}
+
+int unib200_ctx_run(unib200_ctx* c, const char* name, void* stream) {
+  if (!c || !name) return fail("unib200_ctx_run: bad arguments");
+  return ctx_replay(c, name, stream, true);
+}
+int unib200_unet_forward(unib200_ctx* c, void* stream) { return unib200_ctx_run(c, "unet", stream); }
+int unib200_attr_enc_forward(unib200_ctx* c, void* stream) { return unib200_ctx_run(c, "attr_enc", stream); }
+int unib200_attr_dec_forward(unib200_ctx* c, void* stream) { return unib200_ctx_run(c, "attr_dec", stream); }
+int unib200_dual_step(unib200_ctx* c, void* stream) { return unib200_ctx_run(c, "step", stream); }
+
+int unib200_sample_loop(unib200_ctx* c, int n_steps, const void* lat_img, const void* lat_attr, const void* ehs,
+                        void* out_lat_img, void* out_lat_attr, void* stream) {
+  if (!c || n_steps < 0) return fail("unib200_sample_loop: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unib200_ctx::Buf *bi = ctx_buf(c, "lat_img"), *ba = ctx_buf(c, "lat_attr"), *be = ctx_buf(c, "ehs"),
+                   *bs = ctx_buf(c, "step");
+  if (!bi || !ba || !be || !bs) return fail("unib200_sample_loop: bind lat_img, lat_attr, ehs and step first");
+  cudaError_t e;
+  if (lat_img && (e = cudaMemcpyAsync(bi->ptr, lat_img, bi->bytes, cudaMemcpyDefault, s)) != cudaSuccess)
+    return fail_cuda("sample_loop (lat_img in)", e);
+  if (lat_attr && (e = cudaMemcpyAsync(ba->ptr, lat_attr, ba->bytes, cudaMemcpyDefault, s)) != cudaSuccess)
+    return fail_cuda("sample_loop (lat_attr in)", e);
+  if (ehs && (e = cudaMemcpyAsync(be->ptr, ehs, be->bytes, cudaMemcpyDefault, s)) != cudaSuccess)
+    return fail_cuda("sample_loop (ehs in)", e);
+  if ((e = cudaMemsetAsync(bs->ptr, 0, bs->bytes, s)) != cudaSuccess) return fail_cuda("sample_loop (step counter)", e);
+  int rc = 0;
+  if (c->progs.count("setup") && (rc = ctx_replay(c, "setup", stream, false)) != 0) return rc;
+  for (int i = 0; i < n_steps; ++i)
+    if ((rc = ctx_replay(c, "step", stream, true)) != 0) return rc;
+  if (out_lat_img && (e = cudaMemcpyAsync(out_lat_img, bi->ptr, bi->bytes, cudaMemcpyDefault, s)) != cudaSuccess)
+    return fail_cuda("sample_loop (lat_img out)", e);
+  if (out_lat_attr && (e = cudaMemcpyAsync(out_lat_attr, ba->ptr, ba->bytes, cudaMemcpyDefault, s)) != cudaSuccess)
+    return fail_cuda("sample_loop (lat_attr out)", e);
+  return 0;
 }
 
 int unib200_add_int(unib200_program* prog, int* p, int v, void* stream) {

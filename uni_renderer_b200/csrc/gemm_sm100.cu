@@ -219,6 +219,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
+    if (p.dual) tma_prefetch_desc(&maps.b2);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -260,7 +261,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
     uint32_t stage = 0, ph = 0;
     for (int w = cta; w < total_work; w += ncta) {
       const WorkItem wi = decode_work(p, w);
-      const int p0 = (wi.mt * CG + static_cast<int>(rank)) * kBM;
+      const int grp = (p.dual && wi.mt >= p.mt_single) ? 1 : 0;       // dual launch: which of the two problems
+      const int p0 = ((wi.mt - grp * p.mt_single) * CG + static_cast<int>(rank)) * kBM;
       const int w0 = p0 & ((1 << p.w_shift) - 1);                     // W, H are powers of two (linear: W = 2^30)
       const int h0 = (p0 >> p.w_shift) & ((1 << p.h_shift) - 1);
       const int b0 = p0 >> (p.w_shift + p.h_shift);
@@ -301,10 +303,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
           dh = (tap >> 1) - 1 + (par >> 1);
           dw = (tap & 1) - 1 + (par & 1);
         }
-        amap = &maps.a[tm];
+        amap = &maps.a[tm + grp];
         cw = w0 + dw;
         ch = h0 + dh;
       };
+      const CUtensorMap* bmap = grp ? &maps.b2 : &maps.b;
       set_tap();
       const int brow = wi.nt * BN + static_cast<int>(rank) * (BN / CG);   // pair: this CTA's half of the B tile
 #ifdef UNIB_GEMM_TRACE
@@ -322,11 +325,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             const uint32_t full_leader = mapa_u32(full_bar(stage), 0);
             if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
             tma_load_4d_2cta(a_dst, amap, full_leader, cb * kBK, cw, ch, b0);
-            tma_load_2d_2cta(a_dst + Cfg::kABytes, &maps.b, full_leader, kb * kBK, brow);
+            tma_load_2d_2cta(a_dst + Cfg::kABytes, bmap, full_leader, kb * kBK, brow);
           } else {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
             tma_load_4d(a_dst, amap, full_bar(stage), cb * kBK, cw, ch, b0);
-            tma_load_2d(a_dst + Cfg::kABytes, &maps.b, full_bar(stage), kb * kBK, brow);
+            tma_load_2d(a_dst + Cfg::kABytes, bmap, full_bar(stage), kb * kBK, brow);
           }
         }
         if (++cb == nkb) {
@@ -424,15 +427,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       float* const stat_s = reinterpret_cast<float*>(smem + Cfg::kStatOff);
       const int et = threadIdx.x - 64;                          // 0..255 within the epilogue group
       const bool per_batch = p.bias_bstride != 0;
-      const float* const bias_base = p.bias + ((p.bias != nullptr && p.bias_step != nullptr)
-                                                   ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0);
-      __half* const outp = reinterpret_cast<__half*>(p.out);
+      const float* const bias_base0 = p.bias + ((p.bias != nullptr && p.bias_step != nullptr)
+                                                    ? static_cast<size_t>(*p.bias_step) * p.bias_step_stride : 0);
       for (int w = cta; w < total_work; w += ncta, ++tl) {
         const WorkItem wi = decode_work(p, w);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
         const int h = (hw + static_cast<int>(tl)) & 1;         // my sub-tiles: h, h + 2, ...
-        const int m0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + q * 32;   // first row of this warp
+        const int grp = (p.dual && wi.mt >= p.mt_single) ? 1 : 0;               // dual launch: second problem's pointers
+        const float* const bias_base = grp ? p.bias2 : bias_base0;
+        __half* const outp = reinterpret_cast<__half*>(grp ? p.out2 : p.out);
+        const __half* const resp = grp ? p.res2 : p.res;
+        float* const gnp = grp ? p.gn_part2 : p.gn_part;
+        const int m0 = ((wi.mt - grp * p.mt_single) * CG + static_cast<int>(rank)) * kBM + q * 32;   // first row of this warp
         const int m = m0 + lane;
         const bool row_ok = m < p.M;
         int n0 = wi.nt * out_bn;                               // first output column of this tile
@@ -490,7 +497,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
         }
         float st_sum = 0.f, st_sq = 0.f;                       // row statistics of my output columns
         uint32_t rnext[16];
-        const __half* const res_row = p.res + static_cast<size_t>(m) * p.ldr + n0;
+        const __half* const res_row = resp + static_cast<size_t>(m) * p.ldr + n0;
         if (has_res && row_ok && h < nsub) {
           ldg256(res_row + h * 32, rnext);
           ldg256(res_row + h * 32 + 16, rnext + 8);
@@ -642,10 +649,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             float acc = 0.f;
             for (int qq = rb * qpb; qq < (rb + 1) * qpb; ++qq)
               for (int pp = 0; pp < (p.gn_gran >> 1); ++pp) acc += sb[qq * BN + (mg * (p.gn_gran >> 1) + pp) * 2 + st];
-            const int row0 = (wi.mt * CG + static_cast<int>(rank)) * kBM + rb * p.gn_rows;
+            const int row0 = ((wi.mt - grp * p.mt_single) * CG + static_cast<int>(rank)) * kBM + rb * p.gn_rows;
             const int gmg = n0 / p.gn_gran + mg;
             if (row0 < p.M && wi.nt * ng + mg < ngN)
-              p.gn_part[(static_cast<size_t>(row0 / p.gn_rows * gn_blk_mul + gn_blk_add) * (gn_blk_mul == 4 ? p.up_cout / p.gn_gran : ngN) + gmg) * 2 + st] = acc;
+              gnp[(static_cast<size_t>(row0 / p.gn_rows * gn_blk_mul + gn_blk_add) * (gn_blk_mul == 4 ? p.up_cout / p.gn_gran : ngN) + gmg) * 2 + st] = acc;
           }
           // the other parity buffer is written during the next tile; this one is rewritten two tiles from now, after
           // every thread has passed the next tile's barrier

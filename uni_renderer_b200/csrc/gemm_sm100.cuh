@@ -74,6 +74,14 @@ struct GemmParams {
   // high-resolution image.  up_shift < 0: off.
   int up_shift;
   int up_cout;
+  // G = 2 grouped launch (the two directions of the dual-stream residual exchange at one skip site): m-tiles
+  // [mt_single, 2 * mt_single) belong to a second problem of identical shape with its own A / B tensor maps
+  // (maps.a[1], maps.b2) and its own epilogue pointers.  dual = 0: off.
+  int dual, mt_single;
+  const float* bias2;
+  const __half* res2;
+  void* out2;
+  float* gn_part2;
   float* gn_part;            // GroupNorm statistics of the output: [M / gn_rows][N / gn_gran][2] (sum, sumsq), or null
   int gn_gran;               // channels per micro-group (even, divides the N tile and N)
   int gn_rows;               // rows per partial block: 32, 64 or 128 (divides the rows of one sample)
@@ -84,6 +92,7 @@ struct GemmParams {
 struct alignas(64) GemmMaps {
   CUtensorMap a[kMaxAMaps];
   CUtensorMap b;
+  CUtensorMap b2;            // weights of the second problem of a dual launch
 };
 
 // host-side launcher (gemm_sm100.cu)

@@ -37,6 +37,7 @@ class NetConfig:
     norm_eps: float = 1e-5
     down_has_attn: Tuple[bool, ...] = (True, True, True, False)
     up_has_attn: Tuple[bool, ...] = (False, True, True, True)
+    up_res: bool = False          # UpResBlock2D / CrossAttnUpResBlock2D: every decoder layer adds an extra residual
 
     @property
     def time_embed_dim(self) -> int:

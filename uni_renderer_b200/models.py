@@ -370,7 +370,8 @@ def _net_config(in_channels, out_channels, block_out_channels, layers_per_block,
                              f"(supported: {unsupported[k]})")
     return NetConfig(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
                      layers_per_block=layers_per_block, num_heads=attention_head_dim,
-                     cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups, norm_eps=norm_eps)
+                     cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
+                     up_res=tuple(up_block_types) == _SD_UPRES)
 
 
 class UNet2DConditionModel(_NetModule):
@@ -633,7 +634,8 @@ class AttributeDecoderModel(_NetModule):
     def _program(self, B, H, W, L, srcs):
         """srcs: dict of Act inputs.  Programs are keyed by the input pointers so the steady-state loop (inputs are
         the sibling modules' static buffers) replays with zero copies."""
-        key = (B, H, W, L, tuple(a.t.data_ptr() for a in srcs["skipA"] + srcs["skipU"] + [srcs["midA"], srcs["midU"]]))
+        key = (B, H, W, L, tuple(a.t.data_ptr() for a in srcs["skipA"] + srcs["skipU"] + [srcs["midA"], srcs["midU"]]
+                                 + list(srcs.get("up") or [])))
         if key in self._progs:
             return self._progs[key]
         net, ws, cfg, dev = self.finalize(), self._ws, self.net_cfg, self._net.device
@@ -645,7 +647,7 @@ class AttributeDecoderModel(_NetModule):
         tproj = net.rec_temb(prog, ws, P["t"], B)
         kv = net.rec_kv(prog, ws, P["ehs"], B, L)
         skips, mid = net.rec_exchange(prog, ws, srcs["skipU"], srcs["midU"], srcs["skipA"], srcs["midA"])
-        net.rec_decoder(prog, ws, mid, skips, tproj, kv, L, out_nchw=P["out"])
+        net.rec_decoder(prog, ws, mid, skips, tproj, kv, L, out_nchw=P["out"], up_additional=srcs.get("up"))
         self._progs[key] = P
         return P
 
@@ -677,6 +679,19 @@ class AttributeDecoderModel(_NetModule):
         if down_block_additional_residuals is None or mid_block_additional_residual is None:
             raise ValueError("AttributeDecoderModel needs the RGB stream's raw skips and mid (controlnet.py:2476 "
                              "dereferences mid_block_additional_residual unconditionally)")
+        n_layers = len(self.net_cfg.block_out_channels) * (self.net_cfg.layers_per_block + 1)
+        if self.net_cfg.up_res:
+            # UpResBlock2D / CrossAttnUpResBlock2D (the class-default up_block_types): each decoder layer adds
+            # up_block_additional_residuals[k] to its output (models/unet_2d_blocks.py:2408,2814) -- SURVEY row a8
+            if up_block_additional_residuals is None or len(up_block_additional_residuals) != n_layers:
+                raise ValueError(f"up_block_types {_SD_UPRES} need {n_layers} up_block_additional_residuals "
+                                 "(one per decoder layer, in layer order)")
+        elif up_block_additional_residuals is not None:
+            import warnings
+            warnings.warn("up_block_additional_residuals is ignored with UpBlock2D / CrossAttnUpBlock2D up blocks -- exactly "
+                          "like the reference, whose live forward has the argument commented out "
+                          "(models/controlnet.py:2464-2510)", stacklevel=2)
+            up_block_additional_residuals = None
         self.finalize(sample.device)
         B, _, h8, w8 = sample.shape
         H, W = down_block_res_samples[0].shape[-2:]
@@ -684,6 +699,8 @@ class AttributeDecoderModel(_NetModule):
         srcs = {"skipA": [self._ingest(f"a{i}", t) for i, t in enumerate(down_block_res_samples)],
                 "skipU": [self._ingest(f"u{i}", t) for i, t in enumerate(down_block_additional_residuals)],
                 "midA": self._ingest("am", sample), "midU": self._ingest("um", mid_block_additional_residual)}
+        if up_block_additional_residuals is not None:
+            srcs["up"] = [self._ingest(f"x{i}", t) for i, t in enumerate(up_block_additional_residuals)]
         P = self._program(B, H, W, L, srcs)
         P["t"].copy_(self._timesteps(timestep, B, P["t"].device))
         P["ehs"].copy_(encoder_hidden_states.reshape(B * L, -1))

@@ -13,7 +13,7 @@ from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SE
                    SEG_3x3_S2P0, SEG_UP2x2)
 
 __all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
-           "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "softmax_rows", "gaussian_sample", "Program", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
+           "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "softmax_rows", "gaussian_sample", "Program", "Context", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
            "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "SEG_3x3_S2P0", "SEG_UP2x2", "pack_upsample_conv", "upfold_supported", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
 
@@ -102,9 +102,55 @@ class Program:
 
     def __del__(self):
         try:
-            if self.handle:
+            if self.handle and getattr(self, "_owned", True):
                 self.lib.unib200_program_destroy(self.handle)
+            self.handle = None
+        except Exception:
+            pass
+
+
+class Context:
+    """Step-level context of the C ABI (include/unib200.h unib200_ctx): owns the programs attached to it and the buffer
+    bindings of one sampling plan, so that a whole sampling loop is ONE C call (`sample_loop`) -- no Python inside it."""
+
+    def __init__(self, device_index: int, use_graph: bool = True):
+        self.lib = L.load()
+        cfg = (C.c_int * 8)(int(use_graph), 0, 0, 0, 0, 0, 0, 0)
+        self.handle = self.lib.unib200_create(device_index, cfg)
+        if not self.handle:
+            raise L.Unib200Error("unib200_create failed")
+        self._keep: list = []
+
+    def attach(self, name: str, prog: Program):
+        """Ownership of the program passes to the context (the Python handle stays usable while the context lives)."""
+        L.check(self.lib.unib200_ctx_attach(self.handle, name.encode(), prog.handle), "ctx_attach")
+        prog._owned = False
+        self._keep.append(prog)
+
+    def bind(self, key: str, t: torch.Tensor):
+        assert t.is_cuda and t.is_contiguous()
+        L.check(self.lib.unib200_bind(self.handle, key.encode(), t.data_ptr(), t.numel() * t.element_size()), "ctx_bind")
+        self._keep.append(t)
+
+    def run(self, name: str):
+        L.check(self.lib.unib200_ctx_run(self.handle, name.encode(), _stream()), "ctx_run")
+
+    def dual_step(self):
+        L.check(self.lib.unib200_dual_step(self.handle, _stream()), "dual_step")
+
+    def sample_loop(self, n_steps: int, lat_img=None, lat_attr=None, ehs=None, out_img=None, out_attr=None):
+        """Pointers (ints) or None: host or device memory of exactly the bound buffers' sizes."""
+        L.check(self.lib.unib200_sample_loop(self.handle, n_steps, lat_img, lat_attr, ehs, out_img, out_attr, _stream()),
+                "sample_loop")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.unib200_destroy(self.handle)
                 self.handle = None
+                for p in self._keep:
+                    if isinstance(p, Program):
+                        p.handle = None
         except Exception:
             pass
 

@@ -54,6 +54,7 @@ class _Plan:
     net_batch: int = 0
     schedule: object = None    # the DDIMSchedule / UniPCSchedule whose tables were uploaded
     timesteps: Optional[list] = None
+    ctx: object = None         # ops.Context: the step-level C context that owns setup / step and runs the loop
 
 
 class DualStreamSampler:
@@ -305,6 +306,15 @@ class DualStreamSampler:
             with torch.cuda.stream(side):
                 step.instantiate_graph()
             side.synchronize()
+        if self.device.type == "cuda" and hasattr(ops, "Context"):
+            # hand the recorded programs to a step-level C context (include/unib200.h): from here on one call of
+            # unib200_sample_loop runs setup + every denoising step, with no Python between the graph launches
+            ctx = ops.Context(self.device.index or 0, use_graph=self.use_graph)
+            ctx.attach("setup", setup)
+            ctx.attach("step", step)
+            for k in ("lat_img", "lat_attr", "ehs", "step"):
+                ctx.bind(k, b[k])
+            plan.ctx = ctx
         self._plans[key] = plan
         return plan
 
@@ -402,11 +412,14 @@ class DualStreamSampler:
 
     def run(self, plan: _Plan, steps: Optional[int] = None):
         """setup + `steps` replays of the step program on the current stream (asynchronous)."""
-        plan.bufs["step"].zero_()
-        plan.setup.run()
         n = plan.steps if steps is None else steps
         if n > plan.steps:
             raise ValueError("more steps than the plan's schedule")
+        if plan.ctx is not None:
+            plan.ctx.sample_loop(n)            # one C call: zero the counter, setup, n x step (graph replays)
+            return
+        plan.bufs["step"].zero_()
+        plan.setup.run()
         if self.use_graph:
             for _ in range(n):
                 plan.step.launch_graph()
