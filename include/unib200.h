@@ -144,6 +144,11 @@ typedef struct {
 } unib200_gemm_desc;
 
 int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* desc, void* stream);
+/* G = 2 grouped launch: two GEMMs of identical shape (same M, N, one 1x1 / linear segment of the same C; plain bias /
+ * residual / GroupNorm-statistics epilogue) as ONE kernel whose tile walk covers both.  Used for the dual-stream residual
+ * exchange: at every skip site the RGB stream needs skip_U + zc_enc(skip_A) (models/controlnet.py:1078-1087,1115) and the
+ * attribute stream skip_A + zc_dec(skip_U) (:2446-2461,2476-2477) -- both directions of a site run in one kernel. */
+int unib200_conv_gemm_dual(unib200_program* prog, const unib200_gemm_desc* d0, const unib200_gemm_desc* d1, void* stream);
 size_t unib200_packed_k(int nseg, const unib200_seg* seg);      /* Ktot of the packed weight matrix               */
 int unib200_pick_bn(int N, int flags);   /* N-tile width the kernel will use (EPI_GEGLU weights are interleaved per tile) */
 

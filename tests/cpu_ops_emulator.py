@@ -188,6 +188,14 @@ def conv_gemm(prog, segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_b
     _submit(prog, run)
 
 
+def conv_gemm_dual(prog, a, b):
+    """unib200_conv_gemm_dual: two problems of identical shape in one launch = the two conv_gemm results."""
+    assert a["M"] == b["M"] and a["N"] == b["N"] and len(a["segs"]) == len(b["segs"]) == 1
+    for d in (a, b):
+        d = dict(d)
+        conv_gemm(prog, d.pop("segs"), d.pop("weight"), d.pop("out"), **d)
+
+
 def attention(prog, q, k, v, out, *, B, heads, Nq, Nk, d, scale=None):
     sc = float(scale if scale is not None else d ** -0.5)
 
@@ -316,7 +324,7 @@ def add_f16(prog, a, b, out):
     _submit(prog, lambda: out.copy_(a.float() + b.float()))
 
 
-EMULATED = ("conv_gemm", "attention", "groupnorm", "layernorm", "upsample2x", "to_nhwc", "from_nhwc", "softmax_rows",
+EMULATED = ("conv_gemm", "conv_gemm_dual", "attention", "groupnorm", "layernorm", "upsample2x", "to_nhwc", "from_nhwc", "softmax_rows",
             "gaussian_sample", "add_f16", "add_int", "timestep_sinusoid", "gemv", "axpby", "unipc_step")
 
 
@@ -340,7 +348,7 @@ def cpu_sampler(sds, cfgs, prediction_type="epsilon", scheduler="ddim", split_ba
     s.scheduler = scheduler
     s.schedule = DDIMSchedule(prediction_type=prediction_type)
     s.unipc = UniPCSchedule(prediction_type=prediction_type)
-    s.use_graph, s.split_batch, s.temb_table = False, split_batch, temb_table
+    s.use_graph, s.split_batch, s.temb_table, s.dual_exchange = False, split_batch, temb_table, True
     s.ws, s.ws1 = Workspace("cpu"), Workspace("cpu")
     s._plans = {}
     return s

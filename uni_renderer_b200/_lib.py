@@ -64,7 +64,7 @@ EXPORTS = [
     "unib200_program_graph_instantiate", "unib200_program_graph_launch", "unib200_program_set_lane",
     "unib200_program_barrier",
     "unib200_program_num_ops", "unib200_program_op_info", "unib200_program_op_desc", "unib200_program_profile",
-    "unib200_conv_gemm", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
+    "unib200_conv_gemm", "unib200_conv_gemm_dual", "unib200_packed_k", "unib200_pick_bn", "unib200_debug_set_trace", "unib200_attention", "unib200_groupnorm", "unib200_layernorm",
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
     "unib200_softmax_rows", "unib200_gaussian_sample",
@@ -113,6 +113,7 @@ def load() -> C.CDLL:
     lib.unib200_program_op_desc.restype = C.c_char_p
     lib.unib200_program_profile.argtypes = [vp, vp, ci, C.POINTER(cf)]
     lib.unib200_conv_gemm.argtypes = [vp, C.POINTER(GemmDesc), vp]
+    lib.unib200_conv_gemm_dual.argtypes = [vp, C.POINTER(GemmDesc), C.POINTER(GemmDesc), vp]
     lib.unib200_packed_k.argtypes = [ci, C.POINTER(Seg)]
     lib.unib200_packed_k.restype = C.c_size_t
     lib.unib200_pick_bn.argtypes = [ci, ci]

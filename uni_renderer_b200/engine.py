@@ -561,6 +561,26 @@ class StreamNet:
         return outs, m
 
 
+def rec_exchange_site(prog, enc: StreamNet, dec: StreamNet, suffix: str, a: Act, u: Act, scale: float = 1.0):
+    """Both directions of the dual-stream residual exchange at ONE skip site (suffix "_down_blocks.{i}" / "_mid_block")
+    as ONE kernel (G = 2 grouped launch, unib200_conv_gemm_dual): the RGB decoder's input  skip_U + zc_enc(skip_A)
+    (models/controlnet.py:1754-1775 + :1078-1087,1115) and the attribute decoder's  skip_A + zc_dec(skip_U)
+    (:2446-2461,2476-2477) read the same pair of co-located tensors `a` (attribute stream) and `u` (RGB stream).
+    Returns (exchanged U, exchanged A)."""
+    oU = Act(torch.empty(a.M, a.C, device=enc.device, dtype=torch.float16), a.B, a.H, a.W, a.C)
+    oA = Act(torch.empty(a.M, a.C, device=enc.device, dtype=torch.float16), a.B, a.H, a.W, a.C)
+    gu, ga = enc.gn_plan(a.M, a.C, a.B, a.H * a.W), dec.gn_plan(a.M, a.C, a.B, a.H * a.W)
+    if gu is not None and ga is not None:          # both outputs are second sources of a decoder's concat GroupNorm
+        oU.gn, oA.gn = gu, ga
+    we, be = enc._zc(enc.zc_prefix + suffix, scale)
+    wd, bd = dec._zc(dec.zc_prefix + suffix, 1.0)
+    ops.conv_gemm_dual(
+        prog,
+        dict(segs=[(a.t, a.C, SEG_1x1)], weight=we, out=oU.t, M=a.M, N=a.C, B=a.B, bias=be, res=u.t, gn=oU.gn),
+        dict(segs=[(u.t, u.C, SEG_1x1)], weight=wd, out=oA.t, M=a.M, N=a.C, B=a.B, bias=bd, res=a.t, gn=oA.gn))
+    return oU, oA
+
+
 def pad_channels(c: int) -> int:
     """Channel padding of the tiny network inputs so a pixel row is a multiple of 16 bytes (TMA stride rule)."""
     return (c + 7) // 8 * 8

@@ -12,7 +12,7 @@ from . import _lib as L
 from ._lib import (EPI_AXPBY, EPI_GEGLU, EPI_OUT_F32, EPI_OUT_NCHW, EPI_SILU, SEG_1x1, SEG_3x3, SEG_3x3_S2,
                    SEG_3x3_S2P0, SEG_UP2x2)
 
-__all__ = ["conv_gemm", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
+__all__ = ["conv_gemm", "conv_gemm_dual", "attention", "groupnorm", "layernorm", "to_nhwc", "from_nhwc", "upsample2x",
            "timestep_sinusoid", "gemv", "axpby", "unipc_step", "add_int", "add_f16", "softmax_rows", "gaussian_sample", "Program", "Context", "pack_weight", "pack_geglu", "fold_layernorm", "rowstats_parts", "device_info",
            "SEG_1x1", "SEG_3x3", "SEG_3x3_S2", "SEG_3x3_S2P0", "SEG_UP2x2", "pack_upsample_conv", "upfold_supported", "EPI_GEGLU", "EPI_OUT_NCHW", "EPI_OUT_F32", "EPI_SILU", "EPI_AXPBY"]
 
@@ -272,7 +272,29 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
               gn: Optional[Tuple[torch.Tensor, int, int]] = None):
     """segs: (matrix [pixels, >=C] fp16, C, kind).  H = W = 0 selects the plain row-major [M, K] path.
     gn = (part fp32 [M / rows, N / gran, 2], gran, rows): also emit the GroupNorm statistics of the output."""
-    lib = L.load()
+    d, keep = _gemm_desc(segs, weight, out, M=M, N=N, B=B, H=H, W=W, bias=bias, bias_bstride=bias_bstride,
+                         bias_step=bias_step, bias_step_stride=bias_step_stride, res=res, flags=flags, splits=splits,
+                         partial=partial, axpby=axpby, axpby_step=axpby_step, aux=aux, aux_out=aux_out,
+                         axpby_first_channel=axpby_first_channel, ldc=ldc, rowstats_out=rowstats_out, ln=ln, gn=gn)
+    L.check(L.load().unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
+    if prog is not None:
+        prog.keep(*keep)
+
+
+def conv_gemm_dual(prog: Optional[Program], a: dict, b: dict):
+    """Two conv_gemm problems of identical shape (dicts of conv_gemm's arguments: segs, weight, out, M, N, B, bias, res,
+    gn) as ONE kernel launch (include/unib200.h unib200_conv_gemm_dual) -- both directions of the dual-stream exchange."""
+    da, ka = _gemm_desc(**a)
+    db, kb = _gemm_desc(**b)
+    L.check(L.load().unib200_conv_gemm_dual(_h(prog), C.byref(da), C.byref(db), _stream()), "conv_gemm_dual")
+    if prog is not None:
+        prog.keep(*ka, *kb)
+
+
+def _gemm_desc(segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_bstride=0, bias_step=None,
+               bias_step_stride=0, res=None, flags=0, splits=0, partial=None, axpby=None, axpby_step=None, aux=None,
+               aux_out=None, axpby_first_channel=0, ldc=None, rowstats_out=None, ln=None, gn=None):
+    """unib200_gemm_desc from tensors + the list of tensors a recorded program must keep alive."""
     d = L.GemmDesc()
     d.M, d.N, d.B, d.H, d.W, d.nseg = M, N, B, H, W, len(segs)
     ktot = 0
@@ -316,10 +338,8 @@ def conv_gemm(prog: Optional[Program], segs: Sequence[Tuple[torch.Tensor, int, i
         part, gran, rows = gn
         assert part.dtype == torch.float32 and part.is_contiguous() and part.numel() >= (M // rows) * (N // gran) * 2
         d.gn_part, d.gn_gran, d.gn_rows = part.data_ptr(), gran, rows
-    L.check(lib.unib200_conv_gemm(_h(prog), C.byref(d), _stream()), "conv_gemm")
-    if prog is not None:
-        prog.keep(*(s[0] for s in segs), weight, out, bias, bias_step, res, partial, axpby, axpby_step, aux, aux_out, rowstats_out,
-                  *ln_keep, gn[0] if gn is not None else None)
+    return d, (*(s[0] for s in segs), weight, out, bias, bias_step, res, partial, axpby, axpby_step, aux, aux_out,
+               rowstats_out, *ln_keep, gn[0] if gn is not None else None)
 
 
 def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *,

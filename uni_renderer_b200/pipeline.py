@@ -27,7 +27,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from .engine import Act, NetConfig, StreamNet, Workspace, pad_channels
+from .engine import Act, NetConfig, StreamNet, Workspace, pad_channels, rec_exchange_site
 from .scheduler import DDIMSchedule, UniPCSchedule
 
 SCHEDULERS = ("ddim", "unipc")
@@ -96,6 +96,7 @@ class DualStreamSampler:
         self.split_batch = split_batch
         import os
         self.temb_table = os.environ.get("UNIB200_TEMB_TABLE", "1") != "0"
+        self.dual_exchange = os.environ.get("UNIB200_DUAL_EXCHANGE", "1") != "0"
         self.ws = Workspace(self.device)          # lane 0 (RGB stream)
         self.ws1 = Workspace(self.device)         # lane 1 (attribute stream): lanes run concurrently, no shared scratch
         self._plans: Dict[Tuple, _Plan] = {}
@@ -216,9 +217,23 @@ class DualStreamSampler:
             tpU = temb(unet, step, b["t_img"])
             skU, midU = unet.rec_encoder(step, ws, x_img, tpU, kvU, L)
             step.barrier()
-            dskU, dmidU = enc.rec_exchange(step, ws, skA, midA, skU, midU)      # skipU + zc_enc(skipA)
+            if self.dual_exchange:
+                # both directions of a skip site in ONE kernel (G = 2 grouped launch): 13 launches instead of 26; the
+                # sites alternate between the two lanes, deepest first (the decoders consume them in that order)
+                n_sk = len(skA)
+                outU, outA = {}, {}
+                for n_, i in enumerate(range(n_sk, -1, -1)):
+                    step.lane(n_ & 1)
+                    a_, u_, sfx = (midA, midU, "_mid_block") if i == n_sk else (skA[i], skU[i], f"_down_blocks.{i}")
+                    outU[i], outA[i] = rec_exchange_site(step, enc, dec, sfx, a_, u_)
+                step.barrier()
+                dskU, dmidU = [outU[i] for i in range(n_sk)], outU[n_sk]
+                dskA, dmidA = [outA[i] for i in range(n_sk)], outA[n_sk]
+            else:
+                dskU, dmidU = enc.rec_exchange(step, ws, skA, midA, skU, midU)      # skipU + zc_enc(skipA)
+                step.lane(1)
+                dskA, dmidA = dec.rec_exchange(step, ws1, skU, midU, skA, midA)     # skipA + zc_dec(skipU_raw)
             step.lane(1)
-            dskA, dmidA = dec.rec_exchange(step, ws1, skU, midU, skA, midA)     # skipA + zc_dec(skipU_raw)
             if mode == "joint":
                 decode(dec, ws1, dmidA, dskA, tpD, kvD, ax_attr, "attr")
                 step.lane(0)
