@@ -233,6 +233,33 @@ int unib200_softmax_rows(unib200_program* prog, void* s_fp16, int rows, int n, i
 int unib200_gaussian_sample(unib200_program* prog, const float* moments, const float* noise, float* out, int B, int C,
                             int HW, float scale, void* stream);
 
+/* ---- training, first slice (train/train.py:1324-1427 runs the three modules forward AND backward)
+ * Data gradients of the conv / linear family need no kernel of their own: dX = conv(dY, W') is unib200_conv_gemm with the
+ * weights repacked (taps flipped, in / out channels swapped).  New here: the WEIGHT gradient (pixels are the contraction
+ * dimension: both operands are read MN-major straight from their NHWC tensors), the bias gradient, and the backward of
+ * GroupNorm(+SiLU). */
+typedef struct {
+  const void* x; int C; int ldx;      /* forward input of the conv, fp16 NHWC [M, ldx] (first C channels)                 */
+  const void* dy; int N; int lddy;    /* gradient w.r.t. the conv output, fp16 [M, lddy]                                  */
+  int M, B, H, W;                     /* M = B*H*W; H = W = 0: plain [M, K] matrices (linear layer)                        */
+  int taps;                           /* 9 = 3x3 pad 1 stride 1, 1 = 1x1 / linear                                          */
+  float* dw;                          /* out: fp32 [N][taps][C] (the packed K order of the forward weights, unpadded)      */
+  float* db;                          /* out (optional): fp32 [N] = column sums of dy                                      */
+  float* partial; size_t partial_bytes;   /* fp32 workspace for pixel splits (may be NULL => one split)                    */
+} unib200_wgrad_desc;
+int unib200_conv_wgrad(unib200_program* prog, const unib200_wgrad_desc* desc, void* stream);
+typedef struct {
+  const void* x; int ldx;             /* forward input of the GroupNorm, fp16 [B*HW, ldx]                                  */
+  const void* dz; int ldz;            /* gradient w.r.t. silu(groupnorm(x)) (or groupnorm(x) when silu = 0)                */
+  void* dx; int lddx;                 /* out: gradient w.r.t. x, fp16                                                      */
+  const float* gamma; const float* beta;
+  float* dgamma; float* dbeta;        /* out: fp32 [C]                                                                     */
+  float* scratch;                     /* fp32 [2 * B * C]                                                                  */
+  int B, HW, C, groups, silu;
+  float eps;
+} unib200_gn_bwd_desc;
+int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* desc, void* stream);
+
 /* ---- step-level context -----------------------------------------------------------------
  * A context owns what one dual-stream sampler needs at run time -- recorded programs (ownership passes to it), device
  * buffers it allocated or was handed, weights uploaded into it -- so that, once a plan exists, a denoising step, a

@@ -38,6 +38,19 @@ class GemmDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("C", C.c_int), ("ldx", C.c_int), ("dy", C.c_void_p), ("N", C.c_int), ("lddy", C.c_int),
+                ("M", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("taps", C.c_int),
+                ("dw", C.c_void_p), ("db", C.c_void_p), ("partial", C.c_void_p), ("partial_bytes", C.c_size_t)]
+
+
+class GnBwdDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int), ("dz", C.c_void_p), ("ldz", C.c_int), ("dx", C.c_void_p),
+                ("lddx", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("dgamma", C.c_void_p),
+                ("dbeta", C.c_void_p), ("scratch", C.c_void_p), ("B", C.c_int), ("HW", C.c_int), ("C", C.c_int),
+                ("groups", C.c_int), ("silu", C.c_int), ("eps", C.c_float)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
@@ -68,6 +81,7 @@ EXPORTS = [
     "unib200_to_nhwc", "unib200_from_nhwc", "unib200_upsample2x", "unib200_timestep_sinusoid", "unib200_gemv",
     "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
     "unib200_softmax_rows", "unib200_gaussian_sample",
+    "unib200_conv_wgrad", "unib200_groupnorm_backward",
     "unib200_create", "unib200_destroy", "unib200_load_weight", "unib200_alloc", "unib200_bind", "unib200_buffer",
     "unib200_ctx_attach", "unib200_ctx_run", "unib200_unet_forward", "unib200_attr_enc_forward",
     "unib200_attr_dec_forward", "unib200_dual_step", "unib200_sample_loop",
@@ -133,6 +147,8 @@ def load() -> C.CDLL:
     lib.unib200_unipc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.unib200_softmax_rows.argtypes = [vp, vp, ci, ci, ci, cf, vp]
     lib.unib200_gaussian_sample.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, vp]
+    lib.unib200_conv_wgrad.argtypes = [vp, C.POINTER(WgradDesc), vp]
+    lib.unib200_groupnorm_backward.argtypes = [vp, C.POINTER(GnBwdDesc), vp]
     lib.unib200_create.argtypes = [ci, vp]
     lib.unib200_create.restype = vp
     lib.unib200_destroy.argtypes = [vp]

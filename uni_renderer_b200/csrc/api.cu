@@ -13,6 +13,7 @@
 #include "attention_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "wgrad_sm100.cuh"
 
 using namespace unib;
 
@@ -655,6 +656,100 @@ int unib200_conv_gemm_dual(unib200_program* prog, const unib200_gemm_desc* d0, c
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
   return submit(prog, std::move(op), 1, stream, "conv_gemm_dual", UNIB200_OP_GEMM, g0.flops + g1.flops, g0.bytes + g1.bytes,
                 "dual " + g0.desc);
+}
+
+int unib200_conv_wgrad(unib200_program* prog, const unib200_wgrad_desc* d, void* stream) {
+  if (!d || !d->x || !d->dy || !d->dw) return fail("conv_wgrad: null pointer");
+  if (d->M <= 0 || d->N <= 0 || d->C <= 0 || (d->taps != 1 && d->taps != 9)) return fail("conv_wgrad: bad M / N / C / taps");
+  if (d->ldx % 8 || d->lddy % 8 || d->ldx < d->C || d->lddy < d->N) return fail("conv_wgrad: leading dims must be multiples of 8");
+  const bool linear = (d->H == 0 || d->W == 0);
+  if (linear && d->taps != 1) return fail("conv_wgrad: plain matrices only support taps = 1");
+  WgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  std::string why;
+  int bw = 128, bh = 1, bb = 1;
+  uint64_t Wd = d->M, Hd = 1, Bd = 1;
+  if (linear) {
+    p.w_shift = 30;
+    p.h_shift = 0;
+  } else {
+    if (d->B * d->H * d->W != d->M) return fail("conv_wgrad: M != B*H*W");
+    auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+    if (!pow2(d->W) || !pow2(d->H)) return fail("conv_wgrad: H and W must be powers of two");
+    auto ilog2 = [](int x) { int s = 0; while ((1 << s) < x) ++s; return s; };
+    p.w_shift = ilog2(d->W);
+    p.h_shift = ilog2(d->H);
+    bw = d->W < 128 ? d->W : 128;
+    bh = 128 / bw;
+    if (bh > d->H) bh = d->H;
+    bb = 128 / (bw * bh);
+    Wd = d->W; Hd = d->H; Bd = d->B;
+  }
+  auto mk = [&](CUtensorMap* m, const void* base, int Cn, int ld) {
+    const uint64_t pix = static_cast<uint64_t>(ld) * 2;
+    const uint64_t dims[4] = {static_cast<uint64_t>(Cn), Wd, Hd, Bd};
+    const uint64_t st[3] = {pix, pix * Wd, pix * Wd * Hd};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+    return encode_map(m, base, 4, dims, st, box, &why);
+  };
+  if (!mk(&maps.dy, d->dy, d->N, d->lddy)) return fail("conv_wgrad dY map: " + why);
+  if (!mk(&maps.x, d->x, d->C, d->ldx)) return fail("conv_wgrad X map: " + why);
+  p.M = d->M; p.N = d->N; p.C = d->C; p.taps = d->taps;
+  p.m_blocks = (d->M + 127) / 128;
+  p.n_tiles = (d->N + 127) / 128;
+  p.c_tiles = (d->C + wgrad_cin_tile() - 1) / wgrad_cin_tile();
+  p.dw = d->dw;
+  p.partial = d->partial;
+  const int tiles = p.n_tiles * p.c_tiles * p.taps;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;
+  if (splits > p.m_blocks) splits = p.m_blocks;
+  const size_t slab = static_cast<size_t>(d->N) * d->taps * d->C * sizeof(float);
+  if (!d->partial) splits = 1;
+  else if (static_cast<size_t>(splits) * slab > d->partial_bytes) splits = static_cast<int>(d->partial_bytes / slab);
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  const __half* dy = static_cast<const __half*>(d->dy);
+  float* db = d->db;
+  const int lddy = d->lddy, M = d->M, N = d->N;
+  if (db && N % 8) return fail("conv_wgrad: the bias gradient needs N to be a multiple of 8");
+  Op op = [maps, p, dy, db, lddy, M, N](cudaStream_t s) {
+    cudaError_t e = launch_wgrad(maps, p, s);
+    if (e == cudaSuccess && db) e = launch_colsum(dy, lddy, M, N, db, s);
+    return e;
+  };
+  const double flops = 2.0 * d->M * d->N * d->C * d->taps;
+  return submit(prog, std::move(op), (splits > 1 ? 2 : 1) + (db ? 1 : 0), stream, "conv_wgrad", UNIB200_OP_GEMM, flops,
+                2.0 * d->M * (d->N + d->C) + 4.0 * d->N * d->taps * d->C,
+                "wgrad M=" + std::to_string(d->M) + " N=" + std::to_string(d->N) + " C=" + std::to_string(d->C) + " taps=" +
+                    std::to_string(d->taps) + " splits=" + std::to_string(splits));
+}
+
+int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* d, void* stream) {
+  if (!d || !d->x || !d->dz || !d->dx || !d->gamma || !d->beta || !d->dgamma || !d->dbeta || !d->scratch)
+    return fail("groupnorm_backward: null pointer");
+  if (d->groups <= 0 || d->C % d->groups || d->C / d->groups > 256 || d->B <= 0 || d->HW <= 0)
+    return fail("groupnorm_backward: unsupported channel / group configuration");
+  GnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = static_cast<const __half*>(d->x); p.ldx = d->ldx;
+  p.dz = static_cast<const __half*>(d->dz); p.ldz = d->ldz;
+  p.dx = static_cast<__half*>(d->dx); p.lddx = d->lddx;
+  p.gamma = d->gamma; p.beta = d->beta;
+  p.dgamma_part = d->scratch;
+  p.dbeta_part = d->scratch + static_cast<size_t>(d->B) * d->C;
+  p.HW = d->HW; p.C = d->C; p.G = d->groups; p.silu = d->silu; p.eps = d->eps;
+  const int B = d->B, Cn = d->C;
+  float *dg = d->dgamma, *dbt = d->dbeta;
+  Op op = [p, B, Cn, dg, dbt](cudaStream_t s) {
+    cudaError_t e = launch_gn_backward(p, B, s);
+    if (e == cudaSuccess) e = launch_sum_slabs(p.dgamma_part, dg, Cn, B, s);
+    if (e == cudaSuccess) e = launch_sum_slabs(p.dbeta_part, dbt, Cn, B, s);
+    return e;
+  };
+  return submit(prog, std::move(op), 3, stream, "groupnorm_backward", UNIB200_OP_GROUPNORM, 0.0,
+                6.0 * static_cast<double>(d->B) * d->HW * d->C);
 }
 
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* stream) {

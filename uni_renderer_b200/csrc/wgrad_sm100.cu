@@ -1,0 +1,323 @@
+// Weight-gradient kernel of the implicit-GEMM convolution / linear family for sm_100a (training):
+//
+//   dW[n, tap, c] = sum over pixels m of  dY[m, n] * X[m (+) tap, c]
+//
+// i.e. D = dY^T . Xs with the PIXELS as the contraction dimension.  Both operands live in HBM as NHWC matrices
+// [pixel][channel], so for the tensor core both are "MN-major" (the contiguous dimension is M / N, not K): the same
+// TMA boxes the forward kernel uses for its A operand ({64 channels, 128 pixels}, shifted by the tap for X, zero fill at
+// the image border) land in shared memory as [128 pixel rows x 128 B] tiles, and tcgen05.mma reads them through
+// MN-major SWIZZLE_128B descriptors with the transpose bits of the instruction descriptor set -- no transpose pass.
+// One CTA = one (Cout tile of 128, Cin tile of BN, tap, pixel split): it walks its pixel blocks through a 3-stage ring
+// and keeps the 128 x BN fp32 accumulator in TMEM; the epilogue stores it (fp32) either straight into dW or into the
+// split's partial slab, summed by wgrad_reduce_kernel in a fixed order (no atomics: reruns are bit-exact).
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "wgrad_sm100.cuh"
+
+namespace unib {
+
+constexpr int kWgBN = 128;                       // Cin tile
+constexpr int kWgStages = 3;
+constexpr int kWgABytes = 2 * 128 * 128;         // 128 pixels x 128 Cout channels = two [128 x 64] boxes
+constexpr int kWgBBytes = (kWgBN / 64) * 128 * 128;
+constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
+constexpr int kWgBarOff = kWgStages * kWgStageBytes;
+constexpr int kWgSmemBytes = kWgBarOff + 128 + 1024;
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tcgen05_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + kWgBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgStages);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kWgBarOff + 8 * (2 * kWgStages + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item: blockIdx.x = ((nt * c_tiles) + ct) * taps + tap ; blockIdx.y = pixel split
+  const int tap = blockIdx.x % p.taps;
+  const int ct = (blockIdx.x / p.taps) % p.c_tiles;
+  const int nt = blockIdx.x / (p.taps * p.c_tiles);
+  const int split = blockIdx.y;
+  const int kb0 = static_cast<int>((static_cast<long long>(split) * p.m_blocks) / p.splits);
+  const int kb1 = static_cast<int>((static_cast<long long>(split + 1) * p.m_blocks) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.dy);
+    tma_prefetch_desc(&maps.x);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kWgBN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer: per pixel block, dY [128 px x 128 Cout] and X shifted by the tap [128 px x BN Cin]
+    int dw = 0, dh = 0;
+    if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+    uint32_t stage = 0, ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int p0 = kb * 128;                                    // first pixel of the block
+      const int w0 = p0 & ((1 << p.w_shift) - 1);
+      const int h0 = (p0 >> p.w_shift) & ((1 << p.h_shift) - 1);
+      const int b0 = p0 >> (p.w_shift + p.h_shift);
+      mbar_wait(empty_bar(stage), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t a_dst = base + stage * kWgStageBytes;
+        mbar_arrive_expect_tx(full_bar(stage), kWgStageBytes);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d(a_dst + c * 16384, &maps.dy, full_bar(stage), nt * 128 + c * 64, w0, h0, b0);
+#pragma unroll
+        for (int c = 0; c < kWgBN / 64; ++c)
+          tma_load_4d(a_dst + kWgABytes + c * 16384, &maps.x, full_bar(stage), ct * kWgBN + c * 64, w0 + dw, h0 + dh, b0);
+      }
+      if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: D[128 Cout x BN Cin] += dY_blk^T . X_blk, K = 128 pixels per block in steps of 16
+    constexpr uint32_t idesc = make_idesc_f16(128, kWgBN, 1, 1);    // both operands MN-major (transposed)
+    uint32_t stage = 0, ph = 0;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(full_bar(stage), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = base + stage * kWgStageBytes;
+        // MN-major SWIZZLE_128B: rows = pixels (K), 64-channel blocks 16 KB apart (LBO), 8-pixel atoms 1 KB apart (SBO)
+        const uint64_t a_desc = make_desc_mnmajor_sw128(a_addr, 16384, 1024);
+        const uint64_t b_desc = make_desc_mnmajor_sw128(a_addr + kWgABytes, 16384, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                                // 16 pixels = 2048 B further per step
+          umma_f16_ss(tmem_base, a_desc + ((k * 2048) >> 4), b_desc + ((k * 2048) >> 4), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (kb == kb1 - 1) umma_commit(done_bar);
+      }
+      if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> fp32 global (thread = one Cout row, 32 Cin columns at a time)
+    const int q = warp & 3;
+    const int n = nt * 128 + q * 32 + lane;
+    float* dst = (p.splits > 1 ? p.partial + static_cast<size_t>(split) * p.N * p.taps * p.C : p.dw) +
+                 (static_cast<size_t>(n) * p.taps + tap) * p.C + ct * kWgBN;
+    if (kb1 > kb0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < kWgBN / 32; ++j) {
+      float v[32];
+      if (kb1 > kb0) {
+        tmem_ld32(taddr + j * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (n < p.N) {
+        const int c0 = ct * kWgBN + j * 32;
+        if (c0 + 32 <= p.C && (p.C & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.C) dst[j * 32 + i] = v[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kWgBN);
+  }
+}
+
+// dW = sum over splits of the partial slabs, fixed order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* partial, float* dw, long long n, int splits) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[static_cast<size_t>(s) * n + i];
+    dw[i] = a;
+  }
+}
+
+// db[n] = sum over rows of dY[m, n]: one block per 8-channel vector column group, rows strided over threads, fixed-order
+// tree in shared memory
+__global__ void __launch_bounds__(256) colsum_kernel(const __half* dy, int ld, int M, int N, float* db) {
+  __shared__ float red[256][8];
+  const int c0 = blockIdx.x * 8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(m) * ld + c0);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s[2 * j] += f.x;
+      s[2 * j + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + off][j];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8 && c0 + threadIdx.x < N) db[c0 + threadIdx.x] = red[0][threadIdx.x];
+}
+
+cudaError_t launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(p.n_tiles * p.c_tiles * p.taps, p.splits);
+  wgrad_tcgen05_kernel<<<grid, 192, kWgSmemBytes, stream>>>(maps, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (p.splits > 1) {
+    const long long n = static_cast<long long>(p.N) * p.taps * p.C;
+    int blocks = static_cast<int>((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, p.dw, n, p.splits);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+cudaError_t launch_colsum(const __half* dy, int ld, int M, int N, float* db, cudaStream_t stream) {
+  if (N % 8) return cudaErrorInvalidValue;
+  colsum_kernel<<<N / 8, 256, 0, stream>>>(dy, ld, M, N, db);
+  return cudaGetLastError();
+}
+
+int wgrad_cin_tile() { return kWgBN; }
+
+cudaError_t launch_sum_slabs(const float* partial, float* out, long long n, int slabs, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(partial, out, n, slabs);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) backward, one CTA per (group, sample).  Forward: xhat = (x - mu) * rstd, y = gamma * xhat + beta,
+// z = silu(y).  Given dz:  dy = dz * silu'(y);  dgamma_c = sum dy * xhat, dbeta_c = sum dy (per-sample partials);
+// dxhat = dy * gamma;  dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) over the group's elements.
+// Three sweeps over the group's [HW x cpg] slab (statistics, sums, dx); thread = (channel j, row lane) so the
+// per-channel sums need no atomics and every reduction runs in a fixed order.  Correctness-first (the slab is re-read
+// from L2); the forward's fused-statistics machinery would serve the first sweep the same way.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) gn_backward_kernel(GnBwdParams p) {
+  __shared__ float red[8];
+  extern __shared__ float chan[];                 // [2][R][cpg] per-channel partials of the row lanes
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = p.C / p.G;
+  const int R = blockDim.x / cpg;                 // row lanes (threads beyond R * cpg idle)
+  const int j = threadIdx.x % cpg, rl = threadIdx.x / cpg;
+  const bool active = rl < R;
+  const int c = g * cpg + j;
+  const __half* x = p.x + static_cast<size_t>(b) * p.HW * p.ldx + c;
+  const __half* dz = p.dz + static_cast<size_t>(b) * p.HW * p.ldz + c;
+  const float n_inv = 1.0f / (static_cast<float>(cpg) * p.HW);
+  float s = 0.f, ss = 0.f;
+  if (active)
+    for (int r = rl; r < p.HW; r += R) {
+      const float v = __half2float(x[static_cast<size_t>(r) * p.ldx]);
+      s += v;
+      ss += v * v;
+    }
+  const float mu = block_sum_256(s, red) * n_inv;
+  const float var = fmaxf(block_sum_256(ss, red) * n_inv - mu * mu, 0.f);
+  const float rstd = rsqrtf(var + p.eps);
+  const float ga = active ? p.gamma[c] : 0.f, be = active ? p.beta[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f, dg = 0.f, db = 0.f;
+  if (active)
+    for (int r = rl; r < p.HW; r += R) {
+      const float xh = (__half2float(x[static_cast<size_t>(r) * p.ldx]) - mu) * rstd;
+      float dy = __half2float(dz[static_cast<size_t>(r) * p.ldz]);
+      if (p.silu) {
+        const float y = ga * xh + be;
+        const float sg = 1.0f / (1.0f + __expf(-y));
+        dy *= sg * (1.0f + y * (1.0f - sg));
+      }
+      dg += dy * xh;
+      db += dy;
+      const float dxh = dy * ga;
+      s1 += dxh;
+      s2 += dxh * xh;
+    }
+  const float m1 = block_sum_256(s1, red) * n_inv;
+  const float m2 = block_sum_256(s2, red) * n_inv;
+  if (active) {
+    chan[rl * cpg + j] = dg;
+    chan[(R + rl) * cpg + j] = db;
+  }
+  __syncthreads();
+  if (threadIdx.x < cpg) {
+    float a = 0.f, bb = 0.f;
+    for (int r = 0; r < R; ++r) { a += chan[r * cpg + threadIdx.x]; bb += chan[(R + r) * cpg + threadIdx.x]; }
+    p.dgamma_part[static_cast<size_t>(b) * p.C + g * cpg + threadIdx.x] = a;
+    p.dbeta_part[static_cast<size_t>(b) * p.C + g * cpg + threadIdx.x] = bb;
+  }
+  if (active) {
+    __half* dx = p.dx + static_cast<size_t>(b) * p.HW * p.lddx + c;
+    for (int r = rl; r < p.HW; r += R) {
+      const float xh = (__half2float(x[static_cast<size_t>(r) * p.ldx]) - mu) * rstd;
+      float dy = __half2float(dz[static_cast<size_t>(r) * p.ldz]);
+      if (p.silu) {
+        const float y = ga * xh + be;
+        const float sg = 1.0f / (1.0f + __expf(-y));
+        dy *= sg * (1.0f + y * (1.0f - sg));
+      }
+      dx[static_cast<size_t>(r) * p.lddx] = __float2half_rn(rstd * (dy * ga - m1 - xh * m2));
+    }
+  }
+}
+
+cudaError_t launch_gn_backward(const GnBwdParams& p, int B, cudaStream_t stream) {
+  if (p.C % p.G || p.C / p.G > 256) return cudaErrorInvalidValue;
+  const int cpg = p.C / p.G, R = 256 / cpg;
+  gn_backward_kernel<<<dim3(p.G, B), 256, 2 * R * cpg * sizeof(float), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace unib

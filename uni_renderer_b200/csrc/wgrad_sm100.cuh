@@ -1,0 +1,41 @@
+// Training-side kernels (first slice): weight gradient of the implicit-GEMM conv / linear family,
+// bias gradient, GroupNorm(+SiLU) backward.  See wgrad_sm100.cu / elementwise.cu.
+#pragma once
+#include "common.cuh"
+
+namespace unib {
+
+struct WgradParams {
+  int M, N, C;               // pixels (B*H*W or rows), output channels, input channels
+  int taps;                  // 9 (3x3, pad 1, stride 1) or 1 (1x1 / linear)
+  int w_shift, h_shift;      // log2 of the image dims (linear: 30, 0)
+  int m_blocks;              // ceil(M / 128)
+  int n_tiles, c_tiles;      // ceil(N / 128), ceil(C / 128)
+  int splits;                // pixel splits (fp32 partial slabs + fixed-order reduce when > 1)
+  float* dw;                 // fp32 [N][taps][C]
+  float* partial;            // fp32 [splits][N][taps][C]
+};
+
+struct alignas(64) WgradMaps {
+  CUtensorMap dy;            // 4-D {N, W, H, B}, box {64, bw, bh, bb}
+  CUtensorMap x;             // 4-D {C, W, H, B}, same box (shifted by the tap at load time, zero fill outside)
+};
+
+cudaError_t launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t stream);
+cudaError_t launch_colsum(const __half* dy, int ld, int M, int N, float* db, cudaStream_t stream);
+int wgrad_cin_tile();
+
+struct GnBwdParams {
+  const __half* x; int ldx;      // forward input [B*HW, C]
+  const __half* dz; int ldz;     // gradient w.r.t. the (SiLU'd) output [B*HW, C]
+  __half* dx; int lddx;          // gradient w.r.t. x
+  const float* gamma; const float* beta;
+  float* dgamma_part;            // [B][C] per-sample partials (summed over B by the caller, fixed order)
+  float* dbeta_part;             // [B][C]
+  int HW, C, G, silu;
+  float eps;
+};
+cudaError_t launch_gn_backward(const GnBwdParams& p, int B, cudaStream_t stream);
+cudaError_t launch_sum_slabs(const float* partial, float* out, long long n, int slabs, cudaStream_t stream);
+
+}  // namespace unib
