@@ -259,6 +259,9 @@ typedef struct {
   float eps;
 } unib200_gn_bwd_desc;
 int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* desc, void* stream);
+/* out[n] = sum over the M rows of the fp16 matrix x [M, ld] (first N columns, N % 8 == 0), fp32, fixed order: bias
+ * gradients, and the gradient of a per-sample broadcast add (the time-embedding add of ResnetBlock2D). */
+int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, float* out, void* stream);
 
 /* ---- step-level context -----------------------------------------------------------------
  * A context owns what one dual-stream sampler needs at run time -- recorded programs (ownership passes to it), device

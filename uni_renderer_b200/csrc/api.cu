@@ -726,6 +726,13 @@ int unib200_conv_wgrad(unib200_program* prog, const unib200_wgrad_desc* d, void*
                     std::to_string(d->taps) + " splits=" + std::to_string(splits));
 }
 
+int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, float* out, void* stream) {
+  if (!x || !out || M <= 0 || N <= 0 || N % 8 || ld % 8 || ld < N) return fail("colsum: bad arguments (N and ld multiples of 8)");
+  const __half* xp = static_cast<const __half*>(x);
+  Op op = [=](cudaStream_t s) { return launch_colsum(xp, ld, M, N, out, s); };
+  return submit(prog, std::move(op), 1, stream, "colsum");
+}
+
 int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* d, void* stream) {
   if (!d || !d->x || !d->dz || !d->dx || !d->gamma || !d->beta || !d->dgamma || !d->dbeta || !d->scratch)
     return fail("groupnorm_backward: null pointer");

@@ -1,0 +1,173 @@
+"""Training slice (first row of the backward): forward AND backward of a ResnetBlock2D on the
+B200 kernels -- the block the three networks are mostly made of (22 per stream) and that activation checkpointing
+re-runs (models/unet_2d_blocks.py:1172-1197); train/train.py:1324-1427 runs the modules forward, takes an MSE loss and
+calls `accelerator.backward`.
+
+What maps to what (per conv / norm of the block):
+  dX  of a conv   = the SAME implicit-GEMM forward kernel (unib200_conv_gemm) on dY with the weights repacked
+                    (3x3 taps flipped, in / out channels swapped) -- `dgrad_weight`
+  dW  of a conv   = unib200_conv_wgrad: pixels are the contraction dimension, both operands read MN-major from their NHWC
+                    tensors by tcgen05 (csrc/wgrad_sm100.cu);  db = column sums of dY
+  GroupNorm+SiLU  = unib200_groupnorm_backward (dx, dgamma, dbeta)
+  time embedding  = d(time_emb_proj output)[b, c] = sum over pixels of dh1 -- the same column-sum kernel per sample
+
+Scope of this slice: ResnetBlock2D (with or without the 1x1 shortcut) in fp16 storage / fp32 accumulation, gradients
+w.r.t. the input, the projected time embedding and every parameter, checked against torch autograd of the oracle
+(tests/test_train_gpu.py).  NOT yet built: attention / LayerNorm / GEGLU backward, the optimizer step, bucketed gradient
+all-reduce -- the rest of row 8f-3.  No CPU fallback: everything below launches libunib200.so kernels."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .ops import SEG_1x1, SEG_3x3
+
+
+def dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """Packed weights of the data-gradient convolution: dX = conv(dY, W') with W'[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx]
+    (3x3, pad 1, stride 1) or W'[ci, co] = W[co, ci] (1x1 / linear)."""
+    w = w.detach().float()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    wt = w.permute(1, 0, 2, 3).flip(2, 3).contiguous()
+    return ops.pack_weight([(wt, SEG_3x3 if w.shape[-1] == 3 else SEG_1x1)])
+
+
+def conv_wgrad(x: torch.Tensor, C_in: int, dy: torch.Tensor, N: int, *, B: int, H: int, W: int, taps: int,
+               partial: Optional[torch.Tensor] = None, want_bias: bool = True):
+    """(dW fp32 [N, C_in, k, k], db fp32 [N] | None) of a stride-1 conv (taps 9: 3x3 pad 1; taps 1: 1x1 / linear with
+    H = W = 0) from its forward input x [M, >= C_in] and the output gradient dy [M, >= N], both fp16 NHWC matrices."""
+    lib = L.load()
+    M = x.shape[0]
+    dw = torch.empty(N, taps, C_in, device=x.device, dtype=torch.float32)
+    db = torch.empty(N, device=x.device, dtype=torch.float32) if want_bias else None
+    d = L.WgradDesc()
+    d.x, d.C, d.ldx = x.data_ptr(), C_in, x.stride(0)
+    d.dy, d.N, d.lddy = dy.data_ptr(), N, dy.stride(0)
+    d.M, d.B, d.H, d.W, d.taps = M, B, H, W, taps
+    d.dw, d.db = dw.data_ptr(), db.data_ptr() if db is not None else None
+    if partial is not None:
+        d.partial, d.partial_bytes = partial.data_ptr(), partial.numel() * 4
+    L.check(lib.unib200_conv_wgrad(None, C.byref(d), torch.cuda.current_stream().cuda_stream), "conv_wgrad")
+    k = 3 if taps == 9 else 1
+    return dw.reshape(N, k, k, C_in).permute(0, 3, 1, 2).contiguous(), db
+
+
+def colsum(x: torch.Tensor, N: int) -> torch.Tensor:
+    """fp32 [N] column sums of the fp16 matrix x [M, >= N] (bias gradients; per-sample time-embedding gradients)."""
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    L.check(L.load().unib200_colsum(None, x.data_ptr(), x.stride(0), x.shape[0], N, out.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream), "colsum")
+    return out
+
+
+def groupnorm_backward(x: torch.Tensor, dz: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, B: int, HW: int,
+                       groups: int, eps: float, silu: bool):
+    """(dx fp16 [B*HW, C], dgamma fp32 [C], dbeta fp32 [C]) of z = silu(group_norm(x)) (or group_norm(x)) given dz."""
+    lib = L.load()
+    Cn = x.shape[1]
+    dx = torch.empty(B * HW, Cn, device=x.device, dtype=torch.float16)
+    dg = torch.empty(Cn, device=x.device, dtype=torch.float32)
+    dbt = torch.empty(Cn, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cn, device=x.device, dtype=torch.float32)
+    d = L.GnBwdDesc()
+    d.x, d.ldx, d.dz, d.ldz, d.dx, d.lddx = x.data_ptr(), x.stride(0), dz.data_ptr(), dz.stride(0), dx.data_ptr(), Cn
+    d.gamma, d.beta, d.dgamma, d.dbeta, d.scratch = gamma.data_ptr(), beta.data_ptr(), dg.data_ptr(), dbt.data_ptr(), scratch.data_ptr()
+    d.B, d.HW, d.C, d.groups, d.silu, d.eps = B, HW, Cn, groups, int(silu), eps
+    L.check(lib.unib200_groupnorm_backward(None, C.byref(d), torch.cuda.current_stream().cuda_stream), "groupnorm_backward")
+    return dx, dg, dbt
+
+
+class ResnetBlockTrainer:
+    """ResnetBlock2D(in, out, temb_channels, groups, eps, "default", "silu") forward + backward on the kernels.
+
+    `sd` holds the block's parameters under diffusers names (norm1, conv1, time_emb_proj, norm2, conv2[, conv_shortcut]).
+    Activations are NHWC fp16 matrices [B*H*W, C]; `temb_proj` is the already projected time embedding
+    time_emb_proj(silu(temb)) as fp32 [B, out] (its Linear belongs to the embedding MLP, not to this slice)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], groups: int = 32, eps: float = 1e-5, device="cuda"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("the training slice runs on CUDA (sm_100a) only; there is no CPU fallback")
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()       # noqa: E731
+        self.dev, self.groups, self.eps = dev, groups, eps
+        self.cin, self.cout = sd["conv1.weight"].shape[1], sd["conv1.weight"].shape[0]
+        self.g1, self.b1 = f32(sd["norm1.weight"]), f32(sd["norm1.bias"])
+        self.g2, self.b2 = f32(sd["norm2.weight"]), f32(sd["norm2.bias"])
+        self.w1 = ops.pack_weight([(sd["conv1.weight"], SEG_3x3)]).to(dev)
+        self.w2 = ops.pack_weight([(sd["conv2.weight"], SEG_3x3)]).to(dev)
+        self.w1_t = dgrad_weight(sd["conv1.weight"]).to(dev)
+        self.w2_t = dgrad_weight(sd["conv2.weight"]).to(dev)
+        self.bias1, self.bias2 = f32(sd["conv1.bias"]), f32(sd["conv2.bias"])
+        self.has_sc = "conv_shortcut.weight" in sd
+        if self.has_sc:
+            self.wsc = ops.pack_weight([(sd["conv_shortcut.weight"], SEG_1x1)]).to(dev)
+            self.wsc_t = dgrad_weight(sd["conv_shortcut.weight"]).to(dev)
+            self.bias_sc = f32(sd["conv_shortcut.bias"])
+        self.scratch = torch.empty(1 << 18, device=dev, dtype=torch.float32)
+        self.partial = torch.empty(16 << 20, device=dev, dtype=torch.float32)
+        self.saved = None
+
+    def _gn(self, x, gamma, beta, B, HW):
+        out = torch.empty_like(x)
+        ops.groupnorm(None, x, x.shape[1], None, 0, gamma, beta, out, self.scratch, B=B, HW=HW, groups=self.groups,
+                      eps=self.eps, silu=True)
+        return out
+
+    def forward(self, x: torch.Tensor, temb_proj: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+        """x: fp16 [B*H*W, cin]; temb_proj: fp32 [B, cout].  Saves what the backward needs (x, n1, h1, n2)."""
+        M = B * H * W
+        n1 = self._gn(x, self.g1, self.b1, B, H * W)
+        h1 = torch.empty(M, self.cout, device=self.dev, dtype=torch.float16)
+        bias_tab = (temb_proj + self.bias1[None]).contiguous()                 # conv1 bias + time embedding, per sample
+        ops.conv_gemm(None, [(n1, self.cin, SEG_3x3)], self.w1, h1, M=M, N=self.cout, B=B, H=H, W=W, bias=bias_tab,
+                      bias_bstride=self.cout)
+        n2 = self._gn(h1, self.g2, self.b2, B, H * W)
+        out = torch.empty(M, self.cout, device=self.dev, dtype=torch.float16)
+        if self.has_sc:
+            wcat = torch.cat([self.w2, self.wsc], 1).contiguous()              # shortcut accumulated into conv2's tile
+            ops.conv_gemm(None, [(n2, self.cout, SEG_3x3), (x, self.cin, SEG_1x1)], wcat, out, M=M, N=self.cout, B=B, H=H,
+                          W=W, bias=self.bias2 + self.bias_sc)
+        else:
+            ops.conv_gemm(None, [(n2, self.cout, SEG_3x3)], self.w2, out, M=M, N=self.cout, B=B, H=H, W=W, bias=self.bias2,
+                          res=x)
+        self.saved = (x, n1, h1, n2, B, H, W)
+        return out
+
+    def backward(self, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dout: fp16 [B*H*W, cout].  Returns the gradients: "x" (fp16 NHWC), "temb_proj" (fp32 [B, cout]) and one fp32
+        tensor per parameter under its diffusers name."""
+        x, n1, h1, n2, B, H, W = self.saved
+        M, HW = B * H * W, H * W
+        g: Dict[str, torch.Tensor] = {}
+        # conv2 (+ shortcut): weight / bias gradients, data gradient through the flipped-weight forward kernel
+        g["conv2.weight"], g["conv2.bias"] = conv_wgrad(n2, self.cout, dout, self.cout, B=B, H=H, W=W, taps=9,
+                                                        partial=self.partial)
+        dn2 = torch.empty(M, self.cout, device=self.dev, dtype=torch.float16)
+        ops.conv_gemm(None, [(dout, self.cout, SEG_3x3)], self.w2_t, dn2, M=M, N=self.cout, B=B, H=H, W=W)
+        dx_sc = dout
+        if self.has_sc:
+            g["conv_shortcut.weight"], g["conv_shortcut.bias"] = conv_wgrad(x, self.cin, dout, self.cout, B=B, H=0, W=0,
+                                                                            taps=1, partial=self.partial)
+            dx_sc = torch.empty(M, self.cin, device=self.dev, dtype=torch.float16)
+            ops.conv_gemm(None, [(dout, self.cout, SEG_1x1)], self.wsc_t, dx_sc, M=M, N=self.cin, B=B)
+        # SiLU + GroupNorm 2
+        dh1, g["norm2.weight"], g["norm2.bias"] = groupnorm_backward(h1, dn2, self.g2, self.b2, B=B, HW=HW,
+                                                                     groups=self.groups, eps=self.eps, silu=True)
+        # conv1: dW, db; the time-embedding gradient is the per-sample column sum of dh1
+        g["conv1.weight"], g["conv1.bias"] = conv_wgrad(n1, self.cin, dh1, self.cout, B=B, H=H, W=W, taps=9,
+                                                        partial=self.partial)
+        g["temb_proj"] = torch.stack([colsum(dh1[b * HW:(b + 1) * HW], self.cout) for b in range(B)], 0)
+        dn1 = torch.empty(M, self.cin, device=self.dev, dtype=torch.float16)
+        ops.conv_gemm(None, [(dh1, self.cout, SEG_3x3)], self.w1_t, dn1, M=M, N=self.cin, B=B, H=H, W=W)
+        # SiLU + GroupNorm 1, plus the shortcut / identity branch
+        dx, g["norm1.weight"], g["norm1.bias"] = groupnorm_backward(x, dn1, self.g1, self.b1, B=B, HW=HW,
+                                                                    groups=self.groups, eps=self.eps, silu=True)
+        gx = torch.empty_like(dx)
+        ops.add_f16(None, dx, dx_sc.contiguous(), gx)
+        g["x"] = gx
+        return g
