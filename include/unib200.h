@@ -263,6 +263,20 @@ int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc*
  * gradients, and the gradient of a per-sample broadcast add (the time-embedding add of ResnetBlock2D). */
 int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, float* out, void* stream);
 
+/* transformer-block backward helpers (BasicTransformerBlock: LayerNorm, GEGLU, softmax of a materialised attention) */
+/* LayerNorm backward over [rows, C] fp16: dx, and dgamma_dbeta = fp32 [2 * C] = [dgamma | dbeta]; scratch fp32
+ * [scratch_floats], at least 2 * C */
+int unib200_layernorm_backward(unib200_program* prog, const void* x, const void* dy, void* dx, const float* gamma,
+                               float* dgamma_dbeta, float* scratch, size_t scratch_floats, int rows, int C, float eps,
+                               void* stream);
+/* GEGLU over proj fp16 [rows, 2 * inner] = [a | g]: forward out = a * gelu(g) (dout = NULL), backward out = dproj given
+ * dout [rows, inner] */
+int unib200_geglu(unib200_program* prog, const void* proj, const void* dout, void* out, int64_t rows, int inner, void* stream);
+/* dS = scale * P o (dP - rowsum(dP o P)), written over dP; fp16 [rows, ld], first n columns */
+int unib200_softmax_backward(unib200_program* prog, const void* P, void* dP, int rows, int n, int ld, float scale, void* stream);
+/* fp32 [rows, cols] contiguous -> fp16 with leading dimension ld */
+int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int64_t rows, int cols, int ld, void* stream);
+
 /* ---- step-level context -----------------------------------------------------------------
  * A context owns what one dual-stream sampler needs at run time -- recorded programs (ownership passes to it), device
  * buffers it allocated or was handed, weights uploaded into it -- so that, once a plan exists, a denoising step, a

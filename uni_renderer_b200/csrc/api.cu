@@ -733,6 +733,44 @@ int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, f
   return submit(prog, std::move(op), 1, stream, "colsum");
 }
 
+int unib200_layernorm_backward(unib200_program* prog, const void* x, const void* dy, void* dx, const float* gamma,
+                               float* dgamma_dbeta, float* scratch, size_t scratch_floats, int rows, int C, float eps,
+                               void* stream) {
+  if (!x || !dy || !dx || !gamma || !dgamma_dbeta || !scratch || rows <= 0 || C <= 0 || C > 1536)
+    return fail("layernorm_backward: bad arguments (C <= 1536)");
+  const int max_slabs = static_cast<int>(scratch_floats / (2 * static_cast<size_t>(C)));
+  if (max_slabs < 1) return fail("layernorm_backward: scratch too small");
+  const __half *xp = static_cast<const __half*>(x), *dp = static_cast<const __half*>(dy);
+  __half* dxp = static_cast<__half*>(dx);
+  Op op = [=](cudaStream_t s) {
+    return launch_layernorm_backward(xp, dp, dxp, gamma, dgamma_dbeta, nullptr, scratch, max_slabs, rows, C, eps, s);
+  };
+  return submit(prog, std::move(op), 2, stream, "layernorm_backward", UNIB200_OP_LAYERNORM, 0.0, 6.0 * rows * C);
+}
+
+int unib200_geglu(unib200_program* prog, const void* proj, const void* dout, void* out, int64_t rows, int inner, void* stream) {
+  if (!proj || !out || rows <= 0 || inner <= 0) return fail("geglu: bad arguments");
+  const __half *pp = static_cast<const __half*>(proj), *dp = static_cast<const __half*>(dout);
+  __half* op_ = static_cast<__half*>(out);
+  Op op = [=](cudaStream_t s) { return launch_geglu(pp, dp, op_, rows, inner, dp != nullptr, s); };
+  return submit(prog, std::move(op), 1, stream, "geglu");
+}
+
+int unib200_softmax_backward(unib200_program* prog, const void* P, void* dP, int rows, int n, int ld, float scale, void* stream) {
+  if (!P || !dP || rows <= 0 || n <= 0 || ld < n) return fail("softmax_backward: bad arguments");
+  const __half* pp = static_cast<const __half*>(P);
+  __half* dp = static_cast<__half*>(dP);
+  Op op = [=](cudaStream_t s) { return launch_softmax_backward(pp, dp, rows, n, ld, scale, s); };
+  return submit(prog, std::move(op), 1, stream, "softmax_backward");
+}
+
+int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int64_t rows, int cols, int ld, void* stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || ld < cols) return fail("cvt_f32_f16: bad arguments");
+  __half* dp = static_cast<__half*>(dst);
+  Op op = [=](cudaStream_t s) { return launch_cvt_f32_f16(src, dp, rows, cols, ld, s); };
+  return submit(prog, std::move(op), 1, stream, "cvt_f32_f16");
+}
+
 int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* d, void* stream) {
   if (!d || !d->x || !d->dz || !d->dx || !d->gamma || !d->beta || !d->dgamma || !d->dbeta || !d->scratch)
     return fail("groupnorm_backward: null pointer");

@@ -320,4 +320,157 @@ cudaError_t launch_gn_backward(const GnBwdParams& p, int B, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Transformer-block backward helpers (row-wise, one warp per row; correctness-first)
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm backward: xhat = (x - mu) rstd, y = gamma xhat + beta.  dx = rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),
+// dxh = dy gamma.  dgamma / dbeta: every warp adds its rows into a per-CTA slab [gridDim.x][2][C] (fixed order inside the
+// CTA: warps take rows round-robin and the 8 warp partials are summed in order), summed over CTAs by sum_slabs.
+__global__ void __launch_bounds__(256) layernorm_backward_kernel(const __half* x, const __half* dy, __half* dx,
+                                                                 const float* gamma, float* slabs, int rows, int C,
+                                                                 float eps) {
+  extern __shared__ float wsm[];                   // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* mine = wsm + warp * 2 * C;
+  for (int c = lane; c < 2 * C; c += 32) mine[c] = 0.f;
+  __syncwarp();
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const __half* xr = x + static_cast<size_t>(r) * C;
+    const __half* dr = dy + static_cast<size_t>(r) * C;
+    float s = 0.f, ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __half2float(xr[c]);
+      s += v;
+      ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const float mu = s / C;
+    const float rstd = rsqrtf(fmaxf(ss / C - mu * mu, 0.f) + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (__half2float(xr[c]) - mu) * rstd;
+      const float d = __half2float(dr[c]);
+      mine[c] += d * xh;
+      mine[C + c] += d;
+      const float dxh = d * gamma[c];
+      s1 += dxh;
+      s2 += dxh * xh;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / C, m2 = s2 / C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (__half2float(xr[c]) - mu) * rstd;
+      dx[static_cast<size_t>(r) * C + c] = __float2half_rn(rstd * (__half2float(dr[c]) * gamma[c] - m1 - xh * m2));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += wsm[w * 2 * C + c];
+    slabs[static_cast<size_t>(blockIdx.x) * 2 * C + c] = a;
+  }
+}
+
+cudaError_t launch_layernorm_backward(const __half* x, const __half* dy, __half* dx, const float* gamma, float* dgamma,
+                                      float* dbeta, float* slabs, int max_slabs, int rows, int C, float eps,
+                                      cudaStream_t stream) {
+  int blocks = (rows + 7) / 8;
+  if (blocks > max_slabs) blocks = max_slabs;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1 || static_cast<size_t>(8) * 2 * C * 4 > 96 * 1024) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layernorm_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  layernorm_backward_kernel<<<blocks, 256, 8 * 2 * C * sizeof(float), stream>>>(x, dy, dx, gamma, slabs, rows, C, eps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // slabs are [blocks][2][C]: dgamma = sum over blocks of row 0, dbeta of row 1 -> sum the [2C] vectors, then split
+  e = launch_sum_slabs(slabs, dgamma, 2 * C, blocks, stream);      // dgamma buffer must hold 2*C floats: [dgamma | dbeta]
+  (void)dbeta;
+  return e;
+}
+
+// GEGLU: h = a * gelu(g) with [a | g] = proj[:, :inner | inner:]  (diffusers GEGLU, exact erf GELU)
+__global__ void __launch_bounds__(256) geglu_forward_kernel(const __half* proj, __half* out, long long rows, int inner) {
+  const long long n = rows * inner;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / inner;
+    const int c = static_cast<int>(i - r * inner);
+    const float a = __half2float(proj[r * 2 * inner + c]), g = __half2float(proj[r * 2 * inner + inner + c]);
+    out[i] = __float2half_rn(a * 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)));
+  }
+}
+__global__ void __launch_bounds__(256) geglu_backward_kernel(const __half* proj, const __half* dout, __half* dproj,
+                                                             long long rows, int inner) {
+  const long long n = rows * inner;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / inner;
+    const int c = static_cast<int>(i - r * inner);
+    const float a = __half2float(proj[r * 2 * inner + c]), g = __half2float(proj[r * 2 * inner + inner + c]);
+    const float d = __half2float(dout[i]);
+    const float cdf = 0.5f * (1.0f + erff(g * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * g * g);
+    dproj[r * 2 * inner + c] = __float2half_rn(d * g * cdf);                       // d/da = gelu(g)
+    dproj[r * 2 * inner + inner + c] = __float2half_rn(d * a * (cdf + g * pdf));    // d/dg = a * gelu'(g)
+  }
+}
+cudaError_t launch_geglu(const __half* proj, const __half* dout, __half* out, long long rows, int inner, int backward,
+                         cudaStream_t stream) {
+  long long n = rows * inner;
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  if (backward) geglu_backward_kernel<<<blocks, 256, 0, stream>>>(proj, dout, out, rows, inner);
+  else geglu_forward_kernel<<<blocks, 256, 0, stream>>>(proj, out, rows, inner);
+  return cudaGetLastError();
+}
+
+// softmax backward, one warp per row: dS = scale * P o (dP - sum_j dP_j P_j), written over dP
+__global__ void __launch_bounds__(256) softmax_backward_kernel(const __half* P, __half* dP, int rows, int n, int ld,
+                                                               float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const __half* pr = P + static_cast<size_t>(r) * ld;
+    __half* dr = dP + static_cast<size_t>(r) * ld;
+    float s = 0.f;
+    for (int c = lane; c < n; c += 32) s += __half2float(pr[c]) * __half2float(dr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int c = lane; c < n; c += 32)
+      dr[c] = __float2half_rn(scale * __half2float(pr[c]) * (__half2float(dr[c]) - s));
+  }
+}
+cudaError_t launch_softmax_backward(const __half* P, __half* dP, int rows, int n, int ld, float scale, cudaStream_t stream) {
+  int blocks = (rows + 7) / 8;
+  if (blocks > 1184) blocks = 1184;
+  softmax_backward_kernel<<<blocks, 256, 0, stream>>>(P, dP, rows, n, ld, scale);
+  return cudaGetLastError();
+}
+
+// fp32 [rows, cols] (contiguous) -> fp16 matrix with leading dimension ld (a column slice of a wider gradient matrix)
+__global__ void __launch_bounds__(256) cvt_f32_f16_kernel(const float* src, __half* dst, long long rows, int cols, int ld) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    dst[r * ld + (i - r * cols)] = __float2half_rn(src[i]);
+  }
+}
+cudaError_t launch_cvt_f32_f16(const float* src, __half* dst, long long rows, int cols, int ld, cudaStream_t stream) {
+  long long n = rows * cols;
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  cvt_f32_f16_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(src, dst, rows, cols, ld);
+  return cudaGetLastError();
+}
+
 }  // namespace unib

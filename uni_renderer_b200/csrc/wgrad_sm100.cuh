@@ -37,5 +37,13 @@ struct GnBwdParams {
 };
 cudaError_t launch_gn_backward(const GnBwdParams& p, int B, cudaStream_t stream);
 cudaError_t launch_sum_slabs(const float* partial, float* out, long long n, int slabs, cudaStream_t stream);
+// dgamma must hold 2 * C floats: on return [dgamma | dbeta]; slabs: fp32 [max_slabs][2][C] scratch
+cudaError_t launch_layernorm_backward(const __half* x, const __half* dy, __half* dx, const float* gamma, float* dgamma,
+                                      float* dbeta, float* slabs, int max_slabs, int rows, int C, float eps,
+                                      cudaStream_t stream);
+cudaError_t launch_geglu(const __half* proj, const __half* dout, __half* out, long long rows, int inner, int backward,
+                         cudaStream_t stream);
+cudaError_t launch_softmax_backward(const __half* P, __half* dP, int rows, int n, int ld, float scale, cudaStream_t stream);
+cudaError_t launch_cvt_f32_f16(const float* src, __half* dst, long long rows, int cols, int ld, cudaStream_t stream);
 
 }  // namespace unib

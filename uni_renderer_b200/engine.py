@@ -101,6 +101,39 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def gn_granularity(channels: Sequence[int], groups: int) -> int:
+    """Micro-group size of the fused GroupNorm statistics: the gcd of every group size a tensor of a network with these
+    channel counts can meet (C / G for a single source, (C + C') / G behind a concat); 0 = fusion off."""
+    import math
+    import os
+    g = 0
+    for c in channels:
+        g = math.gcd(g, c // groups)
+    ok = g >= 2 and g % 2 == 0 and all(c % groups == 0 for c in channels) and os.environ.get("UNIB200_GN_FUSED", "1") != "0"
+    return g if ok else 0
+
+
+def plan_gn_stats(net, M: int, N: int, B: int, HW: int) -> Optional[tuple]:
+    """(part, gran, rows) for a GEMM [M, N] of `net` whose output feeds a GroupNorm, or None when the statistics cannot be
+    fused: small samples (<= 256 pixels: the single-launch cluster GroupNorm already reads them from L2 and their GEMMs
+    are split-K), GEMMs that would be split-K (too few tiles), shapes the micro-groups do not divide.
+    `net` provides gn_gran, gn_min_hw, gn_force, device and a cached _sms."""
+    if not net.gn_gran or HW % 32 or M != B * HW or (HW <= net.gn_min_hw and not net.gn_force):
+        return None
+    gran = net.gn_gran
+    bn = ops.pick_bn(N)
+    if N % gran or bn % gran or N % 32:
+        return None
+    if net._sms is None:
+        net._sms = ops.device_info()[0] if net.device.type == "cuda" else 148
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    if tiles * 2 <= net._sms and not net.gn_force:     # csrc/api.cu would pick split-K (fp32 partials, no fused epilogue)
+        return None
+    rows = 128 if HW % 128 == 0 else (64 if HW % 64 == 0 else 32)
+    part = torch.empty(M // rows, N // gran, 2, device=net.device, dtype=torch.float32)
+    return (part, gran, rows)
+
+
 class StreamNet:
     """Packed weights of one network ("unet" | "attr_enc" | "attr_dec") + the recorders for its sub-graphs."""
 
@@ -113,13 +146,8 @@ class StreamNet:
         self._pack(sd)
         # GroupNorm statistics fused into the producing GEMMs' epilogues: micro-groups of `gn_gran` channels, the gcd
         # of every group size a tensor of this network can meet (single source C / G, or (C + C') / G behind a concat)
-        import math
         import os
-        g = 0
-        for c in cfg.block_out_channels:
-            g = math.gcd(g, c // cfg.norm_num_groups)
-        self.gn_gran = g if (g >= 2 and g % 2 == 0 and all(c % cfg.norm_num_groups == 0 for c in cfg.block_out_channels)
-                             and os.environ.get("UNIB200_GN_FUSED", "1") != "0") else 0
+        self.gn_gran = gn_granularity(cfg.block_out_channels, cfg.norm_num_groups)
         self._sms = None
         self.gn_min_hw = 256
         self.gn_force = os.environ.get("UNIB200_GN_FUSED") == "force"    # tests: fuse at every size the kernels allow
@@ -292,23 +320,7 @@ class StreamNet:
         return kv
 
     def gn_plan(self, M: int, N: int, B: int, HW: int) -> Optional[tuple]:
-        """(part, gran, rows) for a GEMM [M, N] whose output feeds a GroupNorm, or None when the statistics cannot be
-        fused: small samples (<= 256 pixels: the single-launch cluster GroupNorm already reads them from L2 and their
-        GEMMs are split-K), GEMMs that would be split-K (too few tiles), shapes the micro-groups do not divide."""
-        if not self.gn_gran or HW % 32 or M != B * HW or (HW <= self.gn_min_hw and not self.gn_force):
-            return None
-        gran = self.gn_gran
-        bn = ops.pick_bn(N)
-        if N % gran or bn % gran or N % 32:
-            return None
-        if self._sms is None:
-            self._sms = ops.device_info()[0] if self.device.type == "cuda" else 148
-        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
-        if tiles * 2 <= self._sms and not self.gn_force:   # csrc/api.cu would pick split-K (fp32 partials, no fused epilogue)
-            return None
-        rows = 128 if HW % 128 == 0 else (64 if HW % 64 == 0 else 32)
-        part = torch.empty(M // rows, N // gran, 2, device=self.device, dtype=torch.float32)
-        return (part, gran, rows)
+        return plan_gn_stats(self, M, N, B, HW)
 
     def _gn(self, prog, ws, name, srcs: Sequence[Act], eps, silu) -> torch.Tensor:
         a = srcs[0]

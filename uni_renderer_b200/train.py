@@ -171,3 +171,196 @@ class ResnetBlockTrainer:
         ops.add_f16(None, dx, dx_sc.contiguous(), gx)
         g["x"] = gx
         return g
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BasicTransformerBlock
+# ---------------------------------------------------------------------------------------------------------------------
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5):
+    """(dx fp16 [rows, C], dgamma fp32 [C], dbeta fp32 [C]) of y = layer_norm(x) * gamma + beta given dy."""
+    rows, Cn = x.shape
+    dx = torch.empty_like(x)
+    gb = torch.empty(2 * Cn, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(592 * 2 * Cn, device=x.device, dtype=torch.float32)
+    L.check(L.load().unib200_layernorm_backward(None, x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr(),
+                                                gb.data_ptr(), scratch.data_ptr(), scratch.numel(), rows, Cn, eps, _stream()),
+            "layernorm_backward")
+    return dx, gb[:Cn], gb[Cn:]
+
+
+def geglu(proj: torch.Tensor, dout: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """forward (dout None): a * gelu(g) of proj = [a | g]; backward: dproj given dout."""
+    rows, two = proj.shape
+    inner = two // 2
+    out = torch.empty(rows, inner if dout is None else two, device=proj.device, dtype=torch.float16)
+    L.check(L.load().unib200_geglu(None, proj.data_ptr(), dout.data_ptr() if dout is not None else None, out.data_ptr(),
+                                   rows, inner, _stream()), "geglu")
+    return out
+
+
+class _Linear:
+    """y = x W^T (+ b) on the implicit-GEMM kernel, with the two gradient paths of the training slice."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], dev):
+        self.N, self.K = w.shape
+        self.w = ops.pack_weight([(w, SEG_1x1)]).to(dev)
+        self.w_t = dgrad_weight(w).to(dev)
+        self.b = b.detach().to(dev, torch.float32).contiguous() if b is not None else None
+
+    def fwd(self, x: torch.Tensor, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = torch.empty(x.shape[0], self.N, device=x.device, dtype=torch.float16)
+        ops.conv_gemm(None, [(x, self.K, SEG_1x1)], self.w, y, M=x.shape[0], N=self.N, bias=self.b, res=res)
+        return y
+
+    def bwd(self, x: torch.Tensor, dy: torch.Tensor, partial: torch.Tensor, need_dx: bool = True):
+        """(dx | None, dW fp32 [N, K], db fp32 [N] | None)"""
+        dw, db = conv_wgrad(x, self.K, dy, self.N, B=1, H=0, W=0, taps=1, partial=partial, want_bias=self.b is not None)
+        dx = None
+        if need_dx:
+            dx = torch.empty(x.shape[0], self.K, device=x.device, dtype=torch.float16)
+            ops.conv_gemm(None, [(dy, self.N, SEG_1x1)], self.w_t, dx, M=x.shape[0], N=self.K)
+        return dx, dw.reshape(self.N, self.K), db
+
+
+class TransformerBlockTrainer:
+    """BasicTransformerBlock (norm1 -> self-attention -> + ; norm2 -> cross-attention on the text context -> + ;
+    norm3 -> GEGLU feed-forward -> +; models/unet_2d_blocks.py:1199-1207 via Transformer2DModel) forward + backward.
+
+    The attention here is the MATERIALISED form (per sample and head: S = Q K^T, row softmax, O = P V through the GEMM
+    kernel; P is kept for the backward) -- the fused flash kernel of the inference path has no backward yet, so this is
+    a correctness-first path whose score matrices cost Nq x Nk fp16 per head.  Context length must be a multiple of 8."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], heads: int, device="cuda"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("the training slice runs on CUDA (sm_100a) only; there is no CPU fallback")
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()       # noqa: E731
+        self.dev, self.heads = dev, heads
+        self.C = sd["norm1.weight"].shape[0]
+        self.ln = [(f32(sd[f"norm{i}.weight"]), f32(sd[f"norm{i}.bias"])) for i in (1, 2, 3)]
+        self.qkv = _Linear(torch.cat([sd["attn1.to_q.weight"], sd["attn1.to_k.weight"], sd["attn1.to_v.weight"]], 0), None, dev)
+        self.out1 = _Linear(sd["attn1.to_out.0.weight"], sd["attn1.to_out.0.bias"], dev)
+        self.q2 = _Linear(sd["attn2.to_q.weight"], None, dev)
+        self.kv2 = _Linear(torch.cat([sd["attn2.to_k.weight"], sd["attn2.to_v.weight"]], 0), None, dev)
+        self.out2 = _Linear(sd["attn2.to_out.0.weight"], sd["attn2.to_out.0.bias"], dev)
+        self.ffp = _Linear(sd["ff.net.0.proj.weight"], sd["ff.net.0.proj.bias"], dev)
+        self.ff2 = _Linear(sd["ff.net.2.weight"], sd["ff.net.2.bias"], dev)
+        self.partial = torch.empty(16 << 20, device=dev, dtype=torch.float32)
+        self.saved = None
+
+    # -- helpers -------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _pack_rows(m: torch.Tensor) -> torch.Tensor:
+        """[rows, d] column slice -> contiguous [rows, ceil(d/64)*64] (zero padded): the [N, K] operand of a GEMM."""
+        rows, d = m.shape
+        dst = torch.empty(rows, (d + 63) // 64 * 64, device=m.device, dtype=torch.float16)
+        ops.to_nhwc(None, torch.as_strided(m, (1, d, rows, 1), (0, 1, m.stride(0), 1)), dst, dst.shape[1])
+        return dst
+
+    @staticmethod
+    def _pack_cols(m: torch.Tensor) -> torch.Tensor:
+        """[rows, d] column slice -> its transpose, contiguous [d, ceil(rows/64)*64] (zero padded)."""
+        rows, d = m.shape
+        dst = torch.empty(d, (rows + 63) // 64 * 64, device=m.device, dtype=torch.float16)
+        ops.to_nhwc(None, torch.as_strided(m, (1, rows, d, 1), (0, m.stride(0), 1, 1)), dst, dst.shape[1])
+        return dst
+
+    def _ln(self, x, i):
+        y = torch.empty_like(x)
+        ops.layernorm(None, x, y, *self.ln[i])
+        return y
+
+    def _attn_fwd(self, q, k, v, B, Nq, Nk):
+        """q [B*Nq, C], k / v [B*Nk, C] (column-sliced views allowed) -> (ao [B*Nq, C], P [B, heads, Nq, Nk])."""
+        d = self.C // self.heads
+        ao = torch.empty(B * Nq, self.C, device=self.dev, dtype=torch.float16)
+        P = torch.empty(B, self.heads, Nq, Nk, device=self.dev, dtype=torch.float16)
+        for b in range(B):
+            for h in range(self.heads):
+                cs = slice(h * d, (h + 1) * d)
+                qs, ks, vs = q[b * Nq:(b + 1) * Nq, cs], k[b * Nk:(b + 1) * Nk, cs], v[b * Nk:(b + 1) * Nk, cs]
+                s = P[b, h]
+                ops.conv_gemm(None, [(qs, d, SEG_1x1)], self._pack_rows(ks), s, M=Nq, N=Nk)             # S = Q K^T
+                ops.softmax_rows(None, s, rows=Nq, n=Nk, scale=d ** -0.5)
+                ops.conv_gemm(None, [(s, Nk, SEG_1x1)], self._pack_cols(vs), ao[b * Nq:(b + 1) * Nq, cs], M=Nq, N=d)
+        return ao, P
+
+    def _attn_bwd(self, dao, q, k, v, P, B, Nq, Nk, dq, dk, dv):
+        """Gradients of softmax(Q K^T d^-1/2) V into the (column-sliced) matrices dq [B*Nq, C], dk / dv [B*Nk, C]."""
+        d = self.C // self.heads
+        lib = L.load()
+        for b in range(B):
+            for h in range(self.heads):
+                cs = slice(h * d, (h + 1) * d)
+                rq, rk = slice(b * Nq, (b + 1) * Nq), slice(b * Nk, (b + 1) * Nk)
+                do, p = dao[rq, cs], P[b, h]
+                dvh, _ = conv_wgrad(do, d, p, Nk, B=1, H=0, W=0, taps=1, want_bias=False)               # dV = P^T dO
+                L.check(lib.unib200_cvt_f32_f16(None, dvh.data_ptr(), dv[rk, cs].data_ptr(), Nk, d, dv.stride(0), _stream()), "cvt")
+                dp = torch.empty(Nq, Nk, device=self.dev, dtype=torch.float16)
+                ops.conv_gemm(None, [(do, d, SEG_1x1)], self._pack_rows(v[rk, cs]), dp, M=Nq, N=Nk)    # dP = dO V^T
+                L.check(lib.unib200_softmax_backward(None, p.data_ptr(), dp.data_ptr(), Nq, Nk, Nk, d ** -0.5, _stream()),
+                        "softmax_backward")                                                            # dp is now dS
+                ops.conv_gemm(None, [(dp, Nk, SEG_1x1)], self._pack_cols(k[rk, cs]), dq[rq, cs], M=Nq, N=d)   # dQ = dS K
+                dkh, _ = conv_wgrad(q[rq, cs], d, dp, Nk, B=1, H=0, W=0, taps=1, want_bias=False)       # dK = dS^T Q
+                L.check(lib.unib200_cvt_f32_f16(None, dkh.data_ptr(), dk[rk, cs].data_ptr(), Nk, d, dk.stride(0), _stream()), "cvt")
+
+    @staticmethod
+    def _add(a, b):
+        o = torch.empty_like(a)
+        ops.add_f16(None, a, b, o)
+        return o
+
+    # -- forward / backward ----------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, ctx: torch.Tensor, B: int) -> torch.Tensor:
+        """x: fp16 [B*N, C] tokens; ctx: fp16 [B*Lc, Dctx] text context (Lc a multiple of 8)."""
+        Cn, N, Lc = self.C, x.shape[0] // B, ctx.shape[0] // B
+        n1 = self._ln(x, 0)
+        qkv = self.qkv.fwd(n1)
+        ao1, P1 = self._attn_fwd(qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:], B, N, N)
+        h2 = self.out1.fwd(ao1, res=x)
+        n2 = self._ln(h2, 1)
+        q2 = self.q2.fwd(n2)
+        kv2 = self.kv2.fwd(ctx)
+        ao2, P2 = self._attn_fwd(q2, kv2[:, :Cn], kv2[:, Cn:], B, N, Lc)
+        h3 = self.out2.fwd(ao2, res=h2)
+        n3 = self._ln(h3, 2)
+        proj = self.ffp.fwd(n3)
+        ffh = geglu(proj)
+        out = self.ff2.fwd(ffh, res=h3)
+        self.saved = (x, ctx, B, N, Lc, n1, qkv, ao1, P1, h2, n2, q2, kv2, ao2, P2, h3, n3, proj, ffh)
+        return out
+
+    def backward(self, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+        x, ctx, B, N, Lc, n1, qkv, ao1, P1, h2, n2, q2, kv2, ao2, P2, h3, n3, proj, ffh = self.saved
+        Cn, pt = self.C, self.partial
+        g: Dict[str, torch.Tensor] = {}
+        # feed-forward
+        dffh, g["ff.net.2.weight"], g["ff.net.2.bias"] = self.ff2.bwd(ffh, dout, pt)
+        dproj = geglu(proj, dffh)
+        dn3, g["ff.net.0.proj.weight"], g["ff.net.0.proj.bias"] = self.ffp.bwd(n3, dproj, pt)
+        d3, g["norm3.weight"], g["norm3.bias"] = layernorm_backward(h3, dn3, self.ln[2][0])
+        dh3 = self._add(dout, d3)
+        # cross-attention
+        dao2, g["attn2.to_out.0.weight"], g["attn2.to_out.0.bias"] = self.out2.bwd(ao2, dh3, pt)
+        dq2 = torch.empty_like(q2)
+        dkv2 = torch.empty_like(kv2)
+        self._attn_bwd(dao2, q2, kv2[:, :Cn], kv2[:, Cn:], P2, B, N, Lc, dq2, dkv2[:, :Cn], dkv2[:, Cn:])
+        dn2, g["attn2.to_q.weight"], _ = self.q2.bwd(n2, dq2, pt)
+        _, dwkv, _ = self.kv2.bwd(ctx, dkv2, pt, need_dx=False)           # the text context is an input without gradient
+        g["attn2.to_k.weight"], g["attn2.to_v.weight"] = dwkv[:Cn], dwkv[Cn:]
+        d2, g["norm2.weight"], g["norm2.bias"] = layernorm_backward(h2, dn2, self.ln[1][0])
+        dh2 = self._add(dh3, d2)
+        # self-attention
+        dao1, g["attn1.to_out.0.weight"], g["attn1.to_out.0.bias"] = self.out1.bwd(ao1, dh2, pt)
+        dqkv = torch.empty_like(qkv)
+        self._attn_bwd(dao1, qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:], P1, B, N, N, dqkv[:, :Cn], dqkv[:, Cn:2 * Cn],
+                       dqkv[:, 2 * Cn:])
+        dn1, dwqkv, _ = self.qkv.bwd(n1, dqkv, pt)
+        g["attn1.to_q.weight"], g["attn1.to_k.weight"], g["attn1.to_v.weight"] = dwqkv[:Cn], dwqkv[Cn:2 * Cn], dwqkv[2 * Cn:]
+        d1, g["norm1.weight"], g["norm1.bias"] = layernorm_backward(x, dn1, self.ln[0][0])
+        g["x"] = self._add(dh2, d1)
+        return g

@@ -30,7 +30,7 @@ from . import ops
 from .engine import Act, Workspace, _f32, pad_channels
 from .models import _Config, _NetModule
 from . import _lib as L
-from .ops import EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2P0
+from .ops import EPI_OUT_F32, EPI_OUT_NCHW, SEG_1x1, SEG_3x3, SEG_3x3_S2P0, SEG_UP2x2
 
 _DOWN = "DownEncoderBlock2D"
 _UP = "UpDecoderBlock2D"
@@ -144,6 +144,12 @@ class VaeNet:
         self._pack(convert_deprecated_attention_keys(sd))
 
     def _pack(self, sd):
+        import os
+        from .engine import gn_granularity
+        # GroupNorm statistics from the producing GEMMs' epilogues + folded upsampling, as in the UNets (engine.py)
+        self.gn_gran = gn_granularity(self.cfg.block_out_channels, self.cfg.norm_num_groups)
+        self.gn_min_hw, self.gn_force, self._sms = 256, os.environ.get("UNIB200_GN_FUSED") == "force", None
+        self.upfold = os.environ.get("UNIB200_UPFOLD", "1") != "0"
         dev, w = self.device, self.w
         need = lambda k: sd[k].detach().to(dev)    # noqa: E731
 
@@ -177,7 +183,12 @@ class VaeNet:
         conv3("encoder.conv_in")
         for i in range(nb - 1):
             conv3(f"encoder.down_blocks.{i}.downsamplers.0.conv", SEG_3x3_S2P0)
-            conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv")
+            n = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+            if self.upfold and ops.upfold_supported(sd[n + ".weight"].shape[0]):
+                w[n + ".wup"] = ops.pack_upsample_conv(need(n + ".weight"))      # nearest-2x folded into the conv
+                w[n + ".b"] = _f32(sd[n + ".bias"], dev)
+            else:
+                conv3(n)
         norm("encoder.conv_norm_out")
         wq, bq = fold_quant_conv(need("encoder.conv_out.weight"), need("encoder.conv_out.bias"),
                                  need("quant_conv.weight"), need("quant_conv.bias"))
@@ -190,10 +201,17 @@ class VaeNet:
         conv3("decoder.conv_out")
 
     # ------------------------------------------------------------------------------------------------------------
+    def gn_plan(self, M: int, N: int, B: int, HW: int):
+        from .engine import plan_gn_stats
+        return plan_gn_stats(self, M, N, B, HW)
+
     def _gn(self, prog, ws, name, x: Act, silu: bool) -> torch.Tensor:
         out = ws.get(x.M, x.C)
+        parts = None
+        if x.gn is not None and (x.C // self.cfg.norm_num_groups) % x.gn[1] == 0:
+            parts = (x.gn[0], None, x.gn[1], x.gn[2])
         ops.groupnorm(prog, x.t, x.C, None, 0, self.w[name + ".g"], self.w[name + ".bt"], out, ws.gn_scratch, B=x.B,
-                      HW=x.H * x.W, groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=silu)
+                      HW=x.H * x.W, groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=silu, parts=parts)
         return out
 
     def rec_resnet(self, prog, ws, r: str, x: Act) -> Act:
@@ -202,10 +220,11 @@ class VaeNet:
         Cout = self.w[r + ".conv1.w"].shape[0]
         n1 = self._gn(prog, ws, r + ".norm1", x, True)
         h1 = ws.get(M, Cout)
+        gn1 = self.gn_plan(M, Cout, B, H * W)
         ops.conv_gemm(prog, [(n1, x.C, SEG_3x3)], self.w[r + ".conv1.w"], h1, M=M, N=Cout, B=B, H=H, W=W,
-                      bias=self.w[r + ".conv1.b"], partial=ws.partial)
+                      bias=self.w[r + ".conv1.b"], partial=None if gn1 else ws.partial, gn=gn1)
         ws.put(n1)
-        n2 = self._gn(prog, ws, r + ".norm2", Act(h1, B, H, W, Cout), True)
+        n2 = self._gn(prog, ws, r + ".norm2", Act(h1, B, H, W, Cout, gn1), True)
         ws.put(h1)
         out = ws.get(M, Cout)
         segs, res = [(n2, Cout, SEG_3x3)], None
@@ -213,10 +232,11 @@ class VaeNet:
             segs.append((x.t, x.C, SEG_1x1))
         else:
             res = x.t
+        gn2 = self.gn_plan(M, Cout, B, H * W)
         ops.conv_gemm(prog, segs, self.w[r + ".conv2.w"], out, M=M, N=Cout, B=B, H=H, W=W, bias=self.w[r + ".conv2.b"],
-                      res=res, partial=ws.partial)
+                      res=res, partial=None if gn2 else ws.partial, gn=gn2)
         ws.put(n2)
-        return Act(out, B, H, W, Cout)
+        return Act(out, B, H, W, Cout, gn2)
 
     def rec_attention(self, prog, ws, a: str, x: Act) -> Act:
         """x + to_out(softmax(q k^T / sqrt(C)) v) with q, k, v = linear(GroupNorm(x)): one head of d = C."""
@@ -258,8 +278,9 @@ class VaeNet:
         boc = cfg.block_out_channels
         B = x_in.B
         h = Act(ws.get(x_in.M, boc[0]), B, x_in.H, x_in.W, boc[0])
+        h.gn = self.gn_plan(h.M, boc[0], B, h.H * h.W)
         ops.conv_gemm(prog, [(x_in.t, x_in.C, SEG_3x3)], self.w["encoder.conv_in.w"], h.t, M=h.M, N=boc[0], B=B,
-                      H=h.H, W=h.W, bias=self.w["encoder.conv_in.b"])
+                      H=h.H, W=h.W, bias=self.w["encoder.conv_in.b"], gn=h.gn)
         for i in range(len(boc)):
             for j in range(cfg.layers_per_block):
                 r = self.rec_resnet(prog, ws, f"encoder.down_blocks.{i}.resnets.{j}", h)
@@ -268,8 +289,9 @@ class VaeNet:
             if i != len(boc) - 1:
                 n = f"encoder.down_blocks.{i}.downsamplers.0.conv"
                 o = Act(ws.get(h.M // 4, h.C), B, h.H // 2, h.W // 2, h.C)
+                o.gn = self.gn_plan(o.M, o.C, B, o.H * o.W)
                 ops.conv_gemm(prog, [(h.t, h.C, SEG_3x3_S2P0)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=B, H=o.H, W=o.W,
-                              bias=self.w[n + ".b"], partial=ws.partial)
+                              bias=self.w[n + ".b"], partial=None if o.gn else ws.partial, gn=o.gn)
                 ws.put(h.t)
                 h = o
         m = self.rec_mid(prog, ws, "encoder.mid_block", h)
@@ -293,8 +315,9 @@ class VaeNet:
         zq = Act(torch.zeros(z_in.M, z_in.C, device=self.device, dtype=torch.float16), B, z_in.H, z_in.W, z_in.C)
         ops.to_nhwc(prog, pq, zq.t, zq.C)
         h = Act(ws.get(zq.M, rev[0]), B, zq.H, zq.W, rev[0])
+        h.gn = self.gn_plan(h.M, rev[0], B, h.H * h.W)
         ops.conv_gemm(prog, [(zq.t, zq.C, SEG_3x3)], self.w["decoder.conv_in.w"], h.t, M=h.M, N=rev[0], B=B, H=h.H,
-                      W=h.W, bias=self.w["decoder.conv_in.b"], partial=ws.partial)
+                      W=h.W, bias=self.w["decoder.conv_in.b"], partial=None if h.gn else ws.partial, gn=h.gn)
         m = self.rec_mid(prog, ws, "decoder.mid_block", h)
         ws.put(h.t)
         h = m
@@ -305,12 +328,22 @@ class VaeNet:
                 h = r
             if i != len(rev) - 1:
                 n = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                up = ws.get(h.M * 4, h.C)
-                ops.upsample2x(prog, h.t, up, B=B, H=h.H, W=h.W, Cn=h.C)
                 o = Act(ws.get(h.M * 4, h.C), B, h.H * 2, h.W * 2, h.C)
-                ops.conv_gemm(prog, [(up, h.C, SEG_3x3)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=B, H=o.H, W=o.W,
-                              bias=self.w[n + ".b"], partial=ws.partial)
-                ws.put(up, h.t)
+                if n + ".wup" in self.w:            # Upsample2D as ONE GEMM over the low-resolution tensor (SEG_UP2x2)
+                    gnu = self.gn_plan(o.M, o.C, B, o.H * o.W)
+                    if gnu is not None and (gnu[2] != 128 or (h.H * h.W) % 128):
+                        gnu = None
+                    o.gn = gnu
+                    ops.conv_gemm(prog, [(h.t, h.C, SEG_UP2x2)], self.w[n + ".wup"], o.t, M=h.M, N=4 * o.C, B=B, H=h.H,
+                                  W=h.W, bias=self.w[n + ".b"], gn=gnu)
+                    ws.put(h.t)
+                else:
+                    up = ws.get(h.M * 4, h.C)
+                    ops.upsample2x(prog, h.t, up, B=B, H=h.H, W=h.W, Cn=h.C)
+                    o.gn = self.gn_plan(o.M, o.C, B, o.H * o.W)
+                    ops.conv_gemm(prog, [(up, h.C, SEG_3x3)], self.w[n + ".w"], o.t, M=o.M, N=o.C, B=B, H=o.H, W=o.W,
+                                  bias=self.w[n + ".b"], partial=None if o.gn else ws.partial, gn=o.gn)
+                    ws.put(up, h.t)
                 h = o
         g = self._gn(prog, ws, "decoder.conv_norm_out", h, True)
         ops.conv_gemm(prog, [(g, h.C, SEG_3x3)], self.w["decoder.conv_out.w"], image_nchw, M=h.M, N=cfg.out_channels,
