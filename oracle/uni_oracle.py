@@ -117,6 +117,18 @@ def attention(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, heads: int) ->
     return _lin(sd, p + ".to_out.0", o)
 
 
+def basic_transformer_block(sd: SD, t: str, h: torch.Tensor, ehs: torch.Tensor, heads: int) -> torch.Tensor:
+    """BasicTransformerBlock on tokens [B, N, C]: LayerNorm -> self-attention -> +, LayerNorm -> cross-attention on the
+    text context -> +, LayerNorm -> GEGLU feed-forward -> + (the body of Transformer2DModel's single layer)."""
+    y = _ln(sd, t + ".norm1", h)
+    h = attention(sd, t + ".attn1", y, y, heads) + h
+    y = _ln(sd, t + ".norm2", h)
+    h = attention(sd, t + ".attn2", y, ehs, heads) + h
+    y = _ln(sd, t + ".norm3", h)
+    a, g = _lin(sd, t + ".ff.net.0.proj", y).chunk(2, dim=-1)
+    return _lin(sd, t + ".ff.net.2", a * F.gelu(g)) + h
+
+
 def transformer_2d(sd: SD, p: str, x: torch.Tensor, ehs: torch.Tensor, cfg: NetConfig) -> torch.Tensor:
     """Transformer2DModel(num_layers=1, use_linear_projection=False) + BasicTransformerBlock + GEGLU FF --
     constructed at models/unet_2d_blocks.py:721,1115,2473; called at :803,1207,2576."""
@@ -125,14 +137,7 @@ def transformer_2d(sd: SD, p: str, x: torch.Tensor, ehs: torch.Tensor, cfg: NetC
     h = _gn(sd, p + ".norm", x, cfg.norm_num_groups, 1e-6)
     h = _conv(sd, p + ".proj_in", h)
     h = h.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
-    t = p + ".transformer_blocks.0"
-    y = _ln(sd, t + ".norm1", h)
-    h = attention(sd, t + ".attn1", y, y, cfg.num_heads) + h
-    y = _ln(sd, t + ".norm2", h)
-    h = attention(sd, t + ".attn2", y, ehs, cfg.num_heads) + h
-    y = _ln(sd, t + ".norm3", h)
-    a, g = _lin(sd, t + ".ff.net.0.proj", y).chunk(2, dim=-1)
-    h = _lin(sd, t + ".ff.net.2", a * F.gelu(g)) + h
+    h = basic_transformer_block(sd, p + ".transformer_blocks.0", h, ehs, cfg.num_heads)
     h = h.reshape(b, hh, ww, c).permute(0, 3, 1, 2)
     return _conv(sd, p + ".proj_out", h) + res
 

@@ -110,3 +110,48 @@ def test_wgrad_and_dgrad_kernels_against_torch():
                           B=B, H=S if k == 3 else 0, W=S if k == 3 else 0)
             torch.cuda.synchronize()
             assert _rel(dx.float().cpu().reshape(B, S, S, cin).permute(0, 3, 1, 2), x.grad) <= 1e-3
+
+
+def _tblock(C, Dctx, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s, k=1.0: (torch.randn(*s, generator=g) * k)          # noqa: E731
+    sd = {}
+    for i in (1, 2, 3):
+        sd[f"norm{i}.weight"], sd[f"norm{i}.bias"] = 1 + 0.2 * r(C), 0.2 * r(C)
+    for a, kd in (("attn1", C), ("attn2", Dctx)):
+        sd[f"{a}.to_q.weight"] = r(C, C, k=C ** -0.5).half().float()
+        sd[f"{a}.to_k.weight"] = r(C, kd, k=kd ** -0.5).half().float()
+        sd[f"{a}.to_v.weight"] = r(C, kd, k=kd ** -0.5).half().float()
+        sd[f"{a}.to_out.0.weight"], sd[f"{a}.to_out.0.bias"] = r(C, C, k=C ** -0.5).half().float(), 0.1 * r(C)
+    sd["ff.net.0.proj.weight"], sd["ff.net.0.proj.bias"] = r(8 * C, C, k=C ** -0.5).half().float(), 0.1 * r(8 * C)
+    sd["ff.net.2.weight"], sd["ff.net.2.bias"] = r(C, 4 * C, k=(4 * C) ** -0.5).half().float(), 0.1 * r(C)
+    return sd, g
+
+
+@gpu
+@pytest.mark.parametrize("B,N,C,heads,Lc,Dctx", [(2, 256, 128, 4, 16, 48), (1, 1024, 320, 8, 80, 768)])
+def test_transformer_block_forward_backward_matches_torch_autograd(B, N, C, heads, Lc, Dctx):
+    """BasicTransformerBlock (self-attention, cross-attention on the text context, GEGLU feed-forward; each behind its
+    LayerNorm with a residual) forward + backward on the kernels vs torch autograd of oracle/uni_oracle.py::
+    basic_transformer_block on the same fp16-rounded weights."""
+    import torch
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.train import TransformerBlockTrainer
+    sd, g = _tblock(C, Dctx, 11)
+    x = torch.randn(B, N, C, generator=g).half().float()
+    ctx = torch.randn(B, Lc, Dctx, generator=g).half().float()
+    dout = (torch.randn(B, N, C, generator=g) * 0.5).half().float()
+    p = {("blk." + k): v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    out_ref = uo.basic_transformer_block(p, "blk", xr, ctx, heads)
+    (out_ref * dout).sum().backward()
+    blk = TransformerBlockTrainer(sd, heads)
+    out = blk.forward(x.reshape(B * N, C).half().cuda().contiguous(), ctx.reshape(B * Lc, Dctx).half().cuda().contiguous(), B)
+    grads = blk.backward(dout.reshape(B * N, C).half().cuda().contiguous())
+    torch.cuda.synchronize()
+    assert _rel(out.reshape(B, N, C), out_ref.detach()) <= 1.5e-3
+    assert _rel(grads["x"].reshape(B, N, C), xr.grad) <= 5e-3, _rel(grads["x"].reshape(B, N, C), xr.grad)
+    for k, v in sd.items():
+        gate = 5e-3 if (k.endswith("weight") and v.dim() == 2) else 1e-2
+        assert _rel(grads[k], p["blk." + k].grad) <= gate, (k, _rel(grads[k], p["blk." + k].grad))
