@@ -226,7 +226,9 @@ int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* o
  * The VAE's convolutions / GroupNorms / upsampling run on the entry points above.  Its one attention (mid block, a
  * single head of d = 512, diffusers Attention with residual_connection) does not fit the flash kernel's TMEM layout
  * and runs as S = Q K^T (unib200_conv_gemm with K as the [N, K] operand), this in-place row softmax
- * P = softmax(scale * S) over fp16 [rows, ld], and O = P V (unib200_conv_gemm with V^T as the [N, K] operand). */
+ * P = softmax(scale * S) over fp16 [rows, ld], and O = P V (unib200_conv_gemm with V^T as the [N, K] operand).
+ * n is the number of real columns (any value, e.g. the 77 text tokens of the training path's cross-attention); ld is a
+ * multiple of 8 covering n rounded up to 8, and the padding columns n .. round8(n) are written as zeros. */
 int unib200_softmax_rows(unib200_program* prog, void* s_fp16, int rows, int n, int ld, float scale, void* stream);
 /* DiagonalGaussianDistribution of `vae.encode(x).latent_dist`: moments fp32 [B, 2C, HW] (mean | logvar) ->
  * out fp32 [B, C, HW] = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * scale; noise == NULL: mode() * scale. */
@@ -276,6 +278,19 @@ int unib200_geglu(unib200_program* prog, const void* proj, const void* dout, voi
 int unib200_softmax_backward(unib200_program* prog, const void* P, void* dP, int rows, int n, int ld, float scale, void* stream);
 /* fp32 [rows, cols] contiguous -> fp16 with leading dimension ld */
 int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int64_t rows, int cols, int ld, void* stream);
+/* network-level training glue (uni_renderer_b200/trainer.py; train/train.py:1324-1427):
+ * SiLU on n fp16 elements (dy NULL: out = silu(x); else out = dy * silu'(x)) -- the time-embedding MLP's activations */
+int unib200_silu_f16(unib200_program* prog, const void* x, const void* dy, void* out, int64_t n, void* stream);
+/* adjoint of nearest-2x upsampling (F.interpolate backward, models/unet_2d_blocks.py:2588): dst [B,H,W,C] = 2x2 block
+ * sums of src [B,2H,2W,C]; fp16 NHWC, C a multiple of 8 */
+int unib200_pool2x2_sum(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream);
+/* zero insertion dst [B,2H,2W,C] <- src [B,H,W,C] at even pixels: the gradients of the stride-2 Downsample2D conv become
+ * stride-1 problems (dX = conv3x3(scatter(dY), flipped W); dW = wgrad(x, scatter(dY))) */
+int unib200_scatter2x(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream);
+/* AdamW on flat fp32 buffers with torch.optim.AdamW's arithmetic (train/train.py:1424 optimizer.step()); gradients are
+ * multiplied by grad_scale first (inverse loss scale x clip coefficient); step counts from 1 */
+int unib200_adamw_step(unib200_program* prog, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* ---- step-level context -----------------------------------------------------------------
  * A context owns what one dual-stream sampler needs at run time -- recorded programs (ownership passes to it), device

@@ -324,6 +324,102 @@ def add_f16(prog, a, b, out):
     _submit(prog, lambda: out.copy_(a.float() + b.float()))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# training ops (uni_renderer_b200/train.py wrappers of the backward kernels): fp32 torch math on the fp16-stored operands,
+# written independently of the kernels (autograd of the forward definition wherever that is the shortest statement)
+# ---------------------------------------------------------------------------------------------------------------------
+def t_conv_wgrad(x, C_in, dy, N, *, B, H, W, taps, partial=None, want_bias=True):
+    M = x.shape[0]
+    xf, dyf = x[:, :C_in].float(), dy[:M, :N].float()
+    if taps == 1:
+        dw = (dyf.t() @ xf).reshape(N, C_in, 1, 1)
+    else:
+        cols = _taps(x, L.SEG_3x3, B, H, W, C_in)                         # nine [M, C_in] shifted copies, (dy, dx) row-major
+        dw = torch.stack([dyf.t() @ c for c in cols], -1).reshape(N, C_in, 3, 3)
+    return dw.contiguous(), (dyf.sum(0) if want_bias else None)
+
+
+def t_colsum(x, N):
+    return x[:, :N].float().sum(0)
+
+
+def t_groupnorm_backward(x, dz, gamma, beta, *, B, HW, groups, eps, silu):
+    Cn = x.shape[1]
+    xr = x.float().reshape(B, HW, Cn).permute(0, 2, 1).clone().requires_grad_(True)
+    g, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr, groups, g, bt, eps)
+    if silu:
+        y = F.silu(y)
+    (y * dz.float().reshape(B, HW, Cn).permute(0, 2, 1)).sum().backward()
+    return xr.grad.permute(0, 2, 1).reshape(B * HW, Cn).half(), g.grad, bt.grad
+
+
+def t_layernorm_backward(x, dy, gamma, eps=1e-5):
+    xr = x.float().clone().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    bt = torch.zeros_like(gamma).requires_grad_(True)
+    (F.layer_norm(xr, (x.shape[1],), g, bt, eps) * dy.float()).sum().backward()
+    return xr.grad.half(), g.grad, bt.grad
+
+
+def t_geglu(proj, dout=None):
+    pr = proj.float().clone().requires_grad_(True)
+    a, g = pr.chunk(2, dim=-1)
+    y = a * _gelu_erf(g)
+    if dout is None:
+        return y.detach().half()
+    (y * dout.float()).sum().backward()
+    return pr.grad.half()
+
+
+def t_softmax_backward(p, dp, n, scale):
+    pf, df = p[:, :n].float(), dp[:, :n].float()
+    dp[:, :n] = (scale * pf * (df - (df * pf).sum(1, keepdim=True))).half()
+
+
+def t_cvt_f32_f16(src, dst):
+    dst.copy_(src.reshape(dst.shape).half())
+
+
+def t_silu_f16(x, dy=None):
+    v = x.float()
+    sg = torch.sigmoid(v)
+    return (v * sg if dy is None else dy.float() * sg * (1 + v * (1 - sg))).half()
+
+
+def t_scatter2x(x, B, H, W):
+    Cn = x.shape[1]
+    out = torch.zeros(B, 2 * H, 2 * W, Cn, dtype=torch.float16)
+    out[:, ::2, ::2] = x.reshape(B, H, W, Cn)
+    return out.reshape(B * 4 * H * W, Cn)
+
+
+def t_pool2x2_sum(x, B, H, W):
+    Cn = x.shape[1]
+    return x.float().reshape(B, H, 2, W, 2, Cn).sum((2, 4)).reshape(B * H * W, Cn).half()
+
+
+def t_adamw_step(p, g, m, v, *, lr, betas, eps, weight_decay, step, grad_scale=1.0):
+    gi = g * grad_scale
+    m.mul_(betas[0]).add_(gi, alpha=1 - betas[0])
+    v.mul_(betas[1]).addcmul_(gi, gi, value=1 - betas[1])
+    p.mul_(1 - lr * weight_decay)
+    p.addcdiv_(m, v.sqrt() / (1 - betas[1] ** step) ** 0.5 + eps, value=-lr / (1 - betas[0] ** step))
+
+
+TRAIN_EMULATED = ("conv_wgrad", "colsum", "groupnorm_backward", "layernorm_backward", "geglu", "softmax_backward",
+                  "cvt_f32_f16", "silu_f16", "scatter2x", "pool2x2_sum", "adamw_step")
+
+
+def install_training(monkeypatch):
+    """install() + the training wrappers of uni_renderer_b200.train, and lift the trainer's CUDA gate (test only)."""
+    from uni_renderer_b200 import train, trainer
+    install(monkeypatch)
+    for name in TRAIN_EMULATED:
+        monkeypatch.setattr(train, name, globals()["t_" + name])
+    monkeypatch.setattr(trainer, "_REQUIRE_CUDA", False)
+
+
 EMULATED = ("conv_gemm", "conv_gemm_dual", "attention", "groupnorm", "layernorm", "upsample2x", "to_nhwc", "from_nhwc", "softmax_rows",
             "gaussian_sample", "add_f16", "add_int", "timestep_sinusoid", "gemv", "axpby", "unipc_step")
 

@@ -69,6 +69,43 @@ def test_all_gather_world2_gloo(tmp_path):
     assert p.stdout.count("OK") == 2
 
 
+_GRAD_WORKER = """
+import sys
+sys.path.insert(0, {root!r})
+import torch
+import torch.distributed as dist
+from uni_renderer_b200.trainer import allreduce_gradients
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+n = allreduce_gradients(g, bucket_bytes=4 * 300)          # 300-element buckets: 4 collectives, the last one ragged
+assert n == 4, n
+assert torch.allclose(g, torch.arange(1000, dtype=torch.float32) * 1.5), (rank, g[:4])
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_bucketed_gradient_allreduce_world2_gloo(tmp_path):
+    """Data-parallel training (train/train.py runs under accelerate DDP): the flat gradient buffer is averaged over the
+    ranks in fixed-size buckets."""
+    script = tmp_path / "g.py"
+    script.write_text(_GRAD_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("OK") == 2
+
+
+def test_allreduce_gradients_is_a_no_op_without_a_process_group():
+    from uni_renderer_b200.trainer import allreduce_gradients
+    g = torch.ones(10)
+    assert allreduce_gradients(g) == 0 and torch.equal(g, torch.ones(10))
+
+
 def test_sampler_requires_cuda():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")

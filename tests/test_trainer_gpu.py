@@ -1,0 +1,114 @@
+"""Network-level training step (train/train.py:1324-1427) on the B200 kernels against torch autograd of
+the oracle: the 3-call dual-stream forward, the reference's losses, the backward through all three networks and their
+exchange, AdamW.  Tiny widths (the oracle's TINY config), B = 2, 32 x 32 latents, a 77-token context.
+
+Gates: predictions at the model gate of tests/test_models_gpu.py (rel_l2 <= 3e-3); every parameter gradient of every
+network against the fp32 autograd gradient -- activations and activation gradients are stored in fp16 through ~100 layers:
+per tensor rel_l2 <= 2e-2 (norm / bias vectors and the zero-convolutions <= 3e-2; measured worst 5.6e-3), the whole flat
+gradient <= 5e-3; the optimizer against torch.optim.AdamW to fp32 rounding."""
+import pytest
+
+gpu = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def _setup(seed=5, B=2, S=32, Lc=77):
+    import torch
+    from dataclasses import replace
+    from oracle import uni_oracle as uo
+    base = uo.TINY
+    cfgs = {"unet": replace(base), "enc": replace(base, in_channels=28), "dec": replace(base, out_channels=28)}
+    kinds = {"unet": "unet", "enc": "attr_enc", "dec": "attr_dec"}
+    nets = {k: uo.random_state_dict(kinds[k], cfgs[k], seed + i) for i, k in enumerate(("unet", "enc", "dec"))}
+    for sd in nets.values():            # the kernels read fp16 matrices: give both sides the same rounded values
+        for k in sd:
+            if sd[k].dim() >= 2:
+                sd[k] = sd[k].half().float()
+    g = torch.Generator().manual_seed(seed + 100)
+    r = lambda *s: torch.randn(*s, generator=g)                               # noqa: E731
+    batch = dict(x_img=r(B, 4, S, S).half().float(), t_img=torch.tensor([981.0, 341.0])[:B],
+                 x_attr=r(B, 28, S, S).half().float(), t_attr=torch.tensor([500.0, 21.0])[:B],
+                 ehs=r(B, Lc, base.cross_attention_dim).half().float(), img_target=r(B, 4, S, S), attr_target=r(B, 24, S, S))
+    return nets, cfgs, batch
+
+
+def _oracle_grads(nets, cfgs, batch, dev):
+    """torch autograd through oracle/uni_oracle.py's 3-call step + the reference's losses (fp32 on the host: the oracle is a
+    CPU restatement)."""
+    import torch
+    from oracle import uni_oracle as uo
+    from uni_renderer_b200.trainer import reference_losses
+    p = {n: {k: v.to(dev).clone().requires_grad_(True) for k, v in sd.items()} for n, sd in nets.items()}
+    b = {k: v.to(dev) for k, v in batch.items()}
+    d, m, raw_a, raw_a_mid = uo.attr_encoder_forward(p["enc"], cfgs["enc"], b["t_attr"], b["ehs"], b["x_attr"])
+    img, raw_u, raw_u_mid, _ = uo.unet_forward(p["unet"], cfgs["unet"], b["x_img"], b["t_img"], b["ehs"], d, m)
+    msk = uo.attr_decoder_forward(p["dec"], cfgs["dec"], raw_a_mid, raw_a, b["t_attr"], b["ehs"], raw_u, raw_u_mid)
+    loss = reference_losses(img, msk, b["img_target"], b["attr_target"])
+    loss.backward()
+    grads = {f"{n}.{k}": v.grad for n, sd in p.items() for k, v in sd.items()}
+    return loss.detach(), img.detach(), msk.detach(), grads
+
+
+@gpu
+def test_three_call_training_step_gradients_match_autograd_of_the_oracle():
+    import torch
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    nets, cfgs, batch = _setup()
+    loss_ref, img_ref, msk_ref, gref = _oracle_grads(nets, cfgs, batch, torch.device("cpu"))
+    tr = DualStreamTrainer(nets, cfgs, loss_scale=256.0, max_grad_norm=None)
+    loss, img, msk = tr.forward_backward(batch["x_img"], batch["t_img"], batch["x_attr"], batch["t_attr"], batch["ehs"],
+                                         batch["img_target"], batch["attr_target"])
+    torch.cuda.synchronize()
+    assert _rel(img, img_ref) <= 3e-3, _rel(img, img_ref)
+    assert _rel(msk, msk_ref) <= 3e-3, _rel(msk, msk_ref)
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+    assert torch.isfinite(tr.P.grad).all()
+    worst, missing = [], []
+    for name, gr in gref.items():
+        if gr is None:
+            missing.append(name)
+            continue
+        got = tr.P.g[name] / tr.loss_scale
+        e = _rel(got, gr)
+        small = gr.dim() <= 1 or "control" in name
+        worst.append((e / (3e-2 if small else 2e-2), e, name))
+    assert not missing, missing
+    worst.sort(reverse=True)
+    print("worst gradient errors:", [(round(e, 5), n) for _, e, n in worst[:5]])
+    assert worst[0][0] <= 1.0, worst[:8]
+    flat_ref = torch.cat([gref[n].reshape(-1) for n in tr.P.g])
+    assert _rel(tr.P.grad / tr.loss_scale, flat_ref) <= 5e-3, _rel(tr.P.grad / tr.loss_scale, flat_ref)
+
+
+@gpu
+def test_adamw_kernel_matches_torch_adamw_and_a_training_step_lowers_the_loss():
+    import torch
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    nets, cfgs, batch = _setup(seed=9, S=16, Lc=16)
+    tr = DualStreamTrainer(nets, cfgs, lr=2e-4, loss_scale=256.0, max_grad_norm=1.0, weight_decay=1e-2)
+    args = (batch["x_img"], batch["t_img"], batch["x_attr"], batch["t_attr"], batch["ehs"], batch["img_target"],
+            batch["attr_target"])
+    l0, _, _ = tr.forward_backward(*args)
+    # torch.optim.AdamW on a copy of the flat parameters with the same (unscaled, clipped) gradient
+    p_ref = tr.P.flat.clone().requires_grad_(True)
+    g = tr.P.grad.clone() / tr.loss_scale
+    gn = g.norm().item()
+    if gn > 1.0:
+        g = g * (1.0 / (gn + 1e-6))
+    opt = torch.optim.AdamW([p_ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    p_ref.grad = g
+    opt.step()
+    info = tr.optimizer_step()
+    torch.cuda.synchronize()
+    assert info["skipped"] == 0.0 and abs(info["grad_norm"] - gn) <= 1e-4 * gn
+    assert (tr.P.flat - p_ref.detach()).abs().max().item() <= 1e-6
+    assert float(tr.P.grad.abs().max()) == 0.0
+    # a few more steps on the same batch: the loss must go down
+    losses = [l0.item()]
+    for _ in range(3):
+        losses.append(tr.step(*args)["loss"])
+    assert losses[-1] < losses[0], losses

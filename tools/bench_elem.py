@@ -48,6 +48,24 @@ for (B, HW, C1, C2) in GN:
     us = timed(prog)
     by = 4.0 * B * HW * C
     print(f"groupnorm B={B} HW={HW} C={C1}+{C2}: {us:7.2f} us  {by / us / 1e3:7.1f} GB/s")
+# the same shapes with the statistics already in (row block, micro-group) partials: ONE apply launch (gn_apply_parts)
+for (B, HW, C1, C2) in GN:
+    if HW < 1024:
+        continue
+    gran, rows = 10, 128
+    x1 = torch.randn(B * HW, C1, device=dev).half()
+    x2 = torch.randn(B * HW, C2, device=dev).half() if C2 else None
+    C = C1 + C2
+    p1 = torch.rand(B * HW // rows, C1 // gran, 2, device=dev) * rows * gran
+    p2 = torch.rand(B * HW // rows, C2 // gran, 2, device=dev) * rows * gran if C2 else None
+    g, bt = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    outs = [torch.empty(B * HW, C, device=dev, dtype=torch.float16) for _ in range(2)]
+    prog = ops.Program()
+    for k in range(reps):
+        ops.groupnorm(prog, x1, C1, x2, C2, g, bt, outs[k & 1], scratch, B=B, HW=HW, groups=32, eps=1e-5, silu=True,
+                      parts=(p1, p2, gran, rows))
+    us = timed(prog)
+    print(f"groupnorm(parts) B={B} HW={HW} C={C1}+{C2}: {us:7.2f} us  {4.0 * B * HW * C / us / 1e3:7.1f} GB/s")
 for (rows, C) in LN:
     x = torch.randn(rows, C, device=dev).half()
     g, bt = torch.randn(C, device=dev), torch.randn(C, device=dev)

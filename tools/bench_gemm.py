@@ -23,7 +23,11 @@ SHAPES = [
     ("proj 1x1 1280 @8 +res", 4, 8, [1280], SEG_1x1, 1280, True, False),
     ("qkv 320->960 @64", 4, 64, [320], SEG_1x1, 960, False, False),
     ("geglu 320->2560 @64", 4, 64, [320], SEG_1x1, 2560, False, True),
+    ("geglu 640->5120 @32", 4, 32, [640], SEG_1x1, 5120, False, True),
+    ("geglu 1280->10240 @16", 4, 16, [1280], SEG_1x1, 10240, False, True),
+    ("qkv 640->1920 @32", 4, 32, [640], SEG_1x1, 1920, False, False),
     ("ff2 1280->320 @64 +res", 4, 64, [1280], SEG_1x1, 320, True, False),
+    ("ff2 2560->640 @32 +res", 4, 32, [2560], SEG_1x1, 640, True, False),
     ("ff2 5120->1280 @16 +res", 4, 16, [5120], SEG_1x1, 1280, True, False),
     ("conv3 320->320 @64", 4, 64, [320], SEG_3x3, 320, False, False),
     ("conv3 640->640 @32", 4, 32, [640], SEG_3x3, 640, False, False),

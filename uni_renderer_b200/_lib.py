@@ -82,7 +82,8 @@ EXPORTS = [
     "unib200_axpby", "unib200_add_int", "unib200_add_f16", "unib200_unipc_step",
     "unib200_softmax_rows", "unib200_gaussian_sample",
     "unib200_conv_wgrad", "unib200_groupnorm_backward", "unib200_colsum", "unib200_layernorm_backward", "unib200_geglu",
-    "unib200_softmax_backward", "unib200_cvt_f32_f16",
+    "unib200_softmax_backward", "unib200_cvt_f32_f16", "unib200_silu_f16", "unib200_pool2x2_sum", "unib200_scatter2x",
+    "unib200_adamw_step",
     "unib200_create", "unib200_destroy", "unib200_load_weight", "unib200_alloc", "unib200_bind", "unib200_buffer",
     "unib200_ctx_attach", "unib200_ctx_run", "unib200_unet_forward", "unib200_attr_enc_forward",
     "unib200_attr_dec_forward", "unib200_dual_step", "unib200_sample_loop",
@@ -155,6 +156,10 @@ def load() -> C.CDLL:
     lib.unib200_geglu.argtypes = [vp, vp, vp, vp, i64, ci, vp]
     lib.unib200_softmax_backward.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp]
     lib.unib200_cvt_f32_f16.argtypes = [vp, vp, vp, i64, ci, ci, vp]
+    lib.unib200_silu_f16.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.unib200_pool2x2_sum.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_scatter2x.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_adamw_step.argtypes = [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, cf, vp]
     lib.unib200_create.argtypes = [ci, vp]
     lib.unib200_create.restype = vp
     lib.unib200_destroy.argtypes = [vp]

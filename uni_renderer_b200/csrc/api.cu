@@ -448,8 +448,11 @@ int prepare_gemm(const unib200_gemm_desc* d, PreparedGemm* out) {
     // tiles and a long K loop.  Measured (tools/bench_gemm.py): conv3x3 +14..18 %, but short-K 1x1 layers lose ~10 %
     // to the pair's cluster synchronisation, so those stay on single CTAs.
     static const int pair_min_kb = getenv("UNIB200_PAIR_MIN_KB") ? atoi(getenv("UNIB200_PAIR_MIN_KB")) : 24;
-    p.cg = (pair_min_kb > 0 && gemm_pair_supported(bn) && d->M > kBM && total_kb >= pair_min_kb &&
-            !(d->flags & UNIB200_EPI_GEGLU)) ? 2 : 1;
+    static const int geglu_pair = getenv("UNIB200_GEGLU_PAIR") ? atoi(getenv("UNIB200_GEGLU_PAIR")) : 0;
+    if (d->flags & UNIB200_EPI_GEGLU)
+      p.cg = (geglu_pair && bn == 256 && d->M >= 2 * kBM) ? 2 : 1;
+    else
+      p.cg = (pair_min_kb > 0 && gemm_pair_supported(bn) && d->M > kBM && total_kb >= pair_min_kb) ? 2 : 1;
     const uint32_t box[2] = {64, static_cast<uint32_t>(bn / p.cg)};
     if (!encode_map(&maps.b, d->weight, 2, dims, st, box, &why)) return fail("conv_gemm B map: " + why);
   }
@@ -771,6 +774,37 @@ int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int6
   return submit(prog, std::move(op), 1, stream, "cvt_f32_f16");
 }
 
+int unib200_silu_f16(unib200_program* prog, const void* x, const void* dy, void* out, int64_t n, void* stream) {
+  if (!x || !out || n <= 0) return fail("silu_f16: bad arguments");
+  const __half *xp = static_cast<const __half*>(x), *dp = static_cast<const __half*>(dy);
+  __half* op_ = static_cast<__half*>(out);
+  Op op = [=](cudaStream_t s) { return launch_silu_f16(xp, dp, op_, n, s); };
+  return submit(prog, std::move(op), 1, stream, "silu_f16");
+}
+
+int unib200_pool2x2_sum(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return fail("pool2x2_sum: bad arguments (C a multiple of 8)");
+  const __half* sp = static_cast<const __half*>(src);
+  __half* dp = static_cast<__half*>(dst);
+  Op op = [=](cudaStream_t s) { return launch_pool2x2_sum(sp, dp, B, H, W, C, s); };
+  return submit(prog, std::move(op), 1, stream, "pool2x2_sum");
+}
+
+int unib200_scatter2x(unib200_program* prog, const void* src, void* dst, int B, int H, int W, int C, void* stream) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return fail("scatter2x: bad arguments (C a multiple of 8)");
+  const __half* sp = static_cast<const __half*>(src);
+  __half* dp = static_cast<__half*>(dst);
+  Op op = [=](cudaStream_t s) { return launch_scatter2x(sp, dp, B, H, W, C, s); };
+  return submit(prog, std::move(op), 1, stream, "scatter2x");
+}
+
+int unib200_adamw_step(unib200_program* prog, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return fail("adamw_step: bad arguments (step counts from 1)");
+  Op op = [=](cudaStream_t s) { return launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, s); };
+  return submit(prog, std::move(op), 1, stream, "adamw_step");
+}
+
 int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc* d, void* stream) {
   if (!d || !d->x || !d->dz || !d->dx || !d->gamma || !d->beta || !d->dgamma || !d->dbeta || !d->scratch)
     return fail("groupnorm_backward: null pointer");
@@ -946,7 +980,8 @@ int unib200_add_f16(unib200_program* prog, const void* a, const void* b, void* o
 }
 
 int unib200_softmax_rows(unib200_program* prog, void* s, int rows, int n, int ld, float scale, void* stream) {
-  if (rows <= 0 || n <= 0 || n % 8 || ld % 8 || ld < n) return fail("softmax_rows: n and ld must be multiples of 8, ld >= n");
+  if (rows <= 0 || n <= 0 || ld % 8 || ld < (n + 7) / 8 * 8)
+    return fail("softmax_rows: ld must be a multiple of 8 and cover n rounded up to 8 (columns n .. are written as zeros)");
   if (!(scale > 0.f)) return fail("softmax_rows: scale must be positive");
   if (reinterpret_cast<uintptr_t>(s) & 15) return fail("softmax_rows: matrix must be 16-byte aligned");
   Op op = [=](cudaStream_t st) { return launch_softmax_rows(static_cast<__half*>(s), rows, n, ld, scale, st); };

@@ -357,6 +357,37 @@ __device__ __forceinline__ f32x2_t add_rm_f32x2(f32x2_t a, f32x2_t b) {      // 
   asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ f32x2_t mul_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t splat_f32x2(float c) { return pack_f32x2(c, c); }
+// erf-GELU of a PAIR on packed fp32 (FFMA2 / FMUL2: two lanes per issue slot).  Same A&S 7.1.26 erf as erf_as_f; the
+// sign never has to be restored because  gelu(x) = x/2 * (1 + sign(x) * (1 - y)) = x/2 + |x|/2 * (1 - y),
+// y = poly(t) * t * exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt2).  ~19 issue slots per pair instead of ~25 per element:
+// the GEGLU epilogue (64 gate elements per thread and tile, two warps per scheduler) was issue-bound on this.
+__device__ __forceinline__ f32x2_t gelu_erf_x2(f32x2_t x) {
+  float x0, x1;
+  unpack_f32x2(x, x0, x1);
+  const f32x2_t ax = pack_f32x2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);   // |x| / sqrt2
+  float d0, d1;
+  unpack_f32x2(fma_f32x2(splat_f32x2(0.3275911f), ax, splat_f32x2(1.0f)), d0, d1);
+  const f32x2_t t = pack_f32x2(fast_rcp(d0), fast_rcp(d1));
+  f32x2_t poly = fma_f32x2(splat_f32x2(1.061405429f), t, splat_f32x2(-1.453152027f));
+  poly = fma_f32x2(poly, t, splat_f32x2(1.421413741f));
+  poly = fma_f32x2(poly, t, splat_f32x2(-0.284496736f));
+  poly = fma_f32x2(poly, t, splat_f32x2(0.254829592f));
+  float e0, e1;
+  unpack_f32x2(mul_f32x2(mul_f32x2(ax, ax), splat_f32x2(-1.4426950408889634f)), e0, e1);    // -ax^2 * log2(e)
+  float y0, y1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(e1));
+  const f32x2_t y = mul_f32x2(mul_f32x2(poly, t), pack_f32x2(y0, y1));
+  const f32x2_t w = fma_f32x2(y, splat_f32x2(-1.0f), splat_f32x2(1.0f));                     // 1 - y = |erf|
+  const f32x2_t kax = mul_f32x2(ax, splat_f32x2(0.70710678118654752f));                      // |x| / 2
+  return fma_f32x2(kax, w, mul_f32x2(x, splat_f32x2(0.5f)));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

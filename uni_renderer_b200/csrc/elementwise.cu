@@ -60,7 +60,14 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GnParams p) {
       const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * rpb) * ld);
       acc(a0); acc(a1); acc(a2); acc(a3);
     }
-    for (; r < r1; r += rpb) acc(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+    if (r < r1) {                             // at most three rows left: every load is issued before the first use
+      const bool k1 = r + rpb < r1, k2 = r + 2 * rpb < r1;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+      const uint4 a1 = k1 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + rpb) * ld) : z;
+      const uint4 a2 = k2 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * rpb) * ld) : z;
+      acc(a0); acc(a1); acc(a2);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       ssum[rsub * C + c0 + j] = s[j];
@@ -165,7 +172,16 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GnParams p) {
         const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
         emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
       }
-      for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+      if (r < r1) {                             // at most three rows left: every load is issued before the first use
+        const bool k1 = r + arp < r1, k2 = r + 2 * arp < r1;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+        const uint4 a1 = k1 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld) : z;
+        const uint4 a2 = k2 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld) : z;
+        emit(r, a0);
+        if (k1) emit(r + arp, a1);
+        if (k2) emit(r + 2 * arp, a2);
+      }
     }
   }
 }
@@ -185,9 +201,15 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank
   return v;
 }
 
+__device__ __forceinline__ void ld_dsmem_f32x2(uint32_t local_addr, uint32_t rank, float& x, float& y) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(remote) : "memory");
+}
+
 __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
   extern __shared__ float sm[];            // [2][rpb][C] reduction scratch, then scale[C] | shift[C]
-  __shared__ float part[2 * 64];           // this CTA's (sum, sumsq) per group -- read by the peers
+  __shared__ __align__(8) float part[2 * 64];           // this CTA's (sum, sumsq) per group -- read by the peers
   __shared__ float gstat[2 * 64];          // (mean, rstd) per group
   pdl_launch();
   pdl_wait();
@@ -229,7 +251,14 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
       const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * rpb) * ld);
       acc(a0); acc(a1); acc(a2); acc(a3);
     }
-    for (; r < r1; r += rpb) acc(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+    if (r < r1) {                             // at most three rows left: every load is issued before the first use
+      const bool k1 = r + rpb < r1, k2 = r + 2 * rpb < r1;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+      const uint4 a1 = k1 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + rpb) * ld) : z;
+      const uint4 a2 = k2 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * rpb) * ld) : z;
+      acc(a0); acc(a1); acc(a2);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       ssum[rsub * C + c0 + j] = s[j];
@@ -244,20 +273,33 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
     ssq[c] = q2;
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
-    float a = 0.f, q2 = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += ssum[c]; q2 += ssq[c]; }
-    part[2 * g] = a;
-    part[2 * g + 1] = q2;
+  // group sums: eight lanes per (group, statistic), channels strided by 8, fixed-order butterfly (a 32-thread loop over
+  // cpg channels each was a serial chain of 2 * cpg bank-conflicting shared loads)
+  for (int t0 = 0; t0 < 16 * p.G; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const int sub = t & 7, st = (t >> 3) & 1, g = t >> 4;
+    float v = 0.f;
+    if (g < p.G) {
+      const float* a = st ? ssq : ssum;
+      for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) v += a[c];
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (sub == 0 && g < p.G) part[2 * g + st] = v;
   }
   cluster_sync_all();                      // every CTA's partials are visible cluster-wide
   for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
     float a = 0.f, q2 = 0.f;
     const uint32_t la = smem_u32(&part[2 * g]);
-    for (uint32_t r = 0; r < cs; ++r) {
-      a += ld_dsmem_f32(la, r);
-      q2 += ld_dsmem_f32(la + 4, r);
+    float pa[16], pq[16];                  // all peers' (sum, sumsq) requested before the first add
+#pragma unroll
+    for (uint32_t r = 0; r < 16; ++r) {
+      if (r < cs) ld_dsmem_f32x2(la, r, pa[r], pq[r]);
+      else { pa[r] = 0.f; pq[r] = 0.f; }
     }
+#pragma unroll
+    for (uint32_t r = 0; r < 16; ++r) { a += pa[r]; q2 += pq[r]; }
     const float inv_n = 1.0f / (static_cast<float>(cpg) * p.HW);
     const float mu = a * inv_n;
     const float var = fmaxf(q2 * inv_n - mu * mu, 0.f);
@@ -310,7 +352,16 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
         const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
         emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
       }
-      for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+      if (r < r1) {                             // at most three rows left: every load is issued before the first use
+        const bool k1 = r + arp < r1, k2 = r + 2 * arp < r1;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+        const uint4 a1 = k1 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld) : z;
+        const uint4 a2 = k2 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld) : z;
+        emit(r, a0);
+        if (k1) emit(r + arp, a1);
+        if (k2) emit(r + 2 * arp, a2);
+      }
     }
   }
   cluster_sync_all();                      // no CTA may exit while a peer can still read its `part`
@@ -324,7 +375,7 @@ __global__ void __launch_bounds__(512) gn_cluster_kernel(GnParams p) {
 __global__ void __launch_bounds__(512) gn_apply_parts_kernel(GnParams p) {
   pdl_launch();
   pdl_wait();
-  extern __shared__ float sm[];            // scale[C], shift[C], mg[(C / gran)][2], gstat[G][2]
+  extern __shared__ float sm[];            // scale[C], shift[C], mg[(C / gran)][2], gstat[G][2], tmp[P][2 C / gran]
   const int C = p.C1 + p.C2;
   const int cpg = C / p.G;
   const int gran = p.part_gran;
@@ -335,22 +386,44 @@ __global__ void __launch_bounds__(512) gn_apply_parts_kernel(GnParams p) {
   float* gstat = mgs + 2 * nmg;
   const int b = blockIdx.y;
   const int nrb = p.HW / p.part_rows;      // row blocks of one sample
-  for (int t = threadIdx.x; t < 2 * nmg; t += blockDim.x) {
-    const int st = t & 1, mg = t >> 1;
+  // (sum, sumsq) chains of the sample: 2 * nmg of them, each over nrb row blocks.  The partials sit in L2, so the cost
+  // is round trips: P threads share a chain (row blocks part, part + P, ...), eight independent loads in flight each,
+  // then the P sub-sums are added in a fixed order -- one or two L2 latencies instead of nrb / 4.
+  const int nchain = 2 * nmg;
+  int P = blockDim.x / nchain;
+  if (P > p.part_split) P = p.part_split;
+  if (P > nrb) P = nrb;
+  if (P < 1) P = 1;
+  float* tmp = gstat + 2 * p.G;            // [P][nchain]
+  for (int t = threadIdx.x; t < nchain * P; t += blockDim.x) {
+    const int chain = t % nchain, part = t / nchain;
+    const int st = chain & 1, mg = chain >> 1;
     const float* src;
-    int stride;
+    size_t stride;
     if (mg < nmg1) { src = p.part1 + (static_cast<size_t>(b) * nrb * nmg1 + mg) * 2 + st; stride = 2 * nmg1; }
     else { src = p.part2 + (static_cast<size_t>(b) * nrb * nmg2 + (mg - nmg1)) * 2 + st; stride = 2 * nmg2; }
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // four interleaved chains, combined in a fixed order
-    int r = 0;
-    for (; r + 3 < nrb; r += 4) {
-      a0 += __ldg(src + static_cast<size_t>(r) * stride);
-      a1 += __ldg(src + static_cast<size_t>(r + 1) * stride);
-      a2 += __ldg(src + static_cast<size_t>(r + 2) * stride);
-      a3 += __ldg(src + static_cast<size_t>(r + 3) * stride);
+    float acc = 0.f;
+    int r = part;
+    for (; r + 7 * P < nrb; r += 8 * P) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(src + static_cast<size_t>(r + i * P) * stride);
+      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
-    for (; r < nrb; ++r) a0 += __ldg(src + static_cast<size_t>(r) * stride);
-    mgs[t] = (a0 + a1) + (a2 + a3);
+    {                                      // up to 7 left: all loads issued before the first add
+      float v[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) v[i] = (r + i * P < nrb) ? __ldg(src + static_cast<size_t>(r + i * P) * stride) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) acc += v[i];
+    }
+    tmp[part * nchain + chain] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nchain; t += blockDim.x) {
+    float a = 0.f;
+    for (int q = 0; q < P; ++q) a += tmp[q * nchain + t];
+    mgs[t] = a;
   }
   __syncthreads();
   const int mpg = cpg / gran;              // micro-groups per group
@@ -407,11 +480,21 @@ __global__ void __launch_bounds__(512) gn_apply_parts_kernel(GnParams p) {
       const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 3 * arp) * ld);
       emit(r, a0); emit(r + arp, a1); emit(r + 2 * arp, a2); emit(r + 3 * arp, a3);
     }
-    for (; r < r1; r += arp) emit(r, *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld));
+    if (r < r1) {                             // at most three rows left: every load is issued before the first use
+        const bool k1 = r + arp < r1, k2 = r + 2 * arp < r1;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld);
+        const uint4 a1 = k1 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + arp) * ld) : z;
+        const uint4 a2 = k2 ? *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r + 2 * arp) * ld) : z;
+        emit(r, a0);
+        if (k1) emit(r + arp, a1);
+        if (k2) emit(r + 2 * arp, a2);
+      }
   }
 }
 
-cudaError_t launch_groupnorm_parts(const GnParams& p, int B, int num_sms, cudaStream_t stream) {
+cudaError_t launch_groupnorm_parts(const GnParams& p_in, int B, int num_sms, cudaStream_t stream) {
+  GnParams p = p_in;
   const int C = p.C1 + p.C2;
   if (C % 8 || p.C1 % 8 || C % p.G || (C >> 3) > 512 || p.part1 == nullptr) return cudaErrorInvalidValue;
   const int CV = C >> 3;
@@ -420,7 +503,10 @@ cudaError_t launch_groupnorm_parts(const GnParams& p, int B, int num_sms, cudaSt
   static const int apply_threads_env = getenv("UNIB200_GN_APPLY_THREADS") ? atoi(getenv("UNIB200_GN_APPLY_THREADS")) : 0;
   int athreads = apply_threads_env ? apply_threads_env : 256;
   if (athreads < CV) athreads = 512;            // a block must hold at least one row of 8-channel vectors
-  const size_t smem = (2 * C + 2 * (C / p.part_gran) + 2 * p.G) * sizeof(float);
+  const int nmg = C / p.part_gran;
+  p.part_split = 8;
+  while (p.part_split > 1 && (2 * C + 2 * nmg * (1 + p.part_split) + 2 * p.G) * sizeof(float) > 40 * 1024) p.part_split /= 2;
+  const size_t smem = (2 * C + 2 * nmg * (1 + p.part_split) + 2 * p.G) * sizeof(float);      // + tmp[part_split][2 nmg]
   UNIB_CHECK_LAUNCH(launch_pdl(gn_apply_parts_kernel, dim3(dim3(achunks, B)), dim3(athreads), smem, stream, p));
   return cudaGetLastError();
 }
@@ -880,7 +966,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
   pdl_launch();
   pdl_wait();
   __shared__ float red[8];
-  const int nv = n >> 3;
+  const int nv = (n + 7) >> 3;               // the last vector may be ragged: columns >= n read as -inf and are written as 0
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     uint4* row = reinterpret_cast<uint4*>(S + static_cast<size_t>(r) * ld);
     float mx = -INFINITY;
@@ -890,7 +976,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
-        mx = fmaxf(mx, fmaxf(f.x, f.y));
+        const int e = v * 8 + 2 * j;
+        mx = fmaxf(mx, fmaxf(e < n ? f.x : -INFINITY, e + 1 < n ? f.y : -INFINITY));
       }
     }
     mx = block_reduce_256(mx, true, red);
@@ -901,7 +988,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
-        sum += exp2f((f.x - mx) * scale_log2e) + exp2f((f.y - mx) * scale_log2e);
+        const int e = v * 8 + 2 * j;
+        sum += (e < n ? exp2f((f.x - mx) * scale_log2e) : 0.f) + (e + 1 < n ? exp2f((f.y - mx) * scale_log2e) : 0.f);
       }
     }
     sum = block_reduce_256(sum, false, red);
@@ -913,7 +1001,9 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
-        o[j] = pack_half2(exp2f((f.x - mx) * scale_log2e) * inv, exp2f((f.y - mx) * scale_log2e) * inv);
+        const int e = v * 8 + 2 * j;
+        o[j] = pack_half2(e < n ? exp2f((f.x - mx) * scale_log2e) * inv : 0.f,
+                          e + 1 < n ? exp2f((f.y - mx) * scale_log2e) * inv : 0.f);
       }
       row[v] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -921,7 +1011,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 }
 
 cudaError_t launch_softmax_rows(__half* S, int rows, int n, int ld, float scale, cudaStream_t stream) {
-  if (rows <= 0 || n <= 0 || n % 8 || ld % 8 || ld < n || !(scale > 0.f)) return cudaErrorInvalidValue;
+  if (rows <= 0 || n <= 0 || ld % 8 || ld < (n + 7) / 8 * 8 || !(scale > 0.f)) return cudaErrorInvalidValue;
   int blocks = rows < 148 * 8 ? rows : 148 * 8;
   UNIB_CHECK_LAUNCH(launch_pdl(softmax_rows_kernel, dim3(blocks), dim3(256), 0, stream, S, rows, n, ld,
                                scale * 1.4426950408889634f));

@@ -18,6 +18,7 @@ struct GnParams {
   // statistics from the producing GEMMs' epilogues (GemmParams::gn_part): [B*HW / part_rows][C{1,2} / part_gran][2]
   const float* part1; const float* part2;
   int part_gran, part_rows;
+  int part_split;            // launcher: threads sharing one statistics chain (sizes the kernel's scratch)
 };
 
 cudaError_t launch_groupnorm(const GnParams& p, int B, int num_sms, cudaStream_t stream);

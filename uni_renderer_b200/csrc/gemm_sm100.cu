@@ -534,6 +534,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             tmem_ld32(taddr + j * 32, v);
             tmem_ld32(taddr + BN / 2 + j * 32, gte);
             tmem_ld_wait();
+            if (tl == 0 && leader && jj == 1) GEMM_TRACE(10);
             if (j == jlast) {                 // my part of the accumulator is read -> release it to the MMA warp
               tc_fence_before();
               __syncwarp();
@@ -541,6 +542,35 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             }
             const float* wv = wsum_s + (2 * jj) * 32;
             const float* bv = my_bias + (2 * jj) * 32;
+#ifndef UNIB_GEGLU_SCALAR
+            // packed fp32 pairs throughout (this epilogue is issue-bound: 64 gate elements per thread and tile)
+            const f32x2_t nmr = splat_f32x2(-ln_mean * ln_rstd), rs = splat_f32x2(ln_rstd);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (has_bias) {
+                ba = *reinterpret_cast<const float4*>(bv + i);
+                bg = *reinterpret_cast<const float4*>(bv + 32 + i);
+              }
+              f32x2_t a0 = pack_f32x2(v[i], v[i + 1]), a1 = pack_f32x2(v[i + 2], v[i + 3]);
+              f32x2_t g0 = pack_f32x2(gte[i], gte[i + 1]), g1 = pack_f32x2(gte[i + 2], gte[i + 3]);
+              if (has_ln) {                                    // rstd * (acc - mean * wsum) + bias
+                const float4 wa = *reinterpret_cast<const float4*>(wv + i);
+                const float4 wg = *reinterpret_cast<const float4*>(wv + 32 + i);
+                a0 = fma_f32x2(a0, rs, fma_f32x2(nmr, pack_f32x2(wa.x, wa.y), pack_f32x2(ba.x, ba.y)));
+                a1 = fma_f32x2(a1, rs, fma_f32x2(nmr, pack_f32x2(wa.z, wa.w), pack_f32x2(ba.z, ba.w)));
+                g0 = fma_f32x2(g0, rs, fma_f32x2(nmr, pack_f32x2(wg.x, wg.y), pack_f32x2(bg.x, bg.y)));
+                g1 = fma_f32x2(g1, rs, fma_f32x2(nmr, pack_f32x2(wg.z, wg.w), pack_f32x2(bg.z, bg.w)));
+              } else {
+                a0 = add_f32x2(a0, pack_f32x2(ba.x, ba.y));
+                a1 = add_f32x2(a1, pack_f32x2(ba.z, ba.w));
+                g0 = add_f32x2(g0, pack_f32x2(bg.x, bg.y));
+                g1 = add_f32x2(g1, pack_f32x2(bg.z, bg.w));
+              }
+              unpack_f32x2(mul_f32x2(a0, gelu_erf_x2(g0)), v[i], v[i + 1]);
+              unpack_f32x2(mul_f32x2(a1, gelu_erf_x2(g1)), v[i + 2], v[i + 3]);
+            }
+#else
             if (has_ln) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -560,6 +590,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
               v[i + 2] = (v[i + 2] + ba.z) * gelu_erf_f(gte[i + 2] + bg.z);
               v[i + 3] = (v[i + 3] + ba.w) * gelu_erf_f(gte[i + 3] + bg.w);
             }
+#endif
           } else {
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
@@ -836,8 +867,11 @@ static cudaError_t launch_mode(const GemmMaps& maps, const GemmParams& p, int nu
 }
 
 cudaError_t launch_gemm(const GemmMaps& maps, const GemmParams& p, int bn, int num_sms, cudaStream_t stream) {
-  if (p.mode == MODE_GEGLU) {                    // GEGLU projections: K = C is short, single CTAs only
-    if (p.cg != 1) return cudaErrorInvalidValue;
+  if (p.mode == MODE_GEGLU) {                    // GEGLU projections
+    if (p.cg == 2) {                             // 256 x 256 pair tiles: the only shape whose operand ingress per FLOP
+      if (bn == 256) return launch_bn<256, 2, MODE_GEGLU>(maps, p, num_sms, stream);    // lets the tensor pipe lead
+      return cudaErrorInvalidValue;
+    }
     switch (bn) {
       case 64: return launch_bn<64, 1, MODE_GEGLU>(maps, p, num_sms, stream);
       case 128: return launch_bn<128, 1, MODE_GEGLU>(maps, p, num_sms, stream);

@@ -473,4 +473,107 @@ cudaError_t launch_cvt_f32_f16(const float* src, __half* dst, long long rows, in
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// network-level training glue (uni_renderer_b200/trainer.py): SiLU forward / backward on fp16 vectors (time-embedding
+// path), the two resampling adjoints and the optimizer.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) silu_f16_kernel(const __half* x, const __half* dy, __half* out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __half2float(x[i]);
+    const float sg = 1.0f / (1.0f + __expf(-v));
+    out[i] = __float2half_rn(dy ? __half2float(dy[i]) * sg * (1.0f + v * (1.0f - sg)) : v * sg);
+  }
+}
+cudaError_t launch_silu_f16(const __half* x, const __half* dy, __half* out, long long n, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  silu_f16_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(x, dy, out, n);
+  return cudaGetLastError();
+}
+
+// adjoint of nearest-2x upsampling: dst[b, h, w, :] = sum of the 2x2 block of src [B, 2H, 2W, C] (fp32 sum, 8 channels
+// per thread)
+__global__ void __launch_bounds__(256) pool2x2_sum_kernel(const __half* src, __half* dst, int B, int H, int W, int C) {
+  const int CV = C >> 3;
+  const long long n = static_cast<long long>(B) * H * W * CV;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    const long long pix = i / CV;
+    const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const size_t sp = (static_cast<size_t>(b) * 2 * H + 2 * h + (q >> 1)) * (2 * W) + 2 * w + (q & 1);
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + sp * C + cv * 8);
+      const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(hp[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = pack_half2(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(pix) * C + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+cudaError_t launch_pool2x2_sum(const __half* src, __half* dst, int B, int H, int W, int C, cudaStream_t stream) {
+  const long long n = static_cast<long long>(B) * H * W * (C >> 3);
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  pool2x2_sum_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(src, dst, B, H, W, C);
+  return cudaGetLastError();
+}
+
+// zero insertion: dst [B, 2H, 2W, C] = src [B, H, W, C] at the even pixels, 0 elsewhere -- turns the data / weight
+// gradient of a stride-2 3x3 convolution into the stride-1 kernels' problem (trainer.py)
+__global__ void __launch_bounds__(256) scatter2x_kernel(const __half* src, __half* dst, int B, int H, int W, int C) {
+  const int CV = C >> 3;
+  const long long n = static_cast<long long>(B) * 4 * H * W * CV;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    const long long pix = i / CV;
+    const int x = static_cast<int>(pix % (2 * W)), y = static_cast<int>((pix / (2 * W)) % (2 * H));
+    const int b = static_cast<int>(pix / (4LL * W * H));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (!(x & 1) && !(y & 1))
+      v = *reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * H + (y >> 1)) * W + (x >> 1)) * C + cv * 8);
+    *reinterpret_cast<uint4*>(dst + static_cast<size_t>(pix) * C + cv * 8) = v;
+  }
+}
+cudaError_t launch_scatter2x(const __half* src, __half* dst, int B, int H, int W, int C, cudaStream_t stream) {
+  const long long n = static_cast<long long>(B) * 4 * H * W * (C >> 3);
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  scatter2x_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(src, dst, B, H, W, C);
+  return cudaGetLastError();
+}
+
+// AdamW on flat fp32 buffers, torch.optim.AdamW's arithmetic: p *= 1 - lr wd; m, v moments of g * grad_scale (the
+// inverse loss scale and the clip coefficient); p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                                    float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                    float grad_scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] * (1.0f - lr * wd) - (lr / bc1) * (mi / denom);
+  }
+}
+cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                         float wd, int step, float grad_scale, cudaStream_t stream) {
+  const float bc1 = 1.0f - powf(b1, static_cast<float>(step));
+  const float bc2_sqrt = sqrtf(1.0f - powf(b2, static_cast<float>(step)));
+  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+  adamw_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  return cudaGetLastError();
+}
+
 }  // namespace unib

@@ -45,5 +45,10 @@ cudaError_t launch_geglu(const __half* proj, const __half* dout, __half* out, lo
                          cudaStream_t stream);
 cudaError_t launch_softmax_backward(const __half* P, __half* dP, int rows, int n, int ld, float scale, cudaStream_t stream);
 cudaError_t launch_cvt_f32_f16(const float* src, __half* dst, long long rows, int cols, int ld, cudaStream_t stream);
+cudaError_t launch_silu_f16(const __half* x, const __half* dy, __half* out, long long n, cudaStream_t stream);
+cudaError_t launch_pool2x2_sum(const __half* src, __half* dst, int B, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_scatter2x(const __half* src, __half* dst, int B, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                         float wd, int step, float grad_scale, cudaStream_t stream);
 
 }  // namespace unib

@@ -202,6 +202,48 @@ def geglu(proj: torch.Tensor, dout: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def softmax_backward(p: torch.Tensor, dp: torch.Tensor, n: int, scale: float):
+    """In place on dp: dS = scale * P o (dP - rowsum(dP o P)) over the first n columns of the fp16 matrices p / dp."""
+    L.check(L.load().unib200_softmax_backward(None, p.data_ptr(), dp.data_ptr(), p.shape[0], n, dp.stride(0), float(scale),
+                                              _stream()), "softmax_backward")
+
+
+def cvt_f32_f16(src: torch.Tensor, dst: torch.Tensor):
+    """fp32 [rows, cols] contiguous -> the fp16 matrix view dst [rows, cols] (any leading dimension)."""
+    rows, cols = dst.shape
+    L.check(L.load().unib200_cvt_f32_f16(None, src.data_ptr(), dst.data_ptr(), rows, cols, dst.stride(0), _stream()), "cvt_f32_f16")
+
+
+def silu_f16(x: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """silu(x) (dy None) or dy * silu'(x), elementwise on fp16."""
+    out = torch.empty_like(x)
+    L.check(L.load().unib200_silu_f16(None, x.data_ptr(), dy.data_ptr() if dy is not None else None, out.data_ptr(),
+                                      x.numel(), _stream()), "silu_f16")
+    return out
+
+
+def scatter2x(x: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    """[B*H*W, C] -> [B*2H*2W, C] with x at the even pixels and zeros elsewhere (stride-2 conv gradients)."""
+    out = torch.empty(4 * x.shape[0], x.shape[1], device=x.device, dtype=torch.float16)
+    L.check(L.load().unib200_scatter2x(None, x.data_ptr(), out.data_ptr(), B, H, W, x.shape[1], _stream()), "scatter2x")
+    return out
+
+
+def pool2x2_sum(x: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    """[B*2H*2W, C] -> [B*H*W, C]: 2x2 block sums (adjoint of nearest-2x upsampling)."""
+    out = torch.empty(x.shape[0] // 4, x.shape[1], device=x.device, dtype=torch.float16)
+    L.check(L.load().unib200_pool2x2_sum(None, x.data_ptr(), out.data_ptr(), B, H, W, x.shape[1], _stream()), "pool2x2_sum")
+    return out
+
+
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas, eps: float,
+               weight_decay: float, step: int, grad_scale: float = 1.0):
+    """torch.optim.AdamW's update on flat fp32 buffers, gradients multiplied by grad_scale first."""
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and p.numel() == g.numel() == m.numel() == v.numel()
+    L.check(L.load().unib200_adamw_step(None, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0],
+                                        betas[1], eps, weight_decay, step, grad_scale, _stream()), "adamw_step")
+
+
 class _Linear:
     """y = x W^T (+ b) on the implicit-GEMM kernel, with the two gradient paths of the training slice."""
 
