@@ -25,6 +25,21 @@ def test_tape_gradients_match_autograd_of_the_oracle_on_the_emulator(monkeypatch
     assert _rel(tr.P.grad / tr.loss_scale, flat_ref) <= 4e-3
 
 
+def test_consistency_pass_on_the_emulator(monkeypatch):
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    emu.install_training(monkeypatch)
+    nets, cfgs, batch = _setup(seed=21, S=16, Lc=16)
+    g = torch.Generator().manual_seed(77)
+    cycle = (torch.randn(2, 4, 16, 16, generator=g).half().float(), torch.tensor([801.0, 121.0]))
+    loss_ref, _, _, gref = _oracle_grads(nets, cfgs, batch, torch.device("cpu"), cycle=cycle)
+    tr = DualStreamTrainer(nets, cfgs, loss_scale=256.0, max_grad_norm=None, device="cpu")
+    loss, _, _ = tr.forward_backward(batch["x_img"], batch["t_img"], batch["x_attr"], batch["t_attr"], batch["ehs"],
+                                     batch["img_target"], batch["attr_target"], cycle=cycle)
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+    errs = sorted(((_rel(tr.P.g[n] / tr.loss_scale, gr), n) for n, gr in gref.items()), reverse=True)
+    assert errs[0][0] <= 2e-2, errs[:8]
+
+
 def test_optimizer_step_bookkeeping_on_the_emulator(monkeypatch):
     from uni_renderer_b200.trainer import DualStreamTrainer
     emu.install_training(monkeypatch)

@@ -36,7 +36,7 @@ def _setup(seed=5, B=2, S=32, Lc=77):
     return nets, cfgs, batch
 
 
-def _oracle_grads(nets, cfgs, batch, dev):
+def _oracle_grads(nets, cfgs, batch, dev, cycle=None):
     """torch autograd through oracle/uni_oracle.py's 3-call step + the reference's losses (fp32 on the host: the oracle is a
     CPU restatement)."""
     import torch
@@ -47,7 +47,14 @@ def _oracle_grads(nets, cfgs, batch, dev):
     d, m, raw_a, raw_a_mid = uo.attr_encoder_forward(p["enc"], cfgs["enc"], b["t_attr"], b["ehs"], b["x_attr"])
     img, raw_u, raw_u_mid, _ = uo.unet_forward(p["unet"], cfgs["unet"], b["x_img"], b["t_img"], b["ehs"], d, m)
     msk = uo.attr_decoder_forward(p["dec"], cfgs["dec"], raw_a_mid, raw_a, b["t_attr"], b["ehs"], raw_u, raw_u_mid)
-    loss = reference_losses(img, msk, b["img_target"], b["attr_target"])
+    if cycle is not None:        # the consistency pass of inverse-rendering batches, train/train.py:1375-1416
+        from uni_renderer_b200.trainer import reference_losses_inverse
+        x2 = torch.cat([b["x_attr"][:, :4], msk[:, 4:]], 1)
+        d2, m2, _, _ = uo.attr_encoder_forward(p["enc"], cfgs["enc"], torch.zeros(x2.shape[0]), b["ehs"], x2)
+        img_c = uo.unet_forward(p["unet"], cfgs["unet"], cycle[0].to(dev), cycle[1].to(dev), b["ehs"], d2, m2)[0]
+        loss = reference_losses_inverse(img, msk, img_c, b["img_target"], b["attr_target"])
+    else:
+        loss = reference_losses(img, msk, b["img_target"], b["attr_target"])
     loss.backward()
     grads = {f"{n}.{k}": v.grad for n, sd in p.items() for k, v in sd.items()}
     return loss.detach(), img.detach(), msk.detach(), grads
@@ -82,6 +89,28 @@ def test_three_call_training_step_gradients_match_autograd_of_the_oracle():
     assert worst[0][0] <= 1.0, worst[:8]
     flat_ref = torch.cat([gref[n].reshape(-1) for n in tr.P.g])
     assert _rel(tr.P.grad / tr.loss_scale, flat_ref) <= 5e-3, _rel(tr.P.grad / tr.loss_scale, flat_ref)
+
+
+@gpu
+def test_inverse_rendering_consistency_pass_gradients_match_autograd_of_the_oracle():
+    """train/train.py:1375-1416: a second encoder + UNet pass on cat(clean mask latents, predicted attributes); its
+    gradient reaches the first pass through the prediction (decoder conv_out -> ... -> all three networks)."""
+    import torch
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    nets, cfgs, batch = _setup(seed=21, S=16, Lc=16)
+    g = torch.Generator().manual_seed(77)
+    cycle = (torch.randn(2, 4, 16, 16, generator=g).half().float(), torch.tensor([801.0, 121.0]))
+    loss_ref, img_ref, msk_ref, gref = _oracle_grads(nets, cfgs, batch, torch.device("cpu"), cycle=cycle)
+    tr = DualStreamTrainer(nets, cfgs, loss_scale=256.0, max_grad_norm=None)
+    loss, img, msk = tr.forward_backward(batch["x_img"], batch["t_img"], batch["x_attr"], batch["t_attr"], batch["ehs"],
+                                         batch["img_target"], batch["attr_target"], cycle=cycle)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+    errs = sorted(((_rel(tr.P.g[n] / tr.loss_scale, gr), n) for n, gr in gref.items()), reverse=True)
+    print("worst gradient errors (cycle):", [(round(e, 5), n) for e, n in errs[:4]])
+    assert errs[0][0] <= 3e-2, errs[:8]
+    flat_ref = torch.cat([gref[n].reshape(-1) for n in tr.P.g])
+    assert _rel(tr.P.grad / tr.loss_scale, flat_ref) <= 5e-3
 
 
 @gpu

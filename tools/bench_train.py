@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""One optimizer step of the reference's training loop (train/train.py:1324-1427) at full SD-1.5 widths on the B200
+kernels: 3-call dual-stream forward, losses, backward through all three networks, clip, AdamW
+(uni_renderer_b200/trainer.py).  Prints one JSON line: seconds per step, images/s, peak memory.  Random-init weights and
+synthetic latents (no checkpoints / datasets in this environment).  The attention of this path is the materialised form
+(no flash backward yet), so this is a correctness-first number, not a tuned one."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=2)
+ap.add_argument("--latent", type=int, default=64)
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--tiny", action="store_true", help="the oracle's TINY widths (smoke run)")
+ap.add_argument("--cycle", action="store_true", help="add the inverse-rendering consistency pass")
+a = ap.parse_args()
+
+from dataclasses import replace  # noqa: E402
+
+from oracle import uni_oracle as uo  # noqa: E402  (random_state_dict only: parameter shapes / names of the three networks)
+from uni_renderer_b200.trainer import DualStreamTrainer  # noqa: E402
+
+base = uo.TINY if a.tiny else uo.SD15
+cfgs = {"unet": replace(base), "enc": replace(base, in_channels=28), "dec": replace(base, out_channels=28)}
+kinds = {"unet": "unet", "enc": "attr_enc", "dec": "attr_dec"}
+t0 = time.time()
+nets = {k: uo.random_state_dict(kinds[k], cfgs[k], 3 + i) for i, k in enumerate(("unet", "enc", "dec"))}
+n_params = sum(v.numel() for sd in nets.values() for v in sd.values())
+tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0)
+del nets
+init_s = time.time() - t0
+B, S = a.batch, a.latent
+g = torch.Generator().manual_seed(0)
+r = lambda *s: torch.randn(*s, generator=g)                                   # noqa: E731
+batch = (r(B, 4, S, S), torch.randint(0, 1000, (B,), generator=g).float(), r(B, 28, S, S),
+         torch.randint(0, 1000, (B,), generator=g).float(), r(B, 77, base.cross_attention_dim), r(B, 4, S, S), r(B, 24, S, S))
+kw = {}
+if a.cycle:
+    kw["cycle"] = (r(B, 4, S, S), torch.randint(0, 1000, (B,), generator=g).float())
+infos = []
+for i in range(a.warmup + a.steps):
+    torch.cuda.synchronize()
+    t1 = time.time()
+    info = tr.step(*batch, **kw)
+    torch.cuda.synchronize()
+    info["seconds"] = time.time() - t1
+    infos.append(info)
+timed = infos[a.warmup:]
+sec = sum(i["seconds"] for i in timed) / len(timed)
+print(json.dumps({"what": "3-call dual-stream training step (forward + backward + clip + AdamW), fp16 activations / fp32 master weights",
+                  "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle),
+                  "parameters": n_params, "seconds_per_step": sec, "images_per_s": B / sec,
+                  "losses": [round(i["loss"], 5) for i in infos], "grad_norms": [round(i["grad_norm"], 4) for i in infos],
+                  "skipped": [i["skipped"] for i in infos], "init_seconds": round(init_s, 1),
+                  "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "data": "synthetic"}))

@@ -196,6 +196,8 @@ def conv(tp: Tape, x: TT, name: str, k: int = 3, stride: int = 1, bias_tab: Opti
             tp.acc(bias_tab, gt)
         if x.needs_grad:
             dx = tp.new(x.rows, _ld8(Cin))
+            if dx.shape[1] != Cin:
+                dx.zero_()
             ops.conv_gemm(None, [(dyw, N, SEG_3x3 if k == 3 else SEG_1x1)], P.weight_t(name), dx, M=x.rows, N=Cin, B=B,
                           H=Hw if k == 3 else 0, W=Ww if k == 3 else 0, partial=tp.partial)
             tp.acc(x, dx if dx.shape[1] == x.C else dx[:, :x.C].contiguous())
@@ -263,6 +265,26 @@ def cat(tp: Tape, a: TT, b: TT) -> TT:
         if y.g is not None:
             tp.acc(a, y.g[:, :a.C].contiguous())
             tp.acc(b, y.g[:, a.C:].contiguous())
+
+    tp.push(bwd)
+    return y
+
+
+def replace_head(tp: Tape, src: TT, head: torch.Tensor, n_head: int, n_valid: int) -> TT:
+    """cat(head[:, :n_head], src[:, n_head:n_valid]) -- `torch.cat((latents_mask, mask_pred), dim=1)` of the consistency
+    pass (train/train.py:1393): the predicted attribute channels stay on the tape, the clean mask channels are data."""
+    v = src.v.clone()
+    v[:, :n_head] = head[:, :n_head]
+    v[:, n_valid:] = 0
+    y = TT(v, src.B, src.H, src.W)
+
+    def bwd():
+        if y.g is None:
+            return
+        g = y.g.clone()
+        g[:, :n_head] = 0
+        g[:, n_valid:] = 0
+        tp.acc(src, g)
 
     tp.push(bwd)
     return y
@@ -532,6 +554,14 @@ def reference_losses(img_pred, mask_pred_full, img_target, attr_target):
     return loss
 
 
+def reference_losses_inverse(img_pred, mask_pred_full, img_pred_c, img_target, attr_target):
+    """The `is_inv_rendering` branch (train/train.py:1375-1416): loss_img + loss_mask + 0.8 x the consistency loss of the
+    second pass (the contrastive term and the x10 mask weight are dropped there)."""
+    import torch.nn.functional as F
+    return (F.mse_loss(img_pred.float(), img_target.float()) + F.mse_loss(mask_pred_full[:, 4:].float(), attr_target.float()) +
+            0.8 * F.mse_loss(img_pred_c.float(), img_target.float()))
+
+
 def allreduce_gradients(flat_grad: torch.Tensor, bucket_bytes: int = 64 << 20, group=None) -> int:
     """Average the flat gradient buffer over the data-parallel ranks in fixed-size buckets (one collective per bucket, so a
     caller can overlap them with the tail of its backward).  Returns the number of collectives issued."""
@@ -564,10 +594,13 @@ class DualStreamTrainer:
         self.dev = self.P.dev
 
     # -- forward + backward ------------------------------------------------------------------------------------------
-    def forward_backward(self, x_img, t_img, x_attr, t_attr, ehs, img_target, attr_target, loss_fn=reference_losses):
+    def forward_backward(self, x_img, t_img, x_attr, t_attr, ehs, img_target, attr_target, loss_fn=None, cycle=None):
         """The 3-call forward, the loss, and the whole backward: gradients accumulate (scaled by loss_scale) in P.grad.
         x_img [B,4,H,W] noisy RGB latents; x_attr [B,28,H,W] = cat(mask latents, noisy attribute latents); ehs [B,L,D].
-        Returns (loss, img_pred [B,4,H,W] fp32, mask_pred [B,28,H,W] fp32)."""
+        cycle = (x_img_c, t_img_c) adds the consistency pass of inverse-rendering batches (train/train.py:1375-1416): the
+        encoder and the UNet run again on cat(clean mask latents, PREDICTED attributes) at attribute timestep 0 -- the
+        gradient of that pass flows back through the prediction into the first pass -- and the loss becomes
+        reference_losses_inverse.  Returns (loss, img_pred [B,4,H,W] fp32, mask_pred [B,28,H,W] fp32)."""
         tp = Tape(self.P)
         dev = self.dev
         ctx = to_matrix(ehs, dev)
@@ -576,16 +609,27 @@ class DualStreamTrainer:
         img, raw_u, raw_u_mid = unet_forward(tp, "unet", self.cfgs["unet"], xi, t_img, ctx, down, mid)
         msk = attr_decoder_forward(tp, "dec", self.cfgs["dec"], raw_a_mid, raw_a, t_attr, ctx, raw_u, raw_u_mid)
         c_img, c_msk = self.P.p["unet.conv_out.weight"].shape[0], self.P.p["dec.conv_out.weight"].shape[0]
-        img_pred = to_nchw(img, c_img).requires_grad_(True)
-        mask_pred = to_nchw(msk, c_msk).requires_grad_(True)
-        loss = loss_fn(img_pred, mask_pred, img_target.to(dev), attr_target.to(dev))
+        heads = [(img, c_img), (msk, c_msk)]
+        if cycle is not None:
+            x_img_c, t_img_c = cycle
+            cond2 = replace_head(tp, msk, xa.v, 4, c_msk)
+            t0 = torch.zeros(xi.B)
+            down2, mid2, _, _ = attr_encoder_forward(tp, "enc", self.cfgs["enc"], t0, ctx, cond2)
+            img_c, _, _ = unet_forward(tp, "unet", self.cfgs["unet"], to_matrix(x_img_c, dev), t_img_c, ctx, down2, mid2)
+            heads.append((img_c, c_img))
+        preds = [to_nchw(t, cn).requires_grad_(True) for t, cn in heads]
+        if cycle is not None:
+            loss = (loss_fn or reference_losses_inverse)(preds[0], preds[1], preds[2], img_target.to(dev), attr_target.to(dev))
+        else:
+            loss = (loss_fn or reference_losses)(preds[0], preds[1], img_target.to(dev), attr_target.to(dev))
         (loss * self.loss_scale).backward()
-        for t, gr, cn in ((img, img_pred.grad, c_img), (msk, mask_pred.grad, c_msk)):
+        # seed the tape: later heads first is irrelevant -- every head's gradient is set before the tape unwinds
+        for (t, cn), pr in zip(heads, preds):
             g = torch.zeros_like(t.v)
-            g[:, :cn] = gr.permute(0, 2, 3, 1).reshape(-1, cn).half()
-            t.g = g
+            g[:, :cn] = pr.grad.permute(0, 2, 3, 1).reshape(-1, cn).half()
+            tp.acc(t, g)
         tp.backward()
-        return loss.detach(), img_pred.detach(), mask_pred.detach()
+        return loss.detach(), preds[0].detach(), preds[1].detach()
 
     # -- optimizer ---------------------------------------------------------------------------------------------------
     def optimizer_step(self) -> Dict[str, float]:
