@@ -40,6 +40,20 @@ def test_consistency_pass_on_the_emulator(monkeypatch):
     assert errs[0][0] <= 2e-2, errs[:8]
 
 
+def test_gradient_checkpointing_gives_the_same_gradients_on_the_emulator(monkeypatch):
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    emu.install_training(monkeypatch)
+    nets, cfgs, batch = _setup(seed=4, S=16, Lc=16)
+    args = (batch["x_img"], batch["t_img"], batch["x_attr"], batch["t_attr"], batch["ehs"], batch["img_target"],
+            batch["attr_target"])
+    grads = []
+    for ck in (False, True):
+        tr = DualStreamTrainer(nets, cfgs, loss_scale=256.0, gradient_checkpointing=ck, device="cpu")
+        tr.forward_backward(*args)
+        grads.append(tr.P.grad.clone())
+    assert _rel(grads[1], grads[0]) <= 1e-3, _rel(grads[1], grads[0])       # regrouped fp16 gradient sums only
+
+
 def test_optimizer_step_bookkeeping_on_the_emulator(monkeypatch):
     from uni_renderer_b200.trainer import DualStreamTrainer
     emu.install_training(monkeypatch)

@@ -21,6 +21,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--tiny", action="store_true", help="the oracle's TINY widths (smoke run)")
 ap.add_argument("--cycle", action="store_true", help="add the inverse-rendering consistency pass")
+ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per resnet / transformer block")
 a = ap.parse_args()
 
 from dataclasses import replace  # noqa: E402
@@ -34,7 +35,7 @@ kinds = {"unet": "unet", "enc": "attr_enc", "dec": "attr_dec"}
 t0 = time.time()
 nets = {k: uo.random_state_dict(kinds[k], cfgs[k], 3 + i) for i, k in enumerate(("unet", "enc", "dec"))}
 n_params = sum(v.numel() for sd in nets.values() for v in sd.values())
-tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0)
+tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0, gradient_checkpointing=a.checkpoint)
 del nets
 init_s = time.time() - t0
 B, S = a.batch, a.latent
@@ -56,7 +57,7 @@ for i in range(a.warmup + a.steps):
 timed = infos[a.warmup:]
 sec = sum(i["seconds"] for i in timed) / len(timed)
 print(json.dumps({"what": "3-call dual-stream training step (forward + backward + clip + AdamW), fp16 activations / fp32 master weights",
-                  "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle),
+                  "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle), "gradient_checkpointing": bool(a.checkpoint),
                   "parameters": n_params, "seconds_per_step": sec, "images_per_s": B / sec,
                   "losses": [round(i["loss"], 5) for i in infos], "grad_norms": [round(i["grad_norm"], 4) for i in infos],
                   "skipped": [i["skipped"] for i in infos], "init_seconds": round(init_s, 1),

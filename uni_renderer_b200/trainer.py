@@ -13,8 +13,9 @@ three networks are written against those ops exactly the way oracle/uni_oracle.p
   Downsample2D (3x3 stride 2)     forward SEG_3x3_S2; gradients through unib200_scatter2x (zero insertion) + the stride-1 kernels
   Upsample2D (nearest 2x + conv)  unib200_upsample2x / unib200_pool2x2_sum around the conv
   GroupNorm(+SiLU), LayerNorm     unib200_groupnorm(_backward), unib200_layernorm(_backward)
-  attention                       materialised per (sample, head): S = Q K^T, softmax rows, O = P V and the four backward
-                                  GEMMs (the flash kernel of the inference path has no backward yet); any context length
+  attention                       forward: the flash kernel of the inference path (unib200_attention); backward: per (sample,
+                                  head) the probabilities are recomputed (S = Q K^T, row softmax) and the four gradient GEMMs
+                                  run on the GEMM / wgrad kernels (no fused flash backward yet); any context length
   GEGLU, SiLU, adds               unib200_geglu, unib200_silu_f16, unib200_add_f16
   time embedding MLP              the same linear ops on a 128-row padded matrix
   optimizer                       unib200_adamw_step on ONE flat fp32 parameter / gradient / moment buffer per trainer
@@ -110,12 +111,16 @@ class ParamSet:
 
 
 class Tape:
-    def __init__(self, params: ParamSet):
+    def __init__(self, params: ParamSet, like: Optional["Tape"] = None, checkpointing: bool = False):
         self.P = params
         self.dev = params.dev
         self._bwd: List[Callable[[], None]] = []
-        self.partial = torch.empty(16 << 20, device=self.dev, dtype=torch.float32)
-        self.scratch = torch.empty(1 << 18, device=self.dev, dtype=torch.float32)
+        self.checkpointing = checkpointing
+        if like is not None:          # a sub-tape of a checkpointed block: same workspaces
+            self.partial, self.scratch = like.partial, like.scratch
+        else:
+            self.partial = torch.empty(16 << 20, device=self.dev, dtype=torch.float32)
+            self.scratch = torch.empty(1 << 18, device=self.dev, dtype=torch.float32)
 
     def push(self, fn: Callable[[], None]):
         self._bwd.append(fn)
@@ -351,15 +356,10 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
     Lp = _ld8(Nk)
     scale = d ** -0.5
     ao = tp.new(q.rows, Cn)
-    Pm = torch.zeros(B, heads, Nq, Lp, device=tp.dev, dtype=torch.float16)
-    for b in range(B):
-        for h in range(heads):
-            cs = slice(h * d, (h + 1) * d)
-            qs, ks, vs = q.v[b * Nq:(b + 1) * Nq, cs], k.v[b * Nk:(b + 1) * Nk, cs], v.v[b * Nk:(b + 1) * Nk, cs]
-            s = Pm[b, h]
-            ops.conv_gemm(None, [(qs, d, SEG_1x1)], _pack_rows(ks), s, M=Nq, N=Nk)                          # S = Q K^T
-            ops.softmax_rows(None, s, rows=Nq, n=Nk, scale=scale)
-            ops.conv_gemm(None, [(s, Nk, SEG_1x1)], _pack_cols(vs), ao[b * Nq:(b + 1) * Nq, cs], M=Nq, N=d)  # O = P V
+    # forward: the fused flash kernel of the inference path (one launch, nothing but O is kept); the backward below
+    # recomputes each head's probabilities in the materialised form (S = Q K^T, row softmax) -- flash-style recomputation
+    # without a fused backward kernel yet
+    ops.attention(None, q.v, k.v, v.v, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale)
     y = TT(ao, q.B, q.H, q.W)
 
     def bwd():
@@ -372,7 +372,10 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
             for h in range(heads):
                 cs = slice(h * d, (h + 1) * d)
                 rq, rk = slice(b * Nq, (b + 1) * Nq), slice(b * Nk, (b + 1) * Nk)
-                do, p = y.g[rq, cs], Pm[b, h]
+                do = y.g[rq, cs]
+                p = torch.zeros(Nq, Lp, device=tp.dev, dtype=torch.float16)
+                ops.conv_gemm(None, [(q.v[rq, cs], d, SEG_1x1)], _pack_rows(k.v[rk, cs]), p, M=Nq, N=Nk)      # S = Q K^T
+                ops.softmax_rows(None, p, rows=Nq, n=Nk, scale=scale)                                         # P
                 if v.needs_grad:
                     dvh, _ = T.conv_wgrad(do, d, p, Nk, B=1, H=0, W=0, taps=1, want_bias=False)               # dV = P^T dO
                     T.cvt_f32_f16(dvh, dv[rk, cs])
@@ -387,6 +390,35 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
         tp.acc(q, dq)
         tp.acc(k, dk)
         tp.acc(v, dv)
+
+    tp.push(bwd)
+    return y
+
+
+def checkpoint(tp: Tape, fn, *inputs: TT) -> TT:
+    """Activation checkpointing of one block (`torch.utils.checkpoint` around each resnet / transformer when the
+    reference's `gradient_checkpointing` is on, models/unet_2d_blocks.py:1172-1197): the forward keeps only the block's
+    inputs and output; the backward re-runs the block on a private tape and unwinds that.  The kernels are
+    deterministic, so the recomputed activations are bit-identical; the gradients differ only by the fp16 rounding of
+    regrouped sums (a block input's gradient is summed inside the block before it joins the outer sum)."""
+    if not tp.checkpointing:
+        return fn(tp, *inputs)
+    sub = Tape(tp.P, like=tp)
+    out = fn(sub, *inputs)
+    sub._bwd.clear()                                  # drops every intermediate activation of the block
+    y = TT(out.v, out.B, out.H, out.W)
+
+    def bwd():
+        if y.g is None:
+            return
+        again = Tape(tp.P, like=tp)
+        ins = [TT(i.v, i.B, i.H, i.W, i.needs_grad) for i in inputs]
+        o = fn(again, *ins)
+        o.g = y.g
+        again.backward()
+        for i, j in zip(inputs, ins):
+            if j.g is not None:
+                tp.acc(i, j.g)
 
     tp.push(bwd)
     return y
@@ -441,14 +473,22 @@ def transformer_2d(tp: Tape, p: str, x: TT, ctx: TT, cfg) -> TT:
     return conv(tp, h, p + ".proj_out", k=1, res=x)
 
 
+def _resnet_ck(tp: Tape, p: str, x: TT, temb_act: TT, cfg) -> TT:
+    return checkpoint(tp, lambda t, a, e: resnet(t, p, a, e, cfg), x, temb_act)
+
+
+def _transformer_ck(tp: Tape, p: str, x: TT, ctx: TT, cfg) -> TT:
+    return checkpoint(tp, lambda t, a, c: transformer_2d(t, p, a, c, cfg), x, ctx)
+
+
 def down_blocks(tp: Tape, net: str, cfg, sample: TT, temb: TT, ctx: TT):
     skips = [sample]
     nb = len(cfg.block_out_channels)
     for i in range(nb):
         for j in range(cfg.layers_per_block):
-            sample = resnet(tp, f"{net}.down_blocks.{i}.resnets.{j}", sample, temb, cfg)
+            sample = _resnet_ck(tp, f"{net}.down_blocks.{i}.resnets.{j}", sample, temb, cfg)
             if cfg.down_has_attn[i]:
-                sample = transformer_2d(tp, f"{net}.down_blocks.{i}.attentions.{j}", sample, ctx, cfg)
+                sample = _transformer_ck(tp, f"{net}.down_blocks.{i}.attentions.{j}", sample, ctx, cfg)
             skips.append(sample)
         if i != nb - 1:
             sample = conv(tp, sample, f"{net}.down_blocks.{i}.downsamplers.0.conv", k=3, stride=2)
@@ -457,9 +497,9 @@ def down_blocks(tp: Tape, net: str, cfg, sample: TT, temb: TT, ctx: TT):
 
 
 def mid_block(tp: Tape, net: str, cfg, sample: TT, temb: TT, ctx: TT) -> TT:
-    sample = resnet(tp, f"{net}.mid_block.resnets.0", sample, temb, cfg)
-    sample = transformer_2d(tp, f"{net}.mid_block.attentions.0", sample, ctx, cfg)
-    return resnet(tp, f"{net}.mid_block.resnets.1", sample, temb, cfg)
+    sample = _resnet_ck(tp, f"{net}.mid_block.resnets.0", sample, temb, cfg)
+    sample = _transformer_ck(tp, f"{net}.mid_block.attentions.0", sample, ctx, cfg)
+    return _resnet_ck(tp, f"{net}.mid_block.resnets.1", sample, temb, cfg)
 
 
 def up_blocks(tp: Tape, net: str, cfg, sample: TT, skips: Sequence[TT], temb: TT, ctx: TT) -> TT:
@@ -468,9 +508,9 @@ def up_blocks(tp: Tape, net: str, cfg, sample: TT, skips: Sequence[TT], temb: TT
     for i in range(nb):
         for j in range(cfg.layers_per_block + 1):
             sample = cat(tp, sample, skips.pop())
-            sample = resnet(tp, f"{net}.up_blocks.{i}.resnets.{j}", sample, temb, cfg)
+            sample = _resnet_ck(tp, f"{net}.up_blocks.{i}.resnets.{j}", sample, temb, cfg)
             if cfg.up_has_attn[i]:
-                sample = transformer_2d(tp, f"{net}.up_blocks.{i}.attentions.{j}", sample, ctx, cfg)
+                sample = _transformer_ck(tp, f"{net}.up_blocks.{i}.attentions.{j}", sample, ctx, cfg)
         if i != nb - 1:
             sample = conv(tp, upsample(tp, sample), f"{net}.up_blocks.{i}.upsamplers.0.conv", k=3)
     return sample
@@ -586,8 +626,10 @@ class DualStreamTrainer:
     objects (block_out_channels, layers_per_block, num_heads, norm_num_groups, norm_eps, down_has_attn, up_has_attn)."""
 
     def __init__(self, nets: Dict[str, SD], cfgs: Dict[str, object], *, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = 1.0, loss_scale: float = 1024.0, device="cuda"):
+                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = 1.0, loss_scale: float = 1024.0,
+                 gradient_checkpointing: bool = False, device="cuda"):
         self.P = ParamSet(nets, device)
+        self.gradient_checkpointing = gradient_checkpointing      # the reference's enable_gradient_checkpointing()
         self.cfgs = cfgs
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm, self.loss_scale = max_grad_norm, loss_scale
@@ -601,7 +643,7 @@ class DualStreamTrainer:
         encoder and the UNet run again on cat(clean mask latents, PREDICTED attributes) at attribute timestep 0 -- the
         gradient of that pass flows back through the prediction into the first pass -- and the loss becomes
         reference_losses_inverse.  Returns (loss, img_pred [B,4,H,W] fp32, mask_pred [B,28,H,W] fp32)."""
-        tp = Tape(self.P)
+        tp = Tape(self.P, checkpointing=self.gradient_checkpointing)
         dev = self.dev
         ctx = to_matrix(ehs, dev)
         xi, xa = to_matrix(x_img, dev), to_matrix(x_attr, dev)
