@@ -26,6 +26,16 @@ a = ap.parse_args()
 
 from dataclasses import replace  # noqa: E402
 
+import torch.distributed as dist  # noqa: E402
+
+# data-parallel training: one process per GPU under torchrun (the reference trains under accelerate DDP); every rank
+# holds the same weights, draws its own batch, and the flat gradient buffer is averaged over NCCL in fixed-size buckets
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+if world > 1:
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl")
+
 from oracle import uni_oracle as uo  # noqa: E402  (random_state_dict only: parameter shapes / names of the three networks)
 from uni_renderer_b200.trainer import DualStreamTrainer  # noqa: E402
 
@@ -39,7 +49,7 @@ tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0
 del nets
 init_s = time.time() - t0
 B, S = a.batch, a.latent
-g = torch.Generator().manual_seed(0)
+g = torch.Generator().manual_seed(1000 * rank)
 r = lambda *s: torch.randn(*s, generator=g)                                   # noqa: E731
 batch = (r(B, 4, S, S), torch.randint(0, 1000, (B,), generator=g).float(), r(B, 28, S, S),
          torch.randint(0, 1000, (B,), generator=g).float(), r(B, 77, base.cross_attention_dim), r(B, 4, S, S), r(B, 24, S, S))
@@ -49,16 +59,33 @@ if a.cycle:
 infos = []
 for i in range(a.warmup + a.steps):
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t1 = time.time()
     info = tr.step(*batch, **kw)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     info["seconds"] = time.time() - t1
     infos.append(info)
 timed = infos[a.warmup:]
 sec = sum(i["seconds"] for i in timed) / len(timed)
-print(json.dumps({"what": "3-call dual-stream training step (forward + backward + clip + AdamW), fp16 activations / fp32 master weights",
+if world > 1:      # the ranks must hold identical parameters after identical averaged updates
+    chk = tr.P.flat[::4097].double().sum().reshape(1)
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    in_sync = all(float(x) == float(lst[0]) for x in lst)
+    t = torch.tensor([sec], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t)
+else:
+    in_sync = True
+if rank == 0:
+  print(json.dumps({"n_gpus": world, "ranks_in_sync": in_sync, "collectives_per_step": infos[-1]["collectives"],"what": "3-call dual-stream training step (forward + backward + clip + AdamW), fp16 activations / fp32 master weights",
                   "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle), "gradient_checkpointing": bool(a.checkpoint),
-                  "parameters": n_params, "seconds_per_step": sec, "images_per_s": B / sec,
+                  "parameters": n_params, "seconds_per_step": sec, "images_per_s": world * B / sec,
                   "losses": [round(i["loss"], 5) for i in infos], "grad_norms": [round(i["grad_norm"], 4) for i in infos],
                   "skipped": [i["skipped"] for i in infos], "init_seconds": round(init_s, 1),
                   "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "data": "synthetic"}))
+if world > 1:
+    dist.destroy_process_group()
