@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-vae", action="store_true", help="skip the AutoencoderKL side measurement (N=1, 64x64 latents)")
     ap.add_argument("--no-modes", action="store_true",
                     help="skip the `modes` legs (forward / inverse / cycle shards of BASELINE configs[2..4])")
+    ap.add_argument("--no-train", action="store_true",
+                    help="skip the training-step side measurement (tools/bench_train.py as a subprocess, N=1)")
     ap.add_argument("--no-torch-eager", action="store_true",
                     help="skip the live torch-eager fp16 GPU baseline leg (oracle/torch_eager.py as a subprocess)")
     ap.add_argument("--cpu-denoise-steps", type=int, default=2, help="timed CPU denoising steps of the cpu_baseline leg")
@@ -390,6 +392,10 @@ def run_b200(a):
         # SURVEY 8d's "same-box GPU PyTorch" bar, measured LIVE on this box: the reference's arithmetic under torch
         # eager fp16 (cuDNN / cuBLAS / SDPA), as a separate process outside every timed region of this arm
         line["gpu_pytorch_eager"] = torch_eager_leg(local, B, S, ms_res / a.steps / T)
+    if rank == 0 and world == 1 and a.mode == "joint" and B == 4 and S == 64 and not a.no_train:
+        # one optimizer step of the reference's training loop (3-call forward + backward + clip + AdamW,
+        # train/train.py:1324-1427) at full widths on the same kernels; a separate process, beside the headline
+        line["train"] = train_leg(local)
     if rank == 0 and world == 1 and not a.no_vae and S == 64:
         # the next row of the scope table: the AutoencoderKL that brackets every sampling call of the
         # reference (models/pipeline.py:1531-1556 encodes, :1664 / :2335-2349 decodes) on the same kernels.  Reported
@@ -492,6 +498,25 @@ def torch_eager_leg(gpu_index: int, B: int, S: int, our_ms_per_denoise_step: flo
         out["images_per_s"] = B / (50 * best["ms_per_denoise_step"] * 1e-3)
         out["speedup_vs_it"] = best["ms_per_denoise_step"] / our_ms_per_denoise_step
     return out
+
+
+def train_leg(gpu_index: int):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[gpu_index]
+               if os.environ.get("CUDA_VISIBLE_DEVICES") else str(gpu_index))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", "2", "--latent", "64", "--steps", "2",
+           "--warmup", "1"]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+        ln = [x for x in p.stdout.splitlines() if x.startswith("{")]
+        if p.returncode == 0 and ln:
+            d = json.loads(ln[-1])
+            d["parity"] = "tests/test_trainer_gpu.py (every parameter gradient vs torch autograd of the oracle)"
+            return d
+        return {"error": (p.stderr or p.stdout)[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout after 240 s"}
 
 
 def vae_leg(torch, dev, B, image, peaks):

@@ -36,14 +36,17 @@ if world > 1:
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl")
 
-from oracle import uni_oracle as uo  # noqa: E402  (random_state_dict only: parameter shapes / names of the three networks)
+from uni_renderer_b200.engine import NetConfig  # noqa: E402
+from uni_renderer_b200.models import random_init_state_dict  # noqa: E402
 from uni_renderer_b200.trainer import DualStreamTrainer  # noqa: E402
 
-base = uo.TINY if a.tiny else uo.SD15
+base = NetConfig(block_out_channels=(32, 64, 128, 128), num_heads=4, cross_attention_dim=48, norm_num_groups=8) if a.tiny \
+    else NetConfig()
 cfgs = {"unet": replace(base), "enc": replace(base, in_channels=28), "dec": replace(base, out_channels=28)}
 kinds = {"unet": "unet", "enc": "attr_enc", "dec": "attr_dec"}
 t0 = time.time()
-nets = {k: uo.random_state_dict(kinds[k], cfgs[k], 3 + i) for i, k in enumerate(("unet", "enc", "dec"))}
+nets = {k: random_init_state_dict(kinds[k], cfgs[k], 3 + i, "cuda", dtype=torch.float32)
+        for i, k in enumerate(("unet", "enc", "dec"))}
 n_params = sum(v.numel() for sd in nets.values() for v in sd.values())
 tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0, gradient_checkpointing=a.checkpoint)
 del nets
