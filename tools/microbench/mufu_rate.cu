@@ -92,6 +92,44 @@ __global__ void k_mix(float* out, float x0, long long* cyc) {
   out[threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[5] = t1 - t0;
 }
+// fp32 pair -> packed fp16x2 (F2FP.F16.F32.PACK_AB): which pipe, what rate?  (the softmax packs every probability)
+__global__ void k_f2fp(float* out, float x0, long long* cyc) {
+  float a[8]; uint32_t r[8];
+  for (int i = 0; i < 8; ++i) { a[i] = x0 + i * 0.01f + threadIdx.x * 1e-4f; r[i] = 0; }
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t t;
+      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(t) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+      r[i] ^= t;
+    }
+  }
+  long long t1 = clock64();
+  uint32_t s = 0; for (int i = 0; i < 8; ++i) s ^= r[i];
+  out[threadIdx.x] = __uint_as_float(s);
+  if (threadIdx.x == 0) cyc[6] = t1 - t0;
+}
+// 6 MUFU + 4 F2FP per group of 8 elements, the softmax's mix: do they share a pipe?
+__global__ void k_mufu_f2fp(float* out, float x0, long long* cyc) {
+  float a[8]; uint32_t r[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 8; ++i) a[i] = x0 + i * 0.01f + threadIdx.x * 1e-4f;
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t t;
+      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(t) : "f"(a[6]), "f"(a[7]));
+      r[i] ^= t;
+    }
+  }
+  long long t1 = clock64();
+  float s = 0; for (int i = 0; i < 8; ++i) s += a[i];
+  out[threadIdx.x] = s + __uint_as_float(r[0] ^ r[1] ^ r[2] ^ r[3]);
+  if (threadIdx.x == 0) cyc[7] = t1 - t0;
+}
 int main() {
   float* out; long long* cyc;
   cudaMalloc(&out, 4096); cudaMalloc(&cyc, 64); cudaMemset(cyc, 0, 64);
@@ -99,10 +137,12 @@ int main() {
     k_ex2_f32<<<1, nthreads>>>(out, -0.5f, cyc); k_ex2_f16x2<<<1, nthreads>>>(out, -0.5f, cyc);
     k_ex2_f16<<<1, nthreads>>>(out, -0.5f, cyc); k_ffma2<<<1, nthreads>>>(out, 0.5f, cyc);
     k_ffma<<<1, nthreads>>>(out, 0.5f, cyc); k_mix<<<1, nthreads>>>(out, -0.5f, cyc);
+    k_f2fp<<<1, nthreads>>>(out, 0.5f, cyc); k_mufu_f2fp<<<1, nthreads>>>(out, -0.5f, cyc);
     long long h[8]; cudaMemcpy(h, cyc, 64, cudaMemcpyDeviceToHost);
-    const char* names[6] = {"ex2.f32", "ex2.f16x2", "ex2.f16", "ffma2", "ffma", "mix(1 ex2 + 3 ffma2)"};
+    const char* names[8] = {"ex2.f32", "ex2.f16x2", "ex2.f16", "ffma2", "ffma", "mix(1 ex2 + 3 ffma2)", "f2fp (cvt f16x2)",
+                            "group of 6 ex2 + 4 f2fp (per-group cycles x 8)"};
     const double warps_per_smsp = nthreads / 128.0;
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 8; ++i)
       printf("threads=%d %-22s %8lld cycles  %.2f cycles per warp-instr-group per SMSP (8*ITERS groups x %g warps)\n", nthreads,
              names[i], h[i], (double)h[i] / (8.0 * ITERS * warps_per_smsp), warps_per_smsp);
   }
