@@ -505,8 +505,8 @@ def train_leg(gpu_index: int):
                if os.environ.get("CUDA_VISIBLE_DEVICES") else str(gpu_index))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", "2", "--latent", "64", "--steps", "2",
-           "--warmup", "1"]
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_train.py"), "--batch", "2", "--latent", "64", "--steps", "3",
+           "--warmup", "2", "--graph"]
     try:
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
         ln = [x for x in p.stdout.splitlines() if x.startswith("{")]

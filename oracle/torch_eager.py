@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="tiny widths (CPU dry run of this script)")
     ap.add_argument("--cudnn-benchmark", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="NHWC activations and conv weights (cuDNN's fast layout)")
+    ap.add_argument("--train", action="store_true",
+                    help="time one TRAINING step instead (train/train.py:1324-1427: fp32 master weights, fp16 autocast, "
+                         "the reference's losses, backward, clip, fused AdamW) -- the torch-eager bar for uni_renderer_b200/trainer.py")
     a = ap.parse_args()
     import torch
     import torch.nn.functional as F
@@ -64,6 +67,9 @@ def main():
         o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
         return uo._lin(sd, p + ".to_out.0", o)
     uo.attention = sdpa_attention
+
+    if a.train:
+        return train_main(a, torch, uo, dev, base_o, cfgs, cfgs_p, random_init_state_dict)
 
     B, S = a.batch, a.latent
     g = torch.Generator().manual_seed(1234)
@@ -108,6 +114,56 @@ def main():
         "warmup": a.warmup,
         "ms_per_denoise_step": ms, "images_per_s_50_steps": B / (50 * ms * 1e-3),
         "finite": bool(torch.isfinite(x_img.float()).all() and torch.isfinite(x_attr.float()).all())}), flush=True)
+
+
+def train_main(a, torch, uo, dev, base_o, cfgs, cfgs_p, random_init_state_dict):
+    """How the reference trains on this GPU: accelerate mixed_precision="fp16" = fp32 parameters, autocast forward, scaled
+    loss, torch AdamW.  SDPA attention (AttnProcessor2_0), cuDNN / cuBLAS kernels, no gradient checkpointing."""
+    from uni_renderer_b200.trainer import reference_losses
+    sds = [random_init_state_dict(k, c, s, dev, dtype=torch.float32)
+           for k, c, s in zip(("unet", "attr_enc", "attr_dec"), cfgs_p, (3, 4, 5))]
+    params = []
+    for sd in sds:
+        for k in sd:
+            sd[k].requires_grad_(True)
+            params.append(sd[k])
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-2, fused=dev.type == "cuda")
+    B, S = a.batch, a.latent
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)                        # noqa: E731
+    x_img, x_attr, ehs = r(B, 4, S, S), r(B, 28, S, S), r(B, 77, base_o.cross_attention_dim)
+    t_img = torch.randint(0, 1000, (B,), generator=g).float().to(dev)
+    t_attr = torch.randint(0, 1000, (B,), generator=g).float().to(dev)
+    tgt_img, tgt_attr = r(B, 4, S, S), r(B, 24, S, S)
+    scale = 1024.0
+    losses, times = [], []
+    for i in range(a.warmup + a.steps):
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.autocast(device_type=dev.type, dtype=torch.float16 if dev.type == "cuda" else torch.bfloat16):
+            d, m, raw_a, raw_a_mid = uo.attr_encoder_forward(sds[1], cfgs[1], t_attr, ehs, x_attr)
+            img, raw_u, raw_u_mid, _ = uo.unet_forward(sds[0], cfgs[0], x_img, t_img, ehs, d, m)
+            msk = uo.attr_decoder_forward(sds[2], cfgs[2], raw_a_mid, raw_a, t_attr, ehs, raw_u, raw_u_mid)
+        loss = reference_losses(img, msk, tgt_img, tgt_attr)
+        (loss * scale).backward()
+        for p_ in params:
+            p_.grad.div_(scale)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        losses.append(float(loss.detach()))
+    sec = sum(times[a.warmup:]) / a.steps
+    print(json.dumps({
+        "what": "torch eager training step (fp32 weights, fp16 autocast, SDPA, cuDNN / cuBLAS, fused AdamW) of the reference's "
+                "3-call dual-stream step", "device": torch.cuda.get_device_name(0) if dev.type == "cuda" else "cpu",
+        "torch": torch.__version__, "batch": B, "latent": S, "widths": list(base_o.block_out_channels),
+        "cudnn_benchmark": bool(a.cudnn_benchmark), "seconds_per_step": sec, "images_per_s": B / sec,
+        "losses": [round(x, 5) for x in losses],
+        "peak_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2) if dev.type == "cuda" else None}), flush=True)
 
 
 if __name__ == "__main__":

@@ -138,6 +138,25 @@ def test_gradient_checkpointing_gives_the_same_gradients_and_saves_memory():
 
 
 @gpu
+def test_cuda_graph_replay_of_the_step_matches_the_eager_step():
+    """use_cuda_graph: forward + loss + backward captured once and replayed; the same batches must give the same losses
+    and parameters as the eager trainer (deterministic kernels), including on a second, different batch."""
+    import torch
+    from uni_renderer_b200.trainer import DualStreamTrainer
+    nets, cfgs, batch = _setup(seed=31, S=16, Lc=16)
+    _, _, batch2 = _setup(seed=32, S=16, Lc=16)
+    order = ("x_img", "t_img", "x_attr", "t_attr", "ehs", "img_target", "attr_target")
+    runs = []
+    for graph in (False, True):
+        tr = DualStreamTrainer(nets, cfgs, lr=1e-4, loss_scale=256.0, use_cuda_graph=graph)
+        losses = [tr.step(*[b[k].cuda() for k in order])["loss"] for b in (batch, batch2, batch)]
+        torch.cuda.synchronize()
+        runs.append((losses, tr.P.flat.clone()))
+    assert runs[0][0] == pytest.approx(runs[1][0], rel=1e-5), (runs[0][0], runs[1][0])
+    assert _rel(runs[1][1], runs[0][1]) <= 1e-6
+
+
+@gpu
 def test_adamw_kernel_matches_torch_adamw_and_a_training_step_lowers_the_loss():
     import torch
     from uni_renderer_b200.trainer import DualStreamTrainer

@@ -22,6 +22,9 @@ ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--tiny", action="store_true", help="the oracle's TINY widths (smoke run)")
 ap.add_argument("--cycle", action="store_true", help="add the inverse-rendering consistency pass")
 ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per resnet / transformer block")
+ap.add_argument("--graph", action="store_true", help="capture forward + backward into one CUDA graph and replay it")
+ap.add_argument("--profile", action="store_true",
+                help="bracket the LAST step with cudaProfilerStart/Stop (ncu --profile-from-start off ...)")
 a = ap.parse_args()
 
 from dataclasses import replace  # noqa: E402
@@ -48,7 +51,8 @@ t0 = time.time()
 nets = {k: random_init_state_dict(kinds[k], cfgs[k], 3 + i, "cuda", dtype=torch.float32)
         for i, k in enumerate(("unet", "enc", "dec"))}
 n_params = sum(v.numel() for sd in nets.values() for v in sd.values())
-tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0, gradient_checkpointing=a.checkpoint)
+tr = DualStreamTrainer(nets, cfgs, lr=1e-5, loss_scale=1024.0, max_grad_norm=1.0, gradient_checkpointing=a.checkpoint,
+                       use_cuda_graph=a.graph)
 del nets
 init_s = time.time() - t0
 B, S = a.batch, a.latent
@@ -65,8 +69,13 @@ for i in range(a.warmup + a.steps):
     if world > 1:
         dist.barrier()
     t1 = time.time()
+    prof = a.profile and i == a.warmup + a.steps - 1
+    if prof:
+        torch.cuda.profiler.start()
     info = tr.step(*batch, **kw)
     torch.cuda.synchronize()
+    if prof:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     info["seconds"] = time.time() - t1
@@ -85,7 +94,7 @@ else:
     in_sync = True
 if rank == 0:
   print(json.dumps({"n_gpus": world, "ranks_in_sync": in_sync, "collectives_per_step": infos[-1]["collectives"],"what": "3-call dual-stream training step (forward + backward + clip + AdamW), fp16 activations / fp32 master weights",
-                  "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle), "gradient_checkpointing": bool(a.checkpoint),
+                  "widths": "tiny" if a.tiny else "SD-1.5", "batch": B, "latent": S, "cycle_pass": bool(a.cycle), "gradient_checkpointing": bool(a.checkpoint), "cuda_graph": bool(a.graph),
                   "parameters": n_params, "seconds_per_step": sec, "images_per_s": world * B / sec,
                   "losses": [round(i["loss"], 5) for i in infos], "grad_norms": [round(i["grad_norm"], 4) for i in infos],
                   "skipped": [i["skipped"] for i in infos], "init_seconds": round(init_s, 1),

@@ -365,21 +365,21 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
     def bwd():
         if y.g is None:
             return
-        dq = torch.zeros_like(q.v)
-        dk = torch.zeros_like(k.v)
-        dv = torch.zeros_like(v.v)
+        dq = torch.empty_like(q.v)            # every (sample, head) slice below is written in full
+        dk = torch.empty_like(k.v)
+        dv = torch.empty_like(v.v)
         for b in range(B):
             for h in range(heads):
                 cs = slice(h * d, (h + 1) * d)
                 rq, rk = slice(b * Nq, (b + 1) * Nq), slice(b * Nk, (b + 1) * Nk)
                 do = y.g[rq, cs]
-                p = torch.zeros(Nq, Lp, device=tp.dev, dtype=torch.float16)
+                p = (torch.zeros if Lp != Nk else torch.empty)(Nq, Lp, device=tp.dev, dtype=torch.float16)
                 ops.conv_gemm(None, [(q.v[rq, cs], d, SEG_1x1)], _pack_rows(k.v[rk, cs]), p, M=Nq, N=Nk)      # S = Q K^T
                 ops.softmax_rows(None, p, rows=Nq, n=Nk, scale=scale)                                         # P
                 if v.needs_grad:
                     dvh, _ = T.conv_wgrad(do, d, p, Nk, B=1, H=0, W=0, taps=1, want_bias=False)               # dV = P^T dO
                     T.cvt_f32_f16(dvh, dv[rk, cs])
-                dp = torch.zeros(Nq, Lp, device=tp.dev, dtype=torch.float16)
+                dp = (torch.zeros if Lp != Nk else torch.empty)(Nq, Lp, device=tp.dev, dtype=torch.float16)
                 ops.conv_gemm(None, [(do, d, SEG_1x1)], _pack_rows(v.v[rk, cs]), dp, M=Nq, N=Nk)              # dP = dO V^T
                 T.softmax_backward(p, dp, Nk, scale)                                                          # dp := dS
                 if q.needs_grad:
@@ -627,9 +627,14 @@ class DualStreamTrainer:
 
     def __init__(self, nets: Dict[str, SD], cfgs: Dict[str, object], *, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, max_grad_norm: Optional[float] = 1.0, loss_scale: float = 1024.0,
-                 gradient_checkpointing: bool = False, device="cuda"):
+                 gradient_checkpointing: bool = False, use_cuda_graph: bool = False, device="cuda"):
         self.P = ParamSet(nets, device)
         self.gradient_checkpointing = gradient_checkpointing      # the reference's enable_gradient_checkpointing()
+        # use_cuda_graph: `step` captures forward + loss + backward (every kernel launch, the weight packing and the
+        # loss-head autograd) into ONE CUDA graph on its first call and replays it afterwards: the ~13 k launches of a
+        # step then cost no host time.  Shapes (and whether the consistency pass runs) are fixed by the first batch.
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
         self.cfgs = cfgs
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm, self.loss_scale = max_grad_norm, loss_scale
@@ -655,7 +660,7 @@ class DualStreamTrainer:
         if cycle is not None:
             x_img_c, t_img_c = cycle
             cond2 = replace_head(tp, msk, xa.v, 4, c_msk)
-            t0 = torch.zeros(xi.B)
+            t0 = torch.zeros(xi.B, device=dev)
             down2, mid2, _, _ = attr_encoder_forward(tp, "enc", self.cfgs["enc"], t0, ctx, cond2)
             img_c, _, _ = unet_forward(tp, "unet", self.cfgs["unet"], to_matrix(x_img_c, dev), t_img_c, ctx, down2, mid2)
             heads.append((img_c, c_img))
@@ -698,7 +703,44 @@ class DualStreamTrainer:
         return info
 
     def step(self, *batch, **kw):
-        loss, _, _ = self.forward_backward(*batch, **kw)
+        if self.use_cuda_graph:
+            loss = self._graph_step(batch, kw)
+        else:
+            loss, _, _ = self.forward_backward(*batch, **kw)
         info = self.optimizer_step()
         info["loss"] = float(loss.item())
         return info
+
+    def _graph_step(self, batch, kw):
+        dev = self.dev
+        cyc = kw.get("cycle")
+        flat = list(batch) + (list(cyc) if cyc is not None else [])
+        if self._graph is None:
+            self._static = [t.detach().to(dev).clone() for t in flat]
+            nb = len(batch)
+
+            def run():
+                st = self._static
+                k2 = dict(kw)
+                if cyc is not None:
+                    k2["cycle"] = (st[nb], st[nb + 1])
+                return self.forward_backward(*st[:nb], **k2)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):               # eager warm-up: lazy kernel attributes, allocator, autograd
+                run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.P.zero_grad()
+            self.P.invalidate()                         # the weight packing must be part of the captured work
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_out = run()
+            self.P.invalidate()
+        for dst, src in zip(self._static, flat):
+            if tuple(dst.shape) != tuple(src.shape):
+                raise ValueError("use_cuda_graph: batch shapes are fixed by the first step")
+            dst.copy_(src)
+        self._graph.replay()
+        return self._graph_out[0]
