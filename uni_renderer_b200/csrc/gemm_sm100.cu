@@ -13,6 +13,8 @@
 // fused scheduler update) use direct per-thread stores.
 #include "gemm_sm100.cuh"
 
+#include <type_traits>
+
 namespace unib {
 
 // CG = CTAs per MMA: 1 = cta_group::1 (tile 128 x BN per CTA); 2 = cta_group::2 (tile 256 x BN per CTA PAIR: each CTA
@@ -542,55 +544,43 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             }
             const float* wv = wsum_s + (2 * jj) * 32;
             const float* bv = my_bias + (2 * jj) * 32;
-#ifndef UNIB_GEGLU_SCALAR
-            // packed fp32 pairs throughout (this epilogue is issue-bound: 64 gate elements per thread and tile)
+            // packed fp32 pairs throughout (64 gate elements per thread and tile).  The bias / LayerNorm options are
+            // hoisted OUT of the unrolled loop as compile-time flags of a generic lambda: a warp-uniform branch inside
+            // it ends a basic block every four elements, and the scheduler cannot interleave the eight independent
+            // rcp -> polynomial -> ex2 chains across those boundaries.
             const f32x2_t nmr = splat_f32x2(-ln_mean * ln_rstd), rs = splat_f32x2(ln_rstd);
+            auto geglu_block = [&](auto ln_c, auto bias_c) {
+              constexpr bool kLn = decltype(ln_c)::value, kBias = decltype(bias_c)::value;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-              if (has_bias) {
-                ba = *reinterpret_cast<const float4*>(bv + i);
-                bg = *reinterpret_cast<const float4*>(bv + 32 + i);
+              for (int i = 0; i < 32; i += 4) {
+                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                if (kBias) {
+                  ba = *reinterpret_cast<const float4*>(bv + i);
+                  bg = *reinterpret_cast<const float4*>(bv + 32 + i);
+                }
+                f32x2_t a0 = pack_f32x2(v[i], v[i + 1]), a1 = pack_f32x2(v[i + 2], v[i + 3]);
+                f32x2_t g0 = pack_f32x2(gte[i], gte[i + 1]), g1 = pack_f32x2(gte[i + 2], gte[i + 3]);
+                if (kLn) {                                     // rstd * (acc - mean * wsum) + bias
+                  const float4 wa = *reinterpret_cast<const float4*>(wv + i);
+                  const float4 wg = *reinterpret_cast<const float4*>(wv + 32 + i);
+                  a0 = fma_f32x2(a0, rs, fma_f32x2(nmr, pack_f32x2(wa.x, wa.y), pack_f32x2(ba.x, ba.y)));
+                  a1 = fma_f32x2(a1, rs, fma_f32x2(nmr, pack_f32x2(wa.z, wa.w), pack_f32x2(ba.z, ba.w)));
+                  g0 = fma_f32x2(g0, rs, fma_f32x2(nmr, pack_f32x2(wg.x, wg.y), pack_f32x2(bg.x, bg.y)));
+                  g1 = fma_f32x2(g1, rs, fma_f32x2(nmr, pack_f32x2(wg.z, wg.w), pack_f32x2(bg.z, bg.w)));
+                } else if (kBias) {
+                  a0 = add_f32x2(a0, pack_f32x2(ba.x, ba.y));
+                  a1 = add_f32x2(a1, pack_f32x2(ba.z, ba.w));
+                  g0 = add_f32x2(g0, pack_f32x2(bg.x, bg.y));
+                  g1 = add_f32x2(g1, pack_f32x2(bg.z, bg.w));
+                }
+                unpack_f32x2(mul_f32x2(a0, gelu_erf_x2(g0)), v[i], v[i + 1]);
+                unpack_f32x2(mul_f32x2(a1, gelu_erf_x2(g1)), v[i + 2], v[i + 3]);
               }
-              f32x2_t a0 = pack_f32x2(v[i], v[i + 1]), a1 = pack_f32x2(v[i + 2], v[i + 3]);
-              f32x2_t g0 = pack_f32x2(gte[i], gte[i + 1]), g1 = pack_f32x2(gte[i + 2], gte[i + 3]);
-              if (has_ln) {                                    // rstd * (acc - mean * wsum) + bias
-                const float4 wa = *reinterpret_cast<const float4*>(wv + i);
-                const float4 wg = *reinterpret_cast<const float4*>(wv + 32 + i);
-                a0 = fma_f32x2(a0, rs, fma_f32x2(nmr, pack_f32x2(wa.x, wa.y), pack_f32x2(ba.x, ba.y)));
-                a1 = fma_f32x2(a1, rs, fma_f32x2(nmr, pack_f32x2(wa.z, wa.w), pack_f32x2(ba.z, ba.w)));
-                g0 = fma_f32x2(g0, rs, fma_f32x2(nmr, pack_f32x2(wg.x, wg.y), pack_f32x2(bg.x, bg.y)));
-                g1 = fma_f32x2(g1, rs, fma_f32x2(nmr, pack_f32x2(wg.z, wg.w), pack_f32x2(bg.z, bg.w)));
-              } else {
-                a0 = add_f32x2(a0, pack_f32x2(ba.x, ba.y));
-                a1 = add_f32x2(a1, pack_f32x2(ba.z, ba.w));
-                g0 = add_f32x2(g0, pack_f32x2(bg.x, bg.y));
-                g1 = add_f32x2(g1, pack_f32x2(bg.z, bg.w));
-              }
-              unpack_f32x2(mul_f32x2(a0, gelu_erf_x2(g0)), v[i], v[i + 1]);
-              unpack_f32x2(mul_f32x2(a1, gelu_erf_x2(g1)), v[i + 2], v[i + 3]);
-            }
-#else
-            if (has_ln) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                v[i] = ln_rstd * (v[i] - ln_mean * wv[i]);
-                gte[i] = ln_rstd * (gte[i] - ln_mean * wv[32 + i]);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-              if (has_bias) {
-                ba = *reinterpret_cast<const float4*>(bv + i);
-                bg = *reinterpret_cast<const float4*>(bv + 32 + i);
-              }
-              v[i] = (v[i] + ba.x) * gelu_erf_f(gte[i] + bg.x);
-              v[i + 1] = (v[i + 1] + ba.y) * gelu_erf_f(gte[i + 1] + bg.y);
-              v[i + 2] = (v[i + 2] + ba.z) * gelu_erf_f(gte[i + 2] + bg.z);
-              v[i + 3] = (v[i + 3] + ba.w) * gelu_erf_f(gte[i + 3] + bg.w);
-            }
-#endif
+            };
+            if (has_ln && has_bias) geglu_block(std::true_type{}, std::true_type{});
+            else if (has_ln) geglu_block(std::true_type{}, std::false_type{});
+            else if (has_bias) geglu_block(std::false_type{}, std::true_type{});
+            else geglu_block(std::false_type{}, std::false_type{});
           } else {
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
