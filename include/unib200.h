@@ -163,6 +163,8 @@ typedef struct {
   void* out; int ldo;
   int B, heads, Nq, Nk, d;
   float scale;
+  float* lse2;               /* optional fp32 [B, heads, Nq]: log2 of every row's sum of exp2(scale * log2e * s) -- what
+                                unib200_attention_backward needs from the forward (training); NULL in inference    */
 } unib200_attn_desc;
 int unib200_attention(unib200_program* prog, const unib200_attn_desc* desc, void* stream);
 /* debug only: attention kernels launched after this call write clock64 stamps of CTA (0,0,0) into dev_buf
@@ -278,6 +280,27 @@ int unib200_geglu(unib200_program* prog, const void* proj, const void* dout, voi
 int unib200_softmax_backward(unib200_program* prog, const void* P, void* dP, int rows, int n, int ld, float scale, void* stream);
 /* fp32 [rows, cols] contiguous -> fp16 with leading dimension ld */
 int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int64_t rows, int cols, int ld, void* stream);
+/* Flash-attention backward (head dims <= 64): gradients of O = softmax(Q K^T scale) V w.r.t. Q, K, V from dO without
+ * materialising the Nq x Nk matrices (csrc/attention_bwd_sm100.cu).  q / k / v / o / dout are the forward's fp16
+ * matrices (head h in columns [h*d, (h+1)*d)), lse2 the forward's optional output; D is fp32 scratch [B*heads*Nq];
+ * dq_acc is an fp32 [B*Nq, ld_dq] accumulator that the CALLER zeroes (every key block adds into it with atomics:
+ * dQ is not bit-reproducible run to run); dk / dv are written.  Replaces the autograd of
+ * F.scaled_dot_product_attention under accelerator.backward (train/train.py:1421). */
+typedef struct {
+  const void* q; int ldq;
+  const void* k; int ldk;
+  const void* v; int ldv;
+  const void* o; int ldo;
+  const void* dout; int lddo;
+  const float* lse2;
+  float* D;
+  float* dq_acc; int ld_dq;
+  void* dk; int ld_dk;
+  void* dv; int ld_dv;
+  int B, heads, Nq, Nk, d;
+  float scale;
+} unib200_attn_bwd_desc;
+int unib200_attention_backward(unib200_program* prog, const unib200_attn_bwd_desc* desc, void* stream);
 /* network-level training glue (uni_renderer_b200/trainer.py; train/train.py:1324-1427):
  * SiLU on n fp16 elements (dy NULL: out = silu(x); else out = dy * silu'(x)) -- the time-embedding MLP's activations */
 int unib200_silu_f16(unib200_program* prog, const void* x, const void* dy, void* out, int64_t n, void* stream);

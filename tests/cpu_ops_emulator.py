@@ -196,7 +196,18 @@ def conv_gemm_dual(prog, a, b):
         conv_gemm(prog, d.pop("segs"), d.pop("weight"), d.pop("out"), **d)
 
 
-def attention(prog, q, k, v, out, *, B, heads, Nq, Nk, d, scale=None):
+def t_attention_backward(q, k, v, o, dout, lse2, *, B, heads, Nq, Nk, d, scale):
+    Cn = heads * d
+    hs = lambda t, n: t[:, :Cn].float().reshape(B, n, heads, d).transpose(1, 2).clone().requires_grad_(True)  # noqa: E731
+    qh, kh, vh = hs(q, Nq), hs(k, Nk), hs(v, Nk)
+    w = torch.softmax((qh @ kh.transpose(-1, -2)) * scale, dim=-1)
+    oo = w @ vh
+    (oo * dout[:, :Cn].float().reshape(B, Nq, heads, d).transpose(1, 2)).sum().backward()
+    back = lambda g, n: g.transpose(1, 2).reshape(B * n, Cn).half()            # noqa: E731
+    return back(qh.grad, Nq), back(kh.grad, Nk), back(vh.grad, Nk)
+
+
+def attention(prog, q, k, v, out, *, B, heads, Nq, Nk, d, scale=None, lse2=None):
     sc = float(scale if scale is not None else d ** -0.5)
 
     def run():
@@ -205,7 +216,10 @@ def attention(prog, q, k, v, out, *, B, heads, Nq, Nk, d, scale=None):
                 qs = q[b * Nq:(b + 1) * Nq, h * d:(h + 1) * d].float()
                 ks = k[b * Nk:(b + 1) * Nk, h * d:(h + 1) * d].float()
                 vs = v[b * Nk:(b + 1) * Nk, h * d:(h + 1) * d].float()
-                out[b * Nq:(b + 1) * Nq, h * d:(h + 1) * d].copy_(torch.softmax(qs @ ks.t() * sc, -1) @ vs)
+                sc_ = qs @ ks.t() * sc
+                out[b * Nq:(b + 1) * Nq, h * d:(h + 1) * d].copy_(torch.softmax(sc_, -1) @ vs)
+                if lse2 is not None:       # log2-domain log-sum-exp of every row (include/unib200.h unib200_attn_desc.lse2)
+                    lse2.reshape(B, heads, Nq)[b, h].copy_(torch.logsumexp(sc_, -1) * 1.4426950408889634)
     _submit(prog, run)
 
 
@@ -407,7 +421,7 @@ def t_adamw_step(p, g, m, v, *, lr, betas, eps, weight_decay, step, grad_scale=1
     p.addcdiv_(m, v.sqrt() / (1 - betas[1] ** step) ** 0.5 + eps, value=-lr / (1 - betas[0] ** step))
 
 
-TRAIN_EMULATED = ("conv_wgrad", "colsum", "groupnorm_backward", "layernorm_backward", "geglu", "softmax_backward",
+TRAIN_EMULATED = ("attention_backward", "conv_wgrad", "colsum", "groupnorm_backward", "layernorm_backward", "geglu", "softmax_backward",
                   "cvt_f32_f16", "silu_f16", "scatter2x", "pool2x2_sum", "adamw_step")
 
 

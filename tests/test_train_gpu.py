@@ -155,3 +155,39 @@ def test_transformer_block_forward_backward_matches_torch_autograd(B, N, C, head
     for k, v in sd.items():
         gate = 5e-3 if (k.endswith("weight") and v.dim() == 2) else 1e-2
         assert _rel(grads[k], p["blk." + k].grad) <= gate, (k, _rel(grads[k], p["blk." + k].grad))
+
+
+@gpu
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 4, 256, 256, 40), (1, 2, 4096, 4096, 40), (2, 8, 1024, 77, 40), (2, 2, 200, 136, 64),
+                                         (2, 4, 64, 64, 8), (1, 4, 384, 77, 32)])
+def test_flash_attention_backward_matches_torch_autograd(B, H, Nq, Nk, d):
+    """unib200_attention_backward (csrc/attention_bwd_sm100.cu) + the forward's lse2 output against autograd of
+    softmax(Q K^T / sqrt(d)) V in fp32 on the same fp16-rounded inputs (Attention / AttnProcessor2_0 of the reference's
+    transformer blocks): self- and cross-attention shapes, ragged query / key counts, head dims 8 .. 64."""
+    import torch
+    from uni_renderer_b200 import ops
+    from uni_renderer_b200.train import attention_backward
+    g = torch.Generator().manual_seed(B * 1000 + Nq + Nk + d)
+    C = H * d
+    q = torch.randn(B * Nq, C, generator=g).half()
+    k = torch.randn(B * Nk, C, generator=g).half()
+    v = torch.randn(B * Nk, C, generator=g).half()
+    dout = (torch.randn(B * Nq, C, generator=g) * 0.5).half()
+    heads = lambda t, n: t.float().reshape(B, n, H, d).transpose(1, 2).clone().requires_grad_(True)      # noqa: E731
+    qh, kh, vh = heads(q, Nq), heads(k, Nk), heads(v, Nk)
+    w = torch.softmax((qh @ kh.transpose(-1, -2)) * d ** -0.5, dim=-1)
+    o_ref = w @ vh
+    (o_ref * dout.float().reshape(B, Nq, H, d).transpose(1, 2)).sum().backward()
+    back = lambda t, n: t.transpose(1, 2).reshape(B * n, C)                                              # noqa: E731
+    qc, kc, vc, dc = q.cuda(), k.cuda(), v.cuda(), dout.cuda()
+    o = torch.empty(B * Nq, C, device="cuda", dtype=torch.float16)
+    lse2 = torch.empty(B * H * Nq, device="cuda", dtype=torch.float32)
+    ops.attention(None, qc, kc, vc, o, B=B, heads=H, Nq=Nq, Nk=Nk, d=d, lse2=lse2)
+    dq, dk, dv = attention_backward(qc, kc, vc, o, dc, lse2, B=B, heads=H, Nq=Nq, Nk=Nk, d=d, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    lse_ref = torch.logsumexp((qh @ kh.transpose(-1, -2)).detach() * d ** -0.5, -1) * 1.4426950408889634
+    assert (lse2.cpu().reshape(B, H, Nq) - lse_ref).abs().max().item() <= 2e-3
+    assert _rel(o, back(o_ref.detach(), Nq)) <= 1e-3
+    for name, got, ref, n in (("dq", dq, qh.grad, Nq), ("dk", dk, kh.grad, Nk), ("dv", dv, vh.grad, Nk)):
+        e = _rel(got, back(ref, n))
+        assert e <= 3e-3, (name, e)

@@ -56,6 +56,17 @@ class AttnDesc(C.Structure):
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
         ("out", C.c_void_p), ("ldo", C.c_int),
         ("B", C.c_int), ("heads", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("d", C.c_int), ("scale", C.c_float),
+        ("lse2", C.c_void_p),
+    ]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("v", C.c_void_p), ("ldv", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int), ("dout", C.c_void_p), ("lddo", C.c_int),
+        ("lse2", C.c_void_p), ("D", C.c_void_p), ("dq_acc", C.c_void_p), ("ld_dq", C.c_int),
+        ("dk", C.c_void_p), ("ld_dk", C.c_int), ("dv", C.c_void_p), ("ld_dv", C.c_int),
+        ("B", C.c_int), ("heads", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("d", C.c_int), ("scale", C.c_float),
     ]
 
 
@@ -83,7 +94,7 @@ EXPORTS = [
     "unib200_softmax_rows", "unib200_gaussian_sample",
     "unib200_conv_wgrad", "unib200_groupnorm_backward", "unib200_colsum", "unib200_layernorm_backward", "unib200_geglu",
     "unib200_softmax_backward", "unib200_cvt_f32_f16", "unib200_silu_f16", "unib200_pool2x2_sum", "unib200_scatter2x",
-    "unib200_adamw_step",
+    "unib200_adamw_step", "unib200_attention_backward",
     "unib200_create", "unib200_destroy", "unib200_load_weight", "unib200_alloc", "unib200_bind", "unib200_buffer",
     "unib200_ctx_attach", "unib200_ctx_run", "unib200_unet_forward", "unib200_attr_enc_forward",
     "unib200_attr_dec_forward", "unib200_dual_step", "unib200_sample_loop",
@@ -159,6 +170,7 @@ def load() -> C.CDLL:
     lib.unib200_silu_f16.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.unib200_pool2x2_sum.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
     lib.unib200_scatter2x.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.unib200_attention_backward.argtypes = [vp, C.POINTER(AttnBwdDesc), vp]
     lib.unib200_adamw_step.argtypes = [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, cf, vp]
     lib.unib200_create.argtypes = [ci, vp]
     lib.unib200_create.restype = vp

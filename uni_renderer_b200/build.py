@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libunib200.so")
-SOURCES = ["gemm_sm100.cu", "attention_sm100.cu", "elementwise.cu", "wgrad_sm100.cu", "api.cu"]
+SOURCES = ["gemm_sm100.cu", "attention_sm100.cu", "attention_bwd_sm100.cu", "elementwise.cu", "wgrad_sm100.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]

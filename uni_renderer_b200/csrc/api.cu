@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/unib200.h"
+#include "attention_bwd_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
@@ -855,6 +856,7 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   p.scale = d->scale;
   p.out = static_cast<__half*>(d->out);
   p.ldo = d->ldo;
+  p.lse2 = d->lse2;
   p.trace = g_attn_trace;
   p.pdl_early = unib::g_pdl_enabled == 2 ? 1 : 0;
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
@@ -863,6 +865,42 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
                 2.0 * bh * d->d * (2.0 * d->Nq + 2.0 * d->Nk),
                 "attention B=" + std::to_string(d->B) + " h=" + std::to_string(d->heads) + " Nq=" +
                     std::to_string(d->Nq) + " Nk=" + std::to_string(d->Nk) + " d=" + std::to_string(d->d));
+}
+
+int unib200_attention_backward(unib200_program* prog, const unib200_attn_bwd_desc* d, void* stream) {
+  if (!d || !d->q || !d->k || !d->v || !d->o || !d->dout || !d->lse2 || !d->D || !d->dq_acc || !d->dk || !d->dv)
+    return fail("attention_backward: null pointer");
+  if (d->d % 8 != 0 || d->d < 8 || d->d > 64) return fail("attention_backward: head dim must be a multiple of 8 in [8,64]");
+  if (d->ldq % 8 || d->ldk % 8 || d->ldv % 8 || d->ldo % 8 || d->lddo % 8 || d->ld_dk % 8 || d->ld_dv % 8)
+    return fail("attention_backward: leading dims must be multiples of 8");
+  AttnBwdMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  std::string why;
+  auto mk = [&](CUtensorMap* m, const void* base, int ld, int tokens) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->d), static_cast<uint64_t>(tokens),
+                              static_cast<uint64_t>(d->heads), static_cast<uint64_t>(d->B)};
+    const uint64_t st[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(d->d) * 2,
+                            static_cast<uint64_t>(ld) * 2 * tokens};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    return encode_map(m, base, 4, dims, st, box, &why);
+  };
+  if (!mk(&maps.q, d->q, d->ldq, d->Nq)) return fail("attention_backward Q map: " + why);
+  if (!mk(&maps.k, d->k, d->ldk, d->Nk)) return fail("attention_backward K map: " + why);
+  if (!mk(&maps.v, d->v, d->ldv, d->Nk)) return fail("attention_backward V map: " + why);
+  if (!mk(&maps.dout, d->dout, d->lddo, d->Nq)) return fail("attention_backward dO map: " + why);
+  AttnBwdParams p;
+  p.B = d->B; p.heads = d->heads; p.Nq = d->Nq; p.Nk = d->Nk; p.d = d->d;
+  p.scale = d->scale;
+  p.lse2 = d->lse2; p.D = d->D; p.dq_acc = d->dq_acc; p.ld_dq = d->ld_dq;
+  p.dk = static_cast<__half*>(d->dk); p.ld_dk = d->ld_dk;
+  p.dv = static_cast<__half*>(d->dv); p.ld_dv = d->ld_dv;
+  const __half* o = static_cast<const __half*>(d->o);
+  const __half* dout = static_cast<const __half*>(d->dout);
+  const int ldo = d->ldo, lddo = d->lddo;
+  Op op = [maps, p, o, dout, ldo, lddo](cudaStream_t s) { return launch_attention_bwd(maps, p, o, ldo, dout, lddo, s); };
+  const double bh = static_cast<double>(d->B) * d->heads;
+  return submit(prog, std::move(op), 2, stream, "attention_backward", UNIB200_OP_ATTENTION,
+                10.0 * bh * d->Nq * d->Nk * d->d, 2.0 * bh * d->d * (4.0 * d->Nq + 4.0 * d->Nk));
 }
 
 int unib200_groupnorm(unib200_program* prog, const unib200_gn_desc* d, void* stream) {

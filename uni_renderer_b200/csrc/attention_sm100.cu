@@ -405,6 +405,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int q = q_base + t * 128 + row;
+      if (p.lse2 != nullptr && q < p.Nq)      // P was exp2((s - m_ref) * sl2): log2 sum exp2(s * sl2) = m_ref * sl2 + log2(l)
+        p.lse2[(static_cast<size_t>(b) * p.heads + head) * p.Nq + q] = m_ref * sl2 + log2f(l_run);
       __half* op = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * p.d;
 #pragma unroll 1
       for (int c = 0; c < dpad / 16; ++c) {

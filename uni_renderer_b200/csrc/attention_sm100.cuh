@@ -9,6 +9,7 @@ struct AttnParams {
   float scale;       // softmax scale (d^-1/2)
   __half* out;       // [B*Nq, ldo] fp16; head h writes columns [h*d, (h+1)*d)
   int ldo;
+  float* lse2;       // optional [B, heads, Nq]: log2-domain log-sum-exp of every row (training: the backward's input)
   int pdl_early;     // as GemmParams::pdl_early
   long long* trace;  // debug: clock64 stamps of CTA (0,0,0) (unib200_debug_set_trace); nullptr in production
 };

@@ -343,9 +343,15 @@ def _gemm_desc(segs, weight, out, *, M, N, B=0, H=0, W=0, bias=None, bias_bstrid
 
 
 def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *,
-              B: int, heads: int, Nq: int, Nk: int, d: int, scale: Optional[float] = None):
+              B: int, heads: int, Nq: int, Nk: int, d: int, scale: Optional[float] = None,
+              lse2: Optional[torch.Tensor] = None):
+    """lse2 (optional, fp32 [B, heads, Nq]): receives every row's log2-domain log-sum-exp -- the training path's
+    flash backward (train.attention_backward) needs it."""
     lib = L.load()
     a = L.AttnDesc()
+    if lse2 is not None:
+        assert lse2.dtype == torch.float32 and lse2.is_contiguous() and lse2.numel() == B * heads * Nq
+        a.lse2 = lse2.data_ptr()
     a.q, a.ldq = q.data_ptr(), _check_2d(q, "attention q")
     a.k, a.ldk = k.data_ptr(), _check_2d(k, "attention k")
     a.v, a.ldv = v.data_ptr(), _check_2d(v, "attention v")
@@ -354,7 +360,7 @@ def attention(prog: Optional[Program], q: torch.Tensor, k: torch.Tensor, v: torc
     a.scale = float(scale if scale is not None else d ** -0.5)
     L.check(lib.unib200_attention(_h(prog), C.byref(a), _stream()), "attention")
     if prog is not None:
-        prog.keep(q, k, v, out)
+        prog.keep(q, k, v, out, lse2)
 
 
 def groupnorm(prog: Optional[Program], x1: torch.Tensor, C1: int, x2: Optional[torch.Tensor], C2: int,

@@ -236,6 +236,29 @@ def pool2x2_sum(x: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
     return out
 
 
+def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, dout: torch.Tensor,
+                       lse2: torch.Tensor, *, B: int, heads: int, Nq: int, Nk: int, d: int, scale: float):
+    """(dq, dk, dv) fp16, shaped like q / k / v, of O = softmax(Q K^T scale) V by the flash backward kernel (head dims
+    <= 64): q / k / v / o / dout are fp16 matrices [B*N, >= heads*d] (head h in columns [h*d, (h+1)*d)), lse2 the
+    forward's log-sum-exp output (ops.attention(..., lse2=))."""
+    dev = q.device
+    C_ = heads * d
+    dq_acc = torch.zeros(B * Nq, C_, device=dev, dtype=torch.float32)
+    dk = torch.empty(B * Nk, C_, device=dev, dtype=torch.float16)
+    dv = torch.empty(B * Nk, C_, device=dev, dtype=torch.float16)
+    D = torch.empty(B * heads * Nq, device=dev, dtype=torch.float32)
+    a = L.AttnBwdDesc()
+    a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0)
+    a.o, a.ldo, a.dout, a.lddo = o.data_ptr(), o.stride(0), dout.data_ptr(), dout.stride(0)
+    a.lse2, a.D, a.dq_acc, a.ld_dq = lse2.data_ptr(), D.data_ptr(), dq_acc.data_ptr(), C_
+    a.dk, a.ld_dk, a.dv, a.ld_dv = dk.data_ptr(), C_, dv.data_ptr(), C_
+    a.B, a.heads, a.Nq, a.Nk, a.d, a.scale = B, heads, Nq, Nk, d, float(scale)
+    L.check(L.load().unib200_attention_backward(None, C.byref(a), _stream()), "attention_backward")
+    dq = torch.empty(B * Nq, C_, device=dev, dtype=torch.float16)
+    cvt_f32_f16(dq_acc, dq)
+    return dq, dk, dv
+
+
 def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas, eps: float,
                weight_decay: float, step: int, grad_scale: float = 1.0):
     """torch.optim.AdamW's update on flat fp32 buffers, gradients multiplied by grad_scale first."""

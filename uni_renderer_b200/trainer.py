@@ -13,9 +13,10 @@ three networks are written against those ops exactly the way oracle/uni_oracle.p
   Downsample2D (3x3 stride 2)     forward SEG_3x3_S2; gradients through unib200_scatter2x (zero insertion) + the stride-1 kernels
   Upsample2D (nearest 2x + conv)  unib200_upsample2x / unib200_pool2x2_sum around the conv
   GroupNorm(+SiLU), LayerNorm     unib200_groupnorm(_backward), unib200_layernorm(_backward)
-  attention                       forward: the flash kernel of the inference path (unib200_attention); backward: per (sample,
-                                  head) the probabilities are recomputed (S = Q K^T, row softmax) and the four gradient GEMMs
-                                  run on the GEMM / wgrad kernels (no fused flash backward yet); any context length
+  attention                       forward: the flash kernel of the inference path (unib200_attention, which also emits the row
+                                  log-sum-exps); backward: unib200_attention_backward, a tcgen05 flash backward (head dims
+                                  <= 64: S / dP recomputed per tile, P and dS never leave the SM); wider heads (the 8x8 / 16x16
+                                  levels) recompute per (sample, head) in materialised form on the GEMM / wgrad kernels
   GEGLU, SiLU, adds               unib200_geglu, unib200_silu_f16, unib200_add_f16
   time embedding MLP              the same linear ops on a 128-row padded matrix
   optimizer                       unib200_adamw_step on ONE flat fp32 parameter / gradient / moment buffer per trainer
@@ -356,15 +357,23 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
     Lp = _ld8(Nk)
     scale = d ** -0.5
     ao = tp.new(q.rows, Cn)
-    # forward: the fused flash kernel of the inference path (one launch, nothing but O is kept); the backward below
-    # recomputes each head's probabilities in the materialised form (S = Q K^T, row softmax) -- flash-style recomputation
-    # without a fused backward kernel yet
-    ops.attention(None, q.v, k.v, v.v, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale)
+    # forward: the fused flash kernel of the inference path (one launch, nothing but O and the row log-sum-exps kept)
+    flash_bwd = d % 8 == 0 and d <= 64
+    lse2 = torch.empty(B * heads * Nq, device=tp.dev, dtype=torch.float32) if flash_bwd else None
+    ops.attention(None, q.v, k.v, v.v, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale, lse2=lse2)
     y = TT(ao, q.B, q.H, q.W)
 
     def bwd():
         if y.g is None:
             return
+        if flash_bwd:         # head dims <= 64: the flash backward kernel (csrc/attention_bwd_sm100.cu), one launch
+            dq, dk, dv = T.attention_backward(q.v, k.v, v.v, ao, y.g, lse2, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale)
+            tp.acc(q, dq)
+            tp.acc(k, dk)
+            tp.acc(v, dv)
+            return
+        # wider heads (the 8x8 / 16x16 levels, few tokens): per (sample, head) the probabilities are recomputed in the
+        # materialised form (S = Q K^T, row softmax) and the four gradient GEMMs run on the GEMM / wgrad kernels
         dq = torch.empty_like(q.v)            # every (sample, head) slice below is written in full
         dk = torch.empty_like(k.v)
         dv = torch.empty_like(v.v)
