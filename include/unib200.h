@@ -280,7 +280,7 @@ int unib200_geglu(unib200_program* prog, const void* proj, const void* dout, voi
 int unib200_softmax_backward(unib200_program* prog, const void* P, void* dP, int rows, int n, int ld, float scale, void* stream);
 /* fp32 [rows, cols] contiguous -> fp16 with leading dimension ld */
 int unib200_cvt_f32_f16(unib200_program* prog, const float* src, void* dst, int64_t rows, int cols, int ld, void* stream);
-/* Flash-attention backward (head dims <= 64): gradients of O = softmax(Q K^T scale) V w.r.t. Q, K, V from dO without
+/* Flash-attention backward (head dims <= 80): gradients of O = softmax(Q K^T scale) V w.r.t. Q, K, V from dO without
  * materialising the Nq x Nk matrices (csrc/attention_bwd_sm100.cu).  q / k / v / o / dout are the forward's fp16
  * matrices (head h in columns [h*d, (h+1)*d)), lse2 the forward's optional output; D is fp32 scratch [B*heads*Nq];
  * dq_acc is an fp32 [B*Nq, ld_dq] accumulator that the CALLER zeroes (every key block adds into it with atomics:

@@ -159,11 +159,11 @@ def test_transformer_block_forward_backward_matches_torch_autograd(B, N, C, head
 
 @gpu
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 4, 256, 256, 40), (1, 2, 4096, 4096, 40), (2, 8, 1024, 77, 40), (2, 2, 200, 136, 64),
-                                         (2, 4, 64, 64, 8), (1, 4, 384, 77, 32)])
+                                         (2, 4, 64, 64, 8), (1, 4, 384, 77, 32), (2, 8, 1024, 1024, 80), (2, 4, 300, 77, 72)])
 def test_flash_attention_backward_matches_torch_autograd(B, H, Nq, Nk, d):
     """unib200_attention_backward (csrc/attention_bwd_sm100.cu) + the forward's lse2 output against autograd of
     softmax(Q K^T / sqrt(d)) V in fp32 on the same fp16-rounded inputs (Attention / AttnProcessor2_0 of the reference's
-    transformer blocks): self- and cross-attention shapes, ragged query / key counts, head dims 8 .. 64."""
+    transformer blocks): self- and cross-attention shapes, ragged query / key counts, head dims 8 .. 80."""
     import torch
     from uni_renderer_b200 import ops
     from uni_renderer_b200.train import attention_backward

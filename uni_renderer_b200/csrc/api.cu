@@ -870,7 +870,7 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
 int unib200_attention_backward(unib200_program* prog, const unib200_attn_bwd_desc* d, void* stream) {
   if (!d || !d->q || !d->k || !d->v || !d->o || !d->dout || !d->lse2 || !d->D || !d->dq_acc || !d->dk || !d->dv)
     return fail("attention_backward: null pointer");
-  if (d->d % 8 != 0 || d->d < 8 || d->d > 64) return fail("attention_backward: head dim must be a multiple of 8 in [8,64]");
+  if (d->d % 8 != 0 || d->d < 8 || d->d > 80) return fail("attention_backward: head dim must be a multiple of 8 in [8,80]");
   if (d->ldq % 8 || d->ldk % 8 || d->ldv % 8 || d->ldo % 8 || d->lddo % 8 || d->ld_dk % 8 || d->ld_dv % 8)
     return fail("attention_backward: leading dims must be multiples of 8");
   AttnBwdMaps maps;

@@ -1,4 +1,4 @@
-// Flash-attention BACKWARD for sm_100a (tcgen05 + TMEM + TMA), head dims <= 64, no mask -- the gradient of
+// Flash-attention BACKWARD for sm_100a (tcgen05 + TMEM + TMA), head dims <= 80, no mask -- the gradient of
 // O = softmax(Q K^T * scale) V used by the training path (uni_renderer_b200/trainer.py; the reference trains through
 // diffusers' AttnProcessor2_0 = F.scaled_dot_product_attention, train/train.py:1421 accelerator.backward).
 //
@@ -10,8 +10,8 @@
 //     dV += P^T dO_i,  dK += dS^T Q_i                 the SAME [q][k] tiles read as MN-major ("transposed") A operands
 //     dQ_i  = dS K                                    K-major A; K block as MN-major B (like V in the forward's P V)
 //     dQ_i -> fp32 atomics into the dQ accumulator    (every key block contributes; converted to fp16 afterwards)
-// dK / dV of the block stay in TMEM for the whole walk and are written once.  TMEM: S 128 | dP 128 | dV 64 | dK 64 |
-// dQ 64 columns.  The walk is NOT software-pipelined (phases run back to back behind mbarriers): it is a
+// dK / dV of the block stay in TMEM for the whole walk and are written once.  TMEM: S 128 | dP 128 | dV, dK, dQ
+// round16(d) columns each (hence d <= 80).  The walk is NOT software-pipelined (phases run back to back behind mbarriers): it is a
 // correctness-first kernel whose point is to keep the N x N matrices out of memory -- the materialised per-head
 // backward it replaces moved ~350 MB and 12 launches per head at 4096 tokens.
 // Warp roles (160 threads): warps 0-3 = softmax / dQ / epilogue (warp w owns TMEM lanes 32 w ..), warp 4 = TMA + MMA.
@@ -21,15 +21,26 @@ namespace unib {
 
 namespace {
 constexpr int kTile = 16384;                       // one [128 rows x 64 fp16] swizzled tile
-constexpr int kKOff = 0, kVOff = kTile, kQOff = 2 * kTile, kDoOff = 3 * kTile;
-constexpr int kPOff = 4 * kTile, kDsOff = 6 * kTile;          // [128 q][128 k] = two 64-column chunks each
-constexpr int kBarOff = 8 * kTile;
-constexpr int kSmem = kBarOff + 128 + 1024;
-constexpr int kColS = 0, kColDp = 128, kColDv = 256, kColDk = 320, kColDq = 384;
+constexpr int kColS = 0, kColDp = 128, kColDv = 256;          // dK at 256 + dpad, dQ at 256 + 2 dpad (3 dpad <= 256)
+// NCH = 64-column chunks of the head dimension: 1 (d <= 64) or 2 (d <= 80: three accumulators of dpad columns must
+// fit the 256 TMEM columns left beside S and dP)
+template <int NCH>
+struct BwdCfg {
+  static constexpr int kOp = NCH * kTile;          // one [128 rows x d] operand tile
+  static constexpr int kKOff = 0, kVOff = kOp, kQOff = 2 * kOp, kDoOff = 3 * kOp;
+  static constexpr int kPOff = 4 * kOp, kDsOff = 4 * kOp + 2 * kTile;       // [128 q][128 k] = two 64-column chunks each
+  static constexpr int kBarOff = 4 * kOp + 4 * kTile;
+  static constexpr int kSmem = kBarOff + 128 + 1024;
+  static_assert(kSmem <= 232448, "shared memory budget");
+};
 }  // namespace
 
+template <int NCH>
 __global__ void __launch_bounds__(160, 1)
 attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdParams p) {
+  using Cfg = BwdCfg<NCH>;
+  constexpr int kKOff = Cfg::kKOff, kVOff = Cfg::kVOff, kQOff = Cfg::kQOff, kDoOff = Cfg::kDoOff;
+  constexpr int kPOff = Cfg::kPOff, kDsOff = Cfg::kDsOff, kBarOff = Cfg::kBarOff;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -42,6 +53,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   const int nq_tiles = (p.Nq + 127) / 128;
   const int dpad = (p.d + 15) & ~15;
   const int ks_d = dpad / 16;
+  const int kColDk = kColDv + dpad, kColDq = kColDv + 2 * dpad;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -79,24 +91,31 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
     const uint64_t qB_desc = make_desc_mnmajor_sw128(base + kQOff, kTile, 1024);
     const uint64_t kB_desc = make_desc_mnmajor_sw128(base + kKOff, kTile, 1024);
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_kv, 2 * kTile);
-      tma_load_4d(base + kKOff, &maps.k, bar_kv, 0, jblk * 128, head, b);
-      tma_load_4d(base + kVOff, &maps.v, bar_kv, 0, jblk * 128, head, b);
+      mbar_arrive_expect_tx(bar_kv, 2 * Cfg::kOp);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        tma_load_4d(base + kKOff + ch * kTile, &maps.k, bar_kv, ch * 64, jblk * 128, head, b);
+        tma_load_4d(base + kVOff + ch * kTile, &maps.v, bar_kv, ch * 64, jblk * 128, head, b);
+      }
     }
     mbar_wait(bar_kv, 0);
     for (int i = 0; i < nq_tiles; ++i) {
       const uint32_t ph = i & 1;
       if (elect_one()) {
-        mbar_arrive_expect_tx(bar_q, 2 * kTile);
-        tma_load_4d(base + kQOff, &maps.q, bar_q, 0, i * 128, head, b);
-        tma_load_4d(base + kDoOff, &maps.dout, bar_q, 0, i * 128, head, b);
+        mbar_arrive_expect_tx(bar_q, 2 * Cfg::kOp);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tma_load_4d(base + kQOff + ch * kTile, &maps.q, bar_q, ch * 64, i * 128, head, b);
+          tma_load_4d(base + kDoOff + ch * kTile, &maps.dout, bar_q, ch * 64, i * 128, head, b);
+        }
       }
       mbar_wait(bar_q, ph);
       tc_fence_after();
       if (elect_one()) {
         for (int ks = 0; ks < ks_d; ++ks) {                        // S = Q K^T, dP = dO V^T: K steps of 16 over d
-          umma_f16_ss(tmem_base + kColS, q_desc + ((ks * 32) >> 4), k_desc + ((ks * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
-          umma_f16_ss(tmem_base + kColDp, do_desc + ((ks * 32) >> 4), v_desc + ((ks * 32) >> 4), idesc_s, ks > 0 ? 1u : 0u);
+          const uint64_t off = static_cast<uint64_t>(((ks >> 2) * kTile + (ks & 3) * 32) >> 4);
+          umma_f16_ss(tmem_base + kColS, q_desc + off, k_desc + off, idesc_s, ks > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + kColDp, do_desc + off, v_desc + off, idesc_s, ks > 0 ? 1u : 0u);
         }
         umma_commit(bar_sdp);
       }
@@ -237,23 +256,31 @@ __global__ void __launch_bounds__(256) attention_bwd_prep_kernel(const __half* _
   }
 }
 
-cudaError_t launch_attention_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, const __half* o, int ldo,
-                                 const __half* dout, int lddo, cudaStream_t stream) {
-  if (p.d % 8 != 0 || p.d < 8 || p.d > 64) return cudaErrorInvalidValue;
+template <int NCH>
+static cudaError_t launch_bwd_cfg(const AttnBwdMaps& maps, const AttnBwdParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         BwdCfg<NCH>::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  dim3 grid((p.Nk + 127) / 128, p.heads, p.B);
+  attention_bwd_kernel<NCH><<<grid, 160, BwdCfg<NCH>::kSmem, stream>>>(maps, p);
+  return cudaGetLastError();
+}
+
+int attention_bwd_max_d() { return 80; }
+
+cudaError_t launch_attention_bwd(const AttnBwdMaps& maps, const AttnBwdParams& p, const __half* o, int ldo,
+                                 const __half* dout, int lddo, cudaStream_t stream) {
+  if (p.d % 8 != 0 || p.d < 8 || p.d > attention_bwd_max_d()) return cudaErrorInvalidValue;
   const long long rows = static_cast<long long>(p.B) * p.heads * p.Nq;
   int blocks = static_cast<int>((rows * 32 + 255) / 256 > 148 * 16 ? 148 * 16 : (rows * 32 + 255) / 256);
   attention_bwd_prep_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(o, ldo, dout, lddo, p.D, p.B, p.heads, p.Nq, p.d);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  dim3 grid((p.Nk + 127) / 128, p.heads, p.B);
-  attention_bwd_kernel<<<grid, 160, kSmem, stream>>>(maps, p);
-  return cudaGetLastError();
+  return p.d <= 64 ? launch_bwd_cfg<1>(maps, p, stream) : launch_bwd_cfg<2>(maps, p, stream);
 }
 
 }  // namespace unib

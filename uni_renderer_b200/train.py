@@ -239,7 +239,7 @@ def pool2x2_sum(x: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
 def attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, dout: torch.Tensor,
                        lse2: torch.Tensor, *, B: int, heads: int, Nq: int, Nk: int, d: int, scale: float):
     """(dq, dk, dv) fp16, shaped like q / k / v, of O = softmax(Q K^T scale) V by the flash backward kernel (head dims
-    <= 64): q / k / v / o / dout are fp16 matrices [B*N, >= heads*d] (head h in columns [h*d, (h+1)*d)), lse2 the
+    <= 80): q / k / v / o / dout are fp16 matrices [B*N, >= heads*d] (head h in columns [h*d, (h+1)*d)), lse2 the
     forward's log-sum-exp output (ops.attention(..., lse2=))."""
     dev = q.device
     C_ = heads * d

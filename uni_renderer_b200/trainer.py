@@ -15,7 +15,7 @@ three networks are written against those ops exactly the way oracle/uni_oracle.p
   GroupNorm(+SiLU), LayerNorm     unib200_groupnorm(_backward), unib200_layernorm(_backward)
   attention                       forward: the flash kernel of the inference path (unib200_attention, which also emits the row
                                   log-sum-exps); backward: unib200_attention_backward, a tcgen05 flash backward (head dims
-                                  <= 64: S / dP recomputed per tile, P and dS never leave the SM); wider heads (the 8x8 / 16x16
+                                  <= 80: S / dP recomputed per tile, P and dS never leave the SM); wider heads (the 8x8 / 16x16
                                   levels) recompute per (sample, head) in materialised form on the GEMM / wgrad kernels
   GEGLU, SiLU, adds               unib200_geglu, unib200_silu_f16, unib200_add_f16
   time embedding MLP              the same linear ops on a 128-row padded matrix
@@ -358,7 +358,7 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
     scale = d ** -0.5
     ao = tp.new(q.rows, Cn)
     # forward: the fused flash kernel of the inference path (one launch, nothing but O and the row log-sum-exps kept)
-    flash_bwd = d % 8 == 0 and d <= 64
+    flash_bwd = d % 8 == 0 and d <= 80
     lse2 = torch.empty(B * heads * Nq, device=tp.dev, dtype=torch.float32) if flash_bwd else None
     ops.attention(None, q.v, k.v, v.v, ao, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale, lse2=lse2)
     y = TT(ao, q.B, q.H, q.W)
@@ -366,7 +366,7 @@ def attention(tp: Tape, q: TT, k: TT, v: TT, heads: int, B: int) -> TT:
     def bwd():
         if y.g is None:
             return
-        if flash_bwd:         # head dims <= 64: the flash backward kernel (csrc/attention_bwd_sm100.cu), one launch
+        if flash_bwd:         # head dims <= 80: the flash backward kernel (csrc/attention_bwd_sm100.cu), one launch
             dq, dk, dv = T.attention_backward(q.v, k.v, v.v, ao, y.g, lse2, B=B, heads=heads, Nq=Nq, Nk=Nk, d=d, scale=scale)
             tp.acc(q, dq)
             tp.acc(k, dk)
