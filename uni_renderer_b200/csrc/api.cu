@@ -617,6 +617,16 @@ int unib200_conv_gemm(unib200_program* prog, const unib200_gemm_desc* d, void* s
   const GemmMaps maps = g.maps;
   const GemmParams p = g.p;
   Op op = [maps, p, bn, sms](cudaStream_t s) { return launch_gemm(maps, p, bn, sms, s); };
+  // measurement aid (see skip_mask): UNIB200_SKIP_GEMM=<bitmask> drops one GEMM class from recorded programs --
+  // 1 short-K single-CTA tiles, 2 GEGLU, 4 split-K (+ finalize), 8 long-K CTA pairs, 16 long-K single CTA
+  static const int skip_cls = getenv("UNIB200_SKIP_GEMM") ? atoi(getenv("UNIB200_SKIP_GEMM")) : 0;
+  if (prog && skip_cls) {
+    const int cls = (d->flags & UNIB200_EPI_GEGLU) ? 2 : p.splits > 1 ? 4 : p.cg == 2 ? 8 : p.total_kb < 24 ? 1 : 16;
+    if (skip_cls & cls) {
+      op = [](cudaStream_t) { return cudaSuccess; };
+      g.launches = 0;
+    }
+  }
   return submit(prog, std::move(op), g.launches, stream, "conv_gemm", UNIB200_OP_GEMM, g.flops, g.bytes, g.desc);
 }
 
