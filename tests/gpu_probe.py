@@ -405,7 +405,11 @@ def case_attention_d40():
             "self_N4096_d40": _attn_case(2, 8, 4096, 4096, 40, g, True),
             "cross_N1024_77_d40": _attn_case(2, 8, 1024, 77, 40, g, False),
             "self_N64_d8": _attn_case(2, 4, 64, 64, 8, g, True),
-            "self_N1024_d32": _attn_case(2, 4, 1024, 1024, 32, g, True)}
+            "self_N1024_d32": _attn_case(2, 4, 1024, 1024, 32, g, True),
+            # head dim 64 fills the tensor-memory budget of the P-in-TMEM softmax (2 x (S 128 + O 64 + P 64) columns);
+            # ragged query / key counts exercise the padded last block
+            "self_N512_d64": _attn_case(1, 2, 512, 512, 64, g, True),
+            "self_N200_d48": _attn_case(1, 2, 200, 200, 48, g, True)}
 
 
 def case_attention_d80():

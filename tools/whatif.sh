@@ -13,6 +13,9 @@ run no_groupnorm UNIB200_SKIP_KINDS=8
 run no_gemm_shortk UNIB200_SKIP_GEMM=1
 run no_gemm_geglu UNIB200_SKIP_GEMM=2
 run no_gemm_splitk UNIB200_SKIP_GEMM=4
+run no_finalize UNIB200_SKIP_FINALIZE=1
+run no_gn_cluster UNIB200_SKIP_GN_CLUSTER=1
+run no_finalize_no_gn_cluster UNIB200_SKIP_FINALIZE=1 UNIB200_SKIP_GN_CLUSTER=1
 run no_gemm_pair UNIB200_SKIP_GEMM=8
 run no_gemm_long_single UNIB200_SKIP_GEMM=16
 run base2 A=0

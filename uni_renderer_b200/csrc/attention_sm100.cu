@@ -18,9 +18,11 @@
 #include <stdlib.h>
 
 // measured on B200 (tools/ab_attn.sh, 4096 x 4096 tokens, d = 40): 0 -> 241.9 us, 1 -> 251.6, 2 -> 248.6, 3 -> 241.1,
-// 5 -> 230.5, 7 -> 219.5, 9 -> 249.4, 11 -> 245.1; at d = 80 (BKV = 64) variant 0 stays the fastest (25.6 vs 27.1 us)
+// 5 -> 230.5, 7 -> 219.5, 9 -> 249.4, 11 -> 245.1; at d = 80 (BKV = 64) variant 0 stays the fastest (25.6 vs 27.1 us).
+// With P in tensor memory (bit 64; profiles/r2z_ab_attention_p_tmem.txt): 71 -> 195.4, 87 -> 201.9, 43091 -> 194.0,
+// 43219 -> 192.8 (within run-to-run noise of 71, which needs neither the ones tile nor d <= 48)
 #ifndef UNIB_ATTN_DEFAULT_VARIANT
-#define UNIB_ATTN_DEFAULT_VARIANT 7
+#define UNIB_ATTN_DEFAULT_VARIANT 71
 #endif
 
 namespace unib {
@@ -28,6 +30,7 @@ namespace unib {
 template <int NCH>
 struct AttnCfg {
   static constexpr int kBKV = (NCH == 1) ? 128 : 64;       // kv rows per block
+  static constexpr int BKV_ones_bytes() { return kBKV * 128; }
   static constexpr int kQBytes = NCH * 128 * 128;          // per tile: NCH chunks of [128 rows x 64 fp16]
   static constexpr int kKBytes = NCH * kBKV * 128;         // NCH chunks of [BKV rows x 64 fp16]
   static constexpr int kStageBytes = 2 * kKBytes;          // K + V
@@ -37,8 +40,12 @@ struct AttnCfg {
   static constexpr int kPOff = kKvOff + kStages * kStageBytes;
   static constexpr int kBarOff = kPOff + 2 * kPBytes;
   static constexpr int kSmemBytes = kBarOff + 256;         // base is declared 1024-aligned (checked at run time)
-  static constexpr int kTmemCols = 512;                    // 2 x S (BKV) + 2 x O (<= 64 | 128 | 192)
+  // tensor-core row sums (variant bit 16, NCH == 1): a [BKV x 64] fp16 tile of ONES, addressed like one V chunk
+  static constexpr int kOnesOff = kBarOff + 1024;
+  static constexpr int kSmemBytesOnes = kOnesOff + BKV_ones_bytes();
+  static constexpr int kTmemCols = 512;                    // 2 x S (BKV) + 2 x O (<= 64 | 128 | 192) [+ 2 x 16 row sums]
   static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget");
+  static_assert(NCH != 1 || kSmemBytesOnes + 1024 <= 232448, "shared memory budget (ones tile)");
 };
 
 // Fully unrolled MMA issue sequences: descriptors differ from a precomputed base only by compile-time constants, so
@@ -81,6 +88,14 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint64_t p_desc, uint6
   }
 }
 
+// O += P V with P read from TENSOR MEMORY (variant bit 64): K step ks reads the 8 columns [8 ks, 8 ks + 8) of P_t
+template <int BKV>
+__device__ __forceinline__ void issue_pv_ts(uint32_t d_tmem, uint32_t p_tmem, uint64_t v_desc, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int ks = 0; ks < BKV / 16; ++ks)
+    umma_f16_ts(d_tmem, p_tmem + ks * 8, v_desc + static_cast<uint64_t>((ks * 2048) >> 4), idesc, (!first || ks > 0) ? 1u : 0u);
+}
+
 // debug stamps: slot layout trace[(who * 16 + j) * 8 + k]
 #ifdef UNIB_ATTN_TRACE
 #define ATTN_TRACE(who, j, k)                                                                                   \
@@ -98,7 +113,33 @@ __device__ __forceinline__ void issue_pv(uint32_t d_tmem, uint64_t p_desc, uint6
 //   2  one-time stagger: warpgroup 1 starts its first block when warpgroup 0 is half-way through its exponentials, so
 //      the two tiles alternate on the MUFU unit instead of running their exponential phases in lockstep
 //   4  every 4th pair of exponentials on the FMA pipe (exp2_poly_x2);  8  every 2nd pair
-constexpr int kAttnPacked = 1, kAttnStagger = 2, kAttnPoly4 = 4, kAttnPoly2 = 8;
+//  16  row sums on the TENSOR CORE: a third MMA per block, L_t += P_t(j) 1 with an all-ones [BKV x 16] B operand, keeps
+//      the softmax denominators in 16 TMEM columns next to O_t (rescaled with it) -- the per-element FADD leaves the
+//      exponential loop, and the denominator sums exactly the fp16 probabilities the P V product uses
+//  32  early S: the tcgen05.ld of S_t(j+1) is issued before the P_t(j) stores / fence / arrive, so the TMEM load
+//      latency hides behind them instead of heading the next block
+//  bits 8..15: explicit polynomial pattern over the 8 pairs of two consecutive 8-element groups (bit (u & 1) * 4 + e);
+//      bits 4 / 8 are the patterns 0x88 / 0xAA
+//  64  P in TENSOR MEMORY (the FlashAttention-4 arrangement): the softmax threads write their fp16 probabilities with
+//      tcgen05.st into 64 TMEM columns per tile and the P V product takes its A operand from there.  The shared-memory
+//      P round trip (32 KB written + 32 KB read per tile and block, of ~116 KB in total) disappears: at head dim 40 the
+//      kernel was bound by the 128 B/clk shared-memory port (1812 predicted vs 1830 measured cycles per block pair)
+// 128  (with 64) the first half of a row's probabilities leaves for P_t half-way through the exponential loop, which
+//      frees 32 registers for the second half (the 3-of-8 / every-2nd-pair polynomial variants spill without it)
+constexpr int kAttnPacked = 1, kAttnStagger = 2, kAttnPoly4 = 4, kAttnPoly2 = 8, kAttnTcSum = 16, kAttnEarlyS = 32,
+              kAttnPTmem = 64, kAttnHalfStore = 128;
+__host__ __device__ constexpr int attn_poly_pattern(int var) {
+  return ((var >> 8) & 0xFF) ? ((var >> 8) & 0xFF) : (var & kAttnPoly2) ? 0xAA : (var & kAttnPoly4) ? 0x88 : 0;
+}
+// zero-instruction register dependency: consumers of v[] cannot be scheduled above the tcgen05.wait::ld that precedes it
+__device__ __forceinline__ void touch32(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                    "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                    "+r"(r[30]), "+r"(r[31]));
+}
 
 template <int NCH, int VAR>
 __global__ void __launch_bounds__(320, 1)
@@ -131,7 +172,19 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   const int ntile = (q_base + 128 < p.Nq) ? 2 : 1;     // second tile may not exist
   const int nblk = (p.Nk + BKV - 1) / BKV;
   const int dpad = (p.d + 15) & ~15;
+  constexpr bool kTcSum = (VAR & kAttnTcSum) != 0, kEarlyS = (VAR & kAttnEarlyS) != 0;
+  constexpr int kPat = attn_poly_pattern(VAR);
+  constexpr bool kPTmem = (VAR & kAttnPTmem) != 0, kHalfStore = kPTmem && (VAR & kAttnHalfStore) != 0;
+  static_assert(!kPTmem || NCH == 1, "P in tensor memory: head dims <= 64 only (2 x (S 128 + O 64 + P 64) = 512 columns)");
+  static_assert(!kTcSum || NCH == 1, "tensor-core row sums: head dims <= 64 only (TMEM / shared-memory budget)");
+  static_assert(!kEarlyS || (NCH == 1 && (VAR & kAttnPacked)), "early S: BKV = 128 and the packed row maximum");
 
+  if (kTcSum) {                              // the ones tile (generic-proxy stores -> visible to the tensor core)
+    uint4* ones = reinterpret_cast<uint4*>(smem + Cfg::kOnesOff);
+    const uint4 one8 = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+    for (int i = threadIdx.x; i < BKV * 128 / 16; i += blockDim.x) ones[i] = one8;
+    fence_proxy_async_shared();
+  }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&maps.q);
     tma_prefetch_desc(&maps.k);
@@ -162,7 +215,11 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   pdl_wait();        // PDL: see common.cuh (trigger at the end of the CTA, as in the GEMM kernel)
   // TMEM columns: [S0 | S1 | O0 | O1]
   auto t_s_col = [&](int t) { return static_cast<uint32_t>(t * BKV); };
-  auto t_o_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + t * (NCH * 64)); };
+  // P in tensor memory AND row sums: 2 x (S 128 + O dpad + P 64 + L 16) columns only fit with dpad <= 48 (launcher)
+  const int o_stride = (kPTmem && kTcSum) ? dpad : NCH * 64;
+  auto t_o_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + t * o_stride); };
+  auto t_p_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + t * 64); };      // kPTmem: fp16 P_t
+  auto t_l_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + (kPTmem ? 128 : 0) + t * 16); };
 
   if (warp == 8) {
     // =============================== TMA producer ===============================
@@ -200,6 +257,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
     const uint64_t p_desc0 = make_desc_kmajor_sw128(base + Cfg::kPOff);
     const uint64_t k_desc0 = make_desc_kmajor_sw128(kv_smem);
     const uint64_t v_desc0 = make_desc_mnmajor_sw128(kv_smem + Cfg::kKBytes, BKV * 128, 1024);
+    const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);
+    const uint64_t ones_desc = make_desc_mnmajor_sw128(base + Cfg::kOnesOff, BKV * 128, 1024);
     constexpr uint64_t kStage16 = Cfg::kStageBytes >> 4;
     mbar_wait(q_full, 0);
     mbar_wait(kv_full(0), 0);
@@ -241,8 +300,15 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
           if (elect_one()) {
             ATTN_TRACE(2 + t, j, 0);
             // K loop over the kv rows of this block in steps of 16
-            issue_pv<BKV>(tmem_base + t_o_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), v_desc0 + st * kStage16, idesc_o,
-                          j == 0);
+            if (kPTmem)
+              issue_pv_ts<BKV>(tmem_base + t_o_col(t), tmem_base + t_p_col(t), v_desc0 + st * kStage16, idesc_o, j == 0);
+            else
+              issue_pv<BKV>(tmem_base + t_o_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), v_desc0 + st * kStage16, idesc_o,
+                            j == 0);
+            if (kTcSum && kPTmem)                             // L_t += P_t(j) 1: the softmax denominators
+              issue_pv_ts<BKV>(tmem_base + t_l_col(t), tmem_base + t_p_col(t), ones_desc, idesc_l, j == 0);
+            else if (kTcSum)
+              issue_pv<BKV>(tmem_base + t_l_col(t), p_desc0 + t * (Cfg::kPBytes >> 4), ones_desc, idesc_l, j == 0);
             umma_commit(pv_done(t));                          // P_t buffer + O_t free again
             if (t == ntile - 1) umma_commit(kv_empty(st));   // K(j)/V(j) fully consumed by both tiles
             if (j == nblk - 1) umma_commit(o_ready(t));
@@ -266,37 +332,75 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       const uint32_t p_row = base + Cfg::kPOff + t * Cfg::kPBytes + row * 128;
       const int sw = row & 7;
       if ((VAR & kAttnStagger) && t == 1) named_bar_sync(1, 256);    // ntile == 2 here: tile 0's warpgroup arrives (j = 0)
+      const uint32_t t_l = tmem_base + lane_off + t_l_col(t);
+      const uint32_t t_p = tmem_base + lane_off + t_p_col(t);
+      float v[BKV];                           // S_t(j) of this thread's row
       for (int j = 0; j < nblk; ++j) {
         const bool tr = (lane == 0 && qd == 0);
         if (tr) ATTN_TRACE(t, j, 0);
-        mbar_wait(s_full(t), j & 1);
-        tc_fence_after();
-        if (tr) ATTN_TRACE(t, j, 1);
-        float v[BKV];
-#pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) tmem_ld32(t_s + c * 32, v + c * 32);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(s_free(t));               // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1)
-        if (tr) ATTN_TRACE(t, j, 2);
         const int kv_valid = p.Nk - j * BKV;     // columns >= kv_valid are padding (last block only)
-        if (kv_valid < BKV) {
+        float mx4[4];                            // 4 independent chains (FMNMX latency, not issue, bounds)
+        auto max_first = [&](int hi) {           // FMNMX3: two new elements per instruction; columns [0, hi)
+          mx4[0] = v[0]; mx4[1] = v[1]; mx4[2] = v[2]; mx4[3] = v[3];
 #pragma unroll
-          for (int i = 0; i < BKV; ++i)
-            if (i >= kv_valid) v[i] = -INFINITY;
-        }
-        float mx4[4] = {v[0], v[1], v[2], v[3]};              // 4 independent chains (FMNMX latency, not issue, bounds)
-        if (VAR & kAttnPacked) {
-#pragma unroll
-          for (int i = 4; i + 8 <= BKV; i += 8) {               // FMNMX3: two new elements per instruction
+          for (int i = 4; i + 8 <= hi; i += 8) {
             mx4[0] = fmax3(mx4[0], v[i], v[i + 1]);
             mx4[1] = fmax3(mx4[1], v[i + 2], v[i + 3]);
             mx4[2] = fmax3(mx4[2], v[i + 4], v[i + 5]);
             mx4[3] = fmax3(mx4[3], v[i + 6], v[i + 7]);
           }
-          mx4[0] = fmax3(mx4[0], v[BKV - 4], v[BKV - 3]);
-          mx4[1] = fmax3(mx4[1], v[BKV - 2], v[BKV - 1]);
+          mx4[0] = fmax3(mx4[0], v[hi - 4], v[hi - 3]);
+          mx4[1] = fmax3(mx4[1], v[hi - 2], v[hi - 1]);
+        };
+        auto max_more = [&](int lo, int hi) {    // columns [lo, hi), (hi - lo) % 8 == 0
+#pragma unroll
+          for (int i = lo; i + 8 <= hi; i += 8) {
+            mx4[0] = fmax3(mx4[0], v[i], v[i + 1]);
+            mx4[1] = fmax3(mx4[1], v[i + 2], v[i + 3]);
+            mx4[2] = fmax3(mx4[2], v[i + 4], v[i + 5]);
+            mx4[3] = fmax3(mx4[3], v[i + 6], v[i + 7]);
+          }
+        };
+        bool half_done = false;
+        if (kEarlyS && j > 0) {
+          // the first half of S_t(j) was requested before the previous block's P stores; the second half's TMEM latency
+          // hides behind the first half's row maximum
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < BKV / 64; ++c) touch32(v + c * 32);
+#pragma unroll
+          for (int c = BKV / 64; c < BKV / 32; ++c) tmem_ld32(t_s + c * 32, v + c * 32);
+          if (kv_valid >= BKV) {                 // warp-uniform; the padded last block takes the plain path below
+            max_first(BKV / 2);
+            half_done = true;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = BKV / 64; c < BKV / 32; ++c) touch32(v + c * 32);
         } else {
+          mbar_wait(s_full(t), j & 1);
+          tc_fence_after();
+          if (tr) ATTN_TRACE(t, j, 1);
+#pragma unroll
+          for (int c = 0; c < BKV / 32; ++c) tmem_ld32(t_s + c * 32, v + c * 32);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(s_free(t));               // S_t(j) is in registers: the tensor core may overwrite it with S_t(j+1)
+        if (tr) ATTN_TRACE(t, j, 2);
+        if (kv_valid < BKV) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (i >= kv_valid) v[i] = -INFINITY;
+        }
+        if (VAR & kAttnPacked) {
+          if (half_done) {
+            max_more(BKV / 2, BKV);
+          } else {
+            max_first(BKV);
+          }
+        } else {
+          mx4[0] = v[0]; mx4[1] = v[1]; mx4[2] = v[2]; mx4[3] = v[3];
 #pragma unroll
           for (int i = 4; i < BKV; i += 4) {
             mx4[0] = fmaxf(mx4[0], v[i]);
@@ -332,6 +436,14 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
               for (int i = 0; i < 16; ++i) o[i] *= alpha;
               tmem_st16(t_o + c * 16, o);
             }
+            if (kTcSum) {
+              float o[16];
+              tmem_ld16(t_l, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] *= alpha;
+              tmem_st16(t_l, o);
+            }
             tmem_st_wait();
           }
         }
@@ -340,26 +452,36 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[BKV / 2];
 
-        if (VAR & (kAttnPacked | kAttnPoly4 | kAttnPoly2)) {
+        if ((VAR & kAttnPacked) || kPat != 0) {
           const f32x2_t sl2_2 = pack_f32x2(sl2, sl2), nmb_2 = pack_f32x2(-mb, -mb);
           f32x2_t rs2[4] = {0ull, 0ull, 0ull, 0ull};             // (0.f, 0.f) pairs
 #pragma unroll
           for (int u = 0; u < BKV / 8; ++u) {
             if ((VAR & kAttnStagger) && j == 0 && t == 0 && ntile == 2 && u == BKV / 16)
               named_bar_arrive(1, 256);                         // half-way through tile 0's first block: release tile 1
+            if (kHalfStore && u == BKV / 16) {
+              // first half of the row's probabilities -> P_t (frees 32 registers for the second half).  P_t V(j-1)
+              // was issued a whole exponential half-phase ago: the wait is free
+              if (!pv_waited) {
+                mbar_wait(pv_done(t), (j - 1) & 1);
+                tc_fence_after();
+                pv_waited = true;
+              }
+              tmem_st32(t_p, pk);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = u * 8 + 2 * e;
               float x0, x1, p0, p1;
               unpack_f32x2(fma_f32x2(pack_f32x2(v[i], v[i + 1]), sl2_2, nmb_2), x0, x1);
-              const bool poly = ((VAR & kAttnPoly2) && (e & 1)) || ((VAR & kAttnPoly4) && e == 3);
+              const bool poly = ((kPat >> ((u & 1) * 4 + e)) & 1) != 0;
               if (poly) {
                 exp2_poly_x2(x0, x1, p0, p1);
               } else {
                 p0 = fast_exp2(x0);
                 p1 = fast_exp2(x1);
               }
-              rs2[e] = add_f32x2(rs2[e], pack_f32x2(p0, p1));
+              if (!kTcSum) rs2[e] = add_f32x2(rs2[e], pack_f32x2(p0, p1));
               pk[u * 4 + e] = pack_half2(p0, p1);
             }
           }
@@ -378,7 +500,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
               const int i = u * 8 + 2 * e;
               const float p0 = fast_exp2(v[i] * sl2 - mb);
               const float p1 = fast_exp2(v[i + 1] * sl2 - mb);
-              rs4[e] += p0 + p1;
+              if (!kTcSum) rs4[e] += p0 + p1;
               pk[u * 4 + e] = pack_half2(p0, p1);
             }
           }
@@ -387,6 +509,17 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
           mbar_wait(pv_done(t), (j - 1) & 1);
           tc_fence_after();
         }
+        if (kEarlyS && j + 1 < nblk) {        // S_t(j+1) was issued when this block's scores left TMEM: long complete
+          mbar_wait(s_full(t), (j + 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < BKV / 64; ++c) tmem_ld32(t_s + c * 32, v + c * 32);     // first half; see the loop head
+        }
+        if (kPTmem) {                           // this row's 128 probabilities = 64 packed columns of P_t
+          if (!kHalfStore) tmem_st32(t_p, pk);  // (else the first 32 columns left half-way through the loop above)
+          tmem_st32(t_p + 32, pk + 32);
+          tmem_st_wait();
+        } else
 #pragma unroll
         for (int u = 0; u < BKV / 8; ++u) {
           // 16 B unit (u & 7) of this row lands at ((u & 7) ^ (row & 7)) in the 128B-swizzled 64-column chunk u >> 3
@@ -396,13 +529,19 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         }
         l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         if (tr) ATTN_TRACE(t, j, 4);
-        fence_proxy_async_shared();           // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+        if (!kPTmem) fence_proxy_async_shared();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
         tc_fence_before();
         mbar_arrive(p_full(t));
         if (tr) ATTN_TRACE(t, j, 5);
       }
       mbar_wait(o_ready(t), 0);
       tc_fence_after();
+      if (kTcSum) {
+        float lt[16];
+        tmem_ld16(t_l, lt);
+        tmem_ld_wait();
+        l_run = lt[0];
+      }
       const float inv_l = 1.0f / l_run;
       const int q = q_base + t * 128 + row;
       if (p.lse2 != nullptr && q < p.Nq)      // P was exp2((s - m_ref) * sl2): log2 sum exp2(s * sl2) = m_ref * sl2 + log2(l)
@@ -443,15 +582,16 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
 template <int NCH, int VAR>
 static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = AttnCfg<NCH>;
+  constexpr int smem_bytes = (VAR & kAttnTcSum) ? Cfg::kSmemBytesOnes : Cfg::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+                                         smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
-  return launch_pdl(attention_tcgen05_kernel<NCH, VAR>, grid, dim3(320), Cfg::kSmemBytes, stream, maps, p);
+  return launch_pdl(attention_tcgen05_kernel<NCH, VAR>, grid, dim3(320), smem_bytes, stream, maps, p);
 }
 
 int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
@@ -459,7 +599,7 @@ int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
 // softmax variant (bits above): the default is the measured optimum; UNIB200_ATTN_VARIANT overrides it for A/B runs
 static int attention_variant(int nch) {
   static const int v = getenv("UNIB200_ATTN_VARIANT") ? atoi(getenv("UNIB200_ATTN_VARIANT")) : -1;
-  if (v >= 0) return v;
+  if (v >= 0 && (nch == 1 || v < 16)) return v;      // variants >= 16 exist for head dims <= 64 only
   return nch == 1 ? UNIB_ATTN_DEFAULT_VARIANT : 0;
 }
 
@@ -474,6 +614,31 @@ static cudaError_t launch_var(const AttnMaps& maps, const AttnParams& p, cudaStr
     case 7: return launch_cfg<NCH, 7>(maps, p, stream);
     case 9: return launch_cfg<NCH, 9>(maps, p, stream);
     case 11: return launch_cfg<NCH, 11>(maps, p, stream);
+  }
+  if constexpr (NCH == 1) {                  // round-2 experiments (head dims <= 64)
+    switch (attention_variant(NCH)) {
+      case 23: return launch_cfg<1, 23>(maps, p, stream);                    // 7 + tensor-core row sums
+      case 27: return launch_cfg<1, 27>(maps, p, stream);                    // tc sums, polynomial on every 2nd pair
+      case 39: return launch_cfg<1, 39>(maps, p, stream);                    // 7 + early S
+      case 55: return launch_cfg<1, 55>(maps, p, stream);                    // 7 + tc sums + early S
+      case 59: return launch_cfg<1, 59>(maps, p, stream);                    // 27 + early S
+      case 43011: return launch_cfg<1, 3 | (0xA8 << 8)>(maps, p, stream);    // polynomial on 3 of 8 pairs
+      case 43027: return launch_cfg<1, 19 | (0xA8 << 8)>(maps, p, stream);   // + tc sums
+      case 43059: return launch_cfg<1, 51 | (0xA8 << 8)>(maps, p, stream);   // + tc sums + early S
+      case 67: return launch_cfg<1, 67>(maps, p, stream);                    // P in tensor memory, no polynomial
+      case 71: return launch_cfg<1, 71>(maps, p, stream);                    // 7 + P in tensor memory
+      case 199: return launch_cfg<1, 199>(maps, p, stream);                  // + half-way P store
+      case 203: return launch_cfg<1, 203>(maps, p, stream);                  // polynomial on every 2nd pair
+      case 43203: return launch_cfg<1, 195 | (0xA8 << 8)>(maps, p, stream);  // polynomial on 3 of 8 pairs
+      // P in tensor memory + tensor-core row sums: TMEM only has room for head dims <= 48
+      case 87: return p.d <= 48 ? launch_cfg<1, 87>(maps, p, stream) : launch_cfg<1, 71>(maps, p, stream);
+      case 215: return p.d <= 48 ? launch_cfg<1, 215>(maps, p, stream) : launch_cfg<1, 199>(maps, p, stream);
+      case 219: return p.d <= 48 ? launch_cfg<1, 219>(maps, p, stream) : launch_cfg<1, 203>(maps, p, stream);
+      case 43091: return p.d <= 48 ? launch_cfg<1, 83 | (0xA8 << 8)>(maps, p, stream)
+                                   : launch_cfg<1, 195 | (0xA8 << 8)>(maps, p, stream);
+      case 43219: return p.d <= 48 ? launch_cfg<1, 211 | (0xA8 << 8)>(maps, p, stream)
+                                   : launch_cfg<1, 195 | (0xA8 << 8)>(maps, p, stream);
+    }
   }
   return cudaErrorInvalidValue;
 }

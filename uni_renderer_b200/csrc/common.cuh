@@ -150,6 +150,17 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand comes from tensor memory (K-major only: lane = row, two fp16 per
+// 32-bit column, 8 columns per K = 16 step) -- the attention kernel's P V product with P written by tcgen05.st
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -285,6 +296,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 256-bit global accesses (sm_100+: LDG/STG.256), 32-byte aligned
@@ -367,10 +388,32 @@ __device__ __forceinline__ f32x2_t splat_f32x2(float c) { return pack_f32x2(c, c
 // sign never has to be restored because  gelu(x) = x/2 * (1 + sign(x) * (1 - y)) = x/2 + |x|/2 * (1 - y),
 // y = poly(t) * t * exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt2).  ~19 issue slots per pair instead of ~25 per element:
 // the GEGLU epilogue (64 gate elements per thread and tile, two warps per scheduler) was issue-bound on this.
+#ifndef UNIB_GELU_VARIANT
+#define UNIB_GELU_VARIANT 2
+#endif
 __device__ __forceinline__ f32x2_t gelu_erf_x2(f32x2_t x) {
+#if UNIB_GELU_VARIANT == 1
+  return x;                                   // what-if timing aid: the epilogue without its GELU (garbage results)
+#endif
   float x0, x1;
   unpack_f32x2(x, x0, x1);
   const f32x2_t ax = pack_f32x2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);   // |x| / sqrt2
+#if UNIB_GELU_VARIANT == 2
+  // ONE MUFU op per element instead of two: erfc(z) = 2^(z P(z)) with a degree-4 minimax P on z >= 0 (fitted on the
+  // erf error: |erf error| <= 6.1e-7, |gelu error| <= 1.1e-6 absolute, 5.5e-7 relative; P -> -inf for large z, so no
+  // clamp is needed).  gelu(x) = x/2 + |x|/2 * (1 - erfc(|x| / sqrt2)).
+  f32x2_t pz = fma_f32x2(splat_f32x2(-0.0029487041756510735f), ax, splat_f32x2(0.029606351628899574f));
+  pz = fma_f32x2(pz, ax, splat_f32x2(-0.14868280291557312f));
+  pz = fma_f32x2(pz, ax, splat_f32x2(-0.9185044169425964f));
+  pz = fma_f32x2(pz, ax, splat_f32x2(-1.6278891563415527f));
+  float e0, e1, y0, y1;
+  unpack_f32x2(mul_f32x2(ax, pz), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(e1));
+  const f32x2_t w = fma_f32x2(pack_f32x2(y0, y1), splat_f32x2(-1.0f), splat_f32x2(1.0f));      // 1 - erfc = |erf|
+  const f32x2_t kax = mul_f32x2(ax, splat_f32x2(0.70710678118654752f));                        // |x| / 2
+  return fma_f32x2(kax, w, mul_f32x2(x, splat_f32x2(0.5f)));
+#else
   float d0, d1;
   unpack_f32x2(fma_f32x2(splat_f32x2(0.3275911f), ax, splat_f32x2(1.0f)), d0, d1);
   const f32x2_t t = pack_f32x2(fast_rcp(d0), fast_rcp(d1));
@@ -387,6 +430,7 @@ __device__ __forceinline__ f32x2_t gelu_erf_x2(f32x2_t x) {
   const f32x2_t w = fma_f32x2(y, splat_f32x2(-1.0f), splat_f32x2(1.0f));                     // 1 - y = |erf|
   const f32x2_t kax = mul_f32x2(ax, splat_f32x2(0.70710678118654752f));                      // |x| / 2
   return fma_f32x2(kax, w, mul_f32x2(x, splat_f32x2(0.5f)));
+#endif
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;

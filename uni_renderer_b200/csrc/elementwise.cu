@@ -565,7 +565,8 @@ cudaError_t launch_groupnorm(const GnParams& p_in, int B, int num_sms, cudaStrea
   static const bool two_kernel = getenv("UNIB200_GN_TWO_KERNEL") != nullptr;      // A/B: the stats + apply pair
   // measured in-graph (tools/bench_elem.py): the cluster kernel (<= 16 CTAs per sample) wins while a sample is small,
   // the stats + apply pair (hundreds of CTAs) wins on the 64x64 / 32x32 tensors
-  if (!two_kernel && p.G <= 64 && p.HW <= 256) return launch_gn_cluster(p, B, stream);
+  static const bool skip_cluster = getenv("UNIB200_SKIP_GN_CLUSTER") != nullptr;   // what-if timing aid (garbage results)
+  if (!two_kernel && p.G <= 64 && p.HW <= 256) return skip_cluster ? cudaSuccess : launch_gn_cluster(p, B, stream);
   int chunks = (2 * num_sms + B - 1) / B;
   if (chunks > p.HW / 4) chunks = p.HW / 4 > 0 ? p.HW / 4 : 1;
   if (chunks > p.max_chunks) chunks = p.max_chunks;
