@@ -141,8 +141,13 @@ __device__ __forceinline__ void touch32(float* v) {
                     "+r"(r[30]), "+r"(r[31]));
 }
 
-template <int NCH, int VAR>
-__global__ void __launch_bounds__(320, 1)
+// SPLIT = 2 (P in tensor memory, head dims <= 64): TWO warpgroups per query tile, each exponentiating one 64-column
+// half of the tile's S block for the same 128 rows (warps w and w + 4 share a TMEM lane quadrant, like the GEMM
+// epilogue): sixteen softmax warps = four per scheduler instead of two, against the per-warp dependency latency that
+// bounds the exponential loop once the shared-memory port is out of the way.  The halves agree on the row maximum
+// through shared memory and one named barrier per block and keep separate row sums.
+template <int NCH, int VAR, int SPLIT = 1>
+__global__ void __launch_bounds__((8 * SPLIT + 2) * 32, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH>;
   constexpr int BKV = Cfg::kBKV;
@@ -175,7 +180,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   constexpr bool kTcSum = (VAR & kAttnTcSum) != 0, kEarlyS = (VAR & kAttnEarlyS) != 0;
   constexpr int kPat = attn_poly_pattern(VAR);
   constexpr bool kPTmem = (VAR & kAttnPTmem) != 0, kHalfStore = kPTmem && (VAR & kAttnHalfStore) != 0;
-  static_assert(!kPTmem || NCH == 1, "P in tensor memory: head dims <= 64 only (2 x (S 128 + O 64 + P 64) = 512 columns)");
+  // TMEM budget: NCH = 1: 2 x (S 128 + O 64 + P 64) = 512 columns; NCH = 2 (BKV = 64): 2 x (S 64 + O 128 + P 32 of 64)
+  static_assert(!kPTmem || NCH <= 2, "P in tensor memory: head dims <= 128 only");
+  static_assert(!kHalfStore || NCH == 1, "half-way P store: BKV = 128 only");
   static_assert(!kTcSum || NCH == 1, "tensor-core row sums: head dims <= 64 only (TMEM / shared-memory budget)");
   static_assert(!kEarlyS || (NCH == 1 && (VAR & kAttnPacked)), "early S: BKV = 128 and the packed row maximum");
 
@@ -185,7 +192,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
     for (int i = threadIdx.x; i < BKV * 128 / 16; i += blockDim.x) ones[i] = one8;
     fence_proxy_async_shared();
   }
-  if (warp == 8 && lane == 0) {
+  constexpr int kProdWarp = 8 * SPLIT, kMmaWarp = 8 * SPLIT + 1;
+  static_assert(SPLIT == 1 || (SPLIT == 2 && NCH == 1 && (VAR & kAttnPTmem) && !(VAR & (kAttnTcSum | kAttnEarlyS | kAttnHalfStore))),
+                "column-split softmax: P in tensor memory, head dims <= 64, plain variants only");
+  if (warp == kProdWarp && lane == 0) {
     tma_prefetch_desc(&maps.q);
     tma_prefetch_desc(&maps.k);
     tma_prefetch_desc(&maps.v);
@@ -196,14 +206,14 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 128);
+      mbar_init(p_full(s), 128 * SPLIT);
       mbar_init(o_ready(s), 1);
       mbar_init(pv_done(s), 1);
-      mbar_init(s_free(s), 128);
+      mbar_init(s_free(s), 128 * SPLIT);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -221,7 +231,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   auto t_p_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + t * 64); };      // kPTmem: fp16 P_t
   auto t_l_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + (kPTmem ? 128 : 0) + t * 16); };
 
-  if (warp == 8) {
+  if (warp == kProdWarp) {
     // =============================== TMA producer ===============================
     // warp-uniform loop, one elected lane issues (operands stay in uniform registers)
     if (elect_one()) {
@@ -245,7 +255,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       }
       if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     // warp-uniform loop; every issue block is executed by one elected lane (always the same one, so the commits
     // track the MMAs it issued)
@@ -317,6 +327,151 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         }
       }
       st = stn;
+    }
+  } else if (SPLIT == 2) {
+    // =============================== softmax + epilogue, column-split ===============================
+    // warp w: TMEM lane quadrant w & 3, warpgroup g = w >> 2: tile t = g & 1, column half hf = g >> 1
+    constexpr int HC = BKV / 2;                    // 64 S columns per thread and block
+    const int g = warp >> 2;
+    const int t = g & 1, hf = g >> 1;
+    if (t < ntile) {
+      const int qd = warp & 3;
+      const int row = qd * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_off + t_s_col(t) + hf * HC;
+      const uint32_t t_o = tmem_base + lane_off + t_o_col(t);
+      const uint32_t t_p = tmem_base + lane_off + t_p_col(t) + hf * (HC / 2);     // my 32 packed columns of P_t
+      const float sl2 = p.scale * 1.4426950408889634f;
+      float m_ref = -INFINITY, l_run = 0.f;
+      // exchange slots xch[buffer j & 1][tile][half][row] in the (unused: P lives in TMEM) shared-memory P region
+      float* const xch = reinterpret_cast<float*>(smem + Cfg::kPOff);
+      if ((VAR & kAttnStagger) && t == 1) named_bar_sync(1, 512);    // tile 0's two warpgroups arrive (j = 0)
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(s_full(t), j & 1);
+        tc_fence_after();
+        float v[HC];
+        tmem_ld32(t_s, v);
+        tmem_ld32(t_s + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free(t));
+        const int kv_valid = p.Nk - j * BKV - hf * HC;          // my columns >= kv_valid are padding (last block only)
+        if (kv_valid < HC) {
+#pragma unroll
+          for (int i = 0; i < HC; ++i)
+            if (i >= kv_valid) v[i] = -INFINITY;
+        }
+        float mx4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+        for (int i = 4; i + 8 <= HC; i += 8) {
+          mx4[0] = fmax3(mx4[0], v[i], v[i + 1]);
+          mx4[1] = fmax3(mx4[1], v[i + 2], v[i + 3]);
+          mx4[2] = fmax3(mx4[2], v[i + 4], v[i + 5]);
+          mx4[3] = fmax3(mx4[3], v[i + 6], v[i + 7]);
+        }
+        mx4[0] = fmax3(mx4[0], v[HC - 4], v[HC - 3]);
+        mx4[1] = fmax3(mx4[1], v[HC - 2], v[HC - 1]);
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // the row maximum of the whole block: one float per row through shared memory, one named barrier per tile
+        float* const slot = xch + (((j & 1) * 2 + t) * 2) * 128;
+        slot[hf * 128 + row] = mx;
+        named_bar_sync(2 + t, 256);
+        mx = fmaxf(mx, slot[(hf ^ 1) * 128 + row]);
+        bool pv_waited = (j == 0);
+        const bool need = (mx - m_ref) * sl2 > 8.0f;            // same rows, same inputs in both halves: same decision
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx);
+          const float alpha = fast_exp2((m_ref - m_new) * sl2);
+          m_ref = m_new;
+          l_run *= alpha;
+          if (j > 0) {
+            mbar_wait(pv_done(t), (j - 1) & 1);
+            tc_fence_after();
+            pv_waited = true;
+#pragma unroll 1
+            for (int c = hf; c < dpad / 16; c += 2) {           // the halves split O's 16-column chunks
+              float o[16];
+              tmem_ld16(t_o + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] *= alpha;
+              tmem_st16(t_o + c * 16, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        const float mb = m_ref * sl2;
+        uint32_t pk[HC / 2];
+        const f32x2_t sl2_2 = pack_f32x2(sl2, sl2), nmb_2 = pack_f32x2(-mb, -mb);
+        f32x2_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int u = 0; u < HC / 8; ++u) {
+          if ((VAR & kAttnStagger) && j == 0 && t == 0 && ntile == 2 && u == HC / 16) named_bar_arrive(1, 512);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = u * 8 + 2 * e;
+            float x0, x1, p0, p1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(v[i], v[i + 1]), sl2_2, nmb_2), x0, x1);
+            const bool poly = ((kPat >> ((u & 1) * 4 + e)) & 1) != 0;
+            if (poly) {
+              exp2_poly_x2(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            rs2[e] = add_f32x2(rs2[e], pack_f32x2(p0, p1));
+            pk[u * 4 + e] = pack_half2(p0, p1);
+          }
+        }
+        float rs4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a, b2;
+          unpack_f32x2(rs2[e], a, b2);
+          rs4[e] = a + b2;
+        }
+        if (!pv_waited) {
+          mbar_wait(pv_done(t), (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st32(t_p, pk);
+        tmem_st_wait();
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        tc_fence_before();
+        mbar_arrive(p_full(t));
+      }
+      // row sums of the two halves -> one normaliser (same exchange pattern, its own buffer parity)
+      float* const slot = xch + (((nblk & 1) * 2 + t) * 2) * 128;
+      slot[hf * 128 + row] = l_run;
+      named_bar_sync(2 + t, 256);
+      l_run += slot[(hf ^ 1) * 128 + row];
+      const float inv_l = 1.0f / l_run;
+      mbar_wait(o_ready(t), 0);
+      tc_fence_after();
+      const int q = q_base + t * 128 + row;
+      if (hf == 0 && p.lse2 != nullptr && q < p.Nq)
+        p.lse2[(static_cast<size_t>(b) * p.heads + head) * p.Nq + q] = m_ref * sl2 + log2f(l_run);
+      __half* op = p.out + (static_cast<size_t>(b) * p.Nq + q) * p.ldo + head * p.d;
+#pragma unroll 1
+      for (int c = hf; c < dpad / 16; c += 2) {
+        float o[16];
+        tmem_ld16(t_o + c * 16, o);
+        tmem_ld_wait();
+        if (q < p.Nq) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c * 16 + u * 8;
+            if (col + 8 <= p.d) {
+              uint4 w;
+              w.x = pack_half2(o[u * 8 + 0] * inv_l, o[u * 8 + 1] * inv_l);
+              w.y = pack_half2(o[u * 8 + 2] * inv_l, o[u * 8 + 3] * inv_l);
+              w.z = pack_half2(o[u * 8 + 4] * inv_l, o[u * 8 + 5] * inv_l);
+              w.w = pack_half2(o[u * 8 + 6] * inv_l, o[u * 8 + 7] * inv_l);
+              *reinterpret_cast<uint4*>(op + col) = w;
+            }
+          }
+        }
+      }
     }
   } else {
     // =============================== softmax + epilogue (warpgroup t = warp / 4) ===============================
@@ -517,7 +672,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
         }
         if (kPTmem) {                           // this row's 128 probabilities = 64 packed columns of P_t
           if (!kHalfStore) tmem_st32(t_p, pk);  // (else the first 32 columns left half-way through the loop above)
-          tmem_st32(t_p + 32, pk + 32);
+          if (BKV == 128) tmem_st32(t_p + 32, pk + 32);
           tmem_st_wait();
         } else
 #pragma unroll
@@ -573,25 +728,25 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   tc_fence_before();
   __syncthreads();
   pdl_launch();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int NCH, int VAR>
+template <int NCH, int VAR, int SPLIT = 1>
 static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStream_t stream) {
   using Cfg = AttnCfg<NCH>;
   constexpr int smem_bytes = (VAR & kAttnTcSum) ? Cfg::kSmemBytesOnes : Cfg::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<NCH, VAR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
-  return launch_pdl(attention_tcgen05_kernel<NCH, VAR>, grid, dim3(320), smem_bytes, stream, maps, p);
+  return launch_pdl(attention_tcgen05_kernel<NCH, VAR, SPLIT>, grid, dim3((8 * SPLIT + 2) * 32), smem_bytes, stream, maps, p);
 }
 
 int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
@@ -600,7 +755,8 @@ int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
 static int attention_variant(int nch) {
   static const int v = getenv("UNIB200_ATTN_VARIANT") ? atoi(getenv("UNIB200_ATTN_VARIANT")) : -1;
   if (v >= 0 && (nch == 1 || v < 16)) return v;      // variants >= 16 exist for head dims <= 64 only
-  return nch == 1 ? UNIB_ATTN_DEFAULT_VARIANT : 0;
+  static const int v2 = getenv("UNIB200_ATTN_VARIANT2") ? atoi(getenv("UNIB200_ATTN_VARIANT2")) : 65;
+  return nch == 1 ? UNIB_ATTN_DEFAULT_VARIANT : nch == 2 ? v2 : 0;    // head dims 65..128: packed softmax, P in TMEM (27.4 -> 24.9 us at 1024 x 1024, d = 80)
 }
 
 template <int NCH>
@@ -615,7 +771,21 @@ static cudaError_t launch_var(const AttnMaps& maps, const AttnParams& p, cudaStr
     case 9: return launch_cfg<NCH, 9>(maps, p, stream);
     case 11: return launch_cfg<NCH, 11>(maps, p, stream);
   }
+  if constexpr (NCH == 2) {
+    if (attention_variant(NCH) == 64) return launch_cfg<2, 64>(maps, p, stream);
+    if (attention_variant(NCH) == 65) return launch_cfg<2, 65>(maps, p, stream);
+  }
   if constexpr (NCH == 1) {                  // round-2 experiments (head dims <= 64)
+    // UNIB200_ATTN_SPLIT=1: column-split softmax (16 softmax warps) for long key sequences
+    static const int split = getenv("UNIB200_ATTN_SPLIT") ? atoi(getenv("UNIB200_ATTN_SPLIT")) : 0;
+    if (split && p.Nk >= 512) {
+      switch (attention_variant(NCH)) {
+        case 67: return launch_cfg<1, 67, 2>(maps, p, stream);
+        case 75: return launch_cfg<1, 75, 2>(maps, p, stream);
+        case 43075: return launch_cfg<1, 67 | (0xA8 << 8), 2>(maps, p, stream);
+        default: return launch_cfg<1, 71, 2>(maps, p, stream);
+      }
+    }
     switch (attention_variant(NCH)) {
       case 23: return launch_cfg<1, 23>(maps, p, stream);                    // 7 + tensor-core row sums
       case 27: return launch_cfg<1, 27>(maps, p, stream);                    // tc sums, polynomial on every 2nd pair
