@@ -870,6 +870,14 @@ int unib200_attention(unib200_program* prog, const unib200_attn_desc* d, void* s
   p.trace = g_attn_trace;
   p.pdl_early = unib::g_pdl_enabled == 2 ? 1 : 0;
   Op op = [maps, p](cudaStream_t s) { return launch_attention(maps, p, s); };
+  // what-if timing aid (garbage results): UNIB200_SKIP_ATTN=1 drops the short launches (cross-attention, <= 1024 tokens),
+  // 2 the long self-attention launches
+  static const int skip_attn = getenv("UNIB200_SKIP_ATTN") ? atoi(getenv("UNIB200_SKIP_ATTN")) : 0;
+  if (prog && skip_attn) {
+    const bool small = d->Nk < 512 || d->Nq <= 1024;
+    if ((skip_attn & 1) && small) op = [](cudaStream_t) { return cudaSuccess; };
+    if ((skip_attn & 2) && !small) op = [](cudaStream_t) { return cudaSuccess; };
+  }
   const double bh = static_cast<double>(d->B) * d->heads;
   return submit(prog, std::move(op), 1, stream, "attention", UNIB200_OP_ATTENTION, 4.0 * bh * d->Nq * d->Nk * d->d,
                 2.0 * bh * d->d * (2.0 * d->Nq + 2.0 * d->Nk),

@@ -33,6 +33,22 @@ def _check_2d(t: torch.Tensor, what: str) -> int:
     return t.stride(0)
 
 
+_pdl_mode = [None]
+
+
+def set_pdl(mode: int) -> int:
+    """Programmatic dependent launch for the kernels launched / captured from now on (0 off, 1 trigger at CTA end,
+    2 early trigger); returns the previous mode.  An explicit UNIB200_PDL (A/B runs) pins the mode: calls are ignored."""
+    import os
+    if _pdl_mode[0] is None:
+        _pdl_mode[0] = int(os.environ.get("UNIB200_PDL", "0"))
+    prev = _pdl_mode[0]
+    if os.environ.get("UNIB200_PDL") is None and mode != prev:
+        L.load().unib200_set_pdl(int(mode))
+        _pdl_mode[0] = int(mode)
+    return prev
+
+
 def device_info() -> Tuple[int, int, int]:
     lib = L.load()
     a, b, c = C.c_int(), C.c_int(), C.c_int()

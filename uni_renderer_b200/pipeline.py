@@ -317,10 +317,20 @@ class DualStreamSampler:
             setup.run()
             step.run()
             torch.cuda.synchronize(dev)
+            # Programmatic dependent launch is captured into the graph as programmatic edges.  Measured on B200
+            # (profiles/r2z_pdl_modes.txt): the single-lane loops (forward / inverse rendering: one dependent chain of
+            # ~330 kernels per step) gain 2 % (5.68 -> 5.56 ms/step); the two-lane joint / cycle graphs do not (the
+            # other lane already fills the launch gaps), so they are captured without it.
+            single_lane = mode in ("forward", "inverse") and not (self.split_batch and B >= 2)
+            prev_pdl = ops.set_pdl(1) if single_lane and hasattr(ops, "set_pdl") else None
             side = torch.cuda.Stream(device=dev)
-            with torch.cuda.stream(side):
-                step.instantiate_graph()
-            side.synchronize()
+            try:
+                with torch.cuda.stream(side):
+                    step.instantiate_graph()
+                side.synchronize()
+            finally:
+                if prev_pdl is not None:
+                    ops.set_pdl(prev_pdl)
         if self.device.type == "cuda" and hasattr(ops, "Context"):
             # hand the recorded programs to a step-level C context (include/unib200.h): from here on one call of
             # unib200_sample_loop runs setup + every denoising step, with no Python between the graph launches
