@@ -146,8 +146,26 @@ __device__ __forceinline__ void touch32(float* v) {
 // epilogue): sixteen softmax warps = four per scheduler instead of two, against the per-warp dependency latency that
 // bounds the exponential loop once the shared-memory port is out of the way.  The halves agree on the row maximum
 // through shared memory and one named barrier per block and keep separate row sums.
+// Register re-allocation between the warp roles (setmaxnreg, as in the FlashAttention-3/4 kernels): the register file
+// is handed out per 4-warp group, so the 10-warp CTA is launched with 12 warps (two idle) at the 168 registers
+// __launch_bounds__(384, 1) allows; the producer / MMA warpgroup then shrinks to 104 registers and each softmax
+// warpgroup grows to 200 (the pool is the 3 x 168 of the launch: 2 x 208 + 96 deadlocks in TRY_ALLOC) -- S (128 fp32) and the packed P (64) of a row fit without spills and the exponential loop
+// has room to interleave independent elements (a plain 320-thread launch cannot get more than 168: 184 and 192 fail
+// with "too many resources requested for launch").  UNIB_ATTN_SETMAXNREG=0 builds the old 320-thread kernel.
+// MEASURED SLOWER (profiles/r2z_ab_attention_p_tmem.txt: variant 71 195 -> 207 us, 67 196 -> 204, 43091 194 -> 196): with
+// 200 registers ptxas schedules the exponential loop differently and loses more than the spills cost.  Off by default.
+#ifndef UNIB_ATTN_SETMAXNREG
+#define UNIB_ATTN_SETMAXNREG 0
+#endif
+template <int SPLIT>
+constexpr int attn_threads() { return (SPLIT == 1 && UNIB_ATTN_SETMAXNREG) ? 384 : (8 * SPLIT + 2) * 32; }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
 template <int NCH, int VAR, int SPLIT = 1>
-__global__ void __launch_bounds__((8 * SPLIT + 2) * 32, 1)
+__global__ void __launch_bounds__(attn_threads<SPLIT>(), 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<NCH>;
   constexpr int BKV = Cfg::kBKV;
@@ -231,6 +249,11 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
   auto t_p_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + t * 64); };      // kPTmem: fp16 P_t
   auto t_l_col = [&](int t) { return static_cast<uint32_t>(2 * BKV + 2 * o_stride + (kPTmem ? 128 : 0) + t * 16); };
 
+  constexpr bool kRegSplit = (SPLIT == 1 && UNIB_ATTN_SETMAXNREG);
+  // the control warpgroup: producer, MMA issuer and (register split) the two idle warps that complete the warpgroup
+  const bool ctrl_wg = kRegSplit ? (warp >= 8) : (warp == kProdWarp || warp == kMmaWarp);
+  if (ctrl_wg) {
+  if (kRegSplit) setmaxnreg_dec<104>();
   if (warp == kProdWarp) {
     // =============================== TMA producer ===============================
     // warp-uniform loop, one elected lane issues (operands stay in uniform registers)
@@ -328,6 +351,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
       }
       st = stn;
     }
+  }
   } else if (SPLIT == 2) {
     // =============================== softmax + epilogue, column-split ===============================
     // warp w: TMEM lane quadrant w & 3, warpgroup g = w >> 2: tile t = g & 1, column half hf = g >> 1
@@ -475,6 +499,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnMaps maps, const __grid_con
     }
   } else {
     // =============================== softmax + epilogue (warpgroup t = warp / 4) ===============================
+    if (kRegSplit) setmaxnreg_inc<200>();    // 2 x 200 + 104 = 504 = 3 x 168: what the CTA was launched with
     const int t = warp >> 2;
     if (t < ntile) {
       const int qd = warp & 3;                // TMEM lane quadrant
@@ -746,7 +771,7 @@ static cudaError_t launch_cfg(const AttnMaps& maps, const AttnParams& p, cudaStr
     attr_set = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, p.B);
-  return launch_pdl(attention_tcgen05_kernel<NCH, VAR, SPLIT>, grid, dim3((8 * SPLIT + 2) * 32), smem_bytes, stream, maps, p);
+  return launch_pdl(attention_tcgen05_kernel<NCH, VAR, SPLIT>, grid, dim3(attn_threads<SPLIT>()), smem_bytes, stream, maps, p);
 }
 
 int attention_bkv(int d) { return d <= 64 ? 128 : 64; }
@@ -789,12 +814,8 @@ static cudaError_t launch_var(const AttnMaps& maps, const AttnParams& p, cudaStr
     switch (attention_variant(NCH)) {
       case 23: return launch_cfg<1, 23>(maps, p, stream);                    // 7 + tensor-core row sums
       case 27: return launch_cfg<1, 27>(maps, p, stream);                    // tc sums, polynomial on every 2nd pair
-      case 39: return launch_cfg<1, 39>(maps, p, stream);                    // 7 + early S
-      case 55: return launch_cfg<1, 55>(maps, p, stream);                    // 7 + tc sums + early S
-      case 59: return launch_cfg<1, 59>(maps, p, stream);                    // 27 + early S
       case 43011: return launch_cfg<1, 3 | (0xA8 << 8)>(maps, p, stream);    // polynomial on 3 of 8 pairs
       case 43027: return launch_cfg<1, 19 | (0xA8 << 8)>(maps, p, stream);   // + tc sums
-      case 43059: return launch_cfg<1, 51 | (0xA8 << 8)>(maps, p, stream);   // + tc sums + early S
       case 67: return launch_cfg<1, 67>(maps, p, stream);                    // P in tensor memory, no polynomial
       case 71: return launch_cfg<1, 71>(maps, p, stream);                    // 7 + P in tensor memory
       case 199: return launch_cfg<1, 199>(maps, p, stream);                  // + half-way P store
