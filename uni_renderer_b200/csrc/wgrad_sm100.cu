@@ -553,26 +553,77 @@ cudaError_t launch_scatter2x(const __half* src, __half* dst, int B, int H, int W
 
 // AdamW on flat fp32 buffers, torch.optim.AdamW's arithmetic: p *= 1 - lr wd; m, v moments of g * grad_scale (the
 // inverse loss scale and the clip coefficient); p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
+                                          float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  const float gi = g * grad_scale;
+  const float mi = b1 * m + (1.0f - b1) * gi;
+  const float vi = b2 * v + (1.0f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p = p * (1.0f - lr * wd) - (lr / bc1) * (mi / denom);
+}
+// One pass over the flat fp32 buffers (p, g, m, v read; p, m, v written: 28 bytes per parameter, 49 GB at SD-1.5 size):
+// pure HBM streaming, so every thread keeps two 128-bit loads of each array in flight (the scalar grid-stride version
+// ran at 4.4 TB/s).  Same arithmetic per element as before: results are bit-identical.
 __global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr,
                                                     float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                     float grad_scale) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] * (1.0f - lr * wd) - (lr / bc1) * (mi / denom);
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  auto upd = [&](float4& pp, const float4& gg, float4& mm, float4& vv) {
+    adamw_one(pp.x, gg.x, mm.x, vv.x, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pp.y, gg.y, mm.y, vv.y, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pp.z, gg.z, mm.z, vv.z, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+    adamw_one(pp.w, gg.w, mm.w, vv.w, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  };
+  for (; i + stride < n4; i += 2 * stride) {
+    float4 pa = p4[i], pb = p4[i + stride];
+    const float4 ga = __ldg(g4 + i), gb = __ldg(g4 + i + stride);
+    float4 ma = m4[i], mb = m4[i + stride];
+    float4 va = v4[i], vb = v4[i + stride];
+    upd(pa, ga, ma, va);
+    upd(pb, gb, mb, vb);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+    p4[i + stride] = pb; m4[i + stride] = mb; v4[i + stride] = vb;
   }
+  if (i < n4) {
+    float4 pa = p4[i], ma = m4[i], va = v4[i];
+    const float4 ga = __ldg(g4 + i);
+    upd(pa, ga, ma, va);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+  }
+  // tail (n not a multiple of 4)
+  for (long long t = (n4 << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < n; t += stride)
+    adamw_one(p[t], g[t], m[t], v[t], lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+}
+__global__ void __launch_bounds__(256) adamw_scalar_kernel(float* p, const float* g, float* m, float* v, long long n,
+                                                           float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                           float bc2_sqrt, float grad_scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    adamw_one(p[i], g[i], m[i], v[i], lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
 }
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                          float wd, int step, float grad_scale, cudaStream_t stream) {
   const float bc1 = 1.0f - powf(b1, static_cast<float>(step));
   const float bc2_sqrt = sqrtf(1.0f - powf(b2, static_cast<float>(step)));
-  int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
-  adamw_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (aligned) {
+    const long long work = (n / 4 + 1) / 2 + 1;                // float4 pairs per thread-iteration
+    int blocks = static_cast<int>((work + 255) / 256 > 2368 ? 2368 : (work + 255) / 256);
+    adamw_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  } else {
+    int blocks = static_cast<int>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+    adamw_scalar_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt,
+                                                                     grad_scale);
+  }
   return cudaGetLastError();
 }
 
