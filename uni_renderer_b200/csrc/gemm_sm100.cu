@@ -411,7 +411,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
       constexpr int out_bn = geglu ? BN / 2 : BN;               // output columns per tile
       constexpr int kWarpFloats = (geglu ? 3 * 2 : 3) * nmine * 32;
       static_assert(kEpiWarps * kWarpFloats * 4 <= Cfg::kBiasBytes, "per-warp bias copies must fit");
+#if defined(UNIB_WHATIF_EPI) && (UNIB_WHATIF_EPI & 2)
+      const bool has_res = false;                // what-if timing aid: the epilogue without its residual loads
+#else
       const bool has_res = !geglu && p.res != nullptr;
+#endif
       const bool has_bias = p.bias != nullptr;
       const int n_out = geglu ? p.N / 2 : p.N;
       // this warp's bias copy: [2 batch rows][slots][32] (+ LayerNorm wsum [slots][32]); slot = local sub-tile index;
@@ -646,7 +650,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const __grid_constant
             // lane < 16: sum of pair `lane`; lane >= 16: sum of squares of pair `lane - 16`
             stat_s[((tl & 1) * 4 + q) * BN + (j * 16 + (lane & 15)) * 2 + (lane >> 4)] = x[0];
           }
+#if defined(UNIB_WHATIF_EPI) && (UNIB_WHATIF_EPI & 1)
+          if (row_ok && p.M < 0) {               // what-if timing aid: the epilogue without its global stores
+#else
           if (row_ok) {
+#endif
             __half* op = outp + orow * p.ldc + n0 + j * 32;
             uint32_t o[16];
 #pragma unroll
