@@ -161,6 +161,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* partial,
   }
 }
 
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  float x;
+  const uint32_t remote = mapa_u32(local_addr, rank);
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(remote) : "memory");
+  return x;
+}
+
 // db[n] = sum over rows of dY[m, n]: one block per 8-channel vector column group, rows strided over threads, fixed-order
 // tree in shared memory
 __global__ void __launch_bounds__(256) colsum_kernel(const __half* dy, int ld, int M, int N, float* db) {
@@ -212,8 +219,73 @@ cudaError_t launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream
   return e;
 }
 
+// The same column sums with the rows split over a cluster of 8 CTAs and 32 columns (64 contiguous bytes per row) per
+// cluster: four lanes read a row's 64 bytes, 64 row lanes per CTA, four loads in flight per thread; the CTA's partial is
+// reduced by a fixed-order tree in shared memory and the cluster's eight partials are summed in rank order by CTA 0
+// through distributed shared memory.  (One CTA per 8 columns walked all M rows alone: 40 CTAs and 17 us at N = 320.)
+__global__ void __launch_bounds__(256) colsum_cluster_kernel(const __half* dy, int ld, int M, int N, float* db) {
+  __shared__ float red[64][32];
+  __shared__ float part[32];
+  const uint32_t rank = cluster_ctarank(), cs = cluster_nctarank();
+  const int c0 = blockIdx.x * 32 + (threadIdx.x & 3) * 8;
+  const int rl = threadIdx.x >> 2;                       // 64 row lanes
+  const int r0 = static_cast<int>((static_cast<long long>(rank) * M) / cs);
+  const int r1 = static_cast<int>((static_cast<long long>(rank + 1) * M) / cs);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  auto acc = [&](const uint4& raw) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s[2 * j] += f.x;
+      s[2 * j + 1] += f.y;
+    }
+  };
+  const __half* src = dy + c0;
+  int m = r0 + rl;
+  for (; m + 192 < r1; m += 256) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(m) * ld);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(m + 64) * ld);
+    const uint4 a2 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(m + 128) * ld);
+    const uint4 a3 = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(m + 192) * ld);
+    acc(a0); acc(a1); acc(a2); acc(a3);
+  }
+  for (; m < r1; m += 64) acc(*reinterpret_cast<const uint4*>(src + static_cast<size_t>(m) * ld));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][(threadIdx.x & 3) * 8 + j] = s[j];
+  __syncthreads();
+  for (int off = 32; off > 0; off >>= 1) {
+    for (int i = threadIdx.x; i < off * 32; i += blockDim.x) red[i >> 5][i & 31] += red[(i >> 5) + off][i & 31];
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) part[threadIdx.x] = red[0][threadIdx.x];
+  cluster_sync_all();
+  if (rank == 0 && threadIdx.x < 32) {
+    const uint32_t la = smem_u32(&part[threadIdx.x]);
+    float a = 0.f;
+    for (uint32_t r = 0; r < cs; ++r) a += ld_dsmem_f32(la, r);
+    db[blockIdx.x * 32 + threadIdx.x] = a;
+  }
+  cluster_sync_all();                                    // CTA 0 may still be reading the peers' partials
+}
+
 cudaError_t launch_colsum(const __half* dy, int ld, int M, int N, float* db, cudaStream_t stream) {
   if (N % 8) return cudaErrorInvalidValue;
+  static const bool old_kernel = getenv("UNIB200_COLSUM_OLD") != nullptr;        // A/B
+  if (!old_kernel && N % 32 == 0 && M >= 512 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(N / 32, 8);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 8; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, colsum_cluster_kernel, dy, ld, M, N, db);
+  }
   colsum_kernel<<<N / 8, 256, 0, stream>>>(dy, ld, M, N, db);
   return cudaGetLastError();
 }
@@ -321,12 +393,6 @@ __global__ void __launch_bounds__(256) gn_backward_kernel(GnBwdParams p) {
 // and over the cluster through distributed shared memory in a fixed order.  Sweep 1: per-group sum / sum of squares ->
 // mu, rstd.  Sweep 2: per-channel dgamma = sum dy xhat, dbeta = sum dy; the group means of dxhat and dxhat * xhat follow
 // from them (sum_c gamma_c dbeta_c, sum_c gamma_c dgamma_c).  Sweep 3: dx.  85 -> ~20 us on a 64x64 x 320 sample batch.
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
-  float x;
-  const uint32_t remote = mapa_u32(local_addr, rank);
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(remote) : "memory");
-  return x;
-}
 
 __global__ void __launch_bounds__(512) gn_backward_cluster_kernel(GnBwdParams p) {
   extern __shared__ float sm[];                    // red[2][rpb][C] | chs[2][C] (this CTA's per-channel sums)
