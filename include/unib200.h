@@ -266,6 +266,17 @@ int unib200_groupnorm_backward(unib200_program* prog, const unib200_gn_bwd_desc*
 /* out[n] = sum over the M rows of the fp16 matrix x [M, ld] (first N columns, N % 8 == 0), fp32, fixed order: bias
  * gradients, and the gradient of a per-sample broadcast add (the time-embedding add of ResnetBlock2D). */
 int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, float* out, void* stream);
+/* Training glue between the fp32 master weights and the kernels (the reference keeps fp32 parameters under
+ * accelerate's fp16 autocast, train/train.py:1324-1427; torch's permute / flip / pad / cast chains cost ~25 ms per
+ * step).  w: fp32 [O][I][taps] (taps 1 = Linear / 1x1, 9 = 3x3, the reference's Conv2d layout).
+ * dgrad = 0: out = fp16 [O][taps * Ipad], the K-major operand unib200_conv_gemm takes (Ipad = I rounded up to 64);
+ * dgrad = 1: out = fp16 [I][taps * Opad], the operand of the data-gradient convolution
+ *            dX = conv(dY, W'), W'[i][o][ky][kx] = W[o][i][2 - ky][2 - kx].
+ * Only the valid columns are written: the caller zeroes the buffer once when it allocates it. */
+int unib200_pack_master_weight(unib200_program* prog, const float* w, int O, int I, int taps, void* out, int dgrad,
+                               void* stream);
+/* grad[n][c][t] += dw[n][t][c]: unib200_conv_wgrad's tap-major fp32 output added into a reference-layout gradient */
+int unib200_wgrad_scatter_add(unib200_program* prog, const float* dw, float* grad, int N, int taps, int C, void* stream);
 
 /* transformer-block backward helpers (BasicTransformerBlock: LayerNorm, GEGLU, softmax of a materialised attention) */
 /* LayerNorm backward over [rows, C] fp16: dx, and dgamma_dbeta = fp32 [2 * C] = [dgamma | dbeta]; scratch fp32

@@ -94,7 +94,7 @@ EXPORTS = [
     "unib200_softmax_rows", "unib200_gaussian_sample",
     "unib200_conv_wgrad", "unib200_groupnorm_backward", "unib200_colsum", "unib200_layernorm_backward", "unib200_geglu",
     "unib200_softmax_backward", "unib200_cvt_f32_f16", "unib200_silu_f16", "unib200_pool2x2_sum", "unib200_scatter2x",
-    "unib200_adamw_step", "unib200_attention_backward",
+    "unib200_adamw_step", "unib200_attention_backward", "unib200_pack_master_weight", "unib200_wgrad_scatter_add",
     "unib200_create", "unib200_destroy", "unib200_load_weight", "unib200_alloc", "unib200_bind", "unib200_buffer",
     "unib200_ctx_attach", "unib200_ctx_run", "unib200_unet_forward", "unib200_attr_enc_forward",
     "unib200_attr_dec_forward", "unib200_dual_step", "unib200_sample_loop",
@@ -163,6 +163,8 @@ def load() -> C.CDLL:
     lib.unib200_conv_wgrad.argtypes = [vp, C.POINTER(WgradDesc), vp]
     lib.unib200_groupnorm_backward.argtypes = [vp, C.POINTER(GnBwdDesc), vp]
     lib.unib200_colsum.argtypes = [vp, vp, ci, ci, ci, vp, vp]
+    lib.unib200_pack_master_weight.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]
+    lib.unib200_wgrad_scatter_add.argtypes = [vp, vp, vp, ci, ci, ci, vp]
     lib.unib200_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, ci, ci, cf, vp]
     lib.unib200_geglu.argtypes = [vp, vp, vp, vp, i64, ci, vp]
     lib.unib200_softmax_backward.argtypes = [vp, vp, vp, ci, ci, ci, cf, vp]

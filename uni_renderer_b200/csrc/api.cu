@@ -740,6 +740,20 @@ int unib200_conv_wgrad(unib200_program* prog, const unib200_wgrad_desc* d, void*
                     std::to_string(d->taps) + " splits=" + std::to_string(splits));
 }
 
+int unib200_pack_master_weight(unib200_program* prog, const float* w, int O, int I, int taps, void* out, int dgrad,
+                               void* stream) {
+  if (!w || !out || O <= 0 || I <= 0 || (taps != 1 && taps != 9)) return fail("pack_master_weight: bad arguments (taps 1 or 9)");
+  __half* op_ = static_cast<__half*>(out);
+  Op op = [=](cudaStream_t s) { return launch_pack_master(w, op_, O, I, taps, dgrad, s); };
+  return submit(prog, std::move(op), 1, stream, "pack_master_weight");
+}
+
+int unib200_wgrad_scatter_add(unib200_program* prog, const float* dw, float* grad, int N, int taps, int C, void* stream) {
+  if (!dw || !grad || N <= 0 || C <= 0 || taps <= 0) return fail("wgrad_scatter_add: bad arguments");
+  Op op = [=](cudaStream_t s) { return launch_wgrad_scatter_add(dw, grad, N, taps, C, s); };
+  return submit(prog, std::move(op), 1, stream, "wgrad_scatter_add");
+}
+
 int unib200_colsum(unib200_program* prog, const void* x, int ld, int M, int N, float* out, void* stream) {
   if (!x || !out || M <= 0 || N <= 0 || N % 8 || ld % 8 || ld < N) return fail("colsum: bad arguments (N and ld multiples of 8)");
   const __half* xp = static_cast<const __half*>(x);

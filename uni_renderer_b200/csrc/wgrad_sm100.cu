@@ -271,6 +271,86 @@ __global__ void __launch_bounds__(256) colsum_cluster_kernel(const __half* dy, i
   cluster_sync_all();                                    // CTA 0 may still be reading the peers' partials
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Training glue between the fp32 master weights (reference layout [O][I][taps], taps = 1 | 9) and the kernels:
+// * pack_master_kernel<false>: the forward GEMM's K-major fp16 operand [O][taps * Ipad]  (channels padded to 64 per tap)
+// * pack_master_kernel<true>:  the data-gradient GEMM's operand [I][taps * Opad] = the transposed, tap-flipped weights
+//   (dX = conv(dY, W'), W'[i][o][ky][kx] = W[o][i][2 - ky][2 - kx])
+//   -- one pass over the master each instead of torch's permute / flip / pad / cast chain; the padding columns are
+//   zeroed once when the buffer is allocated.  Same round-to-nearest-even cast: bit-identical operands.
+// * wgrad_scatter_add_kernel: grad[o][i][t] += dw[o][t][i] -- the weight-gradient kernel's tap-major fp32 output added
+//   into the reference-layout flat gradient (was a strided torch permute copy + an add).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool DGRAD>
+__global__ void __launch_bounds__(256) pack_master_kernel(const float* __restrict__ w, __half* __restrict__ out, int O, int I,
+                                                          int taps, int pad) {
+  const long long total = static_cast<long long>(O) * I;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int o, i;
+    if (DGRAD) { i = static_cast<int>(idx / O); o = static_cast<int>(idx - static_cast<long long>(i) * O); }
+    else { o = static_cast<int>(idx / I); i = static_cast<int>(idx - static_cast<long long>(o) * I); }
+    const float* src = w + (static_cast<size_t>(o) * I + i) * taps;
+    if (DGRAD) {
+      __half* dst = out + static_cast<size_t>(i) * taps * pad + o;           // pad = Opad
+      for (int t = 0; t < taps; ++t) dst[static_cast<size_t>(taps - 1 - t) * pad] = __float2half_rn(src[t]);
+    } else {
+      __half* dst = out + static_cast<size_t>(o) * taps * pad + i;           // pad = Ipad
+      for (int t = 0; t < taps; ++t) dst[static_cast<size_t>(t) * pad] = __float2half_rn(src[t]);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) wgrad_scatter_add_kernel(const float* __restrict__ dw, float* __restrict__ grad, int N,
+                                                                int taps, int C) {
+  const long long total = static_cast<long long>(N) * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / C), c = static_cast<int>(idx - static_cast<long long>(n) * C);
+    float* g = grad + idx * taps;
+    const float* d = dw + static_cast<size_t>(n) * taps * C + c;
+    for (int t = 0; t < taps; ++t) g[t] += d[static_cast<size_t>(t) * C];
+  }
+}
+// taps == 9: a CTA transposes one (n, 128-channel) slab through shared memory, so both the tap-major reads and the
+// reference-layout read-modify-writes are contiguous (the per-thread 9-float walk above runs at a quarter of the
+// rate of torch's permute + add)
+__global__ void __launch_bounds__(128) wgrad_scatter_add9_kernel(const float* __restrict__ dw, float* __restrict__ grad, int N,
+                                                                 int C) {
+  __shared__ float tile[9][129];
+  const int n = blockIdx.y, c0 = blockIdx.x * 128;
+  const int cn = C - c0 < 128 ? C - c0 : 128;
+  if (static_cast<int>(threadIdx.x) < cn) {
+    const float* d = dw + static_cast<size_t>(n) * 9 * C + c0 + threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) tile[t][threadIdx.x] = d[static_cast<size_t>(t) * C];
+  }
+  __syncthreads();
+  float* base = grad + (static_cast<size_t>(n) * C + c0) * 9;
+  for (int e = threadIdx.x; e < cn * 9; e += 128) {
+    const int c = e / 9, t = e - c * 9;
+    base[e] += tile[t][c];
+  }
+}
+cudaError_t launch_pack_master(const float* w, __half* out, int O, int I, int taps, int dgrad, cudaStream_t stream) {
+  const long long total = static_cast<long long>(O) * I;
+  int blocks = static_cast<int>((total + 255) / 256 > 4736 ? 4736 : (total + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (dgrad) pack_master_kernel<true><<<blocks, 256, 0, stream>>>(w, out, O, I, taps, (O + 63) / 64 * 64);
+  else pack_master_kernel<false><<<blocks, 256, 0, stream>>>(w, out, O, I, taps, (I + 63) / 64 * 64);
+  return cudaGetLastError();
+}
+cudaError_t launch_wgrad_scatter_add(const float* dw, float* grad, int N, int taps, int C, cudaStream_t stream) {
+  if (taps == 9 && N <= 65535) {
+    wgrad_scatter_add9_kernel<<<dim3((C + 127) / 128, N), 128, 0, stream>>>(dw, grad, N, C);
+    return cudaGetLastError();
+  }
+  const long long total = static_cast<long long>(N) * C;
+  int blocks = static_cast<int>((total + 255) / 256 > 4736 ? 4736 : (total + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  wgrad_scatter_add_kernel<<<blocks, 256, 0, stream>>>(dw, grad, N, taps, C);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_colsum(const __half* dy, int ld, int M, int N, float* db, cudaStream_t stream) {
   if (N % 8) return cudaErrorInvalidValue;
   static const bool old_kernel = getenv("UNIB200_COLSUM_OLD") != nullptr;        // A/B

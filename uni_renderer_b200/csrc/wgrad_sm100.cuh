@@ -36,6 +36,8 @@ struct GnBwdParams {
   float eps;
 };
 cudaError_t launch_gn_backward(const GnBwdParams& p, int B, cudaStream_t stream);
+cudaError_t launch_pack_master(const float* w, __half* out, int O, int I, int taps, int dgrad, cudaStream_t stream);
+cudaError_t launch_wgrad_scatter_add(const float* dw, float* grad, int N, int taps, int C, cudaStream_t stream);
 cudaError_t launch_sum_slabs(const float* partial, float* out, long long n, int slabs, cudaStream_t stream);
 // dgamma must hold 2 * C floats: on return [dgamma | dbeta]; slabs: fp32 [max_slabs][2][C] scratch
 cudaError_t launch_layernorm_backward(const __half* x, const __half* dy, __half* dx, const float* gamma, float* dgamma,

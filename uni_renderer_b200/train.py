@@ -37,8 +37,17 @@ def dgrad_weight(w: torch.Tensor) -> torch.Tensor:
     return ops.pack_weight([(wt, SEG_3x3 if w.shape[-1] == 3 else SEG_1x1)])
 
 
+def pack_master_weight(w: torch.Tensor, O: int, I: int, taps: int, out: torch.Tensor, dgrad: bool) -> None:
+    """unib200_pack_master_weight: fp32 master weight [O, I, taps] -> the valid columns of the fp16 operand buffer `out`
+    ([O, taps * Ipad] forward, [I, taps * Opad] data gradient; padding columns were zeroed at allocation)."""
+    assert w.dtype == torch.float32 and w.is_contiguous() and out.dtype == torch.float16 and out.is_contiguous()
+    L.check(L.load().unib200_pack_master_weight(None, w.data_ptr(), O, I, taps, out.data_ptr(), int(dgrad),
+                                                torch.cuda.current_stream().cuda_stream), "pack_master_weight")
+
+
 def conv_wgrad(x: torch.Tensor, C_in: int, dy: torch.Tensor, N: int, *, B: int, H: int, W: int, taps: int,
-               partial: Optional[torch.Tensor] = None, want_bias: bool = True):
+               partial: Optional[torch.Tensor] = None, want_bias: bool = True,
+               accumulate_into: Optional[torch.Tensor] = None):
     """(dW fp32 [N, C_in, k, k], db fp32 [N] | None) of a stride-1 conv (taps 9: 3x3 pad 1; taps 1: 1x1 / linear with
     H = W = 0) from its forward input x [M, >= C_in] and the output gradient dy [M, >= N], both fp16 NHWC matrices."""
     lib = L.load()
@@ -53,6 +62,13 @@ def conv_wgrad(x: torch.Tensor, C_in: int, dy: torch.Tensor, N: int, *, B: int, 
     if partial is not None:
         d.partial, d.partial_bytes = partial.data_ptr(), partial.numel() * 4
     L.check(lib.unib200_conv_wgrad(None, C.byref(d), torch.cuda.current_stream().cuda_stream), "conv_wgrad")
+    if accumulate_into is not None:
+        # grad[n][c][t] += dw[n][t][c]: added into the reference-layout fp32 gradient by one kernel; returns (None, db)
+        g = accumulate_into
+        assert g.dtype == torch.float32 and g.is_contiguous() and g.numel() == N * taps * C_in
+        L.check(lib.unib200_wgrad_scatter_add(None, dw.data_ptr(), g.data_ptr(), N, taps, C_in,
+                                              torch.cuda.current_stream().cuda_stream), "wgrad_scatter_add")
+        return None, db
     k = 3 if taps == 9 else 1
     return dw.reshape(N, k, k, C_in).permute(0, 3, 1, 2).contiguous(), db
 

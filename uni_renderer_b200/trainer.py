@@ -83,22 +83,45 @@ class ParamSet:
             self.g[name] = self.grad[off:off + n].view(v.shape)
             off += n
         self._cache: Dict[Tuple[str, str], torch.Tensor] = {}
+        # persistent fp16 operand buffers of the native packing path (padding columns zeroed once, valid columns
+        # rewritten by unib200_pack_master_weight after every optimizer step)
+        self._packed: Dict[Tuple[str, str], torch.Tensor] = {}
+        self.native_pack = dev.type == "cuda"
         self.m = self.v = None            # AdamW moments (allocated by the first step)
         self.steps = 0
 
     def invalidate(self):
         self._cache.clear()
 
+    def _pack_native(self, name: str, dgrad: bool) -> torch.Tensor:
+        """fp32 master weight [O, I(, k, k)] -> the fp16 K-major operand of the forward GEMM ([O, taps * Ipad]) or of the
+        data-gradient GEMM ([I, taps * Opad], transposed + tap-flipped) in ONE kernel pass over the master (torch's
+        permute / flip / pad / cast chains of ops.pack_weight / train.dgrad_weight cost ~25 ms per step)."""
+        w = self.p[name + ".weight"]
+        O, I = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+        key = (name, "t" if dgrad else "w")
+        buf = self._packed.get(key)
+        if buf is None:
+            rows, inner = (I, O) if dgrad else (O, I)
+            buf = torch.zeros(rows, taps * ((inner + 63) // 64 * 64), device=self.dev, dtype=torch.float16)
+            self._packed[key] = buf
+        T.pack_master_weight(w, O, I, taps, buf, dgrad)
+        return buf
+
     def weight(self, name: str, kind: int) -> torch.Tensor:
         key = (name, f"w{kind}")
         if key not in self._cache:
-            self._cache[key] = ops.pack_weight([(self.p[name + ".weight"], SEG_3x3 if kind == SEG_3x3_S2 else kind)])
+            if self.native_pack:
+                self._cache[key] = self._pack_native(name, False)
+            else:
+                self._cache[key] = ops.pack_weight([(self.p[name + ".weight"], SEG_3x3 if kind == SEG_3x3_S2 else kind)])
         return self._cache[key]
 
     def weight_t(self, name: str) -> torch.Tensor:
         key = (name, "t")
         if key not in self._cache:
-            self._cache[key] = T.dgrad_weight(self.p[name + ".weight"])
+            self._cache[key] = self._pack_native(name, True) if self.native_pack else T.dgrad_weight(self.p[name + ".weight"])
         return self._cache[key]
 
     def bias(self, name: str) -> Optional[torch.Tensor]:
@@ -190,9 +213,14 @@ def conv(tp: Tape, x: TT, name: str, k: int = 3, stride: int = 1, bias_tab: Opti
             dyw = T.scatter2x(dy, B, H, W)
             Hw, Ww = 2 * H, 2 * W
         want_b = P.bias(name) is not None and N % 8 == 0
-        dw, db = T.conv_wgrad(x.v, Cin, dyw, N, B=B, H=Hw if k == 3 else 0, W=Ww if k == 3 else 0, taps=k * k,
-                            partial=tp.partial, want_bias=want_b)
-        P.add_grad(name + ".weight", dw if k == 3 else dw.reshape(N, Cin))
+        if P.native_pack and k == 3:
+            # the tap-major fp32 result goes straight into the reference-layout flat gradient (no permute copy + add)
+            _, db = T.conv_wgrad(x.v, Cin, dyw, N, B=B, H=Hw, W=Ww, taps=9, partial=tp.partial, want_bias=want_b,
+                                 accumulate_into=P.g[name + ".weight"])
+        else:
+            dw, db = T.conv_wgrad(x.v, Cin, dyw, N, B=B, H=Hw if k == 3 else 0, W=Ww if k == 3 else 0, taps=k * k,
+                                  partial=tp.partial, want_bias=want_b)
+            P.add_grad(name + ".weight", dw if k == 3 else dw.reshape(N, Cin))
         if P.bias(name) is not None:
             P.add_grad(name + ".bias", db if want_b else dy[:, :N].float().sum(0))
         if bias_tab is not None:
