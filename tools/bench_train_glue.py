@@ -12,7 +12,7 @@ def timeit(f, n=20):
     for _ in range(n): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / n
-for (O, I, k) in [(1280, 1280, 3), (320, 320, 3), (1280, 2560, 3), (1280, 1280, 1)]:
+for (O, I, k) in [(1280, 1280, 3), (320, 320, 3), (1280, 2560, 3), (1280, 1280, 1), (320, 7, 3), (4, 320, 3), (200, 77, 1), (640, 1000, 3)]:
     w = torch.randn(O, I, k, k, device="cuda") if k == 3 else torch.randn(O, I, device="cuda")
     taps = k * k
     bf = torch.zeros(O, taps * ((I + 63) // 64 * 64), device="cuda", dtype=torch.half)

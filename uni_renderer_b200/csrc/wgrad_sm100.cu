@@ -331,7 +331,38 @@ __global__ void __launch_bounds__(128) wgrad_scatter_add9_kernel(const float* __
     base[e] += tile[t][c];
   }
 }
+// data-gradient operand through a shared-memory transpose: a CTA takes 128 output channels x IT input channels
+// (IT * taps <= 72 master floats per output channel, read contiguously) and writes, for each (input channel, tap),
+// 128 consecutive fp16 = 256 B of the [I][taps * Opad] operand (the one-thread-per-element kernel above reads its
+// 36 bytes at a 46 KB stride: 63 us for a 1280 x 1280 3x3 layer)
+__global__ void __launch_bounds__(256) pack_master_dgrad_tile_kernel(const float* __restrict__ w, __half* __restrict__ out,
+                                                                     int O, int I, int taps, int opad, int it) {
+  __shared__ float tile[128][73];
+  const int o0 = blockIdx.x * 128, i0 = blockIdx.y * it;
+  const int in = I - i0 < it ? I - i0 : it;              // input channels of this tile
+  const int kt = in * taps;                              // contiguous master floats per output channel
+  for (int e = threadIdx.x; e < 128 * kt; e += 256) {
+    const int ol = e / kt, k = e - ol * kt;
+    if (o0 + ol < O) tile[ol][k] = w[(static_cast<size_t>(o0 + ol) * I + i0) * taps + k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kt * 128; e += 256) {
+    const int k = e >> 7, ol = e & 127;
+    const int il = k / taps, t = k - il * taps;
+    if (o0 + ol < O)
+      out[static_cast<size_t>(i0 + il) * taps * opad + static_cast<size_t>(taps - 1 - t) * opad + o0 + ol] =
+          __float2half_rn(tile[ol][k]);
+  }
+}
 cudaError_t launch_pack_master(const float* w, __half* out, int O, int I, int taps, int dgrad, cudaStream_t stream) {
+  if (dgrad && (taps == 9 || taps == 1) && O >= 128) {
+    const int it = taps == 9 ? 8 : 64;
+    const dim3 grid((O + 127) / 128, (I + it - 1) / it);
+    if (grid.y <= 65535) {
+      pack_master_dgrad_tile_kernel<<<grid, 256, 0, stream>>>(w, out, O, I, taps, (O + 63) / 64 * 64, it);
+      return cudaGetLastError();
+    }
+  }
   const long long total = static_cast<long long>(O) * I;
   int blocks = static_cast<int>((total + 255) / 256 > 4736 ? 4736 : (total + 255) / 256);
   if (blocks < 1) blocks = 1;
